@@ -1,0 +1,131 @@
+/*
+ * kelvin_b200.h -- C ABI of the B200-native FT-CCSD hot path.
+ *
+ * The reference (awhite862/kelvin) has no FFI of its own: its hot path is
+ * NumPy einsum -> BLAS, reached through the Python functions listed below.
+ * Each entry point here names the reference interface whose arithmetic it
+ * replaces (paths relative to the reference repo root).  All pointers are
+ * DEVICE pointers owned by the caller (PyTorch's allocator) unless marked
+ * "host"; `stream` is a cudaStream_t passed as void*.  Every function returns
+ * 0 on success or a negative code (-1 bad argument, -2 CUDA error; text via
+ * kb200_last_error()).  No hidden allocation, no global state, FP64 throughout.
+ */
+#ifndef KELVIN_B200_H
+#define KELVIN_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+int kb200_version(void);
+const char* kb200_last_error(void);
+/* Number of kernels this library has launched since load / since last reset
+ * (bench.py's "gpu_launches"). */
+int64_t kb200_launch_count(void);
+void kb200_launch_count_reset(void);
+
+/* ------------------------------------------------------------------------
+ * Contraction plans.
+ *
+ * Replaces: the bodies of cqcpy.cc_equations._Stanton / _u_Stanton /
+ * _Lambda_opt / _uccsd_Lambda_opt / _LS_TS / ccsd_{1,2}rdm_*_opt, called from
+ * kelvin/ft_cc_equations.py:106,153-155,399,442-445,407,456,718-720,744-751,
+ * i.e. every pyscf.lib.einsum -> dgemm of the per-tau-point residual.
+ *
+ * One op is a batched tensor contraction with composite ("gathered") indices
+ *   C[b][cm[m]+cn[n]] = beta*C + alpha * sum_k A[b][am[m]+ak[k]] * B[b][bk[k]+bn[n]]
+ * where am/ak/bk/bn/cm/cn are uint32 element-offset tables (one entry per
+ * composite index value) living in one device buffer `tables`; the index
+ * permutations of the reference's einsum strings are folded into these tables,
+ * never materialised.  b runs over imaginary-time grid points (stride 0 for
+ * the tau-independent integrals).  kind==1 is the index-permuted axpby
+ *   C[b][cm[m]+cn[n]] = beta*C + alpha * A[b][am[m]+ak[n]].
+ * ------------------------------------------------------------------------ */
+typedef struct kb200_op {
+    int32_t kind;          /* 0 contraction (DMMA GEMM), 1 permuted axpby      */
+    int32_t a, b, c;       /* tensor slot numbers (b unused for kind 1)        */
+    int64_t a_off, b_off, c_off;   /* constant element offsets inside the slot */
+    int32_t M, N, K, batch;
+    int64_t bsA, bsB, bsC; /* batch strides in elements                        */
+    int64_t tAm, tAk, tBk, tBn, tCm, tCn;  /* table starts (uint32 units)      */
+    double alpha, beta;
+    int32_t a_mode;        /* 0: A gathers contiguously along k, 1: along m    */
+    int32_t b_mode;        /* 0: B gathers contiguously along k, 1: along n    */
+    int32_t tile;          /* 0: 128x128 CTA tile, 1: 128x32 CTA tile          */
+    int32_t splitk;        /* >=1; >1 uses the workspace + deterministic reduce */
+} kb200_op;
+
+/* Bytes of workspace kb200_plan_run needs for these ops (split-K partials). */
+int64_t kb200_plan_workspace_bytes(const kb200_op* ops /*host*/, int nops);
+
+/* Run ops[0..nops) in order on `stream`.  slots[i] is the device base pointer
+ * of tensor slot i (host array of device pointers). */
+int kb200_plan_run(const kb200_op* ops /*host*/, int nops,
+                   const uint32_t* tables, double* const* slots /*host*/, int nslots,
+                   double* workspace, int64_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Imaginary-time integration.
+ * Replaces kelvin/quadrature.py:292-317 (int_tbar1, int_tbar2):
+ *   out[y,p] = sum_x G[y,x] * w(y,x,p) * tbar[x,p],
+ *   w = exp(D[p]*(ti[x]-ti[y])) for x<y, 1 otherwise   (quirk Q4).
+ * n = elements per grid point.  ti[ng], G[ng*ng] row-major, D[n].
+ * mode 0: one exp per (y,x) pair, exactly the reference's formula;
+ * mode 1: ng-1 exps per element, weights built as running products.
+ * ------------------------------------------------------------------------ */
+int kb200_int_tbar(int ng, int64_t n, const double* tbar, const double* D,
+                   const double* ti, const double* G, double* out, int mode, void* stream);
+
+/* Replaces kelvin/quadrature.py:320-345 (int_L1, int_L2):
+ *   out[s,q] = (1/g[s]) sum_y g[y]*G[y,s]*w(s,y,q)*L[y,q],
+ *   w = exp(D[perm(q)]*(ti[s]-ti[y])) for y>=s, 1 otherwise.
+ * L and out are (ng, d0,d1,d2,d3) C-contiguous; D is addressed as
+ * D[i0*ds0+i1*ds1+i2*ds2+i3*ds3] so that the reference's 'yabij,yijab->yijab'
+ * index swap needs no transposed copy. */
+int kb200_int_L(int ng, const int32_t dims[4] /*host*/, const int64_t dstride[4] /*host*/,
+                const double* L, const double* D, const double* ti, const double* g,
+                const double* G, double* out, int mode, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Energy functional pieces.  Replaces kelvin/ft_cc_energy.py:7-32,35-72.
+ *   out[0] = sum_y g[y] sum_{p} (c2*T2[y,p] + c11*T1x[y,a,i]*T1y[y,b,j]) * Iabij[p]
+ * with p=(a,b,i,j) over dims (nva,nvb,noa,nob); Iabij is the oovv block
+ * pre-permuted to abij order (kind-1 plan op).  T1x/T1y may be NULL (c11=0).
+ *   kb200_dot_g: out[0] = sum_y g[y] sum_p X[y,p]*F[p]   (the T1.f_ov term)
+ * `scratch` needs kb200_reduce_scratch_doubles() doubles. */
+int64_t kb200_reduce_scratch_doubles(void);
+int kb200_energy_pair(int ng, int nva, int nvb, int noa, int nob,
+                      const double* T2, const double* T1x, const double* T1y,
+                      const double* Iabij, const double* g, double c2, double c11,
+                      double* out, double* scratch, void* stream);
+int kb200_dot_g(int ng, int64_t n, const double* X, const double* F, const double* g,
+                double* out, double* scratch, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Damping + residual norms.  Replaces kelvin/cc_utils.py:145-151,278-295,
+ * 458-464,533-547:  out[0]=||new-old||^2, out[1]=||old||^2 (before update),
+ * then old <- alpha*old+(1-alpha)*new, out[2]=||old||^2 (after update). */
+int kb200_damp_norms(int64_t n, double* old, const double* neu, double alpha,
+                     double* out3, double* scratch, void* stream);
+
+/* ------------------------------------------------------------------------
+ * Integral dressing.  Replaces kelvin/cc_utils.py:584-601,713-775:
+ *   out[p,q,r,s] = eri[p,q,r,s]*s0[p]*s1[q]*s2[r]*s3[s]   (dims d[4]);
+ *   kb200_dress2: out[p,q] = (f[p,q] - (p==q)*e[p]) * s0[p]*s1[q]. */
+int kb200_dress4(const int32_t d[4] /*host*/, const double* eri, const double* s0,
+                 const double* s1, const double* s2, const double* s3, double* out,
+                 void* stream);
+int kb200_dress2(int n0, int n1, const double* f, const double* e, const double* s0,
+                 const double* s1, double* out, void* stream);
+
+/* out[y,p] = sum over nothing: weighted grid sums used by the RDM drivers
+ * (kelvin/ft_cc_equations.py:713,737): out[p] = sum_y g[y]*X[y,p]. */
+int kb200_gsum(int ng, int64_t n, const double* X, const double* g, double* out, void* stream);
+
+/* Elementwise X[y,p] *= D[p]  (kelvin/ccsd.py:1138-1139,1238-1242). */
+int kb200_scale_by(int ng, int64_t n, double* X, const double* D, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,102 @@
+"""ctypes binding of libkb200.so (include/kelvin_b200.h).
+
+There is deliberately NO fallback: if the shared object is missing, or CUDA is
+unavailable, every compute entry point raises.  The library is built in-tree by
+``__graft_entry__.build()`` (nvcc, sm_100a).
+"""
+import ctypes
+import os
+
+import torch
+
+from .plan import kb200_op
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libkb200.so")
+
+_lib = None
+
+EXPORTS = (
+    "kb200_version", "kb200_last_error", "kb200_launch_count", "kb200_launch_count_reset",
+    "kb200_plan_workspace_bytes", "kb200_plan_run", "kb200_int_tbar", "kb200_int_L",
+    "kb200_reduce_scratch_doubles", "kb200_energy_pair", "kb200_dot_g", "kb200_damp_norms",
+    "kb200_dress4", "kb200_dress2", "kb200_gsum", "kb200_scale_by",
+)
+
+
+class KB200Error(RuntimeError):
+    pass
+
+
+def load():
+    """Load the C-ABI library (no CUDA call is made here)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise KB200Error(
+            "libkb200.so not found at %s -- run `python -c 'import __graft_entry__ as g; g.build()'`; "
+            "kelvin_b200 has no CPU fallback" % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    vp, i32, i64, dbl = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_double
+    lib.kb200_version.restype = ctypes.c_int
+    lib.kb200_last_error.restype = ctypes.c_char_p
+    lib.kb200_launch_count.restype = i64
+    lib.kb200_launch_count_reset.restype = None
+    lib.kb200_reduce_scratch_doubles.restype = i64
+    lib.kb200_plan_workspace_bytes.restype = i64
+    lib.kb200_plan_workspace_bytes.argtypes = [ctypes.POINTER(kb200_op), ctypes.c_int]
+    lib.kb200_plan_run.argtypes = [ctypes.POINTER(kb200_op), ctypes.c_int, vp,
+                                   ctypes.POINTER(vp), ctypes.c_int, vp, i64, vp]
+    lib.kb200_int_tbar.argtypes = [ctypes.c_int, i64, vp, vp, vp, vp, vp, ctypes.c_int, vp]
+    lib.kb200_int_L.argtypes = [ctypes.c_int, ctypes.POINTER(i32), ctypes.POINTER(i64),
+                                vp, vp, vp, vp, vp, vp, ctypes.c_int, vp]
+    lib.kb200_energy_pair.argtypes = [ctypes.c_int] * 5 + [vp, vp, vp, vp, vp, dbl, dbl, vp, vp, vp]
+    lib.kb200_dot_g.argtypes = [ctypes.c_int, i64, vp, vp, vp, vp, vp, vp]
+    lib.kb200_damp_norms.argtypes = [i64, vp, vp, dbl, vp, vp, vp]
+    lib.kb200_dress4.argtypes = [ctypes.POINTER(i32), vp, vp, vp, vp, vp, vp, vp]
+    lib.kb200_dress2.argtypes = [ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, vp, vp]
+    lib.kb200_gsum.argtypes = [ctypes.c_int, i64, vp, vp, vp, vp]
+    lib.kb200_scale_by.argtypes = [ctypes.c_int, i64, vp, vp, vp]
+    for nm in EXPORTS:
+        getattr(lib, nm)
+    _lib = lib
+    return lib
+
+
+def check(rc, what):
+    if rc != 0:
+        raise KB200Error("%s failed (%d): %s" % (what, rc, load().kb200_last_error().decode()))
+
+
+def device():
+    if not torch.cuda.is_available():
+        raise KB200Error("kelvin_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def stream_ptr():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def ptr(t):
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def as_dev(x, dev=None):
+    """NumPy / torch (any device) -> contiguous float64 CUDA tensor."""
+    dev = dev or device()
+    if isinstance(x, torch.Tensor):
+        return x.to(device=dev, dtype=torch.float64).contiguous()
+    return torch.as_tensor(x, dtype=torch.float64).to(dev).contiguous()
+
+
+_scratch = {}
+
+
+def reduce_scratch(dev):
+    key = (dev.index, torch.cuda.current_stream().cuda_stream)
+    if key not in _scratch:
+        n = load().kb200_reduce_scratch_doubles()
+        _scratch[key] = torch.empty(int(n), dtype=torch.float64, device=dev)
+    return _scratch[key]

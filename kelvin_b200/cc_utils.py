@@ -1,0 +1,223 @@
+"""Iteration loops and integral dressing for FT-CCSD on the GPU.
+
+Drop-in for the on-path part of kelvin/cc_utils.py: ``ft_integrals`` (:569),
+``uft_integrals`` (:696), ``form_new_ampl`` (:17), ``form_new_ampl_u`` (:52),
+``ft_cc_iter`` (:111), ``ft_ucc_iter`` (:245), ``ft_lambda_iter`` (:414),
+``ft_ulambda_iter`` (:483).  Same arguments, same log lines, same convergence
+predicates (including the g/u differences in the residual norms, quirk Q5).
+Damping and all norms run in one fused pass per tensor (kb200_damp_norms).
+"""
+import ctypes
+import logging
+import math
+import time
+
+import numpy
+import torch
+
+from . import _lib, ft_cc_energy, ft_cc_equations, ft_utils
+from .ov_blocks import one_e_blocks, two_e_blocks, two_e_blocks_full
+
+
+# ---------------------------------------------------------------------------
+# dressing
+# ---------------------------------------------------------------------------
+def _vec(x, dev):
+    return torch.as_tensor(numpy.asarray(x, dtype=numpy.float64)).to(dev)
+
+
+def _dress4(eri, s0, s1, s2, s3):
+    lib = _lib.load()
+    out = torch.empty_like(eri)
+    d = (ctypes.c_int32*4)(*eri.shape)
+    rc = lib.kb200_dress4(d, _lib.ptr(eri), _lib.ptr(s0), _lib.ptr(s1), _lib.ptr(s2),
+                          _lib.ptr(s3), _lib.ptr(out), _lib.stream_ptr())
+    _lib.check(rc, "kb200_dress4")
+    return out
+
+
+def _dress2(f, e, s0, s1):
+    lib = _lib.load()
+    out = torch.empty_like(f)
+    rc = lib.kb200_dress2(f.shape[0], f.shape[1], _lib.ptr(f), _lib.ptr(e), _lib.ptr(s0),
+                          _lib.ptr(s1), _lib.ptr(out), _lib.stream_ptr())
+    _lib.check(rc, "kb200_dress2")
+    return out
+
+
+def _dress_F(fmo, en, so, sv):
+    """F - diag(e), each index scaled by sqrt(f) (o) / sqrt(1-f) (v)
+    (kelvin/cc_utils.py:577-588)."""
+    s = {"o": so, "v": sv}
+    return one_e_blocks(*[_dress2(fmo, en, s[p[0]], s[p[1]]) for p in ("oo", "ov", "vo", "vv")])
+
+
+def ft_integrals(sys, en, beta, mu):
+    """Return one and two-electron integrals in the general spin orbital basis,
+    pre-contracted with the Fermi factors (kelvin/cc_utils.py:569-602)."""
+    dev = _lib.device()
+    fo = ft_utils.ff(beta, en, mu)
+    fv = ft_utils.ffv(beta, en, mu)
+    so, sv = _vec(numpy.sqrt(fo), dev), _vec(numpy.sqrt(fv), dev)
+    fmo = _lib.as_dev(sys.g_fock_tot(), dev)
+    F = _dress_F(fmo, _vec(en, dev), so, sv)
+    eri = _lib.as_dev(sys.g_aint_tot(), dev)
+    s = {"o": so, "v": sv}
+    I = two_e_blocks(**{p: _dress4(eri, s[p[0]], s[p[1]], s[p[2]], s[p[3]])
+                        for p in two_e_blocks.names})
+    return F, I
+
+
+def uft_integrals(sys, ea, eb, beta, mu):
+    """Unrestricted dressed integrals Fa, Fb, Ia, Ib, Iabab
+    (kelvin/cc_utils.py:696-777)."""
+    dev = _lib.device()
+    sa = {"o": _vec(numpy.sqrt(ft_utils.ff(beta, ea, mu)), dev),
+          "v": _vec(numpy.sqrt(ft_utils.ffv(beta, ea, mu)), dev)}
+    sb = {"o": _vec(numpy.sqrt(ft_utils.ff(beta, eb, mu)), dev),
+          "v": _vec(numpy.sqrt(ft_utils.ffv(beta, eb, mu)), dev)}
+    fa, fb = sys.u_fock_tot()
+    Fa = _dress_F(_lib.as_dev(fa, dev), _vec(ea, dev), sa["o"], sa["v"])
+    Fb = _dress_F(_lib.as_dev(fb, dev), _vec(eb, dev), sb["o"], sb["v"])
+    eriA, eriB, eriAB = sys.u_aint_tot()
+    same = eriB is eriA
+    eriA = _lib.as_dev(eriA, dev)
+    eriB = eriA if same else _lib.as_dev(eriB, dev)
+    eriAB = _lib.as_dev(eriAB, dev)
+    Ia = two_e_blocks(**{p: _dress4(eriA, sa[p[0]], sa[p[1]], sa[p[2]], sa[p[3]])
+                         for p in two_e_blocks.names})
+    Ib = two_e_blocks(**{p: _dress4(eriB, sb[p[0]], sb[p[1]], sb[p[2]], sb[p[3]])
+                         for p in two_e_blocks.names})
+    Iabab = two_e_blocks_full(**{p: _dress4(eriAB, sa[p[0]], sb[p[1]], sa[p[2]], sb[p[3]])
+                                 for p in two_e_blocks_full.names})
+    return Fa, Fb, Ia, Ib, Iabab
+
+
+# ---------------------------------------------------------------------------
+# amplitude updates
+# ---------------------------------------------------------------------------
+def form_new_ampl(method, F, I, T1old, T2old, D1, D2, ti, ng, G):
+    """Form new amplitudes (kelvin/cc_utils.py:17-49).  CCSD only on this path."""
+    if method == "CCSD":
+        return ft_cc_equations.ccsd_stanton(F, I, T1old, T2old, D1, D2, ti, ng, G)
+    if method in ("CCD", "LCCSD", "LCCD"):
+        raise Exception("{} is outside the B200 FT-CCSD path".format(method))
+    raise Exception("Unrecognized method keyword")
+
+
+def form_new_ampl_u(method, Fa, Fb, Ia, Ib, Iabab, T1aold, T1bold, T2aaold, T2abold, T2bbold,
+                    D1a, D1b, D2aa, D2ab, D2bb, ti, ng, G):
+    """Form new amplitudes, unrestricted (kelvin/cc_utils.py:52-86)."""
+    if method == "CCSD":
+        return ft_cc_equations.uccsd_stanton(
+            Fa, Fb, Ia, Ib, Iabab, T1aold, T1bold, T2aaold, T2abold, T2bbold,
+            D1a, D1b, D2aa, D2ab, D2bb, ti, ng, G)
+    raise Exception("Unrecognized method keyword for unrestricted calc")
+
+
+class _Stats(object):
+    """One device buffer for the per-iteration scalars; read back once."""
+    def __init__(self, n, dev):
+        self.buf = torch.zeros(3*n, dtype=torch.float64, device=dev)
+        self.dev = dev
+
+    def damp(self, k, old, new, alpha):
+        lib = _lib.load()
+        rc = lib.kb200_damp_norms(old.numel(), _lib.ptr(old), _lib.ptr(new), alpha,
+                                  self.buf.data_ptr() + 24*k, _lib.ptr(_lib.reduce_scratch(self.dev)),
+                                  _lib.stream_ptr())
+        _lib.check(rc, "kb200_damp_norms")
+
+    def read(self):
+        return self.buf.cpu().numpy().reshape(-1, 3)
+
+
+def _norm(x):
+    """||x||_2 of a device tensor through the fused norm kernel (alpha=1: no update)."""
+    st = _Stats(1, x.device)
+    st.damp(0, x, x, 1.0)
+    return math.sqrt(st.read()[0, 1])
+
+
+def ft_cc_iter(method, T1old, T2old, F, I, D1, D2, g, G, beta, ng, ti, iprint, conv_options):
+    """Fixed-point FT-CCSD loop, general spin orbitals (kelvin/cc_utils.py:111-173)."""
+    tbeg = time.time()
+    dev = _lib.device()
+    converged = False
+    ethresh = conv_options["econv"]
+    tthresh = conv_options["tconv"]
+    max_iter = conv_options["max_iter"]
+    alpha = conv_options["damp"]
+    i = 0
+    Eold = 888888888.888888888
+    T1old = _lib.as_dev(T1old, dev).clone()
+    T2old = _lib.as_dev(T2old, dev).clone()
+    nl1 = _norm(T1old) + 0.1
+    nl2 = _norm(T2old) + 0.1
+    Iabij = ft_cc_energy.oovv_to_abij(I.oovv)
+    st = _Stats(2, dev)
+    while i < max_iter and not converged:
+        T1, T2 = form_new_ampl(method, F, I, T1old, T2old, D1, D2, ti, ng, G)
+        # residuals, damping and new norms in one pass per tensor
+        st.damp(0, T1old, T1, alpha)
+        st.damp(1, T2old, T2, alpha)
+        E = ft_cc_energy.ft_cc_energy(T1old, T2old, F.ov, I.oovv, g, beta, eri_abij=Iabij)
+        s = st.read()
+        res1 = math.sqrt(s[0, 0])/nl1
+        res2 = math.sqrt(s[1, 0])/nl2
+        nl1 = math.sqrt(s[0, 2]) + 0.1
+        nl2 = math.sqrt(s[1, 2]) + 0.1
+        logging.info(' %2d  %.10f   %.4E' % (i + 1, E, res1 + res2))
+        i = i + 1
+        if numpy.abs(E - Eold) < ethresh and res1 + res2 < tthresh:
+            converged = True
+        Eold = E
+    if not converged:
+        logging.warning("{} did not converge!".format(method))
+    tend = time.time()
+    logging.info("Total {} time: {:.4f} s".format(method, (tend - tbeg)))
+    return Eold, T1old, T2old
+
+
+def ft_ucc_iter(method, T1aold, T1bold, T2aaold, T2abold, T2bbold, Fa, Fb, Ia, Ib, Iabab,
+                D1a, D1b, D2aa, D2ab, D2bb, g, G, beta, ng, ti, iprint, conv_options):
+    """Fixed-point FT-UCCSD loop (kelvin/cc_utils.py:245-317).  The norms nl1/nl2
+    are those of the amplitudes *before* the update, as in the reference."""
+    tbeg = time.time()
+    dev = _lib.device()
+    converged = False
+    ethresh = conv_options["econv"]
+    tthresh = conv_options["tconv"]
+    max_iter = conv_options["max_iter"]
+    alpha = conv_options["damp"]
+    i = 0
+    Eold = 888888888.888888888
+    old = [_lib.as_dev(x, dev).clone() for x in (T1aold, T1bold, T2aaold, T2abold, T2bbold)]
+    abij = (ft_cc_energy.oovv_to_abij(Ia.oovv), ft_cc_energy.oovv_to_abij(Iabab.oovv),
+            ft_cc_energy.oovv_to_abij(Ib.oovv))
+    st = _Stats(5, dev)
+    while i < max_iter and not converged:
+        T1out, T2out = form_new_ampl_u(
+            method, Fa, Fb, Ia, Ib, Iabab, old[0], old[1], old[2], old[3], old[4],
+            D1a, D1b, D2aa, D2ab, D2bb, ti, ng, G)
+        new = (T1out[0], T1out[1], T2out[0], T2out[1], T2out[2])
+        for k in range(5):
+            st.damp(k, old[k], new[k], alpha)
+        E = ft_cc_energy.ft_ucc_energy(old[0], old[1], old[2], old[3], old[4],
+                                       Fa.ov, Fb.ov, Ia.oovv, Ib.oovv, Iabab.oovv, g, beta,
+                                       abij=abij)
+        s = numpy.sqrt(st.read())
+        nl1 = s[0, 1] + 0.1 + s[1, 1]
+        nl2 = s[2, 1] + 0.1 + s[3, 1] + s[4, 1]
+        res1 = s[0, 0]/nl1 + s[1, 0]/nl1
+        res2 = s[2, 0]/nl2 + s[3, 0]/nl2 + s[4, 0]/nl2
+        logging.info(' %2d  %.10f   %.4E' % (i + 1, E, res1 + res2))
+        i = i + 1
+        if numpy.abs(E - Eold) < ethresh and res1 + res2 < tthresh:
+            converged = True
+        Eold = E
+    if not converged:
+        logging.warning("{} did not converge!".format(method))
+    tend = time.time()
+    logging.info("Total {} time: {:.4f} s".format(method, (tend - tbeg)))
+    return Eold, (old[0], old[1]), (old[2], old[3], old[4])

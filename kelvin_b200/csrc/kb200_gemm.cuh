@@ -1,0 +1,359 @@
+// kb200_gemm.cuh -- FP64 tensor-core (DMMA) contraction kernel with gathered
+// ("composite index") operands for sm_100a.
+//
+// C[b][cm[m]+cn[n]] = beta*C + alpha * sum_k A[b][am[m]+ak[k]] * B[b][bk[k]+bn[n]]
+//
+// * FP64 on sm_100a has no tcgen05/TMEM path (tcgen05.mma has no .f64 kind);
+//   every mma.sync f64 shape lowers to DMMA.8x8x4 (checked with cuobjdump), so
+//   the kernel issues m8n8k4 directly.
+// * Operands are gathered straight from the natural abij/ijab/... storage of
+//   the amplitudes and integrals through uint32 offset tables, so the index
+//   transposes of the reference's einsum strings are folded into the loads.
+//   (TMA cannot describe these tensors: with an odd orbital count every
+//   stride is 8 mod 16 bytes, and cp.async.bulk needs 16-byte alignment --
+//   so the feed is 8-byte cp.async into a 4-stage shared-memory ring.)
+// * Shared-memory tiles are stored k-contiguous ([row][BK+4]) or
+//   row-contiguous ([k][R+4]) -- whichever matches the operand's contiguous
+//   direction in HBM, so global reads stay coalesced; both paddings make the
+//   DMMA fragment loads bank-conflict free (stride == 4 mod 16 doubles).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace kb200 {
+
+constexpr int BK = 16;
+
+struct GemmParams {
+    const double* A;
+    const double* B;
+    double* C;
+    const uint32_t* am;
+    const uint32_t* ak;
+    const uint32_t* bk;
+    const uint32_t* bn;
+    const uint32_t* cm;
+    const uint32_t* cn;
+    int M, N, K;
+    int splitk, kchunk;          // kchunk is a multiple of BK
+    long long bsA, bsB, bsC;
+    double alpha, beta;
+    double* partial;             // [batch][splitk][M][N] when splitk > 1
+    int tilesM, tilesN;
+};
+
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc, bool valid) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    int sz = valid ? 8 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(s), "l"(gsrc), "r"(sz));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+    asm volatile(
+        "mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+        : "+d"(c0), "+d"(c1)
+        : "d"(a), "d"(b));
+}
+
+// One operand tile (R rows x BK k-values) loader.  MODE 0: k-contiguous in
+// HBM -> smem [R][BK+4]; MODE 1: row-contiguous -> smem [BK][R+4].
+template <int R, int NT, int MODE>
+struct TileLoader {
+    static constexpr int LDK = BK + 4;
+    static constexpr int LDR = R + 4;
+    static constexpr int STAGE = (MODE == 0) ? R * LDK : BK * LDR;
+    // MODE 0 mapping
+    static constexpr int RSTEP = NT / BK;            // rows covered per pass
+    static constexpr int RPT = (R + RSTEP - 1) / RSTEP;
+    // MODE 1 mapping
+    static constexpr int KSTEP = (NT / R) > 0 ? (NT / R) : 1;
+    static constexpr int KPT = BK / KSTEP;
+    static_assert(MODE == 0 || (NT % R == 0 && BK % KSTEP == 0), "bad tile/threads");
+
+    const double* base;
+    const uint32_t* ktab;
+    uint32_t roff[MODE == 0 ? RPT : 1];
+    unsigned rvalid;
+
+    __device__ __forceinline__ void init(const double* base_, const uint32_t* rtab,
+                                         const uint32_t* ktab_, int row0, int nrows, int tid) {
+        base = base_;
+        ktab = ktab_;
+        rvalid = 0;
+        if (MODE == 0) {
+            int r0 = tid / BK;
+#pragma unroll
+            for (int i = 0; i < RPT; ++i) {
+                int r = r0 + i * RSTEP;
+                int row = row0 + r;
+                bool v = (r < R) && (row < nrows);
+                roff[i] = v ? rtab[row] : 0u;
+                rvalid |= (v ? 1u : 0u) << i;
+            }
+        } else {
+            int r = tid % R;
+            int row = row0 + r;
+            bool v = row < nrows;
+            roff[0] = v ? rtab[row] : 0u;
+            rvalid = v ? 1u : 0u;
+        }
+    }
+
+    __device__ __forceinline__ void load(double* stage, int k0, int kend, int tid) const {
+        if (MODE == 0) {
+            int kk = tid % BK;
+            int r0 = tid / BK;
+            int k = k0 + kk;
+            bool kv = k < kend;
+            uint32_t koff = kv ? ktab[k] : 0u;
+#pragma unroll
+            for (int i = 0; i < RPT; ++i) {
+                int r = r0 + i * RSTEP;
+                if (r < R) {
+                    bool v = kv && ((rvalid >> i) & 1u);
+                    cp_async8(stage + r * LDK + kk, base + (size_t)roff[i] + koff, v);
+                }
+            }
+        } else {
+            int r = tid % R;
+            int kk0 = tid / R;
+#pragma unroll
+            for (int i = 0; i < KPT; ++i) {
+                int kk = kk0 + i * KSTEP;
+                int k = k0 + kk;
+                bool kv = k < kend;
+                uint32_t koff = kv ? ktab[k] : 0u;
+                bool v = kv && (rvalid & 1u);
+                cp_async8(stage + kk * LDR + r, base + (size_t)roff[0] + koff, v);
+            }
+        }
+    }
+
+    // fragment element (row r, k index kk) of a stage
+    __device__ __forceinline__ static double frag(const double* stage, int r, int kk) {
+        return (MODE == 0) ? stage[r * LDK + kk] : stage[kk * LDR + r];
+    }
+};
+
+template <int WARPS_M, int WARPS_N, int WM, int WN, int AMODE, int BMODE, int STAGES>
+__global__ void __launch_bounds__(WARPS_M* WARPS_N * 32)
+    gemm_tab_kernel(const GemmParams p) {
+    constexpr int BM = WARPS_M * WM;
+    constexpr int BN = WARPS_N * WN;
+    constexpr int NT = WARPS_M * WARPS_N * 32;
+    constexpr int MI = WM / 8;
+    constexpr int NI = WN / 8;
+    using LA = TileLoader<BM, NT, AMODE>;
+    using LB = TileLoader<BN, NT, BMODE>;
+
+    extern __shared__ double smem[];
+    double* As = smem;
+    double* Bs = smem + STAGES * LA::STAGE;
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    const int wm0 = (warp % WARPS_M) * WM;
+    const int wn0 = (warp / WARPS_M) * WN;
+    const int g = lane >> 2;
+    const int t = lane & 3;
+
+    const int tm = blockIdx.x % p.tilesM;
+    const int tn = blockIdx.x / p.tilesM;
+    const int ks = blockIdx.y;
+    const int b = blockIdx.z;
+    const int m0 = tm * BM;
+    const int n0 = tn * BN;
+    const int kbeg = ks * p.kchunk;
+    const int kend = min(p.K, kbeg + p.kchunk);
+    const int nk = (kend - kbeg + BK - 1) / BK;
+
+    LA la;
+    LB lb;
+    la.init(p.A + (long long)b * p.bsA, p.am, p.ak, m0, p.M, tid);
+    lb.init(p.B + (long long)b * p.bsB, p.bn, p.bk, n0, p.N, tid);
+
+    double acc[MI][NI][2];
+#pragma unroll
+    for (int i = 0; i < MI; ++i)
+#pragma unroll
+        for (int j = 0; j < NI; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+#pragma unroll
+    for (int s = 0; s < STAGES - 1; ++s) {
+        if (s < nk) {
+            la.load(As + s * LA::STAGE, kbeg + s * BK, kend, tid);
+            lb.load(Bs + s * LB::STAGE, kbeg + s * BK, kend, tid);
+        }
+        cp_async_commit();
+    }
+
+    for (int kt = 0; kt < nk; ++kt) {
+        cp_async_wait<STAGES - 2>();
+        __syncthreads();
+        {
+            int nxt = kt + STAGES - 1;
+            if (nxt < nk) {
+                int s = nxt % STAGES;
+                la.load(As + s * LA::STAGE, kbeg + nxt * BK, kend, tid);
+                lb.load(Bs + s * LB::STAGE, kbeg + nxt * BK, kend, tid);
+            }
+            cp_async_commit();
+        }
+        const double* as = As + (kt % STAGES) * LA::STAGE;
+        const double* bs = Bs + (kt % STAGES) * LB::STAGE;
+#pragma unroll
+        for (int k4 = 0; k4 < BK / 4; ++k4) {
+            double af[MI], bf[NI];
+#pragma unroll
+            for (int i = 0; i < MI; ++i) af[i] = LA::frag(as, wm0 + i * 8 + g, k4 * 4 + t);
+#pragma unroll
+            for (int j = 0; j < NI; ++j) bf[j] = LB::frag(bs, wn0 + j * 8 + g, k4 * 4 + t);
+#pragma unroll
+            for (int i = 0; i < MI; ++i)
+#pragma unroll
+                for (int j = 0; j < NI; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        }
+    }
+    cp_async_wait<0>();
+
+    // epilogue: thread holds C[row = g][col = 2t, 2t+1] of each 8x8 tile
+    if (p.splitk == 1) {
+        double* C = p.C + (long long)b * p.bsC;
+#pragma unroll
+        for (int i = 0; i < MI; ++i) {
+            int row = m0 + wm0 + i * 8 + g;
+            if (row >= p.M) continue;
+            size_t ro = p.cm[row];
+#pragma unroll
+            for (int j = 0; j < NI; ++j) {
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    int col = n0 + wn0 + j * 8 + 2 * t + c;
+                    if (col < p.N) {
+                        double* dst = C + ro + p.cn[col];
+                        double v = p.alpha * acc[i][j][c];
+                        if (p.beta != 0.0) v += p.beta * (*dst);
+                        *dst = v;
+                    }
+                }
+            }
+        }
+    } else {
+        double* P = p.partial + ((size_t)b * p.splitk + ks) * (size_t)p.M * p.N;
+#pragma unroll
+        for (int i = 0; i < MI; ++i) {
+            int row = m0 + wm0 + i * 8 + g;
+            if (row >= p.M) continue;
+#pragma unroll
+            for (int j = 0; j < NI; ++j) {
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    int col = n0 + wn0 + j * 8 + 2 * t + c;
+                    if (col < p.N) P[(size_t)row * p.N + col] = acc[i][j][c];
+                }
+            }
+        }
+    }
+}
+
+// deterministic split-K reduction + scatter
+__global__ void splitk_reduce_kernel(const GemmParams p, int batch) {
+    size_t mn = (size_t)p.M * p.N;
+    size_t total = mn * batch;
+    for (size_t idx = blockIdx.x * (size_t)blockDim.x + threadIdx.x; idx < total;
+         idx += (size_t)gridDim.x * blockDim.x) {
+        int b = (int)(idx / mn);
+        size_t r = idx - (size_t)b * mn;
+        int row = (int)(r / p.N);
+        int col = (int)(r - (size_t)row * p.N);
+        const double* P = p.partial + (size_t)b * p.splitk * mn + r;
+        double s = 0.0;
+        for (int ks = 0; ks < p.splitk; ++ks) s += P[(size_t)ks * mn];
+        double* dst = p.C + (long long)b * p.bsC + p.cm[row] + p.cn[col];
+        double v = p.alpha * s;
+        if (p.beta != 0.0) v += p.beta * (*dst);
+        *dst = v;
+    }
+}
+
+// kind 1: C[b][cm[m]+cn[n]] = beta*C + alpha*A[b][am[m]+ak[n]]  (32x32 smem transpose tile)
+struct PermParams {
+    const double* A;
+    double* C;
+    const uint32_t* am;
+    const uint32_t* an;
+    const uint32_t* cm;
+    const uint32_t* cn;
+    int M, N;
+    long long bsA, bsC;
+    double alpha, beta;
+    int a_mode, c_mode;   // 0: contiguous along n, 1: contiguous along m
+};
+
+__global__ void __launch_bounds__(256) permute_axpby_kernel(const PermParams p) {
+    __shared__ double tile[32][33];
+    const int tx = threadIdx.x & 31;
+    const int ty = threadIdx.x >> 5;   // 0..7
+    const int m0 = blockIdx.x * 32;
+    const int n0 = blockIdx.y * 32;
+    const int b = blockIdx.z;
+    const double* A = p.A + (long long)b * p.bsA;
+    double* C = p.C + (long long)b * p.bsC;
+    if (p.a_mode == 0) {
+        int n = n0 + tx;
+        uint32_t no = (n < p.N) ? p.an[n] : 0u;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            int ml = ty + 8 * i;
+            int m = m0 + ml;
+            tile[ml][tx] = (m < p.M && n < p.N) ? A[(size_t)p.am[m] + no] : 0.0;
+        }
+    } else {
+        int m = m0 + tx;
+        uint32_t mo = (m < p.M) ? p.am[m] : 0u;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            int nl = ty + 8 * i;
+            int n = n0 + nl;
+            tile[tx][nl] = (m < p.M && n < p.N) ? A[(size_t)mo + p.an[n]] : 0.0;
+        }
+    }
+    __syncthreads();
+    if (p.c_mode == 0) {
+        int n = n0 + tx;
+        uint32_t no = (n < p.N) ? p.cn[n] : 0u;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            int ml = ty + 8 * i;
+            int m = m0 + ml;
+            if (m < p.M && n < p.N) {
+                double* dst = C + (size_t)p.cm[m] + no;
+                double v = p.alpha * tile[ml][tx];
+                if (p.beta != 0.0) v += p.beta * (*dst);
+                *dst = v;
+            }
+        }
+    } else {
+        int m = m0 + tx;
+        uint32_t mo = (m < p.M) ? p.cm[m] : 0u;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            int nl = ty + 8 * i;
+            int n = n0 + nl;
+            if (m < p.M && n < p.N) {
+                double* dst = C + (size_t)mo + p.cn[n];
+                double v = p.alpha * tile[tx][nl];
+                if (p.beta != 0.0) v += p.beta * (*dst);
+                *dst = v;
+            }
+        }
+    }
+}
+
+}  // namespace kb200

@@ -1,0 +1,135 @@
+"""Finite-temperature CC iteration maps on the GPU.
+
+Drop-in for the on-path functions of kelvin/ft_cc_equations.py (same names and
+positional signatures):
+
+* ``ccsd_stanton`` (:96), ``uccsd_stanton`` (:130) -- one amplitude update:
+  per-grid-point Stanton residual, then exp-weighted time integration;
+* ``ccsd_lambda_opt`` (:385), ``uccsd_lambda_opt`` (:412),
+  ``ccsd_lambda_guess`` (:502), ``uccsd_lambda_guess`` (:515);
+* ``ccsd_1rdm`` (:704), ``uccsd_1rdm`` (:756), ``ccsd_2rdm`` (:725),
+  ``uccsd_2rdm`` (:801).
+
+Inputs may be NumPy arrays or torch tensors; outputs are fresh CUDA float64
+tensors (inputs are never modified, as in the reference).  The per-grid-point
+loop of the reference (``for y in range(ng): cqcpy._Stanton(...)``) is replaced
+by one batched contraction plan over all grid points (kelvin_b200/plan.py).
+"""
+import torch
+
+from . import _lib, engine, plan as _plan, programs, quadrature
+
+_F_NAMES = ("oo", "ov", "vo", "vv")
+
+
+def _chunk_for(p, ng, dev):
+    """Largest tau chunk whose scratch fits in ~60% of the free HBM."""
+    per = max(1, p.tmp_bytes_per_point())
+    free, _ = torch.cuda.mem_get_info(dev)
+    return int(max(1, min(ng, (0.6*free)//per)))
+
+
+# ---------------------------------------------------------------------------
+# plan builders
+# ---------------------------------------------------------------------------
+def _g_sizes(F):
+    no, nv = F.ov.shape
+    return {"o": int(no), "v": int(nv)}
+
+
+def _u_sizes(Fa, Fb):
+    noa, nva = Fa.ov.shape
+    nob, nvb = Fb.ov.shape
+    return {("o", "a"): int(noa), ("v", "a"): int(nva), ("o", "b"): int(nob), ("v", "b"): int(nvb)}
+
+
+def stanton_plan(mode, sizes, fac=-1.0):
+    key = ("stanton", mode, tuple(sorted(sizes.items(), key=str)), fac)
+
+    def build():
+        T = programs.tensor_defs()
+        rops = _plan.expand(programs.stanton(fac), T, mode)
+        if mode == "g":
+            ins, outs = ("t1", "t2"), ("o1", "o2")
+        else:
+            ins = ("t1.a", "t1.b", "t2.aa", "t2.ab", "t2.bb")
+            outs = ("o1.a", "o1.b", "o2.aa", "o2.ab", "o2.bb")
+        return engine.Plan(rops, mode, sizes, ins, outs, name="stanton-" + mode)
+    return engine.cached(key, build)
+
+
+def _g_integral_slots(F, I, dev):
+    t = {}
+    for nm in _F_NAMES:
+        t["F." + nm] = _lib.as_dev(getattr(F, nm), dev)
+    for nm in programs._INT2:
+        t["I." + nm] = _lib.as_dev(getattr(I, nm), dev)
+    return t
+
+
+def _u_integral_slots(Fa, Fb, Ia, Ib, Iabab, dev, needed):
+    t = {}
+    src = {"Fa": Fa, "Fb": Fb, "Ia": Ia, "Ib": Ib, "Iabab": Iabab}
+    for slot in needed:
+        pre, pat = slot.split(".")
+        t[slot] = _lib.as_dev(getattr(src[pre], pat), dev)
+    return t
+
+
+# ---------------------------------------------------------------------------
+# amplitude equations
+# ---------------------------------------------------------------------------
+def ccsd_stanton_bar(F, I, T1old, T2old, fac=-1.0):
+    """T1bar, T2bar: drivers + fac*StantonTerms at every grid point, i.e. the
+    state of T1new/T2new just before the integration at
+    kelvin/ft_cc_equations.py:109."""
+    dev = _lib.device()
+    T1old = _lib.as_dev(T1old, dev)
+    T2old = _lib.as_dev(T2old, dev)
+    ng = T1old.shape[0]
+    p = stanton_plan("g", _g_sizes(F), fac)
+    t = _g_integral_slots(F, I, dev)
+    t["t1"], t["t2"] = T1old, T2old
+    t["o1"] = torch.empty_like(T1old)
+    t["o2"] = torch.empty_like(T2old)
+    p.run(t, ng, _chunk_for(p, ng, dev))
+    return t["o1"], t["o2"]
+
+
+def ccsd_stanton(F, I, T1old, T2old, D1, D2, ti, ng, G):
+    """Time-dependent CCSD iteration using Stanton-Gauss intermediates
+    (kelvin/ft_cc_equations.py:96-113)."""
+    T1bar, T2bar = ccsd_stanton_bar(F, I, T1old, T2old)
+    T1new = quadrature.int_tbar1(ng, T1bar, ti, D1, G)
+    T2new = quadrature.int_tbar2(ng, T2bar, ti, D2, G)
+    return T1new, T2new
+
+
+def uccsd_stanton_bar(Fa, Fb, Ia, Ib, Iabab, T1aold, T1bold, T2aaold, T2abold, T2bbold, fac=-1.0):
+    dev = _lib.device()
+    ins = [_lib.as_dev(x, dev) for x in (T1aold, T1bold, T2aaold, T2abold, T2bbold)]
+    ng = ins[0].shape[0]
+    p = stanton_plan("u", _u_sizes(Fa, Fb), fac)
+    t = _u_integral_slots(Fa, Fb, Ia, Ib, Iabab, dev,
+                          [s for s in p.inputs if _plan.is_integral_slot(s)])
+    for nm, x in zip(("t1.a", "t1.b", "t2.aa", "t2.ab", "t2.bb"), ins):
+        t[nm] = x
+    outs = []
+    for nm, x in zip(("o1.a", "o1.b", "o2.aa", "o2.ab", "o2.bb"), ins):
+        t[nm] = torch.empty_like(x)
+        outs.append(t[nm])
+    p.run(t, ng, _chunk_for(p, ng, dev))
+    return tuple(outs)
+
+
+def uccsd_stanton(Fa, Fb, Ia, Ib, Iabab, T1aold, T1bold, T2aaold, T2abold,
+                  T2bbold, D1a, D1b, D2aa, D2ab, D2bb, ti, ng, G):
+    """Unrestricted CCSD iteration (kelvin/ft_cc_equations.py:130-164)."""
+    b1a, b1b, b2aa, b2ab, b2bb = uccsd_stanton_bar(
+        Fa, Fb, Ia, Ib, Iabab, T1aold, T1bold, T2aaold, T2abold, T2bbold)
+    T1a = quadrature.int_tbar1(ng, b1a, ti, D1a, G)
+    T1b = quadrature.int_tbar1(ng, b1b, ti, D1b, G)
+    T2aa = quadrature.int_tbar2(ng, b2aa, ti, D2aa, G)
+    T2ab = quadrature.int_tbar2(ng, b2ab, ti, D2ab, G)
+    T2bb = quadrature.int_tbar2(ng, b2bb, ti, D2bb, G)
+    return (T1a, T1b), (T2aa, T2ab, T2bb)

@@ -1,0 +1,483 @@
+"""Contraction-plan compiler for the per-tau-point FT-CCSD residual.
+
+The reference evaluates the residual with ~60 ``einsum`` calls per grid point
+inside the external ``cqcpy.cc_equations._Stanton`` / ``_u_Stanton`` /
+``_Lambda_opt`` kernels (called from kelvin/ft_cc_equations.py:106,153,399,442).
+Here the same algebra is written once as a list of statements
+
+    ``out[idx] += coef * A[idx] * B[idx]``   /   ``out[idx] += coef * A[idx]``
+
+over spin-orbital index letters (a-h virtual, i-p occupied) and compiled into
+``kb200_op`` descriptors for the gathered DMMA GEMM kernel
+(include/kelvin_b200.h): every index permutation becomes an offset table, every
+statement is batched over the imaginary-time grid, nothing is transposed in
+memory.  Two back ends share one statement list:
+
+* ``mode='g'``: general spin orbitals, one dense array per tensor
+  (kelvin/ft_cc_equations.py:96 ``ccsd_stanton``);
+* ``mode='u'``: Sz-blocked.  Each statement is expanded over the spin cases of
+  its indices; antisymmetric tensors keep only the (aa, ab, bb) blocks the
+  reference stores (T2ab[a,B,i,J], Iabab[p,Q,r,S] = <pQ|rS>) and
+  every other spin block is read as a signed, permuted *view* of a stored one
+  (kelvin/ft_cc_equations.py:130 ``uccsd_stanton``).
+
+The Lambda map (kelvin/ft_cc_equations.py:385,412) is the vector-Jacobian
+product of the residual; ``adjoint`` derives it mechanically
+from the resolved forward ops, so the g and u Lambda kernels are generated, not
+hand-written.
+"""
+import ctypes
+import re
+from collections import OrderedDict
+
+import numpy
+
+VIRT = "abcdefgh"
+OCC = "ijklmnop"
+
+
+def space_of(letter):
+    if letter in VIRT:
+        return "v"
+    if letter in OCC:
+        return "o"
+    raise ValueError("bad index letter %r" % letter)
+
+
+# ---------------------------------------------------------------------------
+# statements
+# ---------------------------------------------------------------------------
+_ref = re.compile(r"([A-Za-z_0-9.]+)\[([a-p]*)\]")
+
+
+class Stmt(object):
+    """out[idx] += coef * prod(ins)."""
+    __slots__ = ("out", "coef", "ins")
+
+    def __init__(self, out, coef, ins):
+        self.out = out        # (name, letters)
+        self.coef = float(coef)
+        self.ins = ins        # list of (name, letters), len 1 or 2
+
+    def __repr__(self):
+        return "%s[%s] += %g %s" % (self.out[0], self.out[1], self.coef,
+                                    " ".join("%s[%s]" % x for x in self.ins))
+
+
+def parse(text):
+    """'X[abij] += 0.5 A[aeim] B[mbej]' -> Stmt."""
+    lhs, rhs = text.split("+=")
+    m = _ref.search(lhs)
+    out = (m.group(1), m.group(2))
+    rhs = rhs.strip()
+    first = rhs.split()[0]
+    coef = float(first)
+    ins = [(mm.group(1), mm.group(2)) for mm in _ref.finditer(rhs[len(first):])]
+    assert 1 <= len(ins) <= 2, text
+    return Stmt(out, coef, ins)
+
+
+# ---------------------------------------------------------------------------
+# tensor classes and spin-block resolution
+# ---------------------------------------------------------------------------
+class TDef(object):
+    """kind: 'one'   2-index, blocks a / b
+             'amp2'  4-index antisymmetric in (0,1) and (2,3): blocks aa, ab, bb
+             'gen4'  4-index, no permutational symmetry: 6 Sz-allowed blocks
+             'int1'  Fock block F.xy          (u: Fa.xy / Fb.xy)
+             'int2'  ERI block  I.wxyz        (u: Ia / Ib / Iabab.<pattern>)
+       role: 'in' (caller supplies), 'out' (caller supplies, accumulated into),
+             'tmp' (plan-owned scratch); batched: has a leading tau index."""
+    def __init__(self, name, kind, role, batched, spaces):
+        self.name, self.kind, self.role, self.batched, self.spaces = name, kind, role, batched, spaces
+
+
+SPIN4 = ("aaaa", "bbbb", "abab", "baba", "abba", "baab")
+
+
+def resolve_u(td, letters, spins):
+    """(slot name, letters in storage order, sign) of spin block `spins`."""
+    s = "".join(spins)
+    if len(letters) == 2:
+        assert s in ("aa", "bb")
+        if td.kind == "int1":
+            return ("F%s.%s" % (s[0], td.name.split(".")[1]), letters, 1.0)
+        return (td.name + "." + s[0], letters, 1.0)
+    assert s in SPIN4, s
+    p, q, r, t = letters
+    if td.kind == "gen4":
+        return (td.name + "." + s, letters, 1.0)
+    if td.kind == "amp2":
+        if s == "aaaa":
+            return (td.name + ".aa", letters, 1.0)
+        if s == "bbbb":
+            return (td.name + ".bb", letters, 1.0)
+        if s == "abab":
+            return (td.name + ".ab", letters, 1.0)
+        if s == "baba":
+            return (td.name + ".ab", q + p + t + r, 1.0)
+        if s == "baab":
+            return (td.name + ".ab", q + p + r + t, -1.0)
+        if s == "abba":
+            return (td.name + ".ab", p + q + t + r, -1.0)
+    if td.kind == "int2":
+        pat = td.name.split(".")[1]
+        w, x, y, z = pat
+        if s == "aaaa":
+            return ("Ia." + pat, letters, 1.0)
+        if s == "bbbb":
+            return ("Ib." + pat, letters, 1.0)
+        if s == "abab":
+            return ("Iabab." + pat, letters, 1.0)
+        if s == "baba":
+            return ("Iabab." + x + w + z + y, q + p + t + r, 1.0)
+        if s == "baab":
+            return ("Iabab." + x + w + y + z, q + p + r + t, -1.0)
+        if s == "abba":
+            return ("Iabab." + w + x + z + y, p + q + t + r, -1.0)
+    raise ValueError("cannot resolve %s %s" % (td.name, s))
+
+
+def canonical_out_blocks(td, nidx):
+    if nidx == 2:
+        return (("a", "a"), ("b", "b"))
+    if td.kind == "amp2":
+        return (tuple("aaaa"), tuple("abab"), tuple("bbbb"))
+    return tuple(tuple(s) for s in SPIN4)
+
+
+def sz_ok(spins):
+    if len(spins) == 2:
+        return spins[0] == spins[1]
+    n = lambda c: 1 if c == "a" else 0  # noqa: E731
+    return n(spins[0]) + n(spins[1]) == n(spins[2]) + n(spins[3])
+
+
+class ROp(object):
+    """Resolved op on concrete slots: out[letters] += coef * prod(ins)."""
+    __slots__ = ("out", "coef", "ins", "spin")
+
+    def __init__(self, out, coef, ins, spin=None):
+        self.out, self.coef, self.ins, self.spin = out, coef, ins, spin
+
+    def __repr__(self):
+        return "%s[%s] += %g %s" % (self.out[0], self.out[1], self.coef,
+                                    " ".join("%s[%s]" % x for x in self.ins))
+
+
+def _canon_key(out, ins, spin):
+    """Key identifying an expanded term up to renaming of summed letters."""
+    ren = {}
+    for l in out[1]:
+        ren[l] = l
+    nxt = [0]
+
+    def r(l):
+        if l not in ren:
+            ren[l] = "#%d" % nxt[0]
+            nxt[0] += 1
+        return ren[l]
+    parts = [(out[0], out[1])]
+    for nm, ls in ins:
+        parts.append((nm, tuple(r(l) for l in ls)))
+    sp = tuple(sorted((ren[l], s) for l, s in spin.items()))
+    return (tuple(parts), sp)
+
+
+def expand(stmts, tdefs, mode):
+    """Statements -> resolved ops (g: 1:1; u: spin expansion + merging)."""
+    rops = []
+    for st in stmts:
+        tds = [tdefs[st.out[0]]] + [tdefs[nm] for nm, _ in st.ins]
+        if mode == "g":
+            rops.append(ROp(st.out, st.coef, list(st.ins)))
+            continue
+        letters = []
+        for _, ls in [st.out] + st.ins:
+            for l in ls:
+                if l not in letters:
+                    letters.append(l)
+        summed = [l for l in letters if l not in st.out[1]]
+        merged = OrderedDict()
+        for ospin in canonical_out_blocks(tds[0], len(st.out[1])):
+            base = dict(zip(st.out[1], ospin))
+            for code in range(1 << len(summed)):
+                spin = dict(base)
+                for k, l in enumerate(summed):
+                    spin[l] = "a" if not (code >> k) & 1 else "b"
+                ok = True
+                for (_, ls) in st.ins:
+                    if not sz_ok([spin[l] for l in ls]):
+                        ok = False
+                        break
+                if not ok:
+                    continue
+                oslot, ols, osg = resolve_u(tds[0], st.out[1], [spin[l] for l in st.out[1]])
+                assert osg == 1.0 and ols == st.out[1]
+                coef = st.coef
+                rins = []
+                for td, (_, ls) in zip(tds[1:], st.ins):
+                    slot, sls, sg = resolve_u(td, ls, [spin[l] for l in ls])
+                    coef *= sg
+                    rins.append((slot, sls))
+                # put the two operands in a canonical order for merging
+                key_ins = rins
+                if len(rins) == 2 and rins[0][0] == rins[1][0]:
+                    key_ins = sorted(rins)
+                key = _canon_key((oslot, ols), key_ins, spin)
+                if key in merged:
+                    merged[key].coef += coef
+                else:
+                    merged[key] = ROp((oslot, ols), coef, rins, dict(spin))
+        for op in merged.values():
+            if op.coef != 0.0:
+                rops.append(op)
+    return rops
+
+
+# ---------------------------------------------------------------------------
+# reverse mode (Lambda / RDM)
+# ---------------------------------------------------------------------------
+def adjoint(rops, wrt, seeds, bar=lambda s: s + "~"):
+    """Reverse-mode sweep over resolved ops.
+
+    wrt:   predicate(slot name) -> True if the adjoint of that slot is needed
+           (i.e. the slot depends on the differentiation variables or is one).
+    seeds: slot names whose adjoints are supplied by the caller.
+    Returns the list of adjoint ROps (in execution order); adjoint slots are
+    named bar(slot)."""
+    out = []
+    for op in reversed(rops):
+        cbar = (bar(op.out[0]), op.out[1])
+        if not (wrt(op.out[0]) or op.out[0] in seeds):
+            continue
+        for k, (slot, ls) in enumerate(op.ins):
+            if not wrt(slot):
+                continue
+            others = [x for j, x in enumerate(op.ins) if j != k]
+            out.append(ROp((bar(slot), ls), op.coef, [cbar] + others, op.spin))
+    return out
+
+
+# ---------------------------------------------------------------------------
+# lowering to kb200_op
+# ---------------------------------------------------------------------------
+class kb200_op(ctypes.Structure):
+    _fields_ = [("kind", ctypes.c_int32), ("a", ctypes.c_int32), ("b", ctypes.c_int32),
+                ("c", ctypes.c_int32),
+                ("a_off", ctypes.c_int64), ("b_off", ctypes.c_int64), ("c_off", ctypes.c_int64),
+                ("M", ctypes.c_int32), ("N", ctypes.c_int32), ("K", ctypes.c_int32),
+                ("batch", ctypes.c_int32),
+                ("bsA", ctypes.c_int64), ("bsB", ctypes.c_int64), ("bsC", ctypes.c_int64),
+                ("tAm", ctypes.c_int64), ("tAk", ctypes.c_int64), ("tBk", ctypes.c_int64),
+                ("tBn", ctypes.c_int64), ("tCm", ctypes.c_int64), ("tCn", ctypes.c_int64),
+                ("alpha", ctypes.c_double), ("beta", ctypes.c_double),
+                ("a_mode", ctypes.c_int32), ("b_mode", ctypes.c_int32),
+                ("tile", ctypes.c_int32), ("splitk", ctypes.c_int32)]
+
+
+def _strides(shape):
+    st = [1] * len(shape)
+    for k in range(len(shape) - 2, -1, -1):
+        st[k] = st[k + 1] * shape[k + 1]
+    return st
+
+
+class TableBank(object):
+    """Deduplicated uint32 offset tables, concatenated into one buffer."""
+    def __init__(self):
+        self.chunks = []
+        self.pos = 0
+        self.index = {}
+
+    def get(self, dims_strides):
+        key = tuple(dims_strides)
+        if key in self.index:
+            return self.index[key]
+        off = numpy.zeros((1,), dtype=numpy.int64)
+        for d, s in dims_strides:
+            off = (off[:, None] + (numpy.arange(d, dtype=numpy.int64) * s)[None, :]).reshape(-1)
+        assert off.max(initial=0) < 2 ** 32
+        start = self.pos
+        self.chunks.append(off.astype(numpy.uint32))
+        self.pos += off.size
+        self.index[key] = start
+        return start
+
+    def buffer(self):
+        if not self.chunks:
+            return numpy.zeros((1,), dtype=numpy.uint32)
+        return numpy.concatenate(self.chunks)
+
+
+N_SM = 148
+
+
+class Lowered(object):
+    """A resolved program lowered to kb200_op descriptors + offset tables."""
+
+    def __init__(self, rops, slot_shapes, batched, preset=()):
+        """slot_shapes: slot -> per-tau-point shape; batched: slot -> bool;
+        preset: slots that already hold data when the plan starts (inputs and
+        accumulate-into outputs); every other slot is overwritten (beta=0) by
+        its first write."""
+        self.rops = rops
+        self.slot_names = list(slot_shapes.keys())
+        self.slot_index = {nm: k for k, nm in enumerate(self.slot_names)}
+        self.slot_shapes = slot_shapes
+        self.batched = batched
+        self.bank = TableBank()
+        self.descs = []
+        self.flops = 0.0          # per tau point, executed (2*M*N*K)
+        written = set(preset)
+        for op in rops:
+            beta = 1.0 if op.out[0] in written else 0.0
+            written.add(op.out[0])
+            for slot, _ in op.ins:
+                if slot not in written:
+                    raise ValueError("slot %s read before it is written: %r" % (slot, op))
+            self.descs.append(self._lower(op, beta))
+        self.tables = self.bank.buffer()
+
+    # -- helpers ---------------------------------------------------------
+    def _dims(self, op):
+        dims = {}
+        for slot, ls in [op.out] + list(op.ins):
+            shp = self.slot_shapes[slot]
+            assert len(shp) == len(ls), (slot, shp, ls)
+            for l, d in zip(ls, shp):
+                if dims.setdefault(l, d) != d:
+                    raise ValueError("dimension clash on %s in %r" % (l, op))
+        return dims
+
+    def _stride_map(self, slot, ls):
+        return dict(zip(ls, _strides(self.slot_shapes[slot])))
+
+    @staticmethod
+    def _order(group, primary, secondary):
+        """Order a composite index: innermost = stride-1 letter of the primary
+        operand when it belongs to the group, rest by decreasing stride."""
+        g = sorted(group, key=lambda l: -primary.get(l, 0))
+        if not g:
+            return g
+        # make sure a stride-1 letter of the secondary operand is not lost
+        # when the primary has none in this group
+        if primary.get(g[-1], 0) != 1:
+            for l in g:
+                if secondary.get(l, 0) == 1:
+                    g.remove(l)
+                    g.append(l)
+                    break
+        return g
+
+    def _lower(self, op, beta):
+        d = kb200_op()
+        dims = self._dims(op)
+        sc = self._stride_map(*op.out)
+        size = lambda grp: int(numpy.prod([dims[l] for l in grp])) if grp else 1  # noqa: E731
+        tab = lambda grp, smap: self.bank.get([(dims[l], smap[l]) for l in grp])  # noqa: E731
+        bs = lambda slot: int(numpy.prod(self.slot_shapes[slot])) if self.batched[slot] else 0  # noqa: E731
+        d.c = self.slot_index[op.out[0]]
+        d.bsC = bs(op.out[0])
+        d.alpha, d.beta = op.coef, beta
+        d.batch = 1
+        d.splitk = 1
+        if len(op.ins) == 1:
+            (sa_name, la) = op.ins[0]
+            sa = self._stride_map(sa_name, la)
+            assert sorted(la) == sorted(op.out[1]), op
+            lc = op.out[1]
+            last_c = lc[-1]
+            last_a = la[-1]
+            ngrp = [last_c]
+            if len(lc) >= 2 and lc[-2] != last_a and len(lc) > 2:
+                ngrp = [lc[-2], last_c]
+            mgrp = [l for l in lc if l not in ngrp]
+            if last_a in mgrp:
+                mgrp.remove(last_a)
+                mgrp.append(last_a)
+            d.kind = 1
+            d.a = self.slot_index[sa_name]
+            d.b = 0
+            d.M, d.N, d.K = size(mgrp), size(ngrp), 1
+            d.bsA = bs(sa_name)
+            d.tAm, d.tAk = tab(mgrp, sa), tab(ngrp, sa)
+            d.tCm, d.tCn = tab(mgrp, sc), tab(ngrp, sc)
+            d.a_mode = 0 if last_a in ngrp else 1
+            d.b_mode = 0
+            return d
+        (na, la), (nb, lb) = op.ins
+        lc = op.out[1]
+        M = [l for l in la if l in lc]
+        N = [l for l in lb if l in lc]
+        K = [l for l in la if l in lb]
+        if set(M) & set(N) or set(K) & set(lc) or len(M) + len(K) != len(la) \
+                or len(N) + len(K) != len(lb) or len(M) + len(N) != len(lc):
+            raise ValueError("unsupported contraction pattern %r" % op)
+        if size(N) > size(M):
+            (na, la), (nb, lb) = (nb, lb), (na, la)
+            M, N = N, M
+        sa, sb = self._stride_map(na, la), self._stride_map(nb, lb)
+        a_mode = 0 if la[-1] in K else 1
+        b_mode = 0 if lb[-1] in K else 1
+        if a_mode == 0:
+            K = self._order(K, sa, sb)
+        elif b_mode == 0:
+            K = self._order(K, sb, sa)
+        else:
+            K = self._order(K, sa, sb)
+        M = self._order(M, sa, sc) if a_mode == 1 else self._order(M, sc, sa)
+        N = self._order(N, sb, sc) if b_mode == 1 else self._order(N, sc, sb)
+        d.kind = 0
+        d.a, d.b = self.slot_index[na], self.slot_index[nb]
+        d.M, d.N, d.K = size(M), size(N), size(K)
+        d.bsA, d.bsB = bs(na), bs(nb)
+        d.tAm, d.tAk = tab(M, sa), tab(K, sa)
+        d.tBk, d.tBn = tab(K, sb), tab(N, sb)
+        d.tCm, d.tCn = tab(M, sc), tab(N, sc)
+        d.a_mode, d.b_mode = a_mode, b_mode
+        d.tile = 1 if d.N <= 48 else 0
+        self.flops += 2.0 * d.M * d.N * d.K
+        return d
+
+    def finalize(self, nbatch):
+        """Set the tau batch and the split-K factors; return the ctypes array."""
+        arr = (kb200_op * len(self.descs))()
+        for k, d in enumerate(self.descs):
+            ctypes.memmove(ctypes.byref(arr[k]), ctypes.byref(d), ctypes.sizeof(kb200_op))
+            o = arr[k]
+            o.batch = nbatch if (o.bsC != 0 or o.bsA != 0 or (o.kind == 0 and o.bsB != 0)) else 1
+            if o.batch > 1 and o.bsC == 0:
+                raise ValueError("batched operands reduce into an unbatched output")
+            if o.kind == 0:
+                bn = 128 if o.tile == 0 else 32
+                ctas = ((o.M + 127) // 128) * ((o.N + bn - 1) // bn) * o.batch
+                if ctas < N_SM and o.K >= 512:
+                    o.splitk = int(min(max(1, (2 * N_SM) // ctas), max(1, o.K // 128)))
+        return arr
+
+
+# ---------------------------------------------------------------------------
+# slot bookkeeping shared by the g and u back ends
+# ---------------------------------------------------------------------------
+_INT_SLOT = re.compile(r"^(I|Ia|Ib|Iabab|F|Fa|Fb)\.")
+
+
+def is_integral_slot(slot):
+    return _INT_SLOT.match(slot.rstrip("~")) is not None
+
+
+def slot_shapes(rops, mode, sizes):
+    """Per-tau-point shape of every slot touched by `rops`.
+
+    sizes: g -> {'o': no, 'v': nv};  u -> {('o','a'): noa, ('o','b'): nob, ...}."""
+    shapes = OrderedDict()
+    for op in rops:
+        for slot, ls in [op.out] + list(op.ins):
+            if mode == "g":
+                shp = tuple(sizes[space_of(l)] for l in ls)
+            else:
+                shp = tuple(sizes[(space_of(l), op.spin[l])] for l in ls)
+            if shapes.setdefault(slot, shp) != shp:
+                raise ValueError("shape clash for slot %s" % slot)
+    return shapes

@@ -1,0 +1,134 @@
+"""Statement lists for the FT-CCSD residual (Stanton-Gauss-Watts-Bartlett
+factorisation, JCP 94, 4334 (1991)) in the block conventions of the reference
+(kelvin/lambda_stanton.py:7-34): t1[a,i], t2[a,b,i,j],
+I.wxyz[p,q,r,s] = <pq||rs>, F.oo/F.vv with the orbital energies removed
+(kelvin/cc_utils.py:578).
+
+``stanton(fac)`` is the body of cqcpy.cc_equations._Stanton as the reference
+uses it at kelvin/ft_cc_equations.py:101-107: the outputs o1/o2 start from the
+drivers -F.vo / -I.vvoo and accumulate fac*R1 / fac*R2.
+"""
+from .plan import TDef, parse
+
+_INT2 = ("vvvv", "vvvo", "vovv", "vvoo", "vovo", "oovv", "vooo", "ooov", "oooo")
+
+
+def tensor_defs():
+    T = {}
+
+    def add(name, kind, role, batched, spaces):
+        T[name] = TDef(name, kind, role, batched, spaces)
+    for xy in ("oo", "ov", "vo", "vv"):
+        add("F." + xy, "int1", "in", False, xy)
+    for pat in _INT2:
+        add("I." + pat, "int2", "in", False, pat)
+    add("t1", "one", "in", True, "vo")
+    add("t2", "amp2", "in", True, "vvoo")
+    add("o1", "one", "out", True, "vo")
+    add("o2", "amp2", "out", True, "vvoo")
+    add("tau", "amp2", "tmp", True, "vvoo")
+    add("tauh", "amp2", "tmp", True, "vvoo")
+    add("Fvv", "one", "tmp", True, "vv")
+    add("Foo", "one", "tmp", True, "oo")
+    add("Fov", "one", "tmp", True, "ov")
+    add("Xvv", "one", "tmp", True, "vv")
+    add("Xoo", "one", "tmp", True, "oo")
+    add("Woooo", "amp2", "tmp", True, "oooo")
+    add("Wvvvv", "amp2", "tmp", True, "vvvv")
+    add("Wovvo", "gen4", "tmp", True, "ovvo")
+    add("t2x", "gen4", "tmp", True, "vvoo")
+    add("Z", "gen4", "tmp", True, "vooo")
+    add("rg", "gen4", "tmp", True, "vvoo")
+    return T
+
+
+_INTERMEDIATES = """
+tau[abij] += 1 t2[abij]
+tau[abij] += 1 t1[ai] t1[bj]
+tau[abij] += -1 t1[bi] t1[aj]
+tauh[abij] += 1 t2[abij]
+tauh[abij] += 0.5 t1[ai] t1[bj]
+tauh[abij] += -0.5 t1[bi] t1[aj]
+Fvv[ae] += 1 F.vv[ae]
+Fvv[ae] += -0.5 F.ov[me] t1[am]
+Fvv[ae] += 1 I.vovv[amef] t1[fm]
+Fvv[ae] += -0.5 I.oovv[mnef] tauh[afmn]
+Foo[mi] += 1 F.oo[mi]
+Foo[mi] += 0.5 F.ov[me] t1[ei]
+Foo[mi] += 1 I.ooov[mnie] t1[en]
+Foo[mi] += 0.5 I.oovv[mnef] tauh[efin]
+Fov[me] += 1 F.ov[me]
+Fov[me] += 1 I.oovv[mnef] t1[fn]
+Woooo[mnij] += 1 I.oooo[mnij]
+Woooo[mnij] += 1 I.ooov[mnie] t1[ej]
+Woooo[mnij] += -1 I.ooov[mnje] t1[ei]
+Woooo[mnij] += 0.25 I.oovv[mnef] tau[efij]
+Wvvvv[abef] += 1 I.vvvv[abef]
+Wvvvv[abef] += -1 I.vovv[amef] t1[bm]
+Wvvvv[abef] += 1 I.vovv[bmef] t1[am]
+Wvvvv[abef] += 0.25 I.oovv[mnef] tau[abmn]
+t2x[fbjn] += 0.5 t2[fbjn]
+t2x[fbjn] += 1 t1[fj] t1[bn]
+Wovvo[mbej] += -1 I.vovo[bmej]
+Wovvo[mbej] += -1 I.vovv[bmef] t1[fj]
+Wovvo[mbej] += 1 I.ooov[mnje] t1[bn]
+Wovvo[mbej] += -1 I.oovv[mnef] t2x[fbjn]
+Xvv[be] += 1 Fvv[be]
+Xvv[be] += -0.5 t1[bm] Fov[me]
+Xoo[mj] += 1 Foo[mj]
+Xoo[mj] += 0.5 t1[ej] Fov[me]
+Z[bmij] += 1 I.vovo[bmej] t1[ei]
+rg[abij] += 1 t2[aeim] Wovvo[mbej]
+rg[abij] += 1 t1[am] Z[bmij]
+"""
+
+# residual statements; coefficient is multiplied by `fac`
+_RESIDUAL = """
+o1[ai] += 1 Fvv[ae] t1[ei]
+o1[ai] += -1 Foo[mi] t1[am]
+o1[ai] += 1 Fov[me] t2[aeim]
+o1[ai] += -1 I.vovo[anfi] t1[fn]
+o1[ai] += 0.5 I.vovv[amef] t2[efim]
+o1[ai] += -0.5 I.ooov[mnie] t2[aemn]
+o2[abij] += 1 t2[aeij] Xvv[be]
+o2[abij] += -1 t2[beij] Xvv[ae]
+o2[abij] += -1 t2[abim] Xoo[mj]
+o2[abij] += 1 t2[abjm] Xoo[mi]
+o2[abij] += 0.5 tau[abmn] Woooo[mnij]
+o2[abij] += 0.5 tau[efij] Wvvvv[abef]
+o2[abij] += 1 rg[abij]
+o2[abij] += -1 rg[baij]
+o2[abij] += -1 rg[abji]
+o2[abij] += 1 rg[baji]
+o2[abij] += 1 t1[ei] I.vvvo[abej]
+o2[abij] += -1 t1[ej] I.vvvo[abei]
+o2[abij] += 1 t1[am] I.vooo[bmij]
+o2[abij] += -1 t1[bm] I.vooo[amij]
+"""
+
+_DRIVERS = """
+o1[ai] += -1 F.vo[ai]
+o2[abij] += -1 I.vvoo[abij]
+"""
+
+
+def _parse_block(text, scale=1.0):
+    out = []
+    for line in text.strip().splitlines():
+        line = line.strip()
+        if not line:
+            continue
+        st = parse(line)
+        st.coef *= scale
+        out.append(st)
+    return out
+
+
+def stanton(fac=-1.0, drivers=True):
+    """Statements of one residual evaluation: o = drivers + fac*StantonTerms."""
+    st = []
+    if drivers:
+        st += _parse_block(_DRIVERS)
+    st += _parse_block(_INTERMEDIATES)
+    st += _parse_block(_RESIDUAL, fac)
+    return st

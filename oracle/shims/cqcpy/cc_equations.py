@@ -1,0 +1,3 @@
+from kelvin_oracle.cc_equations import *  # noqa: F401,F403
+from kelvin_oracle.cc_equations import (  # noqa: F401
+    _Stanton, _u_Stanton, _LS_TS, _u_LS_TS, _Lambda_opt, _uccsd_Lambda_opt)

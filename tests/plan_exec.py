@@ -1,0 +1,42 @@
+"""NumPy executor for lowered contraction plans (TEST INFRASTRUCTURE).
+
+Runs the exact ``kb200_op`` descriptors and offset tables the CUDA library
+would receive, with NumPy gathers, so that the plan compiler (spin expansion,
+merging, reverse mode, table construction) is verified on CPU boxes.  The
+product never imports this module.
+"""
+import numpy
+
+
+def run_lowered(low, arrays, nbatch):
+    """arrays: slot name -> ndarray; batched slots have a leading tau axis."""
+    ops = low.finalize(nbatch)
+    tabs = low.tables.astype(numpy.int64)
+    flat = {}
+    for nm in low.slot_names:
+        a = arrays[nm]
+        assert a.flags.c_contiguous, nm
+        flat[nm] = a.reshape(-1)
+    for o in ops:
+        A = flat[low.slot_names[o.a]]
+        C = flat[low.slot_names[o.c]]
+        cm = tabs[o.tCm:o.tCm + o.M]
+        cn = tabs[o.tCn:o.tCn + o.N]
+        am = tabs[o.tAm:o.tAm + o.M]
+        for b in range(o.batch):
+            cidx = (o.c_off + b * o.bsC + cm[:, None] + cn[None, :]).reshape(-1)
+            if o.kind == 1:
+                an = tabs[o.tAk:o.tAk + o.N]
+                val = A[(o.a_off + b * o.bsA + am[:, None] + an[None, :]).reshape(-1)]
+            else:
+                B = flat[low.slot_names[o.b]]
+                ak = tabs[o.tAk:o.tAk + o.K]
+                bk = tabs[o.tBk:o.tBk + o.K]
+                bn = tabs[o.tBn:o.tBn + o.N]
+                Am = A[o.a_off + b * o.bsA + am[:, None] + ak[None, :]]
+                Bm = B[o.b_off + b * o.bsB + bk[:, None] + bn[None, :]]
+                val = (Am @ Bm).reshape(-1)
+            if o.beta == 0.0:
+                C[cidx] = o.alpha * val
+            else:
+                C[cidx] = o.beta * C[cidx] + o.alpha * val

@@ -1,0 +1,143 @@
+"""GPU parity tests of the individual kernels through the C ABI (-m gpu)."""
+import math
+
+import numpy
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from kelvin_oracle import cqc, driver as odrv  # noqa: E402
+import util  # noqa: E402
+
+
+def _dev(x):
+    return torch.as_tensor(numpy.ascontiguousarray(x)).cuda()
+
+
+@pytest.mark.parametrize("shape", [
+    # letters out / A / B, dims
+    ("abij", "aeim", "mbej", dict(a=7, b=5, i=6, j=4, e=9, m=3)),      # ring-like, permuted
+    ("abij", "abef", "efij", dict(a=13, b=11, i=9, j=10, e=12, f=7)),  # ladder, natural
+    ("ae", "mnef", "afmn", dict(a=9, e=8, m=7, n=6, f=5)),             # long K, tiny output (split-K)
+    ("abef", "amef", "bm", dict(a=6, b=7, e=5, f=8, m=9)),             # skinny N (tile 1)
+    ("abij", "ai", "bj", dict(a=5, b=6, i=7, j=8)),                    # outer product (K=1)
+    ("ai", "me", "aeim", dict(a=33, i=33, m=33, e=33)),                # N=1 (matrix-vector)
+])
+def test_contraction_vs_einsum(built, shape):
+    from kelvin_b200 import engine, plan
+    lc, la, lb, dims = shape
+    rng = numpy.random.default_rng(3)
+    nb = 3
+    A = rng.standard_normal((nb,) + tuple(dims[l] for l in la))
+    B = rng.standard_normal(tuple(dims[l] for l in lb))       # batch-invariant operand
+    C0 = rng.standard_normal((nb,) + tuple(dims[l] for l in lc))
+    ops = [plan.ROp(("C", lc), 0.75, [("A", la), ("B", lb)]),
+           plan.ROp(("C", lc), -1.25, [("B", lb), ("A", la)])]
+    shapes = {"C": C0.shape[1:], "A": A.shape[1:], "B": B.shape}
+    batched = {"C": True, "A": True, "B": False}
+    p = engine.Plan(ops, "g", None, ["A", "B"], ["C"], preset_outputs=["C"], shapes=shapes,
+                    batched=batched)
+    t = {"A": _dev(A), "B": _dev(B), "C": _dev(C0)}
+    p.run(t, nb)
+    ref = C0 + (0.75 - 1.25)*numpy.einsum("y%s,%s->y%s" % (la, lb, lc), A, B)
+    got = t["C"].cpu().numpy()
+    assert numpy.abs(got - ref).max() < 1e-11*max(1.0, numpy.abs(ref).max())
+
+
+def test_contraction_large_tiles(built):
+    """Multiple 128x128 tiles, ragged edges, k not a multiple of 16, both operand modes."""
+    from kelvin_b200 import engine, plan
+    rng = numpy.random.default_rng(4)
+    dims = dict(a=19, b=17, i=19, j=18, e=19, f=13)
+    for la, lb in (("abef", "efij"), ("efab", "ijef"), ("abef", "ijef"), ("efab", "efij")):
+        A = rng.standard_normal(tuple(dims[l] for l in la))
+        B = rng.standard_normal(tuple(dims[l] for l in lb))
+        ops = [plan.ROp(("C", "abij"), 1.0, [("A", la), ("B", lb)])]
+        shapes = {"C": tuple(dims[l] for l in "abij"), "A": A.shape, "B": B.shape}
+        p = engine.Plan(ops, "g", None, ["A", "B"], ["C"], shapes=shapes,
+                        batched={"C": False, "A": False, "B": False})
+        t = {"A": _dev(A), "B": _dev(B),
+             "C": torch.full(shapes["C"], float("nan"), dtype=torch.float64, device="cuda")}
+        p.run(t, 1)
+        ref = numpy.einsum("%s,%s->abij" % (la, lb), A, B)
+        assert numpy.abs(t["C"].cpu().numpy() - ref).max() < 1e-11*numpy.abs(ref).max()
+
+
+@pytest.mark.parametrize("ng,n,mode", [(10, 7, 0), (10, 7, 1), (5, 33, 1), (40, 5, 1), (2, 4, 0), (17, 6, 1)])
+def test_int_tbar(built, ng, n, mode):
+    from kelvin_b200 import quadrature
+    rng = numpy.random.default_rng(ng*100 + n)
+    e = util.random_D(n)
+    D2 = cqc.D2(e, e)
+    beta = 2.0
+    ti, g, G = odrv.simpsons(ng, beta)
+    for Guse in (G, rng.standard_normal((ng, ng))):            # incl. non-triangular G (quirk Q4)
+        tb = rng.standard_normal((ng,) + D2.shape)
+        ref = odrv.int_tbar(ng, tb, ti, D2, Guse)
+        got = quadrature.int_tbar(ng, tb, ti, D2, Guse, mode=mode).cpu().numpy()
+        assert numpy.abs(got - ref).max() < 1e-12*numpy.abs(ref).max()
+    D1 = cqc.D1(e, e)
+    tb = rng.standard_normal((ng,) + D1.shape)
+    ref = odrv.int_tbar(ng, tb, ti, D1, G)
+    got = quadrature.int_tbar1(ng, tb, ti, D1, G).cpu().numpy()
+    assert numpy.abs(got - ref).max() < 1e-12*numpy.abs(ref).max()
+
+
+@pytest.mark.parametrize("ng,n,mode", [(10, 6, 0), (10, 6, 1), (9, 7, 1), (40, 4, 1)])
+def test_int_L(built, ng, n, mode):
+    from kelvin_b200 import quadrature
+    rng = numpy.random.default_rng(ng*10 + n)
+    ea, eb = util.random_D(n, 1), util.random_D(n + 1, 2)
+    D2 = cqc.D2u(ea, eb, ea, eb)                     # (a,B,i,J), rectangular
+    ti, g, G = odrv.simpsons(ng, 2.0)
+    for Guse in (G, rng.standard_normal((ng, ng))):
+        L2 = rng.standard_normal((ng, n, n + 1, n, n + 1))
+        ref = odrv.int_L(ng, L2, ti, D2, g, Guse)
+        got = quadrature.int_L(ng, L2, ti, D2, g, Guse, mode=mode).cpu().numpy()
+        assert numpy.abs(got - ref).max() < 1e-12*numpy.abs(ref).max()
+    D1 = cqc.D1(ea, eb)                              # (a, i) with different sizes
+    L1 = rng.standard_normal((ng, n + 1, n))
+    ref = odrv.int_L(ng, L1, ti, D1, g, G)
+    got = quadrature.int_L1(ng, L1, ti, D1, g, G).cpu().numpy()
+    assert numpy.abs(got - ref).max() < 1e-12*numpy.abs(ref).max()
+
+
+def test_energy_and_norms(built):
+    from kelvin_b200 import cc_utils, ft_cc_energy
+    ng, n = 6, 7
+    F, I, t1, t2 = util.random_g(n, ng, seed=11)
+    ti, g, G = odrv.simpsons(ng, 1.5)
+    for q in (True, False):
+        ref = odrv.ft_cc_energy(t1, t2, F.ov, I.oovv, g, 1.5, Qterm=q)
+        got = ft_cc_energy.ft_cc_energy(t1, t2, F.ov, I.oovv, g, 1.5, Qterm=q)
+        assert abs(got - ref) < 1e-12*abs(ref)
+    (Fa, Fb, Ia, Ib, Iabab), (T1a, T1b, T2aa, T2ab, T2bb) = util.random_u(5, 5, ng, seed=12)
+    for q in (True, False):
+        ref = odrv.ft_ucc_energy(T1a, T1b, T2aa, T2ab, T2bb, Fa.ov, Fb.ov, Ia.oovv, Ib.oovv,
+                                 Iabab.oovv, g, 1.5, Qterm=q)
+        got = ft_cc_energy.ft_ucc_energy(T1a, T1b, T2aa, T2ab, T2bb, Fa.ov, Fb.ov, Ia.oovv,
+                                         Ib.oovv, Iabab.oovv, g, 1.5, Qterm=q)
+        assert abs(got - ref) < 1e-12*abs(ref)
+    # damping + norms
+    old = _dev(t2.copy())
+    new = _dev(t2[::-1].copy())
+    st = cc_utils._Stats(1, old.device)
+    st.damp(0, old, new, 0.3)
+    s = st.read()[0]
+    assert abs(s[0] - numpy.sum((t2[::-1] - t2)**2)) < 1e-12*s[0]
+    assert abs(s[1] - numpy.sum(t2**2)) < 1e-12*s[1]
+    upd = 0.3*t2 + 0.7*t2[::-1]
+    assert numpy.abs(old.cpu().numpy() - upd).max() < 1e-15
+    assert abs(s[2] - numpy.sum(upd**2)) < 1e-12*s[2]
+
+
+def test_empty_and_bad_inputs(built):
+    from kelvin_b200 import quadrature, _lib
+    ti, g, G = odrv.simpsons(4, 1.0)
+    with pytest.raises(Exception):
+        quadrature.int_tbar(4, numpy.zeros((3, 2, 2)), ti, numpy.zeros((2, 2)), G)
+    with pytest.raises(Exception):
+        quadrature.ft_quad(4, 1.0, 'nope')
+    out = quadrature.int_tbar(4, numpy.zeros((4, 0, 3)), ti, numpy.zeros((0, 3)), G)
+    assert out.shape == (4, 0, 3)

@@ -1,0 +1,62 @@
+"""GPU parity of the per-grid-point residual + integration against the oracle."""
+import numpy
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from kelvin_oracle import cqc, driver as odrv  # noqa: E402
+import util  # noqa: E402
+
+
+def _relerr(got, ref):
+    return numpy.abs(got.cpu().numpy() - ref).max()/numpy.abs(ref).max()
+
+
+@pytest.mark.parametrize("n,ng", [(4, 3), (9, 2), (14, 2)])
+def test_ccsd_stanton_g(built, n, ng):
+    from kelvin_b200 import ft_cc_equations
+    F, I, t1, t2 = util.random_g(n, ng, seed=n)
+    e = util.random_D(n)
+    D1, D2 = cqc.D1(e, e), cqc.D2(e, e)
+    ti, g, G = odrv.simpsons(ng, 1.3)
+    r1, r2 = odrv.ccsd_stanton(F, I, t1, t2, D1, D2, ti, ng, G)
+    o1, o2 = ft_cc_equations.ccsd_stanton(F, I, t1, t2, D1, D2, ti, ng, G)
+    assert _relerr(o1, r1) < 1e-11
+    assert _relerr(o2, r2) < 1e-11
+
+
+@pytest.mark.parametrize("na,nb,ng", [(4, 3, 2), (7, 7, 3), (10, 9, 2)])
+def test_uccsd_stanton(built, na, nb, ng):
+    from kelvin_b200 import ft_cc_equations
+    ints, amps = util.random_u(na, nb, ng, seed=na + nb)
+    ea, eb = util.random_D(na, 1), util.random_D(nb, 2)
+    D1a, D1b = cqc.D1(ea, ea), cqc.D1(eb, eb)
+    D2aa, D2ab, D2bb = cqc.D2(ea, ea), cqc.D2u(ea, eb, ea, eb), cqc.D2(eb, eb)
+    ti, g, G = odrv.simpsons(ng, 0.9)
+    r1, r2 = odrv.uccsd_stanton(*ints, *amps, D1a, D1b, D2aa, D2ab, D2bb, ti, ng, G)
+    o1, o2 = ft_cc_equations.uccsd_stanton(*ints, *amps, D1a, D1b, D2aa, D2ab, D2bb, ti, ng, G)
+    for got, ref in zip(list(o1) + list(o2), list(r1) + list(r2)):
+        assert _relerr(got, ref) < 1e-11
+
+
+def test_u_equals_g_on_spin_packed_inputs(built):
+    """The reference's own u==g check (kelvin/tests/test_ft_cc_ampl.py:41-110)
+    applied to the CUDA kernels."""
+    from kelvin_b200 import ft_cc_equations
+    na = nb = 6
+    ng = 2
+    ints, amps = util.random_u(na, nb, ng, seed=21)
+    Fa, Fb, Ia, Ib, Iabab = ints
+    F, I = cqc.F_to_spin(Fa, Fb), cqc.I_to_spin(Ia, Ib, Iabab)
+    t1 = numpy.stack([cqc.T1_to_spin(amps[0][y], amps[1][y], na, na, nb, nb) for y in range(ng)])
+    t2 = numpy.stack([cqc.T2_to_spin(amps[2][y], amps[3][y], amps[4][y], na, na, nb, nb)
+                      for y in range(ng)])
+    g1, g2 = ft_cc_equations.ccsd_stanton_bar(F, I, t1, t2)
+    u = ft_cc_equations.uccsd_stanton_bar(*ints, *amps)
+    g1, g2 = g1.cpu().numpy(), g2.cpu().numpy()
+    sc = numpy.abs(g2).max()
+    assert numpy.abs(u[0].cpu().numpy() - g1[:, :na, :na]).max() < 1e-11*sc
+    assert numpy.abs(u[1].cpu().numpy() - g1[:, na:, na:]).max() < 1e-11*sc
+    assert numpy.abs(u[2].cpu().numpy() - g2[:, :na, :na, :na, :na]).max() < 1e-11*sc
+    assert numpy.abs(u[3].cpu().numpy() - g2[:, :na, na:, :na, na:]).max() < 1e-11*sc
+    assert numpy.abs(u[4].cpu().numpy() - g2[:, na:, na:, na:, na:]).max() < 1e-11*sc

@@ -1,0 +1,62 @@
+"""Shared helpers for the test-suite (seeded random FT-CC inputs)."""
+import numpy
+
+from kelvin_oracle import cqc
+
+
+def asym(x):
+    x = x - x.swapaxes(-4, -3)
+    return x - x.swapaxes(-2, -1)
+
+
+def random_g(n, ng, seed=0, scale=0.3):
+    """Random dressed-integral-like blocks + amplitudes, general spin orbitals."""
+    rng = numpy.random.default_rng(seed)
+    F = cqc.one_e_blocks(*[rng.standard_normal((n, n)) for _ in range(4)])
+    blocks = {}
+    for p in cqc.two_e_blocks.names:
+        x = rng.standard_normal((n,)*4)
+        if p[0] == p[1]:
+            x = x - x.transpose(1, 0, 2, 3)
+        if p[2] == p[3]:
+            x = x - x.transpose(0, 1, 3, 2)
+        blocks[p] = numpy.ascontiguousarray(x)
+    I = cqc.two_e_blocks(**blocks)
+    t1 = scale*rng.standard_normal((ng, n, n))
+    t2 = numpy.ascontiguousarray(scale*asym(rng.standard_normal((ng, n, n, n, n))))
+    return F, I, t1, t2
+
+
+def random_u(na, nb, ng, seed=1, scale=0.3):
+    """Random unrestricted inputs whose 34 integral blocks are distinct but
+    mutually consistent (one underlying <pq|rs> per spin case, dressed with
+    random o/v factors), so that u == g-embedding holds exactly."""
+    rng = numpy.random.default_rng(seed)
+    rnd = rng.standard_normal
+    Va, Vb, Vab = asym(rnd((na,)*4)), asym(rnd((nb,)*4)), rnd((na, nb, na, nb))
+    sc = {("o", "a"): rnd(na), ("v", "a"): rnd(na), ("o", "b"): rnd(nb), ("v", "b"): rnd(nb)}
+
+    def dress(V, pat, spins):
+        f = [sc[(c, s)] for s, c in zip(spins, pat)]
+        return numpy.ascontiguousarray(numpy.einsum('pqrs,p,q,r,s->pqrs', V, *f))
+    Ia = cqc.two_e_blocks(**{p: dress(Va, p, "aaaa") for p in cqc.two_e_blocks.names})
+    Ib = cqc.two_e_blocks(**{p: dress(Vb, p, "bbbb") for p in cqc.two_e_blocks.names})
+    Iabab = cqc.two_e_blocks_full(**{p: dress(Vab, p, "abab") for p in cqc.two_e_blocks_full.names})
+    fa, fb = rnd((na, na)), rnd((nb, nb))
+
+    def dressF(f, pat, sp):
+        return numpy.ascontiguousarray(
+            numpy.einsum('pq,p,q->pq', f, sc[(pat[0], sp)], sc[(pat[1], sp)]))
+    Fa = cqc.one_e_blocks(*[dressF(fa, p, "a") for p in ("oo", "ov", "vo", "vv")])
+    Fb = cqc.one_e_blocks(*[dressF(fb, p, "b") for p in ("oo", "ov", "vo", "vv")])
+    T1a, T1b = scale*rnd((ng, na, na)), scale*rnd((ng, nb, nb))
+    T2aa = numpy.ascontiguousarray(scale*asym(rnd((ng, na, na, na, na))))
+    T2bb = numpy.ascontiguousarray(scale*asym(rnd((ng, nb, nb, nb, nb))))
+    T2ab = scale*rnd((ng, na, nb, na, nb))
+    return (Fa, Fb, Ia, Ib, Iabab), (T1a, T1b, T2aa, T2ab, T2bb)
+
+
+def random_D(n, seed=5):
+    rng = numpy.random.default_rng(seed)
+    e = numpy.sort(rng.uniform(0.0, 5.0, n))
+    return e
