@@ -64,6 +64,14 @@ int kb200_plan_run(const kb200_op* ops /*host*/, int nops,
                    const uint32_t* tables, double* const* slots /*host*/, int nslots,
                    double* workspace, int64_t workspace_bytes, void* stream);
 
+/* Same as kb200_plan_run, but brackets every op with CUDA events on `stream`,
+ * synchronises, and returns the device time of each op in op_ms[nops] (host).
+ * Used by bench.py for the live roofline measurement; not on the product path. */
+int kb200_plan_run_timed(const kb200_op* ops /*host*/, int nops,
+                         const uint32_t* tables, double* const* slots /*host*/, int nslots,
+                         double* workspace, int64_t workspace_bytes, void* stream,
+                         float* op_ms /*host*/);
+
 /* ------------------------------------------------------------------------
  * Imaginary-time integration.
  * Replaces kelvin/quadrature.py:292-317 (int_tbar1, int_tbar2):
@@ -76,6 +84,12 @@ int kb200_plan_run(const kb200_op* ops /*host*/, int nops,
 int kb200_int_tbar(int ng, int64_t n, const double* tbar, const double* D,
                    const double* ti, const double* G, double* out, int mode, void* stream);
 
+/* Rows y0 <= y < y1 only (out has y1-y0 rows): the tau-sharded form -- each GPU
+ * integrates its own grid points from the all-gathered tbar. */
+int kb200_int_tbar_rows(int ng, int64_t n, const double* tbar, const double* D,
+                        const double* ti, const double* G, double* out, int y0, int y1,
+                        int mode, void* stream);
+
 /* Replaces kelvin/quadrature.py:320-345 (int_L1, int_L2):
  *   out[s,q] = (1/g[s]) sum_y g[y]*G[y,s]*w(s,y,q)*L[y,q],
  *   w = exp(D[perm(q)]*(ti[s]-ti[y])) for y>=s, 1 otherwise.
@@ -85,6 +99,10 @@ int kb200_int_tbar(int ng, int64_t n, const double* tbar, const double* D,
 int kb200_int_L(int ng, const int32_t dims[4] /*host*/, const int64_t dstride[4] /*host*/,
                 const double* L, const double* D, const double* ti, const double* g,
                 const double* G, double* out, int mode, void* stream);
+
+int kb200_int_L_rows(int ng, const int32_t dims[4] /*host*/, const int64_t dstride[4] /*host*/,
+                     const double* L, const double* D, const double* ti, const double* g,
+                     const double* G, double* out, int s0, int s1, int mode, void* stream);
 
 /* ------------------------------------------------------------------------
  * Energy functional pieces.  Replaces kelvin/ft_cc_energy.py:7-32,35-72.

@@ -18,7 +18,7 @@ _lib = None
 
 EXPORTS = (
     "kb200_version", "kb200_last_error", "kb200_launch_count", "kb200_launch_count_reset",
-    "kb200_plan_workspace_bytes", "kb200_plan_run", "kb200_int_tbar", "kb200_int_L",
+    "kb200_plan_workspace_bytes", "kb200_plan_run", "kb200_plan_run_timed", "kb200_int_tbar", "kb200_int_L", "kb200_int_tbar_rows", "kb200_int_L_rows",
     "kb200_reduce_scratch_doubles", "kb200_energy_pair", "kb200_dot_g", "kb200_damp_norms",
     "kb200_dress4", "kb200_dress2", "kb200_gsum", "kb200_scale_by",
 )
@@ -48,9 +48,17 @@ def load():
     lib.kb200_plan_workspace_bytes.argtypes = [ctypes.POINTER(kb200_op), ctypes.c_int]
     lib.kb200_plan_run.argtypes = [ctypes.POINTER(kb200_op), ctypes.c_int, vp,
                                    ctypes.POINTER(vp), ctypes.c_int, vp, i64, vp]
+    lib.kb200_plan_run_timed.argtypes = [ctypes.POINTER(kb200_op), ctypes.c_int, vp,
+                                         ctypes.POINTER(vp), ctypes.c_int, vp, i64, vp,
+                                         ctypes.POINTER(ctypes.c_float)]
     lib.kb200_int_tbar.argtypes = [ctypes.c_int, i64, vp, vp, vp, vp, vp, ctypes.c_int, vp]
     lib.kb200_int_L.argtypes = [ctypes.c_int, ctypes.POINTER(i32), ctypes.POINTER(i64),
                                 vp, vp, vp, vp, vp, vp, ctypes.c_int, vp]
+    lib.kb200_int_tbar_rows.argtypes = [ctypes.c_int, i64, vp, vp, vp, vp, vp, ctypes.c_int,
+                                        ctypes.c_int, ctypes.c_int, vp]
+    lib.kb200_int_L_rows.argtypes = [ctypes.c_int, ctypes.POINTER(i32), ctypes.POINTER(i64),
+                                     vp, vp, vp, vp, vp, vp, ctypes.c_int, ctypes.c_int,
+                                     ctypes.c_int, vp]
     lib.kb200_energy_pair.argtypes = [ctypes.c_int] * 5 + [vp, vp, vp, vp, vp, dbl, dbl, vp, vp, vp]
     lib.kb200_dot_g.argtypes = [ctypes.c_int, i64, vp, vp, vp, vp, vp, vp]
     lib.kb200_damp_norms.argtypes = [i64, vp, vp, dbl, vp, vp, vp]

@@ -221,3 +221,86 @@ def ft_ucc_iter(method, T1aold, T1bold, T2aaold, T2abold, T2bbold, Fa, Fb, Ia, I
     tend = time.time()
     logging.info("Total {} time: {:.4f} s".format(method, (tend - tbeg)))
     return Eold, (old[0], old[1]), (old[2], old[3], old[4])
+
+
+def ft_lambda_iter(method, L1old, L2old, T1, T2, F, I, D1, D2, g, G, beta, ng, ti, iprint,
+                   conv_options):
+    """Fixed-point FT-CCSD Lambda loop (kelvin/cc_utils.py:414-480)."""
+    if method != "CCSD":
+        raise Exception("Unrecognized method keyword")
+    tbeg = time.time()
+    dev = _lib.device()
+    converged = False
+    thresh = conv_options["tconv"]
+    max_iter = conv_options["max_iter"]
+    alpha = conv_options["damp"]
+    i = 0
+    L1old = _lib.as_dev(L1old, dev).clone()
+    L2old = _lib.as_dev(L2old, dev).clone()
+    nl1 = _norm(L1old) + 0.1
+    nl2 = _norm(L2old) + 0.1
+    st = _Stats(2, dev)
+    while i < max_iter and not converged:
+        L1, L2 = ft_cc_equations.ccsd_lambda_opt(
+            F, I, T1, T2, L1old, L2old, D1, D2, ti, ng, g, G, beta)
+        st.damp(0, L1old, L1, alpha)
+        st.damp(1, L2old, L2, alpha)
+        s = st.read()
+        res1 = math.sqrt(s[0, 0])/nl1
+        res2 = math.sqrt(s[1, 0])/nl2
+        nl1 = math.sqrt(s[0, 2]) + 0.1
+        nl2 = math.sqrt(s[1, 2]) + 0.1
+        L1 = None
+        L2 = None
+        logging.info(' %2d  %.10f' % (i + 1, res1 + res2))
+        i = i + 1
+        if res1 + res2 < thresh:
+            converged = True
+    if not converged:
+        logging.warning("CCSD Lambda-equations did not converge!")
+    tend = time.time()
+    logging.info("Total CCSD Lambda time: %f s" % (tend - tbeg))
+    return L1old, L2old
+
+
+def ft_ulambda_iter(method, L1ain, L1bin, L2aain, L2abin, L2bbin, T1aold, T1bold,
+                    T2aaold, T2abold, T2bbold, Fa, Fb, Ia, Ib, Iabab, D1a, D1b, D2aa, D2ab, D2bb,
+                    g, G, beta, ng, ti, iprint, conv_options):
+    """Fixed-point FT-UCCSD Lambda loop (kelvin/cc_utils.py:483-566); the
+    doubles norm weights the ab block by 4 (:514-517)."""
+    if method != "CCSD":
+        raise Exception("Unrecognized method keyword")
+    tbeg = time.time()
+    dev = _lib.device()
+    converged = False
+    thresh = conv_options["tconv"]
+    max_iter = conv_options["max_iter"]
+    alpha = conv_options["damp"]
+    i = 0
+    old = [_lib.as_dev(x, dev).clone() for x in (L1ain, L1bin, L2aain, L2abin, L2bbin)]
+    nrm = [_norm(x) for x in old]
+    nl1 = nrm[0] + nrm[1] + 0.1
+    nl2 = nrm[2] + 0.1 + nrm[4] + 4*nrm[3]
+    st = _Stats(5, dev)
+    while i < max_iter and not converged:
+        new = ft_cc_equations.uccsd_lambda_opt(
+            Fa, Fb, Ia, Ib, Iabab, T1aold, T1bold, T2aaold, T2abold, T2bbold,
+            old[0], old[1], old[2], old[3], old[4], D1a, D1b, D2aa, D2ab, D2bb,
+            ti, ng, g, G, beta)
+        for k in range(5):
+            st.damp(k, old[k], new[k], alpha)
+        new = None
+        s = numpy.sqrt(st.read())
+        res1 = s[0, 0]/nl1 + s[1, 0]/nl1
+        res2 = s[2, 0]/nl2 + s[3, 0]/nl2 + s[4, 0]/nl2
+        nl1 = s[0, 2] + s[1, 2] + 0.1
+        nl2 = s[2, 2] + 0.1 + s[4, 2] + 4*s[3, 2]
+        logging.info(' %2d  %.10f' % (i + 1, res1 + res2))
+        i = i + 1
+        if res1 + res2 < thresh:
+            converged = True
+    if not converged:
+        logging.warning("CCSD Lambda-equations did not converge!")
+    tend = time.time()
+    logging.info("Total CCSD Lambda time: %f s" % (tend - tbeg))
+    return old[0], old[1], old[2], old[3], old[4]

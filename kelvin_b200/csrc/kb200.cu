@@ -80,7 +80,7 @@ template <int MODE>
 __global__ void __launch_bounds__(INT_THREADS)
     int_tbar_kernel(int ng, long long n, const double* __restrict__ tbar,
                     const double* __restrict__ D, const double* __restrict__ ti,
-                    const double* __restrict__ G, double* __restrict__ out) {
+                    const double* __restrict__ G, double* __restrict__ out, int y0, int y1) {
     extern __shared__ double sm[];
     double* tb = sm;
     double* E = sm + (size_t)ng * INT_THREADS;
@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(INT_THREADS)
         for (int x = 0; x < ng; ++x) tb[x * INT_THREADS + tx] = act ? tbar[(size_t)x * n + p] : 0.0;
         if (MODE == 1)
             for (int k = 1; k < ng; ++k) E[k * INT_THREADS + tx] = exp(d * (tis[k - 1] - tis[k]));
-        for (int y = 0; y < ng; ++y) {
+        for (int y = y0; y < y1; ++y) {
             const double* Gy = G + (size_t)y * ng;
             double acc = 0.0;
             if (MODE == 0) {
@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(INT_THREADS)
                 double gw = __ldg(Gy + x);
                 if (gw != 0.0) acc += gw * tb[x * INT_THREADS + tx];
             }
-            if (act) out[(size_t)y * n + p] = acc;
+            if (act) out[(size_t)(y - y0) * n + p] = acc;
         }
     }
 }
@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(INT_THREADS)
     int_L_kernel(int ng, long long n, Dims4 dm, const double* __restrict__ L,
                  const double* __restrict__ D, const double* __restrict__ ti,
                  const double* __restrict__ g, const double* __restrict__ G,
-                 double* __restrict__ out) {
+                 double* __restrict__ out, int s0, int s1) {
     extern __shared__ double sm[];
     double* lb = sm;
     double* E = sm + (size_t)ng * INT_THREADS;
@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(INT_THREADS)
         for (int y = 0; y < ng; ++y) lb[y * INT_THREADS + tx] = act ? L[(size_t)y * n + p] : 0.0;
         if (MODE == 1)
             for (int k = 1; k < ng; ++k) E[k * INT_THREADS + tx] = exp(d * (tis[k - 1] - tis[k]));
-        for (int s = 0; s < ng; ++s) {
+        for (int s = s0; s < s1; ++s) {
             double acc = 0.0;
             for (int y = 0; y < s; ++y) {
                 double gw = gs[y] * __ldg(G + (size_t)y * ng + s);
@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(INT_THREADS)
                     if (gw != 0.0) acc += gw * w * lb[y * INT_THREADS + tx];
                 }
             }
-            if (act) out[(size_t)s * n + p] = acc / gs[s];
+            if (act) out[(size_t)(s - s0) * n + p] = acc / gs[s];
         }
     }
 }
@@ -361,11 +361,12 @@ int64_t kb200_plan_workspace_bytes(const kb200_op* ops, int nops) {
     return w;
 }
 
-int kb200_plan_run(const kb200_op* ops, int nops, const uint32_t* tables, double* const* slots,
-                   int nslots, double* workspace, int64_t workspace_bytes, void* stream) {
-    cudaStream_t st = (cudaStream_t)stream;
+static int run_plan_impl(const kb200_op* ops, int nops, const uint32_t* tables,
+                         double* const* slots, int nslots, double* workspace,
+                         int64_t workspace_bytes, cudaStream_t st, cudaEvent_t* ev) {
     for (int i = 0; i < nops; ++i) {
         const kb200_op& o = ops[i];
+        if (ev) cudaEventRecord(ev[2 * i], st);
         if (o.a < 0 || o.a >= nslots || o.c < 0 || o.c >= nslots) return fail(-1, "plan: bad slot");
         if (o.M <= 0 || o.N <= 0 || o.batch <= 0) return fail(-1, "plan: empty op");
         if (o.kind == 0) {
@@ -421,13 +422,45 @@ int kb200_plan_run(const kb200_op* ops, int nops, const uint32_t* tables, double
         } else {
             return fail(-1, "plan: unknown op kind");
         }
+        if (ev) cudaEventRecord(ev[2 * i + 1], st);
     }
     return 0;
 }
 
+int kb200_plan_run(const kb200_op* ops, int nops, const uint32_t* tables, double* const* slots,
+                   int nslots, double* workspace, int64_t workspace_bytes, void* stream) {
+    return run_plan_impl(ops, nops, tables, slots, nslots, workspace, workspace_bytes,
+                         (cudaStream_t)stream, nullptr);
+}
+
+int kb200_plan_run_timed(const kb200_op* ops, int nops, const uint32_t* tables,
+                         double* const* slots, int nslots, double* workspace,
+                         int64_t workspace_bytes, void* stream, float* op_ms) {
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaEvent_t* ev = new cudaEvent_t[2 * (size_t)nops];
+    for (int i = 0; i < 2 * nops; ++i) cudaEventCreate(&ev[i]);
+    int rc = run_plan_impl(ops, nops, tables, slots, nslots, workspace, workspace_bytes, st, ev);
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (rc == 0 && e != cudaSuccess) rc = cuda_fail(e, "plan_run_timed sync");
+    for (int i = 0; i < nops; ++i) {
+        float ms = 0.f;
+        if (rc == 0) cudaEventElapsedTime(&ms, ev[2 * i], ev[2 * i + 1]);
+        op_ms[i] = ms;
+    }
+    for (int i = 0; i < 2 * nops; ++i) cudaEventDestroy(ev[i]);
+    delete[] ev;
+    return rc;
+}
+
 int kb200_int_tbar(int ng, int64_t n, const double* tbar, const double* D, const double* ti,
                    const double* G, double* out, int mode, void* stream) {
-    if (ng <= 0 || n < 0) return fail(-1, "int_tbar: bad size");
+    return kb200_int_tbar_rows(ng, n, tbar, D, ti, G, out, 0, ng, mode, stream);
+}
+
+int kb200_int_tbar_rows(int ng, int64_t n, const double* tbar, const double* D, const double* ti,
+                        const double* G, double* out, int y0, int y1, int mode, void* stream) {
+    if (ng <= 0 || n < 0 || y0 < 0 || y1 > ng || y0 > y1) return fail(-1, "int_tbar: bad size");
+    if (y0 == y1) return 0;
     if (n == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     size_t smem = ((size_t)ng * INT_THREADS * (mode == 1 ? 2 : 1) + ng) * 8;
@@ -435,10 +468,10 @@ int kb200_int_tbar(int ng, int64_t n, const double* tbar, const double* D, const
     int grid = grid_for(n, INT_THREADS, 148 * 8);
     if (mode == 1) {
         cudaFuncSetAttribute(int_tbar_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        int_tbar_kernel<1><<<grid, INT_THREADS, smem, st>>>(ng, n, tbar, D, ti, G, out);
+        int_tbar_kernel<1><<<grid, INT_THREADS, smem, st>>>(ng, n, tbar, D, ti, G, out, y0, y1);
     } else {
         cudaFuncSetAttribute(int_tbar_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        int_tbar_kernel<0><<<grid, INT_THREADS, smem, st>>>(ng, n, tbar, D, ti, G, out);
+        int_tbar_kernel<0><<<grid, INT_THREADS, smem, st>>>(ng, n, tbar, D, ti, G, out, y0, y1);
     }
     KB_CHECK_LAUNCH("int_tbar_kernel");
     return 0;
@@ -447,7 +480,14 @@ int kb200_int_tbar(int ng, int64_t n, const double* tbar, const double* D, const
 int kb200_int_L(int ng, const int32_t dims[4], const int64_t dstride[4], const double* L,
                 const double* D, const double* ti, const double* g, const double* G, double* out,
                 int mode, void* stream) {
-    if (ng <= 0) return fail(-1, "int_L: bad size");
+    return kb200_int_L_rows(ng, dims, dstride, L, D, ti, g, G, out, 0, ng, mode, stream);
+}
+
+int kb200_int_L_rows(int ng, const int32_t dims[4], const int64_t dstride[4], const double* L,
+                     const double* D, const double* ti, const double* g, const double* G,
+                     double* out, int s0, int s1, int mode, void* stream) {
+    if (ng <= 0 || s0 < 0 || s1 > ng || s0 > s1) return fail(-1, "int_L: bad size");
+    if (s0 == s1) return 0;
     Dims4 dm;
     long long n = 1;
     for (int i = 0; i < 4; ++i) {
@@ -462,10 +502,10 @@ int kb200_int_L(int ng, const int32_t dims[4], const int64_t dstride[4], const d
     int grid = grid_for(n, INT_THREADS, 148 * 8);
     if (mode == 1) {
         cudaFuncSetAttribute(int_L_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        int_L_kernel<1><<<grid, INT_THREADS, smem, st>>>(ng, n, dm, L, D, ti, g, G, out);
+        int_L_kernel<1><<<grid, INT_THREADS, smem, st>>>(ng, n, dm, L, D, ti, g, G, out, s0, s1);
     } else {
         cudaFuncSetAttribute(int_L_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        int_L_kernel<0><<<grid, INT_THREADS, smem, st>>>(ng, n, dm, L, D, ti, g, G, out);
+        int_L_kernel<0><<<grid, INT_THREADS, smem, st>>>(ng, n, dm, L, D, ti, g, G, out, s0, s1);
     }
     KB_CHECK_LAUNCH("int_L_kernel");
     return 0;

@@ -74,7 +74,7 @@ class Plan(object):
         return self._ops[nb]
 
     # -- run -----------------------------------------------------------------
-    def run(self, tensors, ng, chunk=None):
+    def run(self, tensors, ng, chunk=None, timings=None):
         """tensors: slot -> CUDA float64 tensor (batched slots: leading axis ng).
         Scratch is allocated for `chunk` grid points at a time (default: all)."""
         lib = _lib.load()
@@ -104,9 +104,21 @@ class Plan(object):
                     t = tensors[s]
                     off = y0*t.stride(0)*8 if self.batched[s] else 0
                     ptrs[k] = t.data_ptr() + off
-            rc = lib.kb200_plan_run(ops, len(ops), _lib.ptr(tables), ptrs, len(names),
-                                    _lib.ptr(self._ws) if wsb > 0 else None, wsb,
-                                    _lib.stream_ptr())
+            if timings is None:
+                rc = lib.kb200_plan_run(ops, len(ops), _lib.ptr(tables), ptrs, len(names),
+                                        _lib.ptr(self._ws) if wsb > 0 else None, wsb,
+                                        _lib.stream_ptr())
+            else:
+                ms = (ctypes.c_float*len(ops))()
+                rc = lib.kb200_plan_run_timed(ops, len(ops), _lib.ptr(tables), ptrs, len(names),
+                                              _lib.ptr(self._ws) if wsb > 0 else None, wsb,
+                                              _lib.stream_ptr(), ms)
+                for k in range(len(ops)):
+                    o = ops[k]
+                    timings.append((int(o.kind), 2.0*o.M*o.N*o.K*o.batch if o.kind == 0 else 0.0,
+                                    float(ms[k])*1e-3, (int(o.M), int(o.N), int(o.K), int(o.batch),
+                                                        int(o.tile), int(o.splitk),
+                                                        int(o.a_mode), int(o.b_mode))))
             _lib.check(rc, "kb200_plan_run(%s)" % self.name)
             y0 += nb
 

@@ -133,3 +133,121 @@ def uccsd_stanton(Fa, Fb, Ia, Ib, Iabab, T1aold, T1bold, T2aaold, T2abold,
     T2ab = quadrature.int_tbar2(ng, b2ab, ti, D2ab, G)
     T2bb = quadrature.int_tbar2(ng, b2bb, ti, D2bb, G)
     return (T1a, T1b), (T2aa, T2ab, T2bb)
+
+
+# ---------------------------------------------------------------------------
+# Lambda equations
+# ---------------------------------------------------------------------------
+_U_T = ("t1.a", "t1.b", "t2.aa", "t2.ab", "t2.bb")
+_U_L = ("l1.a", "l1.b", "l2.aa", "l2.ab", "l2.bb")
+_U_LO = ("lo1.a", "lo1.b", "lo2.aa", "lo2.ab", "lo2.bb")
+
+
+def lambda_plan(mode, sizes, fac=-1.0):
+    """Plan of -J(T)^T.Lbar - (F.ov + <ji||ba>t, I.oovv): intermediates of the
+    forward residual followed by its mechanically derived reverse sweep."""
+    key = ("lambda", mode, tuple(sorted(sizes.items(), key=str)), fac)
+
+    def build():
+        inter, rest = programs.lambda_rops(mode, fac)
+        if mode == "g":
+            ins, outs = ("t1", "t2", "l1", "l2"), ("lo1", "lo2")
+        else:
+            ins, outs = _U_T + _U_L, _U_LO
+        return engine.Plan(inter + rest, mode, sizes, ins, outs, name="lambda-" + mode)
+    return engine.cached(key, build)
+
+
+def lambda_guess_plan(mode, sizes, beta, ls_ts_fac):
+    key = ("lguess", mode, tuple(sorted(sizes.items(), key=str)), beta, ls_ts_fac)
+
+    def build():
+        rops = programs.lambda_guess_rops(mode, beta, ls_ts_fac)
+        if mode == "g":
+            ins, outs = ("t1",), ("lo1", "lo2")
+        else:
+            ins, outs = ("t1.a", "t1.b"), _U_LO
+        return engine.Plan(rops, mode, sizes, ins, outs, name="lguess-" + mode)
+    return engine.cached(key, build)
+
+
+def _l_like(T1, T2):
+    """Empty Lambda-shaped (o..v..) tensors matching amplitudes (v..o..)."""
+    L1 = torch.empty((T1.shape[0], T1.shape[2], T1.shape[1]), dtype=torch.float64, device=T1.device)
+    L2 = torch.empty((T2.shape[0], T2.shape[3], T2.shape[4], T2.shape[1], T2.shape[2]),
+                     dtype=torch.float64, device=T2.device)
+    return L1, L2
+
+
+def ccsd_lambda_opt(F, I, T1old, T2old, L1old, L2old, D1, D2, ti, ng, g, G, beta):
+    """Time-dependent CCSD Lambda iteration with intermediates
+    (kelvin/ft_cc_equations.py:385-409)."""
+    dev = _lib.device()
+    T1old, T2old = _lib.as_dev(T1old, dev), _lib.as_dev(T2old, dev)
+    L1int = quadrature.int_L1(ng, L1old, ti, D1, g, G)
+    L2int = quadrature.int_L2(ng, L2old, ti, D2, g, G)
+    p = lambda_plan("g", _g_sizes(F))
+    t = _g_integral_slots(F, I, dev)
+    t.update({"t1": T1old, "t2": T2old, "l1": L1int, "l2": L2int})
+    t["lo1"], t["lo2"] = _l_like(T1old, T2old)
+    p.run(t, ng, _chunk_for(p, ng, dev))
+    return t["lo1"], t["lo2"]
+
+
+def uccsd_lambda_opt(Fa, Fb, Ia, Ib, Iabab, T1aold, T1bold, T2aaold, T2abold,
+                     T2bbold, L1aold, L1bold, L2aaold, L2abold, L2bbold, D1a,
+                     D1b, D2aa, D2ab, D2bb, ti, ng, g, G, beta):
+    """Unrestricted Lambda iteration (kelvin/ft_cc_equations.py:412-458)."""
+    dev = _lib.device()
+    Ts = [_lib.as_dev(x, dev) for x in (T1aold, T1bold, T2aaold, T2abold, T2bbold)]
+    assert(Ts[0].shape[0] == ng)
+    Ls = [quadrature.int_L(ng, L, ti, D, g, G) for L, D in
+          zip((L1aold, L1bold, L2aaold, L2abold, L2bbold), (D1a, D1b, D2aa, D2ab, D2bb))]
+    p = lambda_plan("u", _u_sizes(Fa, Fb))
+    t = _u_integral_slots(Fa, Fb, Ia, Ib, Iabab, dev,
+                          [s for s in p.inputs if _plan.is_integral_slot(s)])
+    for nm, x in zip(_U_T, Ts):
+        t[nm] = x
+    for nm, x in zip(_U_L, Ls):
+        t[nm] = x
+    outs = []
+    for nm, x in zip(_U_LO, Ls):
+        t[nm] = torch.empty_like(x)
+        outs.append(t[nm])
+    p.run(t, ng, _chunk_for(p, ng, dev))
+    return tuple(outs)
+
+
+def ccsd_lambda_guess(F, I, T1old, beta, ng):
+    """CCSD Lambda guess (kelvin/ft_cc_equations.py:502-512)."""
+    dev = _lib.device()
+    T1old = _lib.as_dev(T1old, dev)
+    p = lambda_guess_plan("g", _g_sizes(F), beta, 1.0/beta)
+    t = _g_integral_slots(F, I, dev)
+    t["t1"] = T1old
+    no, nv = F.ov.shape
+    t["lo1"] = torch.empty((ng, no, nv), dtype=torch.float64, device=dev)
+    t["lo2"] = torch.empty((ng, no, no, nv, nv), dtype=torch.float64, device=dev)
+    p.run({k: v for k, v in t.items() if k in p.shapes}, ng)
+    return t["lo1"], t["lo2"]
+
+
+def uccsd_lambda_guess(Fa, Fb, Ia, Ib, Iabab, T1aold, T1bold, beta, ng):
+    """Unrestricted Lambda guess; the <ji||ba>t term is NOT scaled by 1/beta,
+    as in the reference (kelvin/ft_cc_equations.py:515-526, quirk Q3)."""
+    dev = _lib.device()
+    T1a, T1b = _lib.as_dev(T1aold, dev), _lib.as_dev(T1bold, dev)
+    p = lambda_guess_plan("u", _u_sizes(Fa, Fb), beta, 1.0)
+    t = _u_integral_slots(Fa, Fb, Ia, Ib, Iabab, dev,
+                          [s for s in p.inputs if _plan.is_integral_slot(s)])
+    t["t1.a"], t["t1.b"] = T1a, T1b
+    noa, nva = Fa.ov.shape
+    nob, nvb = Fb.ov.shape
+    shp = {"lo1.a": (noa, nva), "lo1.b": (nob, nvb), "lo2.aa": (noa, noa, nva, nva),
+           "lo2.ab": (noa, nob, nva, nvb), "lo2.bb": (nob, nob, nvb, nvb)}
+    outs = []
+    for nm in _U_LO:
+        t[nm] = torch.empty((ng,) + shp[nm], dtype=torch.float64, device=dev)
+        outs.append(t[nm])
+    p.run(t, ng)
+    return tuple(outs)

@@ -132,3 +132,97 @@ def stanton(fac=-1.0, drivers=True):
     st += _parse_block(_INTERMEDIATES)
     st += _parse_block(_RESIDUAL, fac)
     return st
+
+
+# ---------------------------------------------------------------------------
+# Lambda map = vector-Jacobian product of StantonTerms
+# ---------------------------------------------------------------------------
+def _subst_in(op, table):
+    """Replace input slots by (new slot, letter permutation, scale)."""
+    from .plan import ROp
+    coef = op.coef
+    ins = []
+    for slot, ls in op.ins:
+        if slot in table:
+            new, perm, scale = table[slot]
+            ins.append((new, "".join(ls[p] for p in perm)))
+            coef *= scale
+        else:
+            ins.append((slot, ls))
+    return ROp(op.out, coef, ins, op.spin)
+
+
+def lambda_rops(mode, fac=-1.0):
+    """Resolved ops of cqcpy.cc_equations._Lambda_opt / _uccsd_Lambda_opt as the
+    reference uses them (kelvin/ft_cc_equations.py:396-407, 437-456):
+
+        lo1[i,a]     = -F.ov - sum <ji||ba> t[b,j] + fac * d<Lbar,R(t)>/d t1[a,i]
+        lo2[i,j,a,b] = -I.oovv                     + fac * P(ij)P(ab) d<Lbar,R(t)>/d t2[a,b,i,j]
+
+    with <L,R> = L1.R1 + 1/4 L2.R2 over spin orbitals.  Inputs: t1,t2 (amplitudes),
+    l1,l2 (time-integrated Lambda, o..v.. order); outputs lo1, lo2."""
+    from .plan import ROp, adjoint, expand, is_integral_slot
+    T = tensor_defs()
+    fwd = expand(stanton(1.0, drivers=False), T, mode)
+    if mode == "g":
+        outs1, outs2 = ["o1"], ["o2"]
+        seed = {"o1~": ("l1", (1, 0), 1.0), "o2~": ("l2", (2, 3, 0, 1), 0.25)}
+        t1s, t2s = [("t1", "lo1")], [("t2", "lo2", True)]
+    else:
+        outs1, outs2 = ["o1.a", "o1.b"], ["o2.aa", "o2.ab", "o2.bb"]
+        seed = {"o1.a~": ("l1.a", (1, 0), 1.0), "o1.b~": ("l1.b", (1, 0), 1.0),
+                "o2.aa~": ("l2.aa", (2, 3, 0, 1), 0.25), "o2.bb~": ("l2.bb", (2, 3, 0, 1), 0.25),
+                "o2.ab~": ("l2.ab", (2, 3, 0, 1), 1.0)}
+        t1s = [("t1.a", "lo1.a"), ("t1.b", "lo1.b")]
+        t2s = [("t2.aa", "lo2.aa", True), ("t2.ab", "lo2.ab", False), ("t2.bb", "lo2.bb", True)]
+    outset = set(outs1 + outs2)
+    inter = [op for op in fwd if op.out[0] not in outset]        # intermediates only
+    bwd = adjoint(fwd, wrt=lambda s: not is_integral_slot(s), seeds=outset)
+    bwd = [_subst_in(op, seed) for op in bwd]
+
+    # energy term (kelvin/ft_cc_equations.py:403-407) written first so that the
+    # outputs are initialised by it
+    Tl = dict(T)
+    from .plan import TDef
+    Tl["lo1"] = TDef("lo1", "one", "out", True, "ov")
+    Tl["lo2"] = TDef("lo2", "amp2", "out", True, "oovv")
+    eterm = expand(_parse_block("""
+        lo1[ia] += -1 F.ov[ia]
+        lo1[ia] += -1 I.oovv[jiba] t1[bj]
+        lo2[ijab] += -1 I.oovv[ijab]
+    """), Tl, mode)
+
+    # scatter the amplitude adjoints into the outputs
+    tail = []
+
+    def sp(slot, src_letters, new_letters):
+        if mode == "g":
+            return None
+        suf = slot.split(".")[-1]
+        spins = {"a": "aa", "b": "bb", "aa": "aaaa", "ab": "abab", "bb": "bbbb"}[suf]
+        return dict(zip(new_letters, spins))
+    for tslot, lslot in t1s:
+        tail.append(ROp((lslot, "ia"), fac, [(tslot + "~", "ai")], sp(tslot, "ai", "ai")))
+    for tslot, lslot, anti in t2s:
+        spn = sp(tslot, "abij", "abij")
+        tail.append(ROp((lslot, "ijab"), fac, [(tslot + "~", "abij")], spn))
+        if anti:
+            tail.append(ROp((lslot, "ijab"), -fac, [(tslot + "~", "baij")], spn))
+            tail.append(ROp((lslot, "ijab"), -fac, [(tslot + "~", "abji")], spn))
+            tail.append(ROp((lslot, "ijab"), fac, [(tslot + "~", "baji")], spn))
+    return inter, eterm + bwd + tail
+
+
+def lambda_guess_rops(mode, beta, ls_ts_fac):
+    """L1 = F.ov/beta + ls_ts_fac * sum <ji||ba> t[b,j];  L2 = I.oovv/beta
+    (kelvin/ft_cc_equations.py:502-526; the g guess uses ls_ts_fac = 1/beta, the u
+    guess 1 -- quirk Q3)."""
+    from .plan import TDef, expand
+    T = tensor_defs()
+    T["lo1"] = TDef("lo1", "one", "out", True, "ov")
+    T["lo2"] = TDef("lo2", "amp2", "out", True, "oovv")
+    st = _parse_block("""
+        lo1[ia] += 1 F.ov[ia]
+        lo2[ijab] += 1 I.oovv[ijab]
+    """, 1.0/beta) + _parse_block("lo1[ia] += 1 I.oovv[jiba] t1[bj]", ls_ts_fac)
+    return expand(st, T, mode)

@@ -29,13 +29,11 @@ def get_G(ng, delta):
     G = numpy.zeros((ng, ng))
     if ng > 1:
         G[1, 0] = G[1, 1] = 0.5*delta
-    panel = numpy.array([1.0, 4.0, 1.0])*delta/3.0
     for y in range(2, ng):
         G[y] = G[y - 2]
         G[y, y - 2] += delta/3.0
         G[y, y - 1] += 4.0*delta/3.0
         G[y, y] += delta/3.0
-    del panel
     return G
 
 
@@ -163,9 +161,10 @@ def _small(x, dev):
         if not isinstance(x, torch.Tensor) else x.to(device=dev, dtype=torch.float64).contiguous()
 
 
-def int_tbar(ng, tbar, ti, D, G, out=None, mode=None):
+def int_tbar(ng, tbar, ti, D, G, out=None, mode=None, rows=None):
     """out[y] = sum_x G[y,x] * exp(D*(ti[x]-ti[y]))_{x<y} * tbar[x]
-    for any amplitude rank (kelvin/quadrature.py:292-317)."""
+    for any amplitude rank (kelvin/quadrature.py:292-317).  rows=(y0, y1)
+    restricts the output to those grid points (tau-sharded runs)."""
     lib = _lib.load()
     dev = _lib.device()
     tbar = _lib.as_dev(tbar, dev)
@@ -173,12 +172,14 @@ def int_tbar(ng, tbar, ti, D, G, out=None, mode=None):
     if tbar.shape[0] != ng or tuple(tbar.shape[1:]) != tuple(D.shape):
         raise Exception("int_tbar: shape mismatch {} vs ng={} D{}".format(
             tuple(tbar.shape), ng, tuple(D.shape)))
+    y0, y1 = (0, ng) if rows is None else rows
     if out is None:
-        out = torch.empty_like(tbar)
+        out = torch.empty((y1 - y0,) + tuple(D.shape), dtype=torch.float64, device=dev)
     n = D.numel()
     tid, Gd = _small(ti, dev), _small(G, dev)
-    rc = lib.kb200_int_tbar(ng, n, _lib.ptr(tbar), _lib.ptr(D), _lib.ptr(tid), _lib.ptr(Gd),
-                            _lib.ptr(out), INT_MODE if mode is None else mode, _lib.stream_ptr())
+    rc = lib.kb200_int_tbar_rows(ng, n, _lib.ptr(tbar), _lib.ptr(D), _lib.ptr(tid), _lib.ptr(Gd),
+                                 _lib.ptr(out), y0, y1, INT_MODE if mode is None else mode,
+                                 _lib.stream_ptr())
     _lib.check(rc, "kb200_int_tbar")
     return out
 
@@ -193,15 +194,13 @@ def int_tbar2(ng, t2bar, ti, D2, G):
     return int_tbar(ng, t2bar, ti, D2, G)
 
 
-def int_L(ng, Lold, ti, D, g, G, out=None, mode=None):
+def int_L(ng, Lold, ti, D, g, G, out=None, mode=None, rows=None):
     """Lbar[s] = (1/g[s]) sum_y g[y] G[y,s] exp(D^T*(ti[s]-ti[y]))_{y>=s} L[y]
     with D indexed (v..,o..) and L indexed (o..,v..) (kelvin/quadrature.py:320-345)."""
     lib = _lib.load()
     dev = _lib.device()
     Lold = _lib.as_dev(Lold, dev)
     D = _lib.as_dev(D, dev)
-    if out is None:
-        out = torch.empty_like(Lold)
     r = D.dim()
     h = r // 2
     # L axes (o..., v...) <- D axes (v..., o...)
@@ -214,10 +213,13 @@ def int_L(ng, Lold, ti, D, g, G, out=None, mode=None):
     strs = [0]*(4 - r) + dstr
     cd = (ctypes.c_int32*4)(*dims)
     cs = (ctypes.c_int64*4)(*strs)
+    s0, s1 = (0, ng) if rows is None else rows
+    if out is None:
+        out = torch.empty((s1 - s0,) + tuple(Lold.shape[1:]), dtype=torch.float64, device=dev)
     tid, gd, Gd = _small(ti, dev), _small(g, dev), _small(G, dev)
-    rc = lib.kb200_int_L(ng, cd, cs, _lib.ptr(Lold), _lib.ptr(D), _lib.ptr(tid), _lib.ptr(gd),
-                         _lib.ptr(Gd), _lib.ptr(out), INT_MODE if mode is None else mode,
-                         _lib.stream_ptr())
+    rc = lib.kb200_int_L_rows(ng, cd, cs, _lib.ptr(Lold), _lib.ptr(D), _lib.ptr(tid),
+                              _lib.ptr(gd), _lib.ptr(Gd), _lib.ptr(out), s0, s1,
+                              INT_MODE if mode is None else mode, _lib.stream_ptr())
     _lib.check(rc, "kb200_int_L")
     return out
 

@@ -25,11 +25,12 @@ def _np_einsum(*a):
     return numpy.einsum(*a, optimize=True)
 
 
-def stanton_terms(F, I, t1, t2, ein=_np_einsum):
+def stanton_terms(F, I, t1, t2, ein=_np_einsum, hints=False):
     """R1[a,i], R2[a,b,i,j] of SURVEY.md A.2 (no drivers, no sign).
 
     Called by the reference as cqcpy.cc_equations._Stanton at
     kelvin/ft_cc_equations.py:106 (which adds fac*R to T1new/T2new)."""
+    kw = {"keep": True} if hints else {}    # spin-blocked back end: canonical blocks only
     tt = ein('ai,bj->abij', t1, t1)
     tt = tt - tt.transpose(1, 0, 2, 3) if not torch.is_tensor(tt) else tt - tt.permute(1, 0, 2, 3)
     tau_h = t2 + 0.5 * tt
@@ -44,9 +45,9 @@ def stanton_terms(F, I, t1, t2, ein=_np_einsum):
     Fov = F.ov + ein('mnef,fn->me', I.oovv, t1)
 
     tmp = ein('mnie,ej->mnij', I.ooov, t1)
-    Woooo = I.oooo + tmp - _swap(tmp, 2, 3) + 0.25 * ein('mnef,efij->mnij', I.oovv, tau)
+    Woooo = I.oooo + tmp - _swap(tmp, 2, 3) + 0.25 * ein('mnef,efij->mnij', I.oovv, tau, **kw)
     tmp = ein('amef,bm->abef', I.vovv, t1)
-    Wvvvv = I.vvvv - tmp + _swap(tmp, 0, 1) + 0.25 * ein('mnef,abmn->abef', I.oovv, tau)
+    Wvvvv = I.vvvv - tmp + _swap(tmp, 0, 1) + 0.25 * ein('mnef,abmn->abef', I.oovv, tau, **kw)
     # Wovvo[m,b,e,j]
     Wovvo = (-_perm(I.vovo, (1, 0, 2, 3))
              - ein('bmef,fj->mbej', I.vovv, t1)
@@ -65,8 +66,8 @@ def stanton_terms(F, I, t1, t2, ein=_np_einsum):
     R2 = tmp - _swap(tmp, 0, 1)
     tmp = ein('abim,mj->abij', t2, Xoo)
     R2 = R2 - (tmp - _swap(tmp, 2, 3))
-    R2 = R2 + 0.5 * ein('abmn,mnij->abij', tau, Woooo)
-    R2 = R2 + 0.5 * ein('efij,abef->abij', tau, Wvvvv)
+    R2 = R2 + 0.5 * ein('abmn,mnij->abij', tau, Woooo, **kw)
+    R2 = R2 + 0.5 * ein('efij,abef->abij', tau, Wvvvv, **kw)
     tmp = ein('aeim,mbej->abij', t2, Wovvo) \
         + ein('ei,am,bmej->abij', t1, t1, I.vovo)
     tmp = tmp - _swap(tmp, 0, 1)
