@@ -48,10 +48,10 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index = index
         self.rows = []
-        self._stop = threading.Event()
+        self._halt = threading.Event()
 
     def run(self):
-        while not self._stop.is_set():
+        while not self._halt.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
                                       "--format=csv,noheader,nounits"], capture_output=True,
@@ -60,10 +60,10 @@ class ClockSampler(threading.Thread):
                     self.rows.append([x.strip() for x in out.split(",")])
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._halt.wait(0.2)
 
     def stop(self):
-        self._stop.set()
+        self._halt.set()
         self.join(timeout=6)
         sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
         mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]

@@ -140,6 +140,15 @@ int kb200_dress2(int n0, int n1, const double* f, const double* e, const double*
  * (kelvin/ft_cc_equations.py:713,737): out[p] = sum_y g[y]*X[y,p]. */
 int kb200_gsum(int ng, int64_t n, const double* X, const double* g, double* out, void* stream);
 
+/* "Keep one index" partial trace, replaces the einsum('cdab,abcd->c', P, I)-type
+ * contractions of kelvin/cc_utils.py:1648-1685,1746-1895 and the per-grid-point
+ * pairings einsum('vijab,vabij->v', L2, T2) of kelvin/ccsd.py:1121-1146,1214-1258:
+ *   out[k] = beta*out[k] + alpha * sum_{i1..i4} A[k*sA[0] + sum_d i_d*sA[d]] * B[k*sB[0] + ...]
+ * over i_d < dims[d-1]; strides in elements (any index permutation).  nkeep <= 65536. */
+int kb200_dot_keep(int nkeep, const int32_t dims[4] /*host*/, const int64_t sA[5] /*host*/,
+                   const int64_t sB[5] /*host*/, const double* A, const double* B,
+                   double alpha, double beta, double* out, double* scratch, void* stream);
+
 /* Elementwise X[y,p] *= D[p]  (kelvin/ccsd.py:1138-1139,1238-1242). */
 int kb200_scale_by(int ng, int64_t n, double* X, const double* D, void* stream);
 

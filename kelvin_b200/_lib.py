@@ -20,7 +20,7 @@ EXPORTS = (
     "kb200_version", "kb200_last_error", "kb200_launch_count", "kb200_launch_count_reset",
     "kb200_plan_workspace_bytes", "kb200_plan_run", "kb200_plan_run_timed", "kb200_int_tbar", "kb200_int_L", "kb200_int_tbar_rows", "kb200_int_L_rows",
     "kb200_reduce_scratch_doubles", "kb200_energy_pair", "kb200_dot_g", "kb200_damp_norms",
-    "kb200_dress4", "kb200_dress2", "kb200_gsum", "kb200_scale_by",
+    "kb200_dress4", "kb200_dress2", "kb200_gsum", "kb200_scale_by", "kb200_dot_keep",
 )
 
 
@@ -64,6 +64,8 @@ def load():
     lib.kb200_damp_norms.argtypes = [i64, vp, vp, dbl, vp, vp, vp]
     lib.kb200_dress4.argtypes = [ctypes.POINTER(i32), vp, vp, vp, vp, vp, vp, vp]
     lib.kb200_dress2.argtypes = [ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, vp, vp]
+    lib.kb200_dot_keep.argtypes = [ctypes.c_int, ctypes.POINTER(i32), ctypes.POINTER(i64),
+                                   ctypes.POINTER(i64), vp, vp, dbl, dbl, vp, vp, vp]
     lib.kb200_gsum.argtypes = [ctypes.c_int, i64, vp, vp, vp, vp]
     lib.kb200_scale_by.argtypes = [ctypes.c_int, i64, vp, vp, vp]
     for nm in EXPORTS:
@@ -108,3 +110,28 @@ def reduce_scratch(dev):
         n = load().kb200_reduce_scratch_doubles()
         _scratch[key] = torch.empty(int(n), dtype=torch.float64, device=dev)
     return _scratch[key]
+
+
+def dot_keep(A, la, B, lb, keep, alpha=1.0, out=None, beta=0.0):
+    """out[keep] (+)= alpha * einsum('<la>,<lb>-><keep>', A, B) for tensors of rank <= 5
+    sharing the same index letters (any order); `keep` is one letter."""
+    lib = load()
+    dev = A.device
+    assert sorted(la) == sorted(lb) and keep in la and len(la) <= 5
+    da = dict(zip(la, A.shape))
+    sa = dict(zip(la, A.stride()))
+    sb = dict(zip(lb, B.stride()))
+    for l, n in zip(lb, B.shape):
+        assert da[l] == n, "dot_keep: shape mismatch on %s" % l
+    rest = [l for l in la if l != keep]
+    pad = 4 - len(rest)
+    dims = (ctypes.c_int32*4)(*([1]*pad + [da[l] for l in rest]))
+    cA = (ctypes.c_int64*5)(*([sa[keep]] + [0]*pad + [sa[l] for l in rest]))
+    cB = (ctypes.c_int64*5)(*([sb[keep]] + [0]*pad + [sb[l] for l in rest]))
+    nk = da[keep]
+    if out is None:
+        out = torch.zeros(nk, dtype=torch.float64, device=dev)
+    rc = lib.kb200_dot_keep(nk, dims, cA, cB, ptr(A), ptr(B), alpha, beta, ptr(out),
+                            ptr(reduce_scratch(dev)), stream_ptr())
+    check(rc, "kb200_dot_keep")
+    return out

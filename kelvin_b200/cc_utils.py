@@ -304,3 +304,89 @@ def ft_ulambda_iter(method, L1ain, L1bin, L2aain, L2abin, L2bbin, T1aold, T1bold
     tend = time.time()
     logging.info("Total CCSD Lambda time: %f s" % (tend - tbeg))
     return old[0], old[1], old[2], old[3], old[4]
+
+
+# ---------------------------------------------------------------------------
+# normal-ordered 2-RDM assembly and occupation-number response
+# ---------------------------------------------------------------------------
+def _scaled(P, facs, beta):
+    return _dress4(P.contiguous(), *facs)/beta
+
+
+def g_n2rdm_full(beta, sfo, sfv, P2):
+    """Dress the nine P blocks with sqrt(f)/sqrt(1-f) and add their
+    antisymmetric images (kelvin/cc_utils.py:1449-1466)."""
+    dev = P2[0].device
+    s = {"o": _vec(sfo, dev), "v": _vec(sfv, dev)}
+    pats = ("vvvv", "vovv", "vvvo", "oovv", "vovo", "vvoo", "oovo", "ovoo", "oooo")
+    blocks = [_scaled(P, [s[c] for c in pat], beta) for P, pat in zip(P2, pats)]
+    n2 = blocks[0].clone()
+    for k, (swap01, swap23) in ((1, (True, False)), (2, (False, True)), (6, (False, True)),
+                                (7, (True, False))):
+        n2 += blocks[k]
+        n2 -= blocks[k].permute(1, 0, 2, 3) if swap01 else blocks[k].permute(0, 1, 3, 2)
+    for k in (3, 5, 8):
+        n2 += blocks[k]
+    b = blocks[4]
+    n2 += b - b.permute(0, 1, 3, 2) - b.permute(1, 0, 2, 3) + b.permute(1, 0, 3, 2)
+    return n2
+
+
+def u_n2rdm_full(beta, sfoa, sfva, sfob, sfvb, P2):
+    """(P2aa, P2bb, P2ab) (kelvin/cc_utils.py:1506-1565)."""
+    dev = P2[0][0].device
+    sa = {"o": _vec(sfoa, dev), "v": _vec(sfva, dev)}
+    sb = {"o": _vec(sfob, dev), "v": _vec(sfvb, dev)}
+    pats = ("vvvv", "vovv", "vvvo", "oovv", "vovo", "vvoo", "oovo", "ovoo", "oooo")
+    out = []
+    for k, s in ((0, sa), (1, sb)):
+        out.append(g_n2rdm_full(beta, s["o"], s["v"], [P2[b][k] for b in range(9)]))
+
+    def sc(P, pat, spins):
+        return _scaled(P, [(sa if sp == "a" else sb)[c] for c, sp in zip(pat, spins)], beta)
+    ab = sc(P2[0][2], pats[0], "abab").clone()
+    for b in range(1, 9):
+        ab += sc(P2[b][2], pats[b], "abab")
+    for b in (1, 2, 6, 7):
+        ab += sc(P2[b][3], pats[b], "baba").permute(1, 0, 3, 2)
+    ab -= sc(P2[4][3], pats[4], "abba").permute(0, 1, 3, 2)
+    ab -= sc(P2[4][4], pats[4], "baab").permute(1, 0, 2, 3)
+    ab += sc(P2[4][5], pats[4], "baba").permute(1, 0, 3, 2)
+    return (out[0], out[1], ab)
+
+
+def g_Fd_on(Fd, ndia, ndba, ndji, ndai):
+    """Perturbed-occupation contribution of the Fock matrix, host O(n^3)
+    (kelvin/cc_utils.py:1628-1633)."""
+    e = numpy.einsum
+    return -(e('ia,aik->k', ndia, Fd) + e('ba,abk->k', ndba, Fd)
+             + e('ji,ijk->k', ndji, Fd) + e('ai,iak->k', ndai, Fd))
+
+
+def u_Fd_on(Fdaa, Fdab, Fdba, Fdbb, ndia, ndba, ndji, ndai):
+    """kelvin/cc_utils.py:1688-1706."""
+    nd = lambda k: (ndia[k], ndba[k], ndji[k], ndai[k])  # noqa: E731
+    tempA = g_Fd_on(Fdaa, *nd(0)) + g_Fd_on(Fdba, *nd(1))
+    tempB = g_Fd_on(Fdbb, *nd(1)) + g_Fd_on(Fdab, *nd(0))
+    return tempA, tempB
+
+
+def on_response(leaves, ints, spin_of_leaf):
+    """Partial traces 'sum over all indices but one' of every Lagrangian
+    derivative block with its dressed integral block, accumulated per
+    (space, spin) of the kept index.  This is the generic form of
+    kelvin/cc_utils.py:1648-1685 (g_d_on_oo / g_d_on_vv) and :1746-1895
+    (u_d_on_oo / u_d_on_vv), whose term lists are exactly these traces with the
+    symmetry-equivalent positions merged.
+
+    leaves: list of (adjoint tensor, its letters, dressed block, its letters,
+                     pattern string, leaf-name prefix, weight)
+    Returns dict (space, spin) -> device vector."""
+    acc = {}
+    for A, la, B, lb, pat, pre, w in leaves:
+        for pos, l in enumerate(lb):
+            key = (pat[pos], spin_of_leaf(pre, pos))
+            out = acc.get(key)
+            res = _lib.dot_keep(A, la, B, lb, l, alpha=w, out=out, beta=0.0 if out is None else 1.0)
+            acc[key] = res
+    return acc

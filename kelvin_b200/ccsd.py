@@ -232,3 +232,290 @@ class ccsd(object):
             g, G, self.beta_max, ng, ti, self.iprint, self._conv_options())
         self.L1 = (L1a, L1b)
         self.L2 = (L2aa, L2ab, L2bb)
+
+    # ------------------------------------------------------------------
+    # response densities
+    # ------------------------------------------------------------------
+    def _occ(self):
+        """Fermi factors (host vectors) of the orbitals, per spin in the u case."""
+        beta, mu = self.beta, self.mu
+        if self.sys.has_u():
+            ea, eb = self.sys.u_energies_tot()
+            return ((ft_utils.ff(beta, ea, mu), ft_utils.ffv(beta, ea, mu)),
+                    (ft_utils.ff(beta, eb, mu), ft_utils.ffv(beta, eb, mu)))
+        en = self.sys.g_energies_tot()
+        return ((ft_utils.ff(beta, en, mu), ft_utils.ffv(beta, en, mu)),)
+
+    @staticmethod
+    def _nd(d, s0, s1):
+        dev = d.device
+        a = torch.as_tensor(s0, dtype=torch.float64).to(dev)
+        b = torch.as_tensor(s1, dtype=torch.float64).to(dev)
+        return d*a[:, None]*b[None, :]
+
+    def _g_ft_1rdm(self):
+        """kelvin/ccsd.py:1333-1387."""
+        if self.L2 is None:
+            self._ft_ccsd_lambda()
+        en, D1, D2, F, I = self._g_setup()
+        (fo, fv), = self._occ()
+        sfo, sfv = numpy.sqrt(fo), numpy.sqrt(fv)
+        pia, pba, pji, pai = ft_cc_equations.ccsd_1rdm(
+            self.T1, self.T2, self.L1, self.L2, D1, D2, self.ti, self.ngrid, self.g, self.G)
+        self.dia, self.dba, self.dji, self.dai = pia, pba, pji, pai
+        self.ndia = self._nd(pia, sfo, sfv)
+        self.ndba = self._nd(pba, sfv, sfv)
+        self.ndji = self._nd(pji, sfo, sfo)
+        self.ndai = self._nd(pai, sfv, sfo)
+        self.n1rdm = (self.ndia + self.ndba + self.ndji + self.ndai)/self.beta
+
+    def _g_ft_2rdm(self):
+        """kelvin/ccsd.py:1389-1432."""
+        if self.L2 is None:
+            self._ft_ccsd_lambda()
+        en, D1, D2, F, I = self._g_setup()
+        (fo, fv), = self._occ()
+        self.P2 = ft_cc_equations.ccsd_2rdm(
+            self.T1, self.T2, self.L1, self.L2, D1, D2, self.ti, self.ngrid, self.g, self.G)
+        self.n2rdm = cc_utils.g_n2rdm_full(self.beta, numpy.sqrt(fo), numpy.sqrt(fv), self.P2)
+
+    def _u_ft_1rdm(self):
+        """kelvin/ccsd.py:1579-1665."""
+        if self.L2 is None:
+            self._ft_uccsd_lambda()
+        ea, eb, Ds, ints = self._u_setup()
+        (foa, fva), (fob, fvb) = self._occ()
+        sq = numpy.sqrt
+        pia, pba, pji, pai = ft_cc_equations.uccsd_1rdm(
+            *self.T1, *self.T2, *self.L1, *self.L2, *Ds, self.ti, self.ngrid, self.g, self.G)
+        self.dia, self.dba, self.dji, self.dai = pia, pba, pji, pai
+        so, sv = (sq(foa), sq(fob)), (sq(fva), sq(fvb))
+        self.ndia = tuple(self._nd(pia[k], so[k], sv[k]) for k in (0, 1))
+        self.ndba = tuple(self._nd(pba[k], sv[k], sv[k]) for k in (0, 1))
+        self.ndji = tuple(self._nd(pji[k], so[k], so[k]) for k in (0, 1))
+        self.ndai = tuple(self._nd(pai[k], sv[k], so[k]) for k in (0, 1))
+        self.n1rdm = [(self.ndia[k] + self.ndba[k] + self.ndji[k] + self.ndai[k])/self.beta
+                      for k in (0, 1)]
+
+    def _u_ft_2rdm(self):
+        """kelvin/ccsd.py:1667-1729."""
+        ea, eb, Ds, ints = self._u_setup()
+        (foa, fva), (fob, fvb) = self._occ()
+        sq = numpy.sqrt
+        self.P2 = ft_cc_equations.uccsd_2rdm(
+            *self.T1, *self.T2, *self.L1, *self.L2, *Ds, self.ti, self.ngrid, self.g, self.G)
+        self.n2rdm = cc_utils.u_n2rdm_full(self.beta, sq(foa), sq(fva), sq(fob), sq(fvb), self.P2)
+
+    # ------------------------------------------------------------------
+    # occupation-number response (kelvin/ccsd.py:1434-1492, 1731-1826)
+    # ------------------------------------------------------------------
+    def _leaf_list(self):
+        """(adjoint, dressed block) pairs of every integral block, drivers included."""
+        u = self.sys.has_u()
+        if u:
+            ea, eb, Ds, (Fa, Fb, Ia, Ib, Iabab) = self._u_setup()
+            src = {"Fa": Fa, "Fb": Fb, "Ia": Ia, "Ib": Ib, "Iabab": Iabab}
+            summed, lsum, _ = ft_cc_equations._rdm_leaves(
+                "u", list(self.T1) + list(self.T2), list(self.L1) + list(self.L2), Ds,
+                self.ti, self.ngrid, self.g, self.G)
+            drivers = [(lsum[0], "ia", Fa.vo, "ai", "vo", "Fa", 1.0),
+                       (lsum[1], "ia", Fb.vo, "ai", "vo", "Fb", 1.0),
+                       (lsum[2], "ijab", Ia.vvoo, "abij", "vvoo", "Ia", 0.25),
+                       (lsum[4], "ijab", Ib.vvoo, "abij", "vvoo", "Ib", 0.25),
+                       (lsum[3], "ijab", Iabab.vvoo, "abij", "vvoo", "Iabab", 1.0)]
+        else:
+            en, D1, D2, F, I = self._g_setup()
+            src = {"F": F, "I": I}
+            summed, lsum, _ = ft_cc_equations._rdm_leaves(
+                "g", [self.T1, self.T2], [self.L1, self.L2], (D1, D2),
+                self.ti, self.ngrid, self.g, self.G)
+            drivers = [(lsum[0], "ia", F.vo, "ai", "vo", "F", 1.0),
+                       (lsum[1], "ijab", I.vvoo, "abij", "vvoo", "I", 0.25)]
+        leaves = list(drivers)
+        for name, A in summed.items():
+            pre, pat = name[:-1].split(".")
+            letters = "pqrs"[:len(pat)]
+            leaves.append((A, letters, _lib.as_dev(getattr(src[pre], pat)), letters, pat, pre, 1.0))
+        return leaves
+
+    @staticmethod
+    def _spin_of_leaf(pre, pos):
+        if pre in ("F", "I"):
+            return "g"
+        if pre in ("Fa", "Ia"):
+            return "a"
+        if pre in ("Fb", "Ib"):
+            return "b"
+        return "a" if pos % 2 == 0 else "b"
+
+    def _g_ft_ron(self):
+        """kelvin/ccsd.py:1434-1492."""
+        (fo, fv), = self._occ()
+        self.ron1 = self.sys.g_mp1_den()
+        Fd = self.sys.g_fock_d_den()
+        c = lambda x: x.cpu().numpy()  # noqa: E731
+        rono = cc_utils.g_Fd_on(Fd, c(self.ndia), c(self.ndba), c(self.ndji), c(self.ndai))
+        acc = cc_utils.on_response(self._leaf_list(), None, self._spin_of_leaf)
+        self.rono = rono - 0.5*c(acc[("o", "g")])*fv
+        self.ronv = 0.5*c(acc[("v", "g")])*fo
+
+    def _u_ft_ron(self):
+        """kelvin/ccsd.py:1731-1826."""
+        (foa, fva), (fob, fvb) = self._occ()
+        mp1da, mp1db = self.sys.u_mp1_den()
+        self.ron1 = [mp1da, mp1db]
+        Fdaa, Fdab, Fdbb, Fdba = self.sys.u_fock_d_den()
+        c = lambda x: x.cpu().numpy()  # noqa: E731
+        cc2 = lambda t: (c(t[0]), c(t[1]))  # noqa: E731
+        tA, tB = cc_utils.u_Fd_on(Fdaa, Fdab, Fdba, Fdbb, cc2(self.ndia), cc2(self.ndba),
+                                  cc2(self.ndji), cc2(self.ndai))
+        acc = cc_utils.on_response(self._leaf_list(), None, self._spin_of_leaf)
+        self.rono = [tA - 0.5*c(acc[("o", "a")])*fva, tB - 0.5*c(acc[("o", "b")])*fvb]
+        self.ronv = [0.5*c(acc[("v", "a")])*foa, 0.5*c(acc[("v", "b")])*fob]
+
+    # ------------------------------------------------------------------
+    # derivative through the quadrature weights (kelvin/ccsd.py:1075-1148, 1150-1260)
+    # ------------------------------------------------------------------
+    def _pair_LT(self, Ls, Ts, weights):
+        """-(1/beta) sum_y g_y [ sum_blocks w <L_y, T_y> ] with L in o..v.. and T in v..o.. order."""
+        dev = Ts[0].device
+        tot = torch.zeros(self.ngrid, dtype=torch.float64, device=dev)
+        first = True
+        for L, Tt, w in zip(Ls, Ts, weights):
+            if L.dim() == 3:
+                _lib.dot_keep(L, "yia", Tt, "yai", "y", alpha=w, out=tot, beta=0.0 if first else 1.0)
+            else:
+                _lib.dot_keep(L, "yijab", Tt, "yabij", "y", alpha=w, out=tot,
+                              beta=0.0 if first else 1.0)
+            first = False
+        return -float(numpy.dot(tot.cpu().numpy(), self.g))/self.beta
+
+    def _nocc_gderiv(self):
+        from . import _lib as lb
+        beta, ng, ti, G, g = self.beta, self.ngrid, self.ti, self.G, self.g
+        gd, Gd = quadrature.d_ft_quad(ng, beta, self.quad)
+        Gnew = G.copy()
+        for i in range(G.shape[0]):
+            for j in range(G.shape[1]):
+                Gnew[i, j] *= (ti[j] - ti[i])/beta
+        lib = lb.load()
+        if self.sys.has_u():
+            ea, eb, Ds, (Fa, Fb, Ia, Ib, Iabab) = self._u_setup()
+            Ts = list(self.T1) + list(self.T2)
+            Ls = list(self.L1) + list(self.L2)
+            w = (1.0, 1.0, 0.25, 1.0, 0.25)
+            dg = ft_cc_energy.ft_ucc_energy(*Ts, Fa.ov, Fb.ov, Ia.oovv, Ib.oovv, Iabab.oovv, gd, beta)
+
+            def stanton(Gx):
+                t1, t2 = ft_cc_equations.uccsd_stanton(Fa, Fb, Ia, Ib, Iabab, *Ts, *Ds, ti, ng, Gx)
+                return list(t1) + list(t2)
+        else:
+            en, D1, D2, F, I = self._g_setup()
+            Ds = (D1, D2)
+            Ts = [self.T1, self.T2]
+            Ls = [self.L1, self.L2]
+            w = (1.0, 0.25)
+            dg = ft_cc_energy.ft_cc_energy(self.T1, self.T2, F.ov, I.oovv, gd, beta)
+
+            def stanton(Gx):
+                return list(ft_cc_equations.ccsd_stanton(F, I, self.T1, self.T2, D1, D2, ti, ng, Gx))
+        Ls = [lb.as_dev(x) for x in Ls]
+        dG = self._pair_LT(Ls, stanton(Gd), w)
+        Tn = stanton(Gnew)
+        for Tt, D in zip(Tn, Ds):
+            rc = lib.kb200_scale_by(ng, D.numel(), lb.ptr(Tt), lb.ptr(D), lb.stream_ptr())
+            lb.check(rc, "kb200_scale_by")
+        dG += self._pair_LT(Ls, Tn, w)
+        return dg, dG
+
+    _g_nocc_gderiv = _nocc_gderiv
+    _u_nocc_gderiv = _nocc_gderiv
+
+    # ------------------------------------------------------------------
+    def compute_ESN(self, L1=None, L2=None, gderiv=True):
+        """Compute energy, entropy, particle number (kelvin/ccsd.py:128-165)."""
+        if not gderiv:
+            raise Exception("gderiv=False (approximate quadrature derivative) is outside the B200 path")
+        if self.T1 is None:
+            raise Exception("run() must be called before compute_ESN()")
+        if self.L1 is None:
+            if self.sys.has_u():
+                self._ft_uccsd_lambda(L1=L1, L2=L2)
+                ti = time.time()
+                self._u_ft_1rdm()
+                self._u_ft_2rdm()
+                tf = time.time()
+                logging.info("RDM construction time: {} s".format(tf - ti))
+            else:
+                self._ft_ccsd_lambda(L1=L1, L2=L2)
+                self._g_ft_1rdm()
+                self._g_ft_2rdm()
+        if self.sys.has_u():
+            ti = time.time()
+            self._u_ft_ESN(L1, L2, gderiv=gderiv)
+            tf = time.time()
+            logging.info("Total derivative time: {} s".format(tf - ti))
+        else:
+            self._g_ft_ESN(L1, L2, gderiv=gderiv)
+
+    def _finish_ESN(self, N0, E0, N1, Ncc, B1, Bcc):
+        beta, mu = self.beta, self.mu
+        Bcc -= self.Gcc/beta               # derivative from the explicit factors of 1/beta
+        dg, dG = self._nocc_gderiv()
+        Bcc += dG + dg
+        E1 = beta*B1 + mu*N1 + self.G1
+        Ecc = beta*Bcc + mu*Ncc + self.Gcc
+        self.N0, self.N1, self.Ncc = N0, N1, Ncc
+        self.N = Ncc + N0 + N1
+        self.E0, self.E1, self.Ecc = E0, E1, Ecc
+        self.E = E0 + E1 + Ecc
+        self.S = -beta*(self.Gtot - self.E + mu*self.N)
+        self.S0 = -beta*(self.G0 - self.E0 + mu*self.N0)
+        self.S1 = -beta*(self.G1 - self.E1 + mu*self.N1)
+        self.Scc = self.S - self.S0 - self.S1
+
+    def _g_ft_ESN(self, L1=None, L2=None, gderiv=True):
+        """kelvin/ccsd.py:167-214."""
+        beta, mu = self.beta, self.mu
+        if self.dia is None:
+            self._g_ft_1rdm()
+            self._g_ft_2rdm()
+        self._g_ft_ron()
+        en = self.sys.g_energies_tot()
+        fo = ft_utils.ff(beta, en, mu)
+        B0 = ft_utils.dGP0(beta, en, mu)
+        N0 = fo.sum()
+        E0 = beta*B0.sum() + mu*N0 + self.G0
+        dvec = -numpy.ones(en.shape)
+        N1 = -numpy.einsum('i,i->', dvec, self.ron1)
+        Ncc = -numpy.einsum('i,i->', dvec, self.rono + self.ronv)
+        dvec = (en - mu)/beta
+        B1 = numpy.einsum('i,i->', dvec, self.ron1)
+        Bcc = numpy.einsum('i,i->', dvec, self.rono + self.ronv)
+        self._finish_ESN(N0, E0, N1, Ncc, B1, Bcc)
+
+    def _u_ft_ESN(self, L1=None, L2=None, gderiv=True):
+        """kelvin/ccsd.py:216-271, including the reference's use of rono[0] + ronv[1]
+        for both spins (quirk Q2, :238-239,246-247)."""
+        beta, mu = self.beta, self.mu
+        if self.dia is None:
+            self._u_ft_1rdm()
+            self._u_ft_2rdm()
+        self._u_ft_ron()
+        ea, eb = self.sys.u_energies_tot()
+        foa = ft_utils.ff(beta, ea, mu)
+        fob = ft_utils.ff(beta, eb, mu)
+        B0a = ft_utils.dGP0(beta, ea, mu)
+        B0b = ft_utils.dGP0(beta, eb, mu)
+        N0 = foa.sum() + fob.sum()
+        E0 = beta*(B0a.sum() + B0b.sum()) + mu*N0 + self.G0
+        dveca = -numpy.ones(ea.shape)
+        dvecb = -numpy.ones(eb.shape)
+        mixed = self.rono[0] + self.ronv[1]
+        N1 = -(numpy.einsum('i,i->', dveca, self.ron1[0]) + numpy.einsum('i,i->', dvecb, self.ron1[1]))
+        Ncc = -(numpy.einsum('i,i->', dveca, mixed) + numpy.einsum('i,i->', dvecb, mixed))
+        dveca = (ea - mu)/beta
+        dvecb = (eb - mu)/beta
+        B1 = numpy.einsum('i,i->', dveca, self.ron1[0]) + numpy.einsum('i,i->', dvecb, self.ron1[1])
+        Bcc = numpy.einsum('i,i->', dveca, mixed) + numpy.einsum('i,i->', dvecb, mixed)
+        self._finish_ESN(N0, E0, N1, Ncc, B1, Bcc)

@@ -298,6 +298,57 @@ __global__ void scale_by_kernel(int ng, long long n, double* __restrict__ X,
         X[q] *= D[q % n];
 }
 
+// ---------------------------------------------------------------------------
+// "keep one index" partial traces (cc_utils.py:1648-1685,1746-1895) and the
+// per-grid-point <L, T> pairings of ccsd.py:1121-1146,1214-1258:
+//   out[k] = beta*out[k] + alpha * sum_{i1..i4} A[k*sa0 + sum i_d*sa_d] * B[k*sb0 + sum i_d*sb_d]
+// ---------------------------------------------------------------------------
+struct Keep5 {
+    int d[4];
+    long long sa[5];
+    long long sb[5];
+};
+
+__global__ void __launch_bounds__(RED_THREADS)
+    dot_keep_kernel(Keep5 q, const double* __restrict__ A, const double* __restrict__ B,
+                    double* part /*[nkeep][gridDim.x]*/) {
+    const int k = blockIdx.y;
+    const long long inner = (long long)q.d[0] * q.d[1] * q.d[2] * q.d[3];
+    const double* Ak = A + k * q.sa[0];
+    const double* Bk = B + k * q.sb[0];
+    double acc = 0.0;
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < inner;
+         p += (long long)gridDim.x * blockDim.x) {
+        long long r = p;
+        int i4 = (int)(r % q.d[3]); r /= q.d[3];
+        int i3 = (int)(r % q.d[2]); r /= q.d[2];
+        int i2 = (int)(r % q.d[1]); r /= q.d[1];
+        int i1 = (int)r;
+        acc += Ak[i1 * q.sa[1] + i2 * q.sa[2] + i3 * q.sa[3] + i4 * q.sa[4]] *
+               Bk[i1 * q.sb[1] + i2 * q.sb[2] + i3 * q.sb[3] + i4 * q.sb[4]];
+    }
+    __shared__ double sh[32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    acc = warp_sum(acc);
+    if (lane == 0) sh[w] = acc;
+    __syncthreads();
+    if (w == 0) {
+        double s2 = (lane < (blockDim.x >> 5)) ? sh[lane] : 0.0;
+        s2 = warp_sum(s2);
+        if (lane == 0) part[(size_t)k * gridDim.x + blockIdx.x] = s2;
+    }
+}
+
+__global__ void final_axpby_kernel(const double* part, int nblocks, int nv, double alpha,
+                                   double beta, double* out) {
+    int i = blockIdx.x;
+    if (i >= nv) return;
+    double s = 0.0;
+    for (int j = threadIdx.x; j < nblocks; j += 32) s += part[(size_t)i * nblocks + j];
+    s = warp_sum(s);
+    if (threadIdx.x == 0) out[i] = (beta != 0.0 ? beta * out[i] : 0.0) + alpha * s;
+}
+
 int grid_for(long long n, int threads, int cap = 148 * 16) {
     long long b = (n + threads - 1) / threads;
     if (b < 1) b = 1;
@@ -308,12 +359,12 @@ int grid_for(long long n, int threads, int cap = 148 * 16) {
 // ---------------------------------------------------------------------------
 // GEMM dispatch
 // ---------------------------------------------------------------------------
-template <int WMs, int WNs, int WM, int WN, int AM, int BM_, int ST>
+template <int WMs, int WNs, int WM, int WN, int AM, int BM_, int ST, bool ILV, int MINB>
 int launch_gemm_inst(const kb200::GemmParams& p, int batch, cudaStream_t st) {
     using namespace kb200;
     constexpr int BMt = WMs * WM, BNt = WNs * WN, NT = WMs * WNs * 32;
     constexpr int smem = ST * (TileLoader<BMt, NT, AM>::STAGE + TileLoader<BNt, NT, BM_>::STAGE) * 8;
-    auto kern = gemm_tab_kernel<WMs, WNs, WM, WN, AM, BM_, ST>;
+    auto kern = gemm_tab_kernel<WMs, WNs, WM, WN, AM, BM_, ST, ILV, MINB>;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -326,16 +377,21 @@ int launch_gemm_inst(const kb200::GemmParams& p, int batch, cudaStream_t st) {
     return 0;
 }
 
-template <int WMs, int WNs, int WM, int WN, int ST>
+template <int WMs, int WNs, int WM, int WN, int ST, bool ILV, int MINB = 1>
 int launch_gemm_modes(const kb200::GemmParams& p, int batch, int am, int bm, cudaStream_t st) {
-    if (am == 0 && bm == 0) return launch_gemm_inst<WMs, WNs, WM, WN, 0, 0, ST>(p, batch, st);
-    if (am == 0 && bm == 1) return launch_gemm_inst<WMs, WNs, WM, WN, 0, 1, ST>(p, batch, st);
-    if (am == 1 && bm == 0) return launch_gemm_inst<WMs, WNs, WM, WN, 1, 0, ST>(p, batch, st);
-    return launch_gemm_inst<WMs, WNs, WM, WN, 1, 1, ST>(p, batch, st);
+    if (am == 0 && bm == 0) return launch_gemm_inst<WMs, WNs, WM, WN, 0, 0, ST, ILV, MINB>(p, batch, st);
+    if (am == 0 && bm == 1) return launch_gemm_inst<WMs, WNs, WM, WN, 0, 1, ST, ILV, MINB>(p, batch, st);
+    if (am == 1 && bm == 0) return launch_gemm_inst<WMs, WNs, WM, WN, 1, 0, ST, ILV, MINB>(p, batch, st);
+    return launch_gemm_inst<WMs, WNs, WM, WN, 1, 1, ST, ILV, MINB>(p, batch, st);
 }
 
+// tile ids: 0 = 128x128, 8 warps (64x32 warp tiles), interleaved loads
+//           1 = 128x32,  8 warps (16x32)
+//           2 = 128x128, 16 warps (32x32 warp tiles), interleaved loads
+//           3 = 128x128, 8 warps, loads issued up front (experiment)
+//           4 = 128x64,  8 warps (32x32 warp tiles), 2 CTAs/SM
 int tile_bm(int tile) { return 128; }
-int tile_bn(int tile) { return tile == 0 ? 128 : 32; }
+int tile_bn(int tile) { return tile == 1 ? 32 : (tile == 4 ? 64 : 128); }
 
 int64_t op_workspace(const kb200_op& o) {
     if (o.kind != 0 || o.splitk <= 1) return 0;
@@ -350,7 +406,36 @@ int kb200_version(void) { return 100; }
 const char* kb200_last_error(void) { return g_err; }
 int64_t kb200_launch_count(void) { return g_launches.load(); }
 void kb200_launch_count_reset(void) { g_launches.store(0); }
-int64_t kb200_reduce_scratch_doubles(void) { return 3 * RED_BLOCKS; }
+int64_t kb200_reduce_scratch_doubles(void) { return 65536; }
+
+int kb200_dot_keep(int nkeep, const int32_t dims[4], const int64_t sA[5], const int64_t sB[5],
+                   const double* A, const double* B, double alpha, double beta, double* out,
+                   double* scratch, void* stream) {
+    if (nkeep <= 0) return fail(-1, "dot_keep: bad nkeep");
+    Keep5 q;
+    long long inner = 1;
+    for (int i = 0; i < 4; ++i) {
+        if (dims[i] <= 0) return fail(-1, "dot_keep: bad dims");
+        q.d[i] = dims[i];
+        inner *= dims[i];
+    }
+    for (int i = 0; i < 5; ++i) {
+        q.sa[i] = sA[i];
+        q.sb[i] = sB[i];
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    long long want = (inner + RED_THREADS * 8 - 1) / (RED_THREADS * 8);
+    long long cap = 65536 / nkeep;
+    if (cap < 1) return fail(-1, "dot_keep: nkeep too large");
+    int nsplit = (int)(want < 1 ? 1 : (want > cap ? cap : want));
+    if (nsplit > 1024) nsplit = 1024;
+    dim3 grid(nsplit, nkeep);
+    dot_keep_kernel<<<grid, RED_THREADS, 0, st>>>(q, A, B, scratch);
+    KB_CHECK_LAUNCH("dot_keep_kernel");
+    final_axpby_kernel<<<nkeep, 32, 0, st>>>(scratch, nsplit, nkeep, alpha, beta, out);
+    KB_CHECK_LAUNCH("final_axpby_kernel");
+    return 0;
+}
 
 int64_t kb200_plan_workspace_bytes(const kb200_op* ops, int nops) {
     int64_t w = 0;
@@ -396,9 +481,17 @@ static int run_plan_impl(const kb200_op* ops, int nops, const uint32_t* tables,
             }
             int rc;
             if (o.tile == 0)
-                rc = launch_gemm_modes<2, 4, 64, 32, 4>(p, o.batch, o.a_mode, o.b_mode, st);
+                rc = launch_gemm_modes<2, 4, 64, 32, 4, true>(p, o.batch, o.a_mode, o.b_mode, st);
+            else if (o.tile == 1)
+                rc = launch_gemm_modes<8, 1, 16, 32, 4, true>(p, o.batch, o.a_mode, o.b_mode, st);
+            else if (o.tile == 2)
+                rc = launch_gemm_modes<4, 4, 32, 32, 4, true>(p, o.batch, o.a_mode, o.b_mode, st);
+            else if (o.tile == 3)
+                rc = launch_gemm_modes<2, 4, 64, 32, 4, false>(p, o.batch, o.a_mode, o.b_mode, st);
+            else if (o.tile == 4)
+                rc = launch_gemm_modes<4, 2, 32, 32, 3, true, 2>(p, o.batch, o.a_mode, o.b_mode, st);
             else
-                rc = launch_gemm_modes<8, 1, 16, 32, 4>(p, o.batch, o.a_mode, o.b_mode, st);
+                return fail(-1, "plan: unknown tile id");
             if (rc) return rc;
             if (p.splitk > 1) {
                 long long total = (long long)o.M * o.N * o.batch;

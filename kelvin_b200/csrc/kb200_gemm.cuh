@@ -62,11 +62,16 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 
 // One operand tile (R rows x BK k-values) loader.  MODE 0: k-contiguous in
 // HBM -> smem [R][BK+4]; MODE 1: row-contiguous -> smem [BK][R+4].
+// The k-offsets of the NEXT tile are prefetched into registers one k-tile
+// ahead (prefetch_k) so the table lookups never sit in front of a cp.async,
+// and a tile's cp.asyncs are issued in NPART slices interleaved with the DMMA
+// groups of the tile being consumed (load_part).
 template <int R, int NT, int MODE>
 struct TileLoader {
     static constexpr int LDK = BK + 4;
     static constexpr int LDR = R + 4;
     static constexpr int STAGE = (MODE == 0) ? R * LDK : BK * LDR;
+    static constexpr int NPART = BK / 4;
     // MODE 0 mapping
     static constexpr int RSTEP = NT / BK;            // rows covered per pass
     static constexpr int RPT = (R + RSTEP - 1) / RSTEP;
@@ -74,17 +79,24 @@ struct TileLoader {
     static constexpr int KSTEP = (NT / R) > 0 ? (NT / R) : 1;
     static constexpr int KPT = BK / KSTEP;
     static_assert(MODE == 0 || (NT % R == 0 && BK % KSTEP == 0), "bad tile/threads");
+    static constexpr int CNT = (MODE == 0) ? RPT : KPT;       // cp.asyncs per thread per tile
+    static constexpr int PER = (CNT + NPART - 1) / NPART;     // per slice
+    static constexpr int NKO = (MODE == 0) ? 1 : KPT;
 
     const double* base;
     const uint32_t* ktab;
     uint32_t roff[MODE == 0 ? RPT : 1];
+    uint32_t koff[NKO];      // k-offsets of the tile being loaded
+    uint32_t koff2[NKO];     // k-offsets of the tile after it (in flight)
     unsigned rvalid;
+    unsigned kvalid, kvalid2;
 
     __device__ __forceinline__ void init(const double* base_, const uint32_t* rtab,
                                          const uint32_t* ktab_, int row0, int nrows, int tid) {
         base = base_;
         ktab = ktab_;
         rvalid = 0;
+        kvalid = 0;
         if (MODE == 0) {
             int r0 = tid / BK;
 #pragma unroll
@@ -104,34 +116,67 @@ struct TileLoader {
         }
     }
 
-    __device__ __forceinline__ void load(double* stage, int k0, int kend, int tid) const {
+    // start fetching the k-offsets of the tile starting at k0 (into koff2)
+    __device__ __forceinline__ void prefetch_k(int k0, int kend, int tid) {
+        kvalid2 = 0;
+        if (MODE == 0) {
+            int k = k0 + tid % BK;
+            bool kv = k < kend;
+            koff2[0] = kv ? __ldg(ktab + k) : 0u;
+            kvalid2 = kv ? 1u : 0u;
+        } else {
+            int kk0 = tid / R;
+#pragma unroll
+            for (int i = 0; i < KPT; ++i) {
+                int k = k0 + kk0 + i * KSTEP;
+                bool kv = k < kend;
+                koff2[i] = kv ? __ldg(ktab + k) : 0u;
+                kvalid2 |= (kv ? 1u : 0u) << i;
+            }
+        }
+    }
+    // make the prefetched offsets current
+    __device__ __forceinline__ void advance_k() {
+#pragma unroll
+        for (int i = 0; i < NKO; ++i) koff[i] = koff2[i];
+        kvalid = kvalid2;
+    }
+
+    // issue slice `part` (0..NPART-1) of the tile whose k-offsets were prefetched
+    __device__ __forceinline__ void load_part(double* stage, int tid, int part) const {
         if (MODE == 0) {
             int kk = tid % BK;
             int r0 = tid / BK;
-            int k = k0 + kk;
-            bool kv = k < kend;
-            uint32_t koff = kv ? ktab[k] : 0u;
+            bool kv = kvalid & 1u;
 #pragma unroll
-            for (int i = 0; i < RPT; ++i) {
-                int r = r0 + i * RSTEP;
-                if (r < R) {
-                    bool v = kv && ((rvalid >> i) & 1u);
-                    cp_async8(stage + r * LDK + kk, base + (size_t)roff[i] + koff, v);
+            for (int j = 0; j < PER; ++j) {
+                int i = part * PER + j;
+                if (i < RPT) {
+                    int r = r0 + i * RSTEP;
+                    if (r < R) {
+                        bool v = kv && ((rvalid >> i) & 1u);
+                        cp_async8(stage + r * LDK + kk, base + (size_t)roff[i] + koff[0], v);
+                    }
                 }
             }
         } else {
             int r = tid % R;
             int kk0 = tid / R;
 #pragma unroll
-            for (int i = 0; i < KPT; ++i) {
-                int kk = kk0 + i * KSTEP;
-                int k = k0 + kk;
-                bool kv = k < kend;
-                uint32_t koff = kv ? ktab[k] : 0u;
-                bool v = kv && (rvalid & 1u);
-                cp_async8(stage + kk * LDR + r, base + (size_t)roff[0] + koff, v);
+            for (int j = 0; j < PER; ++j) {
+                int i = part * PER + j;
+                if (i < KPT) {
+                    int kk = kk0 + i * KSTEP;
+                    bool v = ((kvalid >> i) & 1u) && (rvalid & 1u);
+                    cp_async8(stage + kk * LDR + r, base + (size_t)roff[0] + koff[i], v);
+                }
             }
         }
+    }
+
+    __device__ __forceinline__ void load_all(double* stage, int tid) const {
+#pragma unroll
+        for (int part = 0; part < NPART; ++part) load_part(stage, tid, part);
     }
 
     // fragment element (row r, k index kk) of a stage
@@ -140,8 +185,12 @@ struct TileLoader {
     }
 };
 
-template <int WARPS_M, int WARPS_N, int WM, int WN, int AMODE, int BMODE, int STAGES>
-__global__ void __launch_bounds__(WARPS_M* WARPS_N * 32)
+// Row groups (8 rows) are dealt to the warps round-robin, so that in a ragged
+// edge tile every warp loses the same share of work and whole invalid groups
+// are skipped: edge tiles cost in proportion to their valid area.
+template <int WARPS_M, int WARPS_N, int WM, int WN, int AMODE, int BMODE, int STAGES, bool ILV,
+          int MINB>
+__global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, MINB)
     gemm_tab_kernel(const GemmParams p) {
     constexpr int BM = WARPS_M * WM;
     constexpr int BN = WARPS_N * WN;
@@ -158,8 +207,8 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32)
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const int warp = tid >> 5;
-    const int wm0 = (warp % WARPS_M) * WM;
-    const int wn0 = (warp / WARPS_M) * WN;
+    const int wmi = warp % WARPS_M;
+    const int wni = warp / WARPS_M;
     const int g = lane >> 2;
     const int t = lane & 3;
 
@@ -173,6 +222,17 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32)
     const int kend = min(p.K, kbeg + p.kchunk);
     const int nk = (kend - kbeg + BK - 1) / BK;
 
+    // validity of this warp's row / column groups (warp-uniform)
+    unsigned mval = 0, nval = 0;
+#pragma unroll
+    for (int i = 0; i < MI; ++i)
+        if (m0 + (i * WARPS_M + wmi) * 8 < p.M) mval |= 1u << i;
+#pragma unroll
+    for (int j = 0; j < NI; ++j)
+        if (n0 + (j * WARPS_N + wni) * 8 < p.N) nval |= 1u << j;
+
+    const int mcnt = __popc(mval), ncnt = __popc(nval);   // valid groups form a prefix
+
     LA la;
     LB lb;
     la.init(p.A + (long long)b * p.bsA, p.am, p.ak, m0, p.M, tid);
@@ -184,77 +244,141 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32)
 #pragma unroll
         for (int j = 0; j < NI; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
+    la.prefetch_k(kbeg, kend, tid);
+    lb.prefetch_k(kbeg, kend, tid);
 #pragma unroll
     for (int s = 0; s < STAGES - 1; ++s) {
+        la.advance_k();
+        lb.advance_k();
+        la.prefetch_k(kbeg + (s + 1) * BK, kend, tid);
+        lb.prefetch_k(kbeg + (s + 1) * BK, kend, tid);
         if (s < nk) {
-            la.load(As + s * LA::STAGE, kbeg + s * BK, kend, tid);
-            lb.load(Bs + s * LB::STAGE, kbeg + s * BK, kend, tid);
+            la.load_all(As + s * LA::STAGE, tid);
+            lb.load_all(Bs + s * LB::STAGE, tid);
         }
         cp_async_commit();
     }
 
+    const bool full = (mval == (1u << MI) - 1u) && (nval == (1u << NI) - 1u);
     for (int kt = 0; kt < nk; ++kt) {
         cp_async_wait<STAGES - 2>();
         __syncthreads();
-        {
-            int nxt = kt + STAGES - 1;
-            if (nxt < nk) {
-                int s = nxt % STAGES;
-                la.load(As + s * LA::STAGE, kbeg + nxt * BK, kend, tid);
-                lb.load(Bs + s * LB::STAGE, kbeg + nxt * BK, kend, tid);
-            }
-            cp_async_commit();
+        const int nxt = kt + STAGES - 1;
+        const bool do_load = nxt < nk;
+        la.advance_k();
+        lb.advance_k();
+        if (nxt + 1 < nk) {
+            la.prefetch_k(kbeg + (nxt + 1) * BK, kend, tid);
+            lb.prefetch_k(kbeg + (nxt + 1) * BK, kend, tid);
         }
+        double* an = As + (nxt % STAGES) * LA::STAGE;
+        double* bn = Bs + (nxt % STAGES) * LB::STAGE;
         const double* as = As + (kt % STAGES) * LA::STAGE;
         const double* bs = Bs + (kt % STAGES) * LB::STAGE;
-#pragma unroll
-        for (int k4 = 0; k4 < BK / 4; ++k4) {
-            double af[MI], bf[NI];
-#pragma unroll
-            for (int i = 0; i < MI; ++i) af[i] = LA::frag(as, wm0 + i * 8 + g, k4 * 4 + t);
-#pragma unroll
-            for (int j = 0; j < NI; ++j) bf[j] = LB::frag(bs, wn0 + j * 8 + g, k4 * 4 + t);
-#pragma unroll
-            for (int i = 0; i < MI; ++i)
-#pragma unroll
-                for (int j = 0; j < NI; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        if (!ILV && do_load) {
+            la.load_all(an, tid);
+            lb.load_all(bn, tid);
         }
+        if (full) {
+#pragma unroll
+            for (int k4 = 0; k4 < BK / 4; ++k4) {
+                double af[MI], bf[NI];
+#pragma unroll
+                for (int i = 0; i < MI; ++i)
+                    af[i] = LA::frag(as, (i * WARPS_M + wmi) * 8 + g, k4 * 4 + t);
+#pragma unroll
+                for (int j = 0; j < NI; ++j)
+                    bf[j] = LB::frag(bs, (j * WARPS_N + wni) * 8 + g, k4 * 4 + t);
+                if (ILV && do_load) {
+                    la.load_part(an, tid, k4);
+                    lb.load_part(bn, tid, k4);
+                }
+#pragma unroll
+                for (int i = 0; i < MI; ++i)
+#pragma unroll
+                    for (int j = 0; j < NI; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+            }
+        } else {
+            if (ILV && do_load) {
+                la.load_all(an, tid);
+                lb.load_all(bn, tid);
+            }
+#pragma unroll
+            for (int k4 = 0; k4 < BK / 4; ++k4) {
+#pragma unroll
+                for (int i = 0; i < MI; ++i) {
+                    if (i < mcnt) {
+                        double a = LA::frag(as, (i * WARPS_M + wmi) * 8 + g, k4 * 4 + t);
+#pragma unroll
+                        for (int j = 0; j < NI; ++j) {
+                            if (j < ncnt) {
+                                double bb = LB::frag(bs, (j * WARPS_N + wni) * 8 + g, k4 * 4 + t);
+                                dmma884(acc[i][j][0], acc[i][j][1], a, bb);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        cp_async_commit();
     }
     cp_async_wait<0>();
 
     // epilogue: thread holds C[row = g][col = 2t, 2t+1] of each 8x8 tile
     if (p.splitk == 1) {
         double* C = p.C + (long long)b * p.bsC;
+        uint32_t co[NI][2];
+        unsigned cval = 0;
+#pragma unroll
+        for (int j = 0; j < NI; ++j)
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                int col = n0 + (j * WARPS_N + wni) * 8 + 2 * t + c;
+                bool v = col < p.N;
+                co[j][c] = v ? __ldg(p.cn + col) : 0u;
+                cval |= (v ? 1u : 0u) << (2 * j + c);
+            }
+        uint32_t ro[MI];
 #pragma unroll
         for (int i = 0; i < MI; ++i) {
-            int row = m0 + wm0 + i * 8 + g;
+            int row = m0 + (i * WARPS_M + wmi) * 8 + g;
+            ro[i] = (row < p.M) ? __ldg(p.cm + row) : 0xffffffffu;
+        }
+        const bool rmw = p.beta != 0.0;
+#pragma unroll
+        for (int i = 0; i < MI; ++i) {
+            int row = m0 + (i * WARPS_M + wmi) * 8 + g;
             if (row >= p.M) continue;
-            size_t ro = p.cm[row];
+            double* Cr = C + ro[i];
+            double old[NI][2];
+            if (rmw) {
 #pragma unroll
-            for (int j = 0; j < NI; ++j) {
+                for (int j = 0; j < NI; ++j)
 #pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    int col = n0 + wn0 + j * 8 + 2 * t + c;
-                    if (col < p.N) {
-                        double* dst = C + ro + p.cn[col];
-                        double v = p.alpha * acc[i][j][c];
-                        if (p.beta != 0.0) v += p.beta * (*dst);
-                        *dst = v;
-                    }
-                }
+                    for (int c = 0; c < 2; ++c)
+                        old[j][c] = ((cval >> (2 * j + c)) & 1u) ? Cr[co[j][c]] : 0.0;
             }
+#pragma unroll
+            for (int j = 0; j < NI; ++j)
+#pragma unroll
+                for (int c = 0; c < 2; ++c)
+                    if ((cval >> (2 * j + c)) & 1u) {
+                        double v = p.alpha * acc[i][j][c];
+                        if (rmw) v += p.beta * old[j][c];
+                        Cr[co[j][c]] = v;
+                    }
         }
     } else {
         double* P = p.partial + ((size_t)b * p.splitk + ks) * (size_t)p.M * p.N;
 #pragma unroll
         for (int i = 0; i < MI; ++i) {
-            int row = m0 + wm0 + i * 8 + g;
+            int row = m0 + (i * WARPS_M + wmi) * 8 + g;
             if (row >= p.M) continue;
 #pragma unroll
             for (int j = 0; j < NI; ++j) {
 #pragma unroll
                 for (int c = 0; c < 2; ++c) {
-                    int col = n0 + wn0 + j * 8 + 2 * t + c;
+                    int col = n0 + (j * WARPS_N + wni) * 8 + 2 * t + c;
                     if (col < p.N) P[(size_t)row * p.N + col] = acc[i][j][c];
                 }
             }

@@ -251,3 +251,149 @@ def uccsd_lambda_guess(Fa, Fb, Ia, Ib, Iabab, T1aold, T1bold, beta, ng):
         outs.append(t[nm])
     p.run(t, ng)
     return tuple(outs)
+
+
+# ---------------------------------------------------------------------------
+# response densities
+# ---------------------------------------------------------------------------
+def rdm_plan(mode, sizes):
+    key = ("rdm", mode, tuple(sorted(sizes.items(), key=str)))
+
+    def build():
+        inter, rest = programs.rdm_rops(mode)
+        ins = ("t1", "t2", "l1", "l2") if mode == "g" else _U_T + _U_L
+        rops = inter + rest
+        leaves = sorted({op.out[0] for op in rest
+                         if op.out[0].endswith("~") and _plan._INT_SLOT.match(op.out[0])})
+        p = engine.Plan(rops, mode, sizes, ins, leaves, name="rdm-" + mode)
+        p.leaves = leaves
+        return p
+    return engine.cached(key, build)
+
+
+def rdm_assembly_plan(mode, sizes):
+    key = ("rdm-asm", mode, tuple(sorted(sizes.items(), key=str)))
+
+    def build():
+        ops, outs = programs.rdm2_assembly_rops(mode)
+        shapes = _plan.slot_shapes(ops, mode, sizes)
+        ins = [s for s in shapes if s.endswith("~")]
+        p = engine.Plan(ops, mode, sizes, ins, [o[0] for o in outs], name="rdm-asm-" + mode,
+                        shapes=shapes, batched={s: False for s in shapes})
+        p.inputs = ins
+        p.outs_meta = outs
+        return p
+    return engine.cached(key, build)
+
+
+def _gsum(X, g, dev):
+    """sum_y g[y] X[y]  (kelvin/ft_cc_equations.py:713,737)."""
+    lib = _lib.load()
+    gd = torch.as_tensor(g, dtype=torch.float64).to(dev) if not isinstance(g, torch.Tensor) \
+        else g.to(device=dev, dtype=torch.float64)
+    out = torch.empty(tuple(X.shape[1:]), dtype=torch.float64, device=dev)
+    rc = lib.kb200_gsum(X.shape[0], out.numel(), _lib.ptr(X), _lib.ptr(gd), _lib.ptr(out),
+                        _lib.stream_ptr())
+    _lib.check(rc, "kb200_gsum")
+    return out
+
+
+_rdm_cache = {"key": None, "val": None}
+
+
+def _rdm_leaves(mode, Ts, Ls, Ds, ti, ng, g, G):
+    """Run the reverse sweep once per (T, L) and return
+    (dict of g-summed integral adjoints, list of g-summed integrated Lambdas)."""
+    dev = _lib.device()
+    Ts = [_lib.as_dev(x, dev) for x in Ts]
+    Ls = [_lib.as_dev(x, dev) for x in Ls]
+    key = (mode, ng, tuple((x.data_ptr(), x._version) for x in Ts + Ls),
+           tuple(float(v) for v in g), float(ti[-1]))
+    if _rdm_cache["key"] == key:
+        return _rdm_cache["val"]
+    Lbar = [quadrature.int_L(ng, L, ti, D, g, G) for L, D in zip(Ls, Ds)]
+    t = {}
+    if mode == "g":
+        nv, no = Ts[0].shape[1:]
+        sizes = {"o": int(no), "v": int(nv)}
+        p = rdm_plan("g", sizes)
+        names_t, names_l = ("t1", "t2"), ("l1", "l2")
+    else:
+        nva, noa = Ts[0].shape[1:]
+        nvb, nob = Ts[1].shape[1:]
+        sizes = {("o", "a"): int(noa), ("v", "a"): int(nva), ("o", "b"): int(nob),
+                 ("v", "b"): int(nvb)}
+        p = rdm_plan("u", sizes)
+        names_t, names_l = _U_T, _U_L
+    for nm, x in zip(names_t, Ts):
+        t[nm] = x
+    for nm, x in zip(names_l, Lbar):
+        t[nm] = x
+    for leaf in p.leaves:
+        t[leaf] = torch.empty((ng,) + tuple(p.shapes[leaf]), dtype=torch.float64, device=dev)
+    p.run(t, ng, _chunk_for(p, ng, dev))
+    summed = {leaf: _gsum(t[leaf], g, dev) for leaf in p.leaves}
+    lsum = [_gsum(x, g, dev) for x in Lbar]
+    p.release()
+    _rdm_cache["key"] = key
+    _rdm_cache["val"] = (summed, lsum, sizes)
+    return _rdm_cache["val"]
+
+
+def ccsd_1rdm(T1, T2, L1, L2, D1, D2, ti, ng, g, G):
+    """pia, pba, pji, pai (kelvin/ft_cc_equations.py:704-722), evaluated as
+    d(phi)/d(F blocks) by the reverse sweep of the residual plan."""
+    assert(_lib.as_dev(T1).shape[0] == ng)
+    summed, lsum, _ = _rdm_leaves("g", (T1, T2), (L1, L2), (D1, D2), ti, ng, g, G)
+    return (lsum[0], summed["F.vv~"].t().contiguous(), summed["F.oo~"].t().contiguous(),
+            summed["F.ov~"].t().contiguous())
+
+
+def ccsd_2rdm(T1, T2, L1, L2, D1, D2, ti, ng, g, G):
+    """(Pcdab, Pciab, Pbcai, Pijab, Pbjai, Pabij, Pjkai, Pkaij, Pklij)
+    (kelvin/ft_cc_equations.py:725-753)."""
+    summed, lsum, sizes = _rdm_leaves("g", (T1, T2), (L1, L2), (D1, D2), ti, ng, g, G)
+    pa = rdm_assembly_plan("g", sizes)
+    dev = _lib.device()
+    t = {s: summed[s] for s in pa.inputs}
+    for s in pa.outputs:
+        t[s] = torch.empty(pa.shapes[s], dtype=torch.float64, device=dev)
+    pa.run(t, 1)
+    out = []
+    for pname, pat in programs.RDM2_BLOCKS:
+        out.append(lsum[1] if pat == "vvoo" else t["P" + pname])
+    return tuple(out)
+
+
+def uccsd_1rdm(T1a, T1b, T2aa, T2ab, T2bb, L1a, L1b, L2aa, L2ab, L2bb,
+               D1a, D1b, D2aa, D2ab, D2bb, ti, ng, g, G):
+    """((pia,pIA),(pba,pBA),(pji,pJI),(pai,pAI)) (kelvin/ft_cc_equations.py:756-798)."""
+    summed, lsum, _ = _rdm_leaves("u", (T1a, T1b, T2aa, T2ab, T2bb),
+                                  (L1a, L1b, L2aa, L2ab, L2bb),
+                                  (D1a, D1b, D2aa, D2ab, D2bb), ti, ng, g, G)
+
+    def tr(nm):
+        return (summed["Fa.%s~" % nm].t().contiguous(), summed["Fb.%s~" % nm].t().contiguous())
+    return (lsum[0], lsum[1]), tr("vv"), tr("oo"), tr("ov")
+
+
+def uccsd_2rdm(T1a, T1b, T2aa, T2ab, T2bb, L1a, L1b, L2aa, L2ab, L2bb,
+               D1a, D1b, D2aa, D2ab, D2bb, ti, ng, g, G):
+    """The nine tuples of spin blocks in the reference's order
+    (kelvin/ft_cc_equations.py:801-927)."""
+    summed, lsum, sizes = _rdm_leaves("u", (T1a, T1b, T2aa, T2ab, T2bb),
+                                      (L1a, L1b, L2aa, L2ab, L2bb),
+                                      (D1a, D1b, D2aa, D2ab, D2bb), ti, ng, g, G)
+    pa = rdm_assembly_plan("u", sizes)
+    dev = _lib.device()
+    t = {s: summed[s] for s in pa.inputs}
+    for s in pa.outputs:
+        t[s] = torch.empty(pa.shapes[s], dtype=torch.float64, device=dev)
+    pa.run(t, 1)
+    out = []
+    for pname, pat in programs.RDM2_BLOCKS:
+        if pat == "vvoo":
+            out.append((lsum[2], lsum[4], lsum[3]))          # (aa, bb, ab)
+        else:
+            out.append(tuple(t["P%s.%s" % (pname, sp)] for sp in programs.RDM2_USPINS[pname]))
+    return tuple(out)

@@ -311,6 +311,10 @@ class TableBank(object):
 
 
 N_SM = 148
+# CTA tile used for large contractions (see kb200.cu: tile ids); overridable for experiments
+import os as _os
+BIG_TILE = int(_os.environ.get("KB200_BIG_TILE", "0"))
+_TILE_BN = {0: 128, 1: 32, 2: 128, 3: 128, 4: 64}
 
 
 class Lowered(object):
@@ -436,7 +440,7 @@ class Lowered(object):
         d.tBk, d.tBn = tab(K, sb), tab(N, sb)
         d.tCm, d.tCn = tab(M, sc), tab(N, sc)
         d.a_mode, d.b_mode = a_mode, b_mode
-        d.tile = 1 if d.N <= 48 else 0
+        d.tile = 1 if d.N <= 48 else BIG_TILE
         self.flops += 2.0 * d.M * d.N * d.K
         return d
 
@@ -450,7 +454,7 @@ class Lowered(object):
             if o.batch > 1 and o.bsC == 0:
                 raise ValueError("batched operands reduce into an unbatched output")
             if o.kind == 0:
-                bn = 128 if o.tile == 0 else 32
+                bn = _TILE_BN[o.tile]
                 ctas = ((o.M + 127) // 128) * ((o.N + bn - 1) // bn) * o.batch
                 if ctas < N_SM and o.K >= 512:
                     o.splitk = int(min(max(1, (2 * N_SM) // ctas), max(1, o.K // 128)))
@@ -464,7 +468,8 @@ _INT_SLOT = re.compile(r"^(I|Ia|Ib|Iabab|F|Fa|Fb)\.")
 
 
 def is_integral_slot(slot):
-    return _INT_SLOT.match(slot.rstrip("~")) is not None
+    """True for the caller-supplied dressed-integral slots (not their adjoints)."""
+    return (not slot.endswith("~")) and _INT_SLOT.match(slot) is not None
 
 
 def slot_shapes(rops, mode, sizes):

@@ -226,3 +226,123 @@ def lambda_guess_rops(mode, beta, ls_ts_fac):
         lo2[ijab] += 1 I.oovv[ijab]
     """, 1.0/beta) + _parse_block("lo1[ia] += 1 I.oovv[jiba] t1[bj]", ls_ts_fac)
     return expand(st, T, mode)
+
+
+# ---------------------------------------------------------------------------
+# Response densities = derivatives of the Lagrangian w.r.t. the dressed
+# integral blocks (SURVEY.md A.4; kelvin/tests/test_ft_ccsd_rdm.py:12-21)
+# ---------------------------------------------------------------------------
+def rdm_rops(mode):
+    """Forward intermediates + reverse sweep w.r.t. every integral block of
+
+        phi = t1.F.ov + (t2/4 + t1 t1/2).I.oovv + <Lbar, (F.vo, I.vvoo) + StantonTerms(t)>.
+
+    Adjoint slots are named '<block>~' (g: 'I.vvvv~', 'F.oo~'; u: 'Ia.vvvv~',
+    'Iabab.ovvo~', 'Fb.vv~', ...) and hold d(phi)/d(block element) with all stored
+    elements treated as independent.  The driver terms <Lbar,(F.vo, I.vvoo)> are
+    not swept: their derivative is Lbar itself (kelvin/ft_cc_equations.py:713,737).
+    Inputs t1,t2,l1,l2 as in ``lambda_rops``."""
+    from .plan import ROp, adjoint, expand, is_integral_slot
+    T = tensor_defs()
+    fwd = expand(stanton(1.0, drivers=False), T, mode)
+    if mode == "g":
+        outset = {"o1", "o2"}
+        seed = {"o1~": ("l1", (1, 0), 1.0), "o2~": ("l2", (2, 3, 0, 1), 0.25)}
+        extra = [ROp(("F.ov~", "ia"), 1.0, [("t1", "ai")]),
+                 ROp(("I.oovv~", "ijab"), 0.25, [("t2", "abij")]),
+                 ROp(("I.oovv~", "ijab"), 0.5, [("t1", "ai"), ("t1", "bj")])]
+    else:
+        outset = {"o1.a", "o1.b", "o2.aa", "o2.ab", "o2.bb"}
+        seed = {"o1.a~": ("l1.a", (1, 0), 1.0), "o1.b~": ("l1.b", (1, 0), 1.0),
+                "o2.aa~": ("l2.aa", (2, 3, 0, 1), 0.25), "o2.bb~": ("l2.bb", (2, 3, 0, 1), 0.25),
+                "o2.ab~": ("l2.ab", (2, 3, 0, 1), 1.0)}
+        sa = dict(zip("ijab", "aaaa"))
+        sb = dict(zip("ijab", "bbbb"))
+        sab = dict(zip("ijab", "abab"))
+        extra = [ROp(("Fa.ov~", "ia"), 1.0, [("t1.a", "ai")], sa),
+                 ROp(("Fb.ov~", "ia"), 1.0, [("t1.b", "ai")], sb),
+                 ROp(("Ia.oovv~", "ijab"), 0.25, [("t2.aa", "abij")], sa),
+                 ROp(("Ia.oovv~", "ijab"), 0.5, [("t1.a", "ai"), ("t1.a", "bj")], sa),
+                 ROp(("Ib.oovv~", "ijab"), 0.25, [("t2.bb", "abij")], sb),
+                 ROp(("Ib.oovv~", "ijab"), 0.5, [("t1.b", "ai"), ("t1.b", "bj")], sb),
+                 ROp(("Iabab.oovv~", "ijab"), 1.0, [("t2.ab", "abij")], sab),
+                 ROp(("Iabab.oovv~", "ijab"), 1.0, [("t1.a", "ai"), ("t1.b", "bj")], sab)]
+    dep = set()
+    for op in fwd:
+        if any(is_integral_slot(s) or s in dep for s, _ in op.ins):
+            dep.add(op.out[0])
+    # phi is linear in the integrals, so the sweep only ever reads amplitude-only
+    # intermediates (tau, tauh, t2x): nothing that depends on F/I is evaluated.
+    inter = [op for op in fwd if op.out[0] not in outset and op.out[0] not in dep]
+    bwd = adjoint(fwd, wrt=lambda s: is_integral_slot(s) or s in dep, seeds=outset)
+    bwd = [_subst_in(op, seed) for op in bwd]
+    for op in bwd:
+        for slot, _ in op.ins:
+            assert not is_integral_slot(slot) and slot not in dep, op
+    return inter, extra + bwd
+
+
+# P-block <- integral block it is conjugate to (kelvin/ft_cc_equations.py:737-751)
+RDM2_BLOCKS = (("cdab", "vvvv"), ("ciab", "vvvo"), ("bcai", "vovv"), ("ijab", "vvoo"),
+               ("bjai", "vovo"), ("abij", "oovv"), ("jkai", "vooo"), ("kaij", "ooov"),
+               ("klij", "oooo"))
+# spin patterns (over the P index order) of the unrestricted tuples
+# (kelvin/ft_cc_equations.py:919-927)
+RDM2_USPINS = {
+    "cdab": ("aaaa", "bbbb", "abab"),
+    "ciab": ("aaaa", "bbbb", "abab", "baba"),
+    "bcai": ("aaaa", "bbbb", "abab", "baba"),
+    "ijab": ("aaaa", "bbbb", "abab"),
+    "bjai": ("aaaa", "bbbb", "abab", "abba", "baab", "baba"),
+    "abij": ("aaaa", "bbbb", "abab"),
+    "jkai": ("aaaa", "bbbb", "abab", "baba"),
+    "kaij": ("aaaa", "bbbb", "abab", "baba"),
+    "klij": ("aaaa", "bbbb", "abab"),
+}
+
+
+def rdm2_assembly_rops(mode, skip=("vvoo",)):
+    """Unary ops building the reference's P blocks from the summed adjoints:
+    P_B[r,s,p,q] = c*A(dphi/dI_B)[p,q,r,s], A = antisymmetriser over the index
+    pairs of B that share a space, c = 2 per antisymmetrised pair.  In the u
+    form the mixed-spin blocks are single (signed, permuted) adjoint leaves.
+    Returns (ops, list of (output slot, block name, spin pattern))."""
+    from .plan import ROp, TDef, resolve_u
+    ops, outs = [], []
+
+    def swap(ls, i, j):
+        ls = list(ls)
+        ls[i], ls[j] = ls[j], ls[i]
+        return "".join(ls)
+    for pname, pat in RDM2_BLOCKS:
+        if pat in skip:
+            continue
+        a1 = pat[0] == pat[1]
+        a2 = pat[2] == pat[3]
+        pool = {"v": iter("abcd"), "o": iter("ijkl")}
+        L = "".join(next(pool[c]) for c in pat)            # letters over the integral order
+        dstl = L[2] + L[3] + L[0] + L[1]                   # P index order
+        terms = [(L, 1.0)]
+        if a1:
+            terms += [(swap(L, 0, 1), -1.0)]
+        if a2:
+            terms += [(swap(ls, 2, 3), -sg) for ls, sg in list(terms)]
+        if mode == "g":
+            for ls, sg in terms:
+                ops.append(ROp(("P" + pname, dstl), sg, [("I.%s~" % pat, ls)]))
+            outs.append(("P" + pname, pname, None))
+            continue
+        td = TDef("I." + pat, "int2", "in", False, pat)
+        for sp in RDM2_USPINS[pname]:
+            ispin = sp[2] + sp[3] + sp[0] + sp[1]          # spins over the integral order
+            dst = ("P%s.%s" % (pname, sp), dstl)
+            spin = dict(zip(L, ispin))
+            if ispin in ("aaaa", "bbbb"):
+                leaf = ("Ia.%s~" if ispin == "aaaa" else "Ib.%s~") % pat
+                for ls, sg in terms:
+                    ops.append(ROp(dst, sg, [(leaf, ls)], spin))
+            else:
+                slot, ls, sg = resolve_u(td, L, list(ispin))
+                ops.append(ROp(dst, sg, [(slot + "~", ls)], spin))
+            outs.append((dst[0], pname, sp))
+    return ops, outs

@@ -1,0 +1,132 @@
+"""GPU parity of response densities and E/S/N against the oracle and published values."""
+import logging
+
+import numpy
+import pytest
+
+from golden import published as pub
+
+pytestmark = pytest.mark.gpu
+
+from kelvin_oracle import cqc, cc_equations as ocq, driver as odrv  # noqa: E402
+import util  # noqa: E402
+
+
+def _rel(got, ref):
+    return numpy.abs(got.cpu().numpy() - ref).max()/max(1e-300, numpy.abs(ref).max())
+
+
+def test_ccsd_rdm_g(built):
+    """1-RDM and all nine 2-RDM block types vs the derivative-defined oracle
+    (kelvin/tests/test_ft_ccsd_rdm.py:12-21,60-489)."""
+    from kelvin_b200 import ft_cc_equations
+    n, ng = 5, 3
+    F, I, t1, t2 = util.random_g(n, ng, seed=1)
+    _, _, l1, l2 = util.random_g(n, ng, seed=2)
+    l1 = numpy.ascontiguousarray(l1.transpose(0, 2, 1))
+    e = util.random_D(n)
+    D1, D2 = cqc.D1(e, e), cqc.D2(e, e)
+    ti, g, G = odrv.simpsons(ng, 1.1)
+    L1b, L2b = odrv.int_L(ng, l1, ti, D1, g, G), odrv.int_L(ng, l2, ti, D2, g, G)
+    ref = {}
+    for y in range(ng):
+        for nm in ("ba", "ji", "ai"):
+            ref[nm] = ref.get(nm, 0) + g[y]*getattr(ocq, "ccsd_1rdm_%s_opt" % nm)(t1[y], t2[y], L1b[y], L2b[y])
+        for nm in ("cdab", "ciab", "bcai", "bjai", "abij", "jkai", "kaij", "klij"):
+            ref[nm] = ref.get(nm, 0) + g[y]*getattr(ocq, "ccsd_2rdm_%s_opt" % nm)(t1[y], t2[y], L1b[y], L2b[y])
+    pia, pba, pji, pai = ft_cc_equations.ccsd_1rdm(t1, t2, l1, l2, D1, D2, ti, ng, g, G)
+    assert _rel(pia, numpy.einsum('sia,s->ia', L1b, g)) < 1e-12
+    assert _rel(pba, ref["ba"]) < 1e-11
+    assert _rel(pji, ref["ji"]) < 1e-11
+    assert _rel(pai, ref["ai"]) < 1e-11
+    P2 = ft_cc_equations.ccsd_2rdm(t1, t2, l1, l2, D1, D2, ti, ng, g, G)
+    names = ("cdab", "ciab", "bcai", "ijab", "bjai", "abij", "jkai", "kaij", "klij")
+    for nm, P in zip(names, P2):
+        r = numpy.einsum('sijab,s->ijab', L2b, g) if nm == "ijab" else ref[nm]
+        assert _rel(P, r) < 1e-11, nm
+
+
+def test_uccsd_rdm(built):
+    """u blocks == spin blocks of the g RDMs (kelvin/tests/test_ft_ccsd_rdm.py:495-752)."""
+    from kelvin_b200 import ft_cc_equations
+    na, nb, ng = 4, 3, 2
+    ints, amps = util.random_u(na, nb, ng, seed=7)
+    _, lam = util.random_u(na, nb, ng, seed=8)
+    lam = (numpy.ascontiguousarray(lam[0].transpose(0, 2, 1)),
+           numpy.ascontiguousarray(lam[1].transpose(0, 2, 1)), lam[2], lam[3], lam[4])
+    ea, eb = util.random_D(na, 1), util.random_D(nb, 2)
+    Ds = (cqc.D1(ea, ea), cqc.D1(eb, eb), cqc.D2(ea, ea), cqc.D2u(ea, eb, ea, eb), cqc.D2(eb, eb))
+    ti, g, G = odrv.simpsons(ng, 0.8)
+    Lb = [odrv.int_L(ng, L, ti, D, g, G) for L, D in zip(lam, Ds)]
+    P1 = ft_cc_equations.uccsd_1rdm(*amps, *lam, *Ds, ti, ng, g, G)
+    P2 = ft_cc_equations.uccsd_2rdm(*amps, *lam, *Ds, ti, ng, g, G)
+    for k, nm in ((1, "ba"), (2, "ji"), (3, "ai")):
+        ref = None
+        for y in range(ng):
+            r = getattr(ocq, "uccsd_1rdm_" + nm)(*[a[y] for a in amps], *[l[y] for l in Lb])
+            ref = [g[y]*x for x in r] if ref is None else [a + g[y]*x for a, x in zip(ref, r)]
+        for got, rr in zip(P1[k], ref):
+            assert _rel(got, rr) < 1e-11, nm
+    names = ("cdab", "ciab", "bcai", "ijab", "bjai", "abij", "jkai", "kaij", "klij")
+    for k, nm in enumerate(names):
+        if nm == "ijab":
+            continue
+        ref = None
+        for y in range(ng):
+            r = getattr(ocq, "uccsd_2rdm_" + nm)(*[a[y] for a in amps], *[l[y] for l in Lb])
+            ref = [g[y]*x for x in r] if ref is None else [a + g[y]*x for a, x in zip(ref, r)]
+        assert len(P2[k]) == len(ref)
+        for got, rr in zip(P2[k], ref):
+            assert _rel(got, rr) < 1e-11, nm
+
+
+def test_ueg7_ng40_ESN(built):
+    """examples/ueg_ft_cc_compare.out:46-48: E, S, N after Lambda, RDMs and relaxation."""
+    from kelvin_b200.ccsd import ccsd
+    from kelvin_b200.ueg_system import UEGSystem
+    T, mu = 0.1, 0.1182968
+    ueg = UEGSystem(T, 2*numpy.pi, 1.2, mu=mu, norb=7, orbtype='u')
+    cc = ccsd(ueg, T=T, mu=mu, iprint=1, max_iter=50, damp=0.1, ngrid=40, tconv=1e-8)
+    cc.run()
+    cc.compute_ESN()
+    assert abs(cc.E - pub.UEG7_NG40["E"]) < 1e-10
+    assert abs(cc.S - pub.UEG7_NG40["S"]) < 1e-9
+    assert abs(cc.N - pub.UEG7_NG40["N"]) < 1e-10
+
+
+def test_ueg7_g_equals_u_ESN(built):
+    """g and u paths give the same E, S, N and 1-RDM
+    (kelvin/tests/test_ft_cc_relden.py:233-275, kelvin/tests/test_hubbard.py:184-213)."""
+    from kelvin_b200.ccsd import ccsd
+    from kelvin_b200.ueg_system import UEGSystem
+    T, mu = 0.2, 0.15
+    out = {}
+    for orb in ("g", "u"):
+        ueg = UEGSystem(T, 2*numpy.pi, 1.2, mu=mu, norb=7, orbtype=orb)
+        cc = ccsd(ueg, T=T, mu=mu, iprint=0, max_iter=80, damp=0.1, ngrid=10, econv=1e-12, tconv=1e-10)
+        Etot, Ecc = cc.run()
+        cc.compute_ESN()
+        out[orb] = (Etot, cc.E, cc.S, cc.N, cc)
+    for k in range(4):
+        assert abs(out["g"][k] - out["u"][k]) < 1e-9, k
+    n = 7
+    g1 = out["g"][4].n1rdm.cpu().numpy()
+    ua, ub = [x.cpu().numpy() for x in out["u"][4].n1rdm]
+    assert numpy.abs(g1[:n, :n] - ua).max() < 1e-9
+    assert numpy.abs(g1[n:, n:] - ub).max() < 1e-9
+
+
+def test_esn19_ESN(built):
+    """bench/ueg_ft_ccsd_ESN19/ulambda_19_04_17.out:42-44 (E, S, N printed to 12 digits;
+    default tconv = 1e-5 leaves ~1e-6 of Lambda iteration error in both codes)."""
+    from kelvin_b200.ccsd import ccsd
+    from kelvin_b200.ueg_system import UEGSystem
+    T, mu = 0.5, 7.0
+    ueg = UEGSystem(T, 1.942, 30.0, mu=mu, norb=19, orbtype='u')
+    cc = ccsd(ueg, T=T, mu=mu, iprint=1, max_iter=50, damp=0.0, ngrid=10)
+    cc.run()
+    cc.compute_ESN()
+    print("ESN19 E S N", repr(cc.E), repr(cc.S), repr(cc.N))
+    assert abs(cc.E - pub.ESN19["E"]) < 5e-5
+    assert abs(cc.S - pub.ESN19["S"]) < 5e-5
+    assert abs(cc.N - pub.ESN19["N"]) < 5e-5

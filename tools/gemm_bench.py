@@ -42,9 +42,13 @@ def main():
     # kb200: ladder-like [ab][ef] x [ef][ij], m = 33, batch 10, all four operand modes
     m = 33
     dims = dict(a=m, b=m, e=m, f=m, i=m, j=m)
-    for la, lb, tag in (("abef", "efij", "A:kc B:nc"), ("efab", "ijef", "A:mc B:kc"),
-                        ("abef", "ijef", "A:kc B:kc"), ("efab", "efij", "A:mc B:nc"),
-                        ("aeim", "mbej", "ring-like")):
+    tiles = [int(x) for x in os.environ.get("KB200_TILES", "0").split(",")]
+    cases = [(t_, la, lb, "tile%d %s" % (t_, tag)) for t_ in tiles for la, lb, tag in
+             (("abef", "efij", "A:kc B:nc"), ("efab", "ijef", "A:mc B:kc"),
+              ("abef", "ijef", "A:kc B:kc"), ("efab", "efij", "A:mc B:nc"),
+              ("aeim", "mbej", "ring-like"))]
+    for tile_, la, lb, tag in cases:
+        plan.BIG_TILE = tile_
         lc = "abij"
         Ash = tuple(dims.get(l, m) for l in la)
         Bsh = tuple(dims.get(l, m) for l in lb)
