@@ -23,6 +23,8 @@ from .ov_blocks import one_e_blocks, two_e_blocks, two_e_blocks_full
 # dressing
 # ---------------------------------------------------------------------------
 def _vec(x, dev):
+    if isinstance(x, torch.Tensor):
+        return x.to(device=dev, dtype=torch.float64).contiguous()
     return torch.as_tensor(numpy.asarray(x, dtype=numpy.float64)).to(dev)
 
 

@@ -1,0 +1,147 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference drivers.
+
+Run in the build container only (needs /root/reference):
+
+    python tests/golden/make_golden.py
+
+The reference's kelvin/*.py (ccsd, cc_utils, ft_cc_equations, quadrature,
+ft_cc_energy, ueg_system, hubbard_system) are imported as they are; their three
+absent dependencies resolve to the shims in oracle/shims (pyscf.lib.einsum ->
+numpy.einsum, cqcpy -> oracle/kelvin_oracle restatement, lattice -> Hubbard1D).
+The fixtures therefore pin (i) every host-side convention of the reference
+(grids, dressing, loops, RDM assembly, E/S/N) exactly and (ii) the restated
+cqcpy arithmetic to the extent the reference's published numbers do
+(tests/golden/published.py).
+"""
+import logging
+import os
+import sys
+
+import numpy
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path[:0] = [os.path.join(ROOT, "oracle", "shims"), os.path.join(ROOT, "oracle"), "/root/reference"]
+
+from kelvin import quadrature  # noqa: E402
+from kelvin.ccsd import ccsd  # noqa: E402
+from kelvin.hubbard_system import HubbardSystem  # noqa: E402
+from kelvin.ueg_system import UEGSystem  # noqa: E402
+from lattice.hubbard import Hubbard1D  # noqa: E402
+
+logging.basicConfig(level=logging.WARNING)
+
+
+def quad_fixture():
+    out = {}
+    beta = 2.5
+    for quad in ('lin', 'ln', 'sin', 'exp', 'quad', 'cub', 'quar', 'mid', 'L'):
+        for ng in (7, 8):
+            ti, g, G = quadrature.ft_quad(ng, beta, quad)
+            out["%s_%d_ti" % (quad, ng)] = ti
+            out["%s_%d_g" % (quad, ng)] = g
+            out["%s_%d_G" % (quad, ng)] = G
+            if quad != 'mid':
+                gd, Gd = quadrature.d_ft_quad(ng, beta, quad)
+                out["%s_%d_gd" % (quad, ng)] = gd
+                out["%s_%d_Gd" % (quad, ng)] = Gd
+    numpy.savez_compressed(os.path.join(HERE, "quadrature.npz"), **out)
+
+
+def system_fixture():
+    out = {}
+    for orb in ("u", "g"):
+        s = UEGSystem(0.5, 1.942, 30.0, mu=7.0, norb=7, orbtype=orb)
+        out["ueg_%s_N" % orb] = s.N
+        out["ueg_%s_mp1" % orb] = s.get_mp1()
+        if orb == "u":
+            out["ueg_u_ea"] = s.u_energies_tot()[0]
+            out["ueg_u_eriab"] = s.u_aint_tot()[2]
+            fa, fb = s.u_fock_tot()
+            out["ueg_u_fa"] = fa
+            da, db = s.u_mp1_den()
+            out["ueg_u_mp1den"] = da
+            out["ueg_u_fdd"] = numpy.stack(s.u_fock_d_den())
+        else:
+            out["ueg_g_en"] = s.g_energies_tot()
+            out["ueg_g_eri"] = s.g_aint_tot()
+            out["ueg_g_f"] = s.g_fock_tot()
+            out["ueg_g_mp1den"] = s.g_mp1_den()
+    hub, Pa, Pb = hubbard_inputs(4, 2.0)
+    for orb in ("u", "g"):
+        s = HubbardSystem(1.0, hub, Pa, Pb, mu=0.3, orbtype=orb)
+        out["hub_%s_mp1" % orb] = s.get_mp1()
+        if orb == "u":
+            out["hub_u_ea"], out["hub_u_eb"] = s.u_energies_tot()
+            va, vb, vab = s.u_aint_tot()
+            out["hub_u_va"], out["hub_u_vb"], out["hub_u_vab"] = va, vb, vab
+            out["hub_u_fa"], out["hub_u_fb"] = s.u_fock_tot()
+            out["hub_u_mp1den"] = numpy.stack(s.u_mp1_den())
+        else:
+            out["hub_g_eri"] = s.g_aint_tot()
+            out["hub_g_f"] = s.g_fock_tot()
+    numpy.savez_compressed(os.path.join(HERE, "systems.npz"), **out)
+
+
+def hubbard_inputs(L, U):
+    hub = Hubbard1D(L, 1.0, U, boundary='p')
+    Oa = numpy.zeros(L)
+    Ob = numpy.zeros(L)
+    Oa[0::2] = 1.0
+    Ob[1::2] = 1.0
+    return hub, numpy.einsum('i,j->ij', Oa, Oa), numpy.einsum('i,j->ij', Ob, Ob)
+
+
+def run_fixture(name, sysm, **kw):
+    cc = ccsd(sysm, **kw)
+    Etot, Ecc = cc.run()
+    cc.compute_ESN()
+    out = dict(Etot=Etot, Ecc=Ecc, E=cc.E, S=cc.S, N=cc.N, E0=cc.E0, E1=cc.E1, Ecc_=cc.Ecc,
+               N0=cc.N0, N1=cc.N1, Ncc=cc.Ncc, S0=cc.S0, S1=cc.S1, Scc=cc.Scc)
+    if sysm.has_u():
+        for k, nm in enumerate(("T1a", "T1b")):
+            out[nm] = cc.T1[k]
+        for k, nm in enumerate(("T2aa", "T2ab", "T2bb")):
+            out[nm] = cc.T2[k]
+        for k, nm in enumerate(("L1a", "L1b")):
+            out[nm] = cc.L1[k]
+        for k, nm in enumerate(("L2aa", "L2ab", "L2bb")):
+            out[nm] = cc.L2[k]
+        for k in (0, 1):
+            out["n1rdm%d" % k] = cc.n1rdm[k]
+            out["rono%d" % k] = cc.rono[k]
+            out["ronv%d" % k] = cc.ronv[k]
+            out["ron1%d" % k] = cc.ron1[k]
+            for nm in ("dia", "dba", "dji", "dai"):
+                out["%s%d" % (nm, k)] = getattr(cc, nm)[k]
+        for k in (0, 1, 2):
+            out["n2rdm%d" % k] = cc.n2rdm[k]
+        for b, tup in enumerate(cc.P2):
+            for k, P in enumerate(tup):
+                out["P2_%d_%d" % (b, k)] = P
+    else:
+        out.update(T1=cc.T1, T2=cc.T2, L1=cc.L1, L2=cc.L2, n1rdm=cc.n1rdm, n2rdm=cc.n2rdm,
+                   rono=cc.rono, ronv=cc.ronv, ron1=cc.ron1, dia=cc.dia, dba=cc.dba,
+                   dji=cc.dji, dai=cc.dai)
+        for b, P in enumerate(cc.P2):
+            out["P2_%d" % b] = P
+    numpy.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(name, Etot, Ecc, cc.E, cc.S, cc.N)
+
+
+def main():
+    quad_fixture()
+    system_fixture()
+    T, mu = 0.1, 0.1
+    for orb in ("u", "g"):
+        ueg = UEGSystem(T, 2*numpy.pi, 1.2, mu=mu, norb=7, orbtype=orb)
+        run_fixture("ueg7_" + orb, ueg, T=T, mu=mu, iprint=0, max_iter=80, damp=0.2, ngrid=6,
+                    econv=1e-11, tconv=1e-9)
+    hub, Pa, Pb = hubbard_inputs(4, 2.0)
+    sysm = HubbardSystem(1.0, hub, Pa, Pb, mu=0.3, orbtype='u')
+    run_fixture("hubbard4_u", sysm, T=1.0, mu=0.3, iprint=0, max_iter=80, ngrid=8, quad='quad',
+                econv=1e-11, tconv=1e-9)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,100 @@
+"""GPU path vs fixtures produced by the unmodified reference drivers
+(tests/golden/make_golden.py): amplitudes to 1e-9 relative, energies to 1e-10."""
+import os
+
+import numpy
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _load(name):
+    return numpy.load(os.path.join(HERE, "golden", name + ".npz"))
+
+
+def _rel(got, ref):
+    got = got.cpu().numpy() if hasattr(got, "cpu") else numpy.asarray(got)
+    return numpy.abs(got - ref).max()/max(1e-300, numpy.abs(ref).max())
+
+
+def _hubbard4():
+    from kelvin_b200.hubbard_system import HubbardSystem, Hubbard1D
+    L = 4
+    hub = Hubbard1D(L, 1.0, 2.0, boundary='p')
+    Oa, Ob = numpy.zeros(L), numpy.zeros(L)
+    Oa[0::2] = 1.0
+    Ob[1::2] = 1.0
+    return HubbardSystem(1.0, hub, numpy.einsum('i,j->ij', Oa, Oa), numpy.einsum('i,j->ij', Ob, Ob),
+                         mu=0.3, orbtype='u')
+
+
+def _check_scalars(cc, Etot, Ecc, ref):
+    assert abs(Etot - float(ref["Etot"])) < 1e-10
+    assert abs(Ecc - float(ref["Ecc"])) < 1e-10
+    for nm, key in (("E", "E"), ("S", "S"), ("N", "N"), ("E0", "E0"), ("E1", "E1"), ("Ecc", "Ecc_"),
+                    ("N0", "N0"), ("N1", "N1"), ("Ncc", "Ncc"), ("S0", "S0"), ("S1", "S1"),
+                    ("Scc", "Scc")):
+        assert abs(getattr(cc, nm) - float(ref[key])) < 1e-9, (nm, getattr(cc, nm), float(ref[key]))
+
+
+def _run_u(sysm, ref, **kw):
+    from kelvin_b200.ccsd import ccsd
+    cc = ccsd(sysm, **kw)
+    Etot, Ecc = cc.run()
+    cc.compute_ESN()
+    _check_scalars(cc, Etot, Ecc, ref)
+    for k, nm in enumerate(("T1a", "T1b")):
+        assert _rel(cc.T1[k], ref[nm]) < 1e-9
+        assert _rel(cc.L1[k], ref["L1" + nm[-1]]) < 1e-8
+    for k, nm in enumerate(("aa", "ab", "bb")):
+        assert _rel(cc.T2[k], ref["T2" + nm]) < 1e-9
+        assert _rel(cc.L2[k], ref["L2" + nm]) < 1e-8
+    for k in (0, 1):
+        assert _rel(cc.n1rdm[k], ref["n1rdm%d" % k]) < 1e-8
+        assert numpy.abs(cc.rono[k] - ref["rono%d" % k]).max() < 1e-9
+        assert numpy.abs(cc.ronv[k] - ref["ronv%d" % k]).max() < 1e-9
+        assert numpy.abs(cc.ron1[k] - ref["ron1%d" % k]).max() < 1e-12
+        for nm in ("dia", "dba", "dji", "dai"):
+            assert _rel(getattr(cc, nm)[k], ref["%s%d" % (nm, k)]) < 1e-8
+    for k in (0, 1, 2):
+        assert _rel(cc.n2rdm[k], ref["n2rdm%d" % k]) < 1e-8
+    for b, tup in enumerate(cc.P2):
+        for k, P in enumerate(tup):
+            assert _rel(P, ref["P2_%d_%d" % (b, k)]) < 1e-8, (b, k)
+
+
+def test_ueg7_u_full_path(built):
+    from kelvin_b200.ueg_system import UEGSystem
+    T, mu = 0.1, 0.1
+    ueg = UEGSystem(T, 2*numpy.pi, 1.2, mu=mu, norb=7, orbtype='u')
+    _run_u(ueg, _load("ueg7_u"), T=T, mu=mu, iprint=0, max_iter=80, damp=0.2, ngrid=6,
+           econv=1e-11, tconv=1e-9)
+
+
+def test_hubbard4_u_full_path(built):
+    _run_u(_hubbard4(), _load("hubbard4_u"), T=1.0, mu=0.3, iprint=0, max_iter=80, ngrid=8,
+           quad='quad', econv=1e-11, tconv=1e-9)
+
+
+def test_ueg7_g_full_path(built):
+    from kelvin_b200.ccsd import ccsd
+    from kelvin_b200.ueg_system import UEGSystem
+    T, mu = 0.1, 0.1
+    ref = _load("ueg7_g")
+    ueg = UEGSystem(T, 2*numpy.pi, 1.2, mu=mu, norb=7, orbtype='g')
+    cc = ccsd(ueg, T=T, mu=mu, iprint=0, max_iter=80, damp=0.2, ngrid=6, econv=1e-11, tconv=1e-9)
+    Etot, Ecc = cc.run()
+    cc.compute_ESN()
+    _check_scalars(cc, Etot, Ecc, ref)
+    assert _rel(cc.T1, ref["T1"]) < 1e-9
+    assert _rel(cc.T2, ref["T2"]) < 1e-9
+    assert _rel(cc.L1, ref["L1"]) < 1e-8
+    assert _rel(cc.L2, ref["L2"]) < 1e-8
+    assert _rel(cc.n1rdm, ref["n1rdm"]) < 1e-8
+    assert _rel(cc.n2rdm, ref["n2rdm"]) < 1e-8
+    assert numpy.abs(cc.rono - ref["rono"]).max() < 1e-9
+    assert numpy.abs(cc.ronv - ref["ronv"]).max() < 1e-9
+    for b, P in enumerate(cc.P2):
+        assert _rel(P, ref["P2_%d" % b]) < 1e-8, b
