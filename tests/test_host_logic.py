@@ -1,0 +1,156 @@
+"""CPU: host-side logic of the product (grids, systems, C-ABI surface, tau sharding)."""
+import ctypes
+import os
+import re
+
+import numpy
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+
+def test_quadrature_matches_reference_fixtures():
+    from kelvin_b200 import quadrature
+    ref = numpy.load(os.path.join(HERE, "golden", "quadrature.npz"))
+    beta = 2.5
+    for quad in ('lin', 'ln', 'sin', 'exp', 'quad', 'cub', 'quar', 'mid', 'L'):
+        for ng in (7, 8):
+            ti, g, G = quadrature.ft_quad(ng, beta, quad)
+            assert numpy.abs(ti - ref["%s_%d_ti" % (quad, ng)]).max() < 1e-15
+            assert numpy.abs(g - ref["%s_%d_g" % (quad, ng)]).max() < 1e-15
+            assert numpy.abs(G - ref["%s_%d_G" % (quad, ng)]).max() < 1e-15
+            if quad == 'mid':
+                with pytest.raises(Exception):
+                    quadrature.d_ft_quad(ng, beta, quad)
+                continue
+            gd, Gd = quadrature.d_ft_quad(ng, beta, quad)
+            assert numpy.abs(gd - ref["%s_%d_gd" % (quad, ng)]).max() < 1e-15
+            assert numpy.abs(Gd - ref["%s_%d_Gd" % (quad, ng)]).max() < 1e-15
+    with pytest.raises(Exception):
+        quadrature.ft_quad(5, 1.0, "nope")
+
+
+def test_quadrature_beta_derivative_by_fd():
+    """d(g)/d(beta) by central differences (kelvin/tests/test_quadrature.py:98-110),
+    here also for G (the reference's G check is vacuous)."""
+    from kelvin_b200 import quadrature
+    beta, d = 1.3, 1e-6
+    for quad in ('lin', 'ln', 'sin', 'exp', 'quad', 'cub', 'quar'):
+        _, gp, Gp = quadrature.ft_quad(9, beta + d, quad)
+        _, gm, Gm = quadrature.ft_quad(9, beta - d, quad)
+        gd, Gd = quadrature.d_ft_quad(9, beta, quad)
+        assert numpy.abs((gp - gm)/(2*d) - gd).max() < 1e-8
+        assert numpy.abs((Gp - Gm)/(2*d) - Gd).max() < 1e-8
+
+
+def test_systems_match_reference_fixtures():
+    from kelvin_b200.ueg_system import UEGSystem
+    from kelvin_b200.hubbard_system import HubbardSystem, Hubbard1D
+    ref = numpy.load(os.path.join(HERE, "golden", "systems.npz"))
+    su = UEGSystem(0.5, 1.942, 30.0, mu=7.0, norb=7, orbtype="u")
+    assert su.N == float(ref["ueg_u_N"])
+    assert abs(su.get_mp1() - float(ref["ueg_u_mp1"])) < 1e-13
+    assert numpy.abs(su.u_energies_tot()[0] - ref["ueg_u_ea"]).max() == 0.0
+    assert numpy.abs(su.u_aint_tot()[2] - ref["ueg_u_eriab"]).max() == 0.0
+    assert numpy.abs(su.u_fock_tot()[0] - ref["ueg_u_fa"]).max() < 1e-14
+    assert numpy.abs(su.u_mp1_den()[0] - ref["ueg_u_mp1den"]).max() < 1e-14
+    assert numpy.abs(numpy.stack(su.u_fock_d_den()) - ref["ueg_u_fdd"]).max() < 1e-14
+    sg = UEGSystem(0.5, 1.942, 30.0, mu=7.0, norb=7, orbtype="g")
+    assert numpy.abs(sg.g_aint_tot() - ref["ueg_g_eri"]).max() == 0.0
+    assert numpy.abs(sg.g_fock_tot() - ref["ueg_g_f"]).max() < 1e-14
+    assert numpy.abs(sg.g_mp1_den() - ref["ueg_g_mp1den"]).max() < 1e-14
+    L = 4
+    hub = Hubbard1D(L, 1.0, 2.0, boundary='p')
+    Oa, Ob = numpy.zeros(L), numpy.zeros(L)
+    Oa[0::2] = 1.0
+    Ob[1::2] = 1.0
+    Pa, Pb = numpy.einsum('i,j->ij', Oa, Oa), numpy.einsum('i,j->ij', Ob, Ob)
+    hu = HubbardSystem(1.0, hub, Pa, Pb, mu=0.3, orbtype='u')
+    assert abs(hu.get_mp1() - float(ref["hub_u_mp1"])) < 1e-13
+    for got, key in zip(hu.u_aint_tot(), ("hub_u_va", "hub_u_vb", "hub_u_vab")):
+        assert numpy.abs(got - ref[key]).max() < 1e-14
+    for got, key in zip(hu.u_fock_tot(), ("hub_u_fa", "hub_u_fb")):
+        assert numpy.abs(got - ref[key]).max() < 1e-14
+    assert numpy.abs(numpy.stack(hu.u_mp1_den()) - ref["hub_u_mp1den"]).max() < 1e-14
+    hg = HubbardSystem(1.0, hub, Pa, Pb, mu=0.3, orbtype='g')
+    assert numpy.abs(hg.g_aint_tot() - ref["hub_g_eri"]).max() < 1e-14
+    assert numpy.abs(hg.g_fock_tot() - ref["hub_g_f"]).max() < 1e-14
+    assert not su.verify(0.4, 7.0) and su.verify(0.5, 7.0)
+
+
+def test_capi_exports_every_declared_symbol(built):
+    """The C-ABI library loads and exports every function include/kelvin_b200.h declares
+    (no compute call is made: there is no GPU here)."""
+    from kelvin_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "kelvin_b200.h")).read()
+    declared = set(re.findall(r"\b(kb200_[A-Za-z0-9_]+)\s*\(", hdr))
+    declared.discard("kb200_op")
+    assert len(declared) >= 18
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for nm in sorted(declared):
+        assert hasattr(lib, nm), nm
+    assert set(_lib.EXPORTS) <= declared
+    assert _lib.load().kb200_version() >= 100
+    # the descriptor struct has the layout the header promises
+    from kelvin_b200.plan import kb200_op
+    assert ctypes.sizeof(kb200_op) == 4*4 + 3*8 + 4*4 + 3*8 + 6*8 + 2*8 + 4*4
+
+
+def test_product_fails_loudly_without_cuda(built):
+    """No CPU fallback: compute entry points raise when there is no CUDA device."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from kelvin_b200 import quadrature, _lib
+    ti, g, G = quadrature.ft_quad(4, 1.0, 'lin')
+    with pytest.raises(_lib.KB200Error):
+        quadrature.int_tbar(4, numpy.zeros((4, 2, 2)), ti, numpy.zeros((2, 2)), G)
+
+
+def test_shard_bounds():
+    from kelvin_b200.parallel import shard_bounds
+    for ng in (1, 7, 10, 16, 24, 40):
+        for world in (1, 2, 3, 4, 8):
+            b, chunk = shard_bounds(ng, world)
+            assert b[0][0] == 0 and b[-1][1] == ng
+            for (a0, a1), (b0, b1) in zip(b[:-1], b[1:]):
+                assert a1 == b0 and a1 - a0 <= chunk
+            assert sum(y1 - y0 for y0, y1 in b) == ng
+
+
+def _gloo_worker(rank, world, port, ng, q):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from kelvin_b200 import parallel
+    bounds, chunk = parallel.shard_bounds(ng, world)
+    y0, y1 = bounds[rank]
+    full = torch.arange(ng*6, dtype=torch.float64).reshape(ng, 2, 3)
+    obj = parallel.TauShardedUCCSD.__new__(parallel.TauShardedUCCSD)
+    obj.world, obj.rank, obj.chunk, obj.nloc, obj.group, obj.ng = world, rank, chunk, y1 - y0, None, ng
+    got = obj._allgather_rows(full[y0:y1].clone())[:ng]
+    stats = torch.tensor([float(y1 - y0)], dtype=torch.float64)
+    dist.all_reduce(stats)
+    q.put((rank, bool(torch.equal(got, full)), float(stats.item())))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("ng", [5, 8])
+def test_tau_allgather_gloo_world2(ng):
+    """The N>1 exchange step (padded all-gather of the per-rank residual rows) on 2 CPU
+    ranks over gloo."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() + ng) % 2000
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, ng, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, ok, tot in res:
+        assert ok and tot == ng

@@ -1,0 +1,147 @@
+"""CPU: the contraction-plan compiler (statement parsing, spin expansion, merging,
+reverse mode, lowering to kb200_op + offset tables) executed with NumPy gathers
+(tests/plan_exec.py) against the oracle."""
+import numpy
+import pytest
+
+from kelvin_b200 import plan, programs
+from kelvin_oracle import cqc, cc_equations as ocq
+from plan_exec import run_lowered
+import util
+
+
+def _run(rops, mode, sizes, inputs, src, ng):
+    shapes = plan.slot_shapes(rops, mode, sizes)
+    batched = {s: not plan.is_integral_slot(s) for s in shapes}
+    preset = [s for s in shapes if plan.is_integral_slot(s)] + list(inputs)
+    low = plan.Lowered(rops, shapes, batched, preset)
+    arrays = {}
+    for s, shp in shapes.items():
+        if plan.is_integral_slot(s):
+            pre, pat = s.split(".")
+            arrays[s] = numpy.ascontiguousarray(getattr(src[pre], pat))
+        elif s in inputs:
+            arrays[s] = numpy.ascontiguousarray(inputs[s])
+        else:
+            arrays[s] = numpy.full((ng,) + shp, numpy.nan)
+    run_lowered(low, arrays, ng)
+    return arrays, low
+
+
+def test_stanton_plan_g():
+    n, ng = 5, 3
+    F, I, t1, t2 = util.random_g(n, ng, seed=0)
+    rops = plan.expand(programs.stanton(-1.0), programs.tensor_defs(), "g")
+    arr, low = _run(rops, "g", {"o": n, "v": n}, {"t1": t1, "t2": t2}, {"F": F, "I": I}, ng)
+    for y in range(ng):
+        R1, R2 = ocq.stanton_terms(F, I, t1[y], t2[y])
+        assert numpy.abs(arr["o1"][y] - (-F.vo - R1)).max() < 1e-12
+        assert numpy.abs(arr["o2"][y] - (-I.vvoo - R2)).max() < 1e-12
+    # executed flops: 12 n^6 + lower order
+    assert 12*n**6 <= low.flops <= 12*n**6 + 50*n**5
+
+
+def test_stanton_plan_u_rectangular():
+    na, nb, ng = 4, 3, 2
+    ints, amps = util.random_u(na, nb, ng, seed=1)
+    Fa, Fb, Ia, Ib, Iabab = ints
+    sizes = {("v", "a"): na, ("o", "a"): na, ("v", "b"): nb, ("o", "b"): nb}
+    names = ("t1.a", "t1.b", "t2.aa", "t2.ab", "t2.bb")
+    rops = plan.expand(programs.stanton(-1.0), programs.tensor_defs(), "u")
+    arr, low = _run(rops, "u", sizes, dict(zip(names, amps)),
+                    {"Fa": Fa, "Fb": Fb, "Ia": Ia, "Ib": Ib, "Iabab": Iabab}, ng)
+    for y in range(ng):
+        r = ocq.u_stanton_terms(*ints, (amps[0][y], amps[1][y]), (amps[2][y], amps[3][y], amps[4][y]))
+        ref = (-Fa.vo - r[0], -Fb.vo - r[1], -Ia.vvoo - r[2], -Iabab.vvoo - r[3], -Ib.vvoo - r[4])
+        for nm, rr in zip(("o1.a", "o1.b", "o2.aa", "o2.ab", "o2.bb"), ref):
+            assert numpy.abs(arr[nm][y] - rr).max() < 1e-12
+
+
+def test_u_plan_has_32_block_gemms():
+    """32 Sz-allowed m^6 block GEMMs per residual (64 m^6 flops)."""
+    m = 6
+    sizes = {("v", "a"): m, ("o", "a"): m, ("v", "b"): m, ("o", "b"): m}
+    rops = plan.expand(programs.stanton(-1.0), programs.tensor_defs(), "u")
+    shapes = plan.slot_shapes(rops, "u", sizes)
+    low = plan.Lowered(rops, shapes, {s: not plan.is_integral_slot(s) for s in shapes},
+                       [s for s in shapes if plan.is_integral_slot(s)] + ["t1.a", "t1.b", "t2.aa", "t2.ab", "t2.bb"])
+    big = [d for d in low.descs if d.kind == 0 and d.M*d.N*d.K == m**6]
+    assert len(big) == 32
+    assert low.flops <= 64*m**6 + 200*m**5
+
+
+@pytest.mark.parametrize("mode", ["g", "u"])
+def test_lambda_plan(mode):
+    ng = 2
+    if mode == "g":
+        n = 4
+        F, I, t1, t2 = util.random_g(n, ng, seed=3)
+        rng = numpy.random.default_rng(9)
+        l1 = rng.standard_normal((ng, n, n))
+        l2 = numpy.ascontiguousarray(util.asym(rng.standard_normal((ng, n, n, n, n))))
+        inter, rest = programs.lambda_rops("g", -1.0)
+        arr, _ = _run(inter + rest, "g", {"o": n, "v": n},
+                      {"t1": t1, "t2": t2, "l1": l1, "l2": l2}, {"F": F, "I": I}, ng)
+        for y in range(ng):
+            d1, d2 = ocq.lambda_terms(F, I, l1[y], l2[y], t1[y], t2[y])
+            r1 = -d1 - F.ov - numpy.einsum('jiba,bj->ia', I.oovv, t1[y])
+            assert numpy.abs(arr["lo1"][y] - r1).max() < 1e-12
+            assert numpy.abs(arr["lo2"][y] - (-d2 - I.oovv)).max() < 1e-12
+        return
+    na, nb = 4, 3
+    ints, amps = util.random_u(na, nb, ng, seed=4)
+    Fa, Fb, Ia, Ib, Iabab = ints
+    _, lam = util.random_u(na, nb, ng, seed=5)
+    lam = [numpy.ascontiguousarray(lam[0].transpose(0, 2, 1)),
+           numpy.ascontiguousarray(lam[1].transpose(0, 2, 1)), lam[2], lam[3], lam[4]]
+    sizes = {("v", "a"): na, ("o", "a"): na, ("v", "b"): nb, ("o", "b"): nb}
+    inputs = dict(zip(("t1.a", "t1.b", "t2.aa", "t2.ab", "t2.bb"), amps))
+    inputs.update(zip(("l1.a", "l1.b", "l2.aa", "l2.ab", "l2.bb"), lam))
+    inter, rest = programs.lambda_rops("u", -1.0)
+    arr, _ = _run(inter + rest, "u", sizes, inputs,
+                  {"Fa": Fa, "Fb": Fb, "Ia": Ia, "Ib": Ib, "Iabab": Iabab}, ng)
+    for y in range(ng):
+        out = [numpy.zeros_like(x[y]) for x in lam]
+        ocq._uccsd_Lambda_opt(*out, *ints, (lam[0][y], lam[1][y]), (lam[2][y], lam[3][y], lam[4][y]),
+                              (amps[0][y], amps[1][y]), (amps[2][y], amps[3][y], amps[4][y]), fac=-1.0)
+        out[0] -= Fa.ov
+        out[1] -= Fb.ov
+        out[2] -= Ia.oovv
+        out[3] -= Iabab.oovv
+        out[4] -= Ib.oovv
+        ocq._u_LS_TS(out[0], out[1], Ia, Ib, Iabab, amps[0][y], amps[1][y], fac=-1.0)
+        for nm, r in zip(("lo1.a", "lo1.b", "lo2.aa", "lo2.ab", "lo2.bb"), out):
+            assert numpy.abs(arr[nm][y] - r).max() < 1e-12
+
+
+def test_rdm_plan_u_all_spin_blocks():
+    """All 31 non-trivial unrestricted 2-RDM spin blocks + 1-RDM blocks equal the spin
+    blocks of the derivative-defined g RDMs (kelvin/tests/test_ft_ccsd_rdm.py:495-752)."""
+    na, nb, ng = 4, 3, 2
+    gw = numpy.array([0.3, 0.7])
+    ints, amps = util.random_u(na, nb, ng, seed=4)
+    _, lam = util.random_u(na, nb, ng, seed=5)
+    lam = [numpy.ascontiguousarray(lam[0].transpose(0, 2, 1)),
+           numpy.ascontiguousarray(lam[1].transpose(0, 2, 1)), lam[2], lam[3], lam[4]]
+    sizes = {("v", "a"): na, ("o", "a"): na, ("v", "b"): nb, ("o", "b"): nb}
+    inputs = dict(zip(("t1.a", "t1.b", "t2.aa", "t2.ab", "t2.bb"), amps))
+    inputs.update(zip(("l1.a", "l1.b", "l2.aa", "l2.ab", "l2.bb"), lam))
+    inter, rest = programs.rdm_rops("u")
+    arr, _ = _run(inter + rest, "u", sizes, inputs, {}, ng)
+    summed = {s: numpy.ascontiguousarray(numpy.tensordot(gw, a, axes=(0, 0)))
+              for s, a in arr.items() if s.endswith("~") and plan._INT_SLOT.match(s)}
+    aops, outs = programs.rdm2_assembly_rops("u")
+    ashapes = plan.slot_shapes(aops, "u", sizes)
+    alow = plan.Lowered(aops, ashapes, {s: False for s in ashapes},
+                        [s for s in ashapes if s.endswith("~")])
+    aarr = {s: (summed[s] if s in summed else numpy.full(ashapes[s], numpy.nan)) for s in ashapes}
+    run_lowered(alow, aarr, 1)
+    args = [[a[y] for a in amps] + [l[y] for l in lam] for y in range(ng)]
+    for slot, pname, sp in outs:
+        k = programs.RDM2_USPINS[pname].index(sp)
+        ref = sum(gw[y]*getattr(ocq, "uccsd_2rdm_" + pname)(*args[y])[k] for y in range(ng))
+        assert numpy.abs(aarr[slot] - ref).max() < 1e-12, slot
+    for nm, leaf in (("ba", "vv"), ("ji", "oo"), ("ai", "ov")):
+        ref = [sum(gw[y]*getattr(ocq, "uccsd_1rdm_" + nm)(*args[y])[k] for y in range(ng)) for k in (0, 1)]
+        assert numpy.abs(summed["Fa.%s~" % leaf].T - ref[0]).max() < 1e-12
+        assert numpy.abs(summed["Fb.%s~" % leaf].T - ref[1]).max() < 1e-12
