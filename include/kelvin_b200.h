@@ -51,7 +51,7 @@ typedef struct kb200_op {
     double alpha, beta;
     int32_t a_mode;        /* 0: A gathers contiguously along k, 1: along m    */
     int32_t b_mode;        /* 0: B gathers contiguously along k, 1: along n    */
-    int32_t tile;          /* 0: 128x128 CTA tile, 1: 128x32 CTA tile          */
+    int32_t tile;          /* CTA tile id: 0 128x128, 1 128x32, 5 64x64 (see kb200.cu) */
     int32_t splitk;        /* >=1; >1 uses the workspace + deterministic reduce */
 } kb200_op;
 

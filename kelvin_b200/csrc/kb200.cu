@@ -390,8 +390,10 @@ int launch_gemm_modes(const kb200::GemmParams& p, int batch, int am, int bm, cud
 //           2 = 128x128, 16 warps (32x32 warp tiles), interleaved loads
 //           3 = 128x128, 8 warps, loads issued up front (experiment)
 //           4 = 128x64,  8 warps (32x32 warp tiles), 2 CTAs/SM
-int tile_bm(int tile) { return 128; }
-int tile_bn(int tile) { return tile == 1 ? 32 : (tile == 4 ? 64 : 128); }
+//           5 = 64x64,   4 warps (32x32 warp tiles), 3 stages, several CTAs/SM: bandwidth-bound
+//               shapes (skinny N, or tiny outputs with long split K)
+int tile_bm(int tile) { return tile == 5 ? 64 : 128; }
+int tile_bn(int tile) { return tile == 1 ? 32 : ((tile == 4 || tile == 5) ? 64 : 128); }
 
 int64_t op_workspace(const kb200_op& o) {
     if (o.kind != 0 || o.splitk <= 1) return 0;
@@ -490,6 +492,8 @@ static int run_plan_impl(const kb200_op* ops, int nops, const uint32_t* tables,
                 rc = launch_gemm_modes<2, 4, 64, 32, 4, false>(p, o.batch, o.a_mode, o.b_mode, st);
             else if (o.tile == 4)
                 rc = launch_gemm_modes<4, 2, 32, 32, 3, true, 2>(p, o.batch, o.a_mode, o.b_mode, st);
+            else if (o.tile == 5)
+                rc = launch_gemm_modes<2, 2, 32, 32, 3, true, 3>(p, o.batch, o.a_mode, o.b_mode, st);
             else
                 return fail(-1, "plan: unknown tile id");
             if (rc) return rc;

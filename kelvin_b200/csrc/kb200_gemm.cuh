@@ -62,10 +62,23 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
 
 // One operand tile (R rows x BK k-values) loader.  MODE 0: k-contiguous in
 // HBM -> smem [R][BK+4]; MODE 1: row-contiguous -> smem [BK][R+4].
-// The k-offsets of the NEXT tile are prefetched into registers one k-tile
-// ahead (prefetch_k) so the table lookups never sit in front of a cp.async,
-// and a tile's cp.asyncs are issued in NPART slices interleaved with the DMMA
-// groups of the tile being consumed (load_part).
+// * k-offsets of the tile after the one being loaded are fetched one k-tile
+//   ahead (prefetch_k / advance_k), so table lookups never sit in front of a
+//   cp.async;
+// * a tile's cp.asyncs are issued in NPART slices between the DMMA groups of the
+//   tile being consumed (load_part);
+// * interior tiles take a FAST path (no zero-fill predicate, row pointers kept
+//   in registers: one IMAD.WIDE + one LDGSTS per element) -- the DMMA warps are
+//   in-order, so every non-DMMA instruction they execute is tensor-pipe idle
+//   time unless the other warp of the sub-partition covers it.
+__device__ __forceinline__ void cp_async8_u32(uint32_t sdst, const double* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sdst), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async8_u32_z(uint32_t sdst, const double* gsrc, bool valid) {
+    int sz = valid ? 8 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(sdst), "l"(gsrc), "r"(sz));
+}
+
 template <int R, int NT, int MODE>
 struct TileLoader {
     static constexpr int LDK = BK + 4;
@@ -82,21 +95,23 @@ struct TileLoader {
     static constexpr int CNT = (MODE == 0) ? RPT : KPT;       // cp.asyncs per thread per tile
     static constexpr int PER = (CNT + NPART - 1) / NPART;     // per slice
     static constexpr int NKO = (MODE == 0) ? 1 : KPT;
+    static constexpr int NRP = (MODE == 0) ? RPT : 1;
 
-    const double* base;
     const uint32_t* ktab;
-    uint32_t roff[MODE == 0 ? RPT : 1];
-    uint32_t koff[NKO];      // k-offsets of the tile being loaded
-    uint32_t koff2[NKO];     // k-offsets of the tile after it (in flight)
+    const double* rptr[NRP];  // row base pointers (invalid rows point at the operand base)
+    uint32_t koff[NKO];       // k-offsets of the tile being loaded
+    uint32_t koff2[NKO];      // k-offsets of the tile after it (in flight)
+    uint32_t soff;            // this thread's byte offset inside a stage
     unsigned rvalid;
     unsigned kvalid, kvalid2;
+    bool rows_full;           // every row of this tile is inside the operand (CTA-uniform)
 
-    __device__ __forceinline__ void init(const double* base_, const uint32_t* rtab,
+    __device__ __forceinline__ void init(const double* base, const uint32_t* rtab,
                                          const uint32_t* ktab_, int row0, int nrows, int tid) {
-        base = base_;
         ktab = ktab_;
         rvalid = 0;
-        kvalid = 0;
+        kvalid = kvalid2 = 0;
+        rows_full = (row0 + R <= nrows);
         if (MODE == 0) {
             int r0 = tid / BK;
 #pragma unroll
@@ -104,15 +119,17 @@ struct TileLoader {
                 int r = r0 + i * RSTEP;
                 int row = row0 + r;
                 bool v = (r < R) && (row < nrows);
-                roff[i] = v ? rtab[row] : 0u;
+                rptr[i] = base + (v ? rtab[row] : 0u);
                 rvalid |= (v ? 1u : 0u) << i;
             }
+            soff = (uint32_t)((r0 * LDK + tid % BK) * 8);
         } else {
             int r = tid % R;
             int row = row0 + r;
             bool v = row < nrows;
-            roff[0] = v ? rtab[row] : 0u;
+            rptr[0] = base + (v ? rtab[row] : 0u);
             rvalid = v ? 1u : 0u;
+            soff = (uint32_t)(((tid / R) * LDR + r) * 8);
         }
     }
 
@@ -142,41 +159,45 @@ struct TileLoader {
         kvalid = kvalid2;
     }
 
-    // issue slice `part` (0..NPART-1) of the tile whose k-offsets were prefetched
-    __device__ __forceinline__ void load_part(double* stage, int tid, int part) const {
+    // issue slice `part` (0..NPART-1) of the tile whose k-offsets are current.
+    // sstage: shared-space byte address of the destination stage.
+    template <bool FAST>
+    __device__ __forceinline__ void load_part(uint32_t sstage, int part) const {
+        const uint32_t sb = sstage + soff;
         if (MODE == 0) {
-            int kk = tid % BK;
-            int r0 = tid / BK;
-            bool kv = kvalid & 1u;
 #pragma unroll
             for (int j = 0; j < PER; ++j) {
-                int i = part * PER + j;
-                if (i < RPT) {
-                    int r = r0 + i * RSTEP;
-                    if (r < R) {
-                        bool v = kv && ((rvalid >> i) & 1u);
-                        cp_async8(stage + r * LDK + kk, base + (size_t)roff[i] + koff[0], v);
+                const int i = part * PER + j;
+                if (i < RPT && (i * RSTEP < R)) {
+                    const uint32_t sd = sb + (uint32_t)(i * RSTEP * LDK * 8);
+                    if (FAST) {
+                        cp_async8_u32(sd, rptr[i] + koff[0]);
+                    } else {
+                        bool v = (kvalid & 1u) && ((rvalid >> i) & 1u);
+                        cp_async8_u32_z(sd, rptr[i] + koff[0], v);
                     }
                 }
             }
         } else {
-            int r = tid % R;
-            int kk0 = tid / R;
 #pragma unroll
             for (int j = 0; j < PER; ++j) {
-                int i = part * PER + j;
+                const int i = part * PER + j;
                 if (i < KPT) {
-                    int kk = kk0 + i * KSTEP;
-                    bool v = ((kvalid >> i) & 1u) && (rvalid & 1u);
-                    cp_async8(stage + kk * LDR + r, base + (size_t)roff[0] + koff[i], v);
+                    const uint32_t sd = sb + (uint32_t)(i * KSTEP * LDR * 8);
+                    if (FAST) {
+                        cp_async8_u32(sd, rptr[0] + koff[i]);
+                    } else {
+                        bool v = ((kvalid >> i) & 1u) && (rvalid & 1u);
+                        cp_async8_u32_z(sd, rptr[0] + koff[i], v);
+                    }
                 }
             }
         }
     }
 
-    __device__ __forceinline__ void load_all(double* stage, int tid) const {
+    __device__ __forceinline__ void load_all(uint32_t sstage) const {
 #pragma unroll
-        for (int part = 0; part < NPART; ++part) load_part(stage, tid, part);
+        for (int part = 0; part < NPART; ++part) load_part<false>(sstage, part);
     }
 
     // fragment element (row r, k index kk) of a stage
@@ -237,6 +258,9 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, MINB)
     LB lb;
     la.init(p.A + (long long)b * p.bsA, p.am, p.ak, m0, p.M, tid);
     lb.init(p.B + (long long)b * p.bsB, p.bn, p.bk, n0, p.N, tid);
+    const uint32_t As_u = (uint32_t)__cvta_generic_to_shared(As);
+    const uint32_t Bs_u = (uint32_t)__cvta_generic_to_shared(Bs);
+    const bool rows_full = la.rows_full && lb.rows_full;
 
     double acc[MI][NI][2];
 #pragma unroll
@@ -253,8 +277,8 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, MINB)
         la.prefetch_k(kbeg + (s + 1) * BK, kend, tid);
         lb.prefetch_k(kbeg + (s + 1) * BK, kend, tid);
         if (s < nk) {
-            la.load_all(As + s * LA::STAGE, tid);
-            lb.load_all(Bs + s * LB::STAGE, tid);
+            la.load_all(As_u + s * LA::STAGE * 8);
+            lb.load_all(Bs_u + s * LB::STAGE * 8);
         }
         cp_async_commit();
     }
@@ -271,15 +295,13 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, MINB)
             la.prefetch_k(kbeg + (nxt + 1) * BK, kend, tid);
             lb.prefetch_k(kbeg + (nxt + 1) * BK, kend, tid);
         }
-        double* an = As + (nxt % STAGES) * LA::STAGE;
-        double* bn = Bs + (nxt % STAGES) * LB::STAGE;
+        const uint32_t an = As_u + (nxt % STAGES) * LA::STAGE * 8;
+        const uint32_t bn = Bs_u + (nxt % STAGES) * LB::STAGE * 8;
         const double* as = As + (kt % STAGES) * LA::STAGE;
         const double* bs = Bs + (kt % STAGES) * LB::STAGE;
-        if (!ILV && do_load) {
-            la.load_all(an, tid);
-            lb.load_all(bn, tid);
-        }
-        if (full) {
+        // interior tile and interior k-tile: no predicates anywhere in the loop body
+        const bool fast = rows_full && (kbeg + (nxt + 1) * BK <= kend);
+        if (full && fast && do_load) {
 #pragma unroll
             for (int k4 = 0; k4 < BK / 4; ++k4) {
                 double af[MI], bf[NI];
@@ -289,9 +311,15 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, MINB)
 #pragma unroll
                 for (int j = 0; j < NI; ++j)
                     bf[j] = LB::frag(bs, (j * WARPS_N + wni) * 8 + g, k4 * 4 + t);
-                if (ILV && do_load) {
-                    la.load_part(an, tid, k4);
-                    lb.load_part(bn, tid, k4);
+                if (ILV) {
+                    la.template load_part<true>(an, k4);
+                    lb.template load_part<true>(bn, k4);
+                } else if (k4 == 0) {
+#pragma unroll
+                    for (int q = 0; q < BK / 4; ++q) {
+                        la.template load_part<true>(an, q);
+                        lb.template load_part<true>(bn, q);
+                    }
                 }
 #pragma unroll
                 for (int i = 0; i < MI; ++i)
@@ -299,21 +327,39 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, MINB)
                     for (int j = 0; j < NI; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
             }
         } else {
-            if (ILV && do_load) {
-                la.load_all(an, tid);
-                lb.load_all(bn, tid);
+            if (do_load) {
+                la.load_all(an);
+                lb.load_all(bn);
             }
+            if (full) {
 #pragma unroll
-            for (int k4 = 0; k4 < BK / 4; ++k4) {
+                for (int k4 = 0; k4 < BK / 4; ++k4) {
+                    double af[MI], bf[NI];
 #pragma unroll
-                for (int i = 0; i < MI; ++i) {
-                    if (i < mcnt) {
-                        double a = LA::frag(as, (i * WARPS_M + wmi) * 8 + g, k4 * 4 + t);
+                    for (int i = 0; i < MI; ++i)
+                        af[i] = LA::frag(as, (i * WARPS_M + wmi) * 8 + g, k4 * 4 + t);
 #pragma unroll
-                        for (int j = 0; j < NI; ++j) {
-                            if (j < ncnt) {
-                                double bb = LB::frag(bs, (j * WARPS_N + wni) * 8 + g, k4 * 4 + t);
-                                dmma884(acc[i][j][0], acc[i][j][1], a, bb);
+                    for (int j = 0; j < NI; ++j)
+                        bf[j] = LB::frag(bs, (j * WARPS_N + wni) * 8 + g, k4 * 4 + t);
+#pragma unroll
+                    for (int i = 0; i < MI; ++i)
+#pragma unroll
+                        for (int j = 0; j < NI; ++j)
+                            dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+                }
+            } else {
+#pragma unroll
+                for (int k4 = 0; k4 < BK / 4; ++k4) {
+#pragma unroll
+                    for (int i = 0; i < MI; ++i) {
+                        if (i < mcnt) {
+                            double a = LA::frag(as, (i * WARPS_M + wmi) * 8 + g, k4 * 4 + t);
+#pragma unroll
+                            for (int j = 0; j < NI; ++j) {
+                                if (j < ncnt) {
+                                    double bb = LB::frag(bs, (j * WARPS_N + wni) * 8 + g, k4 * 4 + t);
+                                    dmma884(acc[i][j][0], acc[i][j][1], a, bb);
+                                }
                             }
                         }
                     }

@@ -313,8 +313,9 @@ class TableBank(object):
 N_SM = 148
 # CTA tile used for large contractions (see kb200.cu: tile ids); overridable for experiments
 import os as _os
-BIG_TILE = int(_os.environ.get("KB200_BIG_TILE", "0"))
-_TILE_BN = {0: 128, 1: 32, 2: 128, 3: 128, 4: 64}
+BIG_TILE = int(_os.environ.get("KB200_BIG_TILE", "2"))
+_TILE_BN = {0: 128, 1: 32, 2: 128, 3: 128, 4: 64, 5: 64}
+_TILE_BM = {0: 128, 1: 128, 2: 128, 3: 128, 4: 128, 5: 64}
 
 
 class Lowered(object):
@@ -440,7 +441,12 @@ class Lowered(object):
         d.tBk, d.tBn = tab(K, sb), tab(N, sb)
         d.tCm, d.tCn = tab(M, sc), tab(N, sc)
         d.a_mode, d.b_mode = a_mode, b_mode
-        d.tile = 1 if d.N <= 48 else BIG_TILE
+        if d.N <= 32:
+            d.tile = 1 if d.M > 64 else 5
+        elif d.N <= 64:
+            d.tile = 5
+        else:
+            d.tile = BIG_TILE
         self.flops += 2.0 * d.M * d.N * d.K
         return d
 
@@ -454,10 +460,11 @@ class Lowered(object):
             if o.batch > 1 and o.bsC == 0:
                 raise ValueError("batched operands reduce into an unbatched output")
             if o.kind == 0:
-                bn = _TILE_BN[o.tile]
-                ctas = ((o.M + 127) // 128) * ((o.N + bn - 1) // bn) * o.batch
-                if ctas < N_SM and o.K >= 512:
-                    o.splitk = int(min(max(1, (2 * N_SM) // ctas), max(1, o.K // 128)))
+                bm, bn = _TILE_BM[o.tile], _TILE_BN[o.tile]
+                ctas = ((o.M + bm - 1) // bm) * ((o.N + bn - 1) // bn) * o.batch
+                target = 4 * N_SM if o.tile == 5 else 2 * N_SM
+                if ctas < target // 2 and o.K >= 512:
+                    o.splitk = int(min(max(1, -(-target // ctas)), max(1, o.K // 128)))
         return arr
 
 
