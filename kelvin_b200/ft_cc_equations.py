@@ -158,6 +158,64 @@ def lambda_plan(mode, sizes, fac=-1.0):
     return engine.cached(key, build)
 
 
+def lambda_split_plans(mode, sizes, fac=-1.0):
+    """(prep, sweep): the amplitude-only forward intermediates (W_oooo, W_vvvv, W_ovvo,
+    F_oo/vv/ov, tau ...) depend on T alone, which is fixed during the whole Lambda
+    solve, so they are built once (prep) and every Lambda iteration runs only the
+    reverse sweep (sweep) with the intermediates as inputs -- the 'cached W' cost
+    model of SURVEY.md 8(d) (92 m^6 instead of 128 m^6 per grid point)."""
+    key = ("lambda-split", mode, tuple(sorted(sizes.items(), key=str)), fac)
+
+    def build():
+        inter, rest = programs.lambda_rops(mode, fac)
+        tins = ("t1", "t2") if mode == "g" else _U_T
+        lins = ("l1", "l2") if mode == "g" else _U_L
+        louts = ("lo1", "lo2") if mode == "g" else _U_LO
+        inter_slots = []
+        for op in inter:
+            if op.out[0] not in inter_slots:
+                inter_slots.append(op.out[0])
+        prep = engine.Plan(inter, mode, sizes, tins, inter_slots, name="lambda-prep-" + mode)
+        used = set()
+        for op in rest:
+            for slot, _ in op.ins:
+                used.add(slot)
+        keep = [s for s in inter_slots if s in used]
+        sweep = engine.Plan(rest, mode, sizes, tuple(tins) + tuple(lins) + tuple(keep), louts,
+                            name="lambda-sweep-" + mode)
+        sweep.cached_slots = keep
+        prep.all_slots = inter_slots
+        return prep, sweep
+    return engine.cached(key, build)
+
+
+_lam_cache = {"key": None, "val": None}
+
+
+def _lambda_intermediates(mode, sizes, ints_slots, tslots, ng, dev):
+    """Forward intermediates for the current amplitudes, cached across Lambda iterations."""
+    prep, sweep = lambda_split_plans(mode, sizes)
+    key = (mode, ng, tuple((v.data_ptr(), v._version) for v in tslots.values()),
+           tuple((v.data_ptr(), v._version) for v in ints_slots.values()))
+    if _lam_cache["key"] == key:
+        return _lam_cache["val"]
+    _lam_cache["key"] = None
+    _lam_cache["val"] = None
+    need = sum(8*ng*int(torch.tensor(prep.shapes[s]).prod()) for s in prep.all_slots)
+    free, _ = torch.cuda.mem_get_info(dev)
+    if need > 0.5*free:
+        return None                      # too large to keep: use the fused (recompute) plan
+    t = dict(ints_slots)
+    t.update(tslots)
+    for s in prep.all_slots:
+        t[s] = torch.empty((ng,) + tuple(prep.shapes[s]), dtype=torch.float64, device=dev)
+    prep.run({k: v for k, v in t.items() if k in prep.shapes}, ng)
+    val = {s: t[s] for s in sweep.cached_slots}
+    _lam_cache["key"] = key
+    _lam_cache["val"] = val
+    return val
+
+
 def lambda_guess_plan(mode, sizes, beta, ls_ts_fac):
     key = ("lguess", mode, tuple(sorted(sizes.items(), key=str)), beta, ls_ts_fac)
 
@@ -186,11 +244,18 @@ def ccsd_lambda_opt(F, I, T1old, T2old, L1old, L2old, D1, D2, ti, ng, g, G, beta
     T1old, T2old = _lib.as_dev(T1old, dev), _lib.as_dev(T2old, dev)
     L1int = quadrature.int_L1(ng, L1old, ti, D1, g, G)
     L2int = quadrature.int_L2(ng, L2old, ti, D2, g, G)
-    p = lambda_plan("g", _g_sizes(F))
+    sizes = _g_sizes(F)
     t = _g_integral_slots(F, I, dev)
+    cached = _lambda_intermediates("g", sizes, t, {"t1": T1old, "t2": T2old}, ng, dev)
     t.update({"t1": T1old, "t2": T2old, "l1": L1int, "l2": L2int})
     t["lo1"], t["lo2"] = _l_like(T1old, T2old)
-    p.run(t, ng, _chunk_for(p, ng, dev))
+    if cached is not None:
+        p = lambda_split_plans("g", sizes)[1]
+        t.update(cached)
+        p.run({k: v for k, v in t.items() if k in p.shapes}, ng, _chunk_for(p, ng, dev))
+    else:
+        p = lambda_plan("g", sizes)
+        p.run(t, ng, _chunk_for(p, ng, dev))
     return t["lo1"], t["lo2"]
 
 
@@ -203,9 +268,11 @@ def uccsd_lambda_opt(Fa, Fb, Ia, Ib, Iabab, T1aold, T1bold, T2aaold, T2abold,
     assert(Ts[0].shape[0] == ng)
     Ls = [quadrature.int_L(ng, L, ti, D, g, G) for L, D in
           zip((L1aold, L1bold, L2aaold, L2abold, L2bbold), (D1a, D1b, D2aa, D2ab, D2bb))]
-    p = lambda_plan("u", _u_sizes(Fa, Fb))
+    sizes = _u_sizes(Fa, Fb)
+    pf = lambda_plan("u", sizes)
     t = _u_integral_slots(Fa, Fb, Ia, Ib, Iabab, dev,
-                          [s for s in p.inputs if _plan.is_integral_slot(s)])
+                          [s for s in pf.inputs if _plan.is_integral_slot(s)])
+    cached = _lambda_intermediates("u", sizes, t, dict(zip(_U_T, Ts)), ng, dev)
     for nm, x in zip(_U_T, Ts):
         t[nm] = x
     for nm, x in zip(_U_L, Ls):
@@ -214,7 +281,12 @@ def uccsd_lambda_opt(Fa, Fb, Ia, Ib, Iabab, T1aold, T1bold, T2aaold, T2abold,
     for nm, x in zip(_U_LO, Ls):
         t[nm] = torch.empty_like(x)
         outs.append(t[nm])
-    p.run(t, ng, _chunk_for(p, ng, dev))
+    if cached is not None:
+        p = lambda_split_plans("u", sizes)[1]
+        t.update(cached)
+        p.run({k: v for k, v in t.items() if k in p.shapes}, ng, _chunk_for(p, ng, dev))
+    else:
+        pf.run(t, ng, _chunk_for(pf, ng, dev))
     return tuple(outs)
 
 

@@ -210,7 +210,25 @@ def lambda_rops(mode, fac=-1.0):
             tail.append(ROp((lslot, "ijab"), -fac, [(tslot + "~", "baij")], spn))
             tail.append(ROp((lslot, "ijab"), -fac, [(tslot + "~", "abji")], spn))
             tail.append(ROp((lslot, "ijab"), fac, [(tslot + "~", "baji")], spn))
-    return inter, eterm + bwd + tail
+    return prune_unused(inter, eterm + bwd + tail), eterm + bwd + tail
+
+
+def prune_unused(inter, rest):
+    """Dead-code elimination: keep only the forward ops whose results the reverse
+    sweep (or another kept forward op) actually reads -- e.g. the ring result
+    itself is never needed, only its adjoint."""
+    needed = set()
+    for op in rest:
+        for slot, _ in op.ins:
+            needed.add(slot)
+    kept = []
+    for op in reversed(inter):
+        if op.out[0] in needed:
+            kept.append(op)
+            for slot, _ in op.ins:
+                needed.add(slot)
+    kept.reverse()
+    return kept
 
 
 def lambda_guess_rops(mode, beta, ls_ts_fac):
