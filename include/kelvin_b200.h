@@ -42,7 +42,8 @@ void kb200_launch_count_reset(void);
  *   C[b][cm[m]+cn[n]] = beta*C + alpha * A[b][am[m]+ak[n]].
  * ------------------------------------------------------------------------ */
 typedef struct kb200_op {
-    int32_t kind;          /* 0 contraction (DMMA GEMM), 1 permuted axpby      */
+    int32_t kind;          /* 0 contraction (DMMA GEMM), 1 permuted axpby,
+                              2 contraction with K,N <= 64 (streaming rank-K update) */
     int32_t a, b, c;       /* tensor slot numbers (b unused for kind 1)        */
     int64_t a_off, b_off, c_off;   /* constant element offsets inside the slot */
     int32_t M, N, K, batch;

@@ -101,6 +101,29 @@ def as_dev(x, dev=None):
     return torch.as_tensor(x, dtype=torch.float64).to(dev).contiguous()
 
 
+_const_cache = {}
+
+
+def const_dev(x, dev=None):
+    """Device copy of a small host array (grids, weights), cached by value so that the
+    iteration loops issue no synchronous host->device copies."""
+    import numpy
+    dev = dev or device()
+    if isinstance(x, torch.Tensor):
+        return x.to(device=dev, dtype=torch.float64).contiguous()
+    a = numpy.ascontiguousarray(numpy.asarray(x, dtype=numpy.float64))
+    if a.nbytes > (1 << 20):
+        return torch.as_tensor(a).to(dev)
+    key = (dev.index, a.shape, a.tobytes())
+    t = _const_cache.get(key)
+    if t is None:
+        if len(_const_cache) > 256:
+            _const_cache.clear()
+        t = torch.as_tensor(a).to(dev)
+        _const_cache[key] = t
+    return t
+
+
 _scratch = {}
 
 

@@ -371,7 +371,7 @@ int launch_gemm_inst(const kb200::GemmParams& p, int batch, cudaStream_t st) {
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(gemm)");
         configured = true;
     }
-    dim3 grid(p.tilesM * p.tilesN, p.splitk, batch);
+    dim3 grid(p.tilesM * p.tilesN * batch, p.splitk, 1);
     kern<<<grid, NT, smem, st>>>(p);
     KB_CHECK_LAUNCH("gemm_tab_kernel");
     return 0;
@@ -396,7 +396,7 @@ int tile_bm(int tile) { return tile == 5 ? 64 : 128; }
 int tile_bn(int tile) { return tile == 1 ? 32 : ((tile == 4 || tile == 5) ? 64 : 128); }
 
 int64_t op_workspace(const kb200_op& o) {
-    if (o.kind != 0 || o.splitk <= 1) return 0;
+    if (o.kind != 0 || o.splitk <= 1) return 0;   // kinds 1, 2 need no workspace
     return (int64_t)o.batch * o.splitk * (int64_t)o.M * o.N * 8;
 }
 
@@ -477,6 +477,7 @@ static int run_plan_impl(const kb200_op* ops, int nops, const uint32_t* tables,
             int BMt = tile_bm(o.tile), BNt = tile_bn(o.tile);
             p.tilesM = (o.M + BMt - 1) / BMt;
             p.tilesN = (o.N + BNt - 1) / BNt;
+            p.batch = o.batch;
             if (p.splitk > 1) {
                 int64_t need = (int64_t)o.batch * p.splitk * (int64_t)o.M * o.N * 8;
                 if (workspace == nullptr || need > workspace_bytes) return fail(-1, "plan: workspace too small");
@@ -502,6 +503,32 @@ static int run_plan_impl(const kb200_op* ops, int nops, const uint32_t* tables,
                 kb200::splitk_reduce_kernel<<<grid_for(total, 256), 256, 0, st>>>(p, o.batch);
                 KB_CHECK_LAUNCH("splitk_reduce_kernel");
             }
+        } else if (o.kind == 2) {
+            if (o.b < 0 || o.b >= nslots || o.K <= 0 || o.K > 64 || o.N > 64)
+                return fail(-1, "plan: bad rank-k op");
+            kb200::GemmParams p;
+            p.A = slots[o.a] + o.a_off;
+            p.B = slots[o.b] + o.b_off;
+            p.C = slots[o.c] + o.c_off;
+            p.am = tables + o.tAm; p.ak = tables + o.tAk;
+            p.bk = tables + o.tBk; p.bn = tables + o.tBn;
+            p.cm = tables + o.tCm; p.cn = tables + o.tCn;
+            p.M = o.M; p.N = o.N; p.K = o.K;
+            p.splitk = 1; p.kchunk = 0;
+            p.bsA = o.bsA; p.bsB = o.bsB; p.bsC = o.bsC;
+            p.alpha = o.alpha; p.beta = o.beta;
+            p.partial = nullptr; p.tilesM = p.tilesN = 0; p.batch = o.batch;
+            // each CTA stages B once and streams several 256-row blocks: aim at ~4 CTAs per SM
+            int nblk = (o.M + 255) / 256;
+            int per = (int)(((long long)nblk * o.batch + 148 * 4 - 1) / (148 * 4));
+            if (per < 1) per = 1;
+            if (per > 16) per = 16;
+            dim3 grid((nblk + per - 1) / per, 1, o.batch);
+            if (o.K <= 40)
+                kb200::rankk_kernel<40><<<grid, 256, 0, st>>>(p, per);
+            else
+                kb200::rankk_kernel<64><<<grid, 256, 0, st>>>(p, per);
+            KB_CHECK_LAUNCH("rankk_kernel");
         } else if (o.kind == 1) {
             kb200::PermParams p;
             p.A = slots[o.a] + o.a_off;

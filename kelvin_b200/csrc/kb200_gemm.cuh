@@ -40,6 +40,7 @@ struct GemmParams {
     double alpha, beta;
     double* partial;             // [batch][splitk][M][N] when splitk > 1
     int tilesM, tilesN;
+    int batch;
 };
 
 __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc, bool valid) {
@@ -233,10 +234,34 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, MINB)
     const int g = lane >> 2;
     const int t = lane & 3;
 
-    const int tm = blockIdx.x % p.tilesM;
-    const int tn = blockIdx.x / p.tilesM;
+    // CTA order: batch-major over the full tiles (CTAs that run together share one
+    // batch's operands in L2), then the ragged -- cheaper -- edge tiles of all batches,
+    // so the final partial wave is filled with the short CTAs.
+    int b, tm, tn;
+    {
+        const int rm = (p.M % BM) ? 1 : 0, rn = (p.N % BN) ? 1 : 0;
+        const int fm = p.tilesM - rm, fn = p.tilesN - rn;
+        const int nf = fm * fn, nr = p.tilesM * p.tilesN - nf;
+        const int f_ = blockIdx.x;
+        if (f_ < nf * p.batch) {
+            b = f_ / nf;
+            const int t_ = f_ - b * nf;
+            tm = t_ % fm;
+            tn = t_ / fm;
+        } else {
+            const int g_ = f_ - nf * p.batch;
+            b = g_ / nr;
+            const int r_ = g_ - b * nr;
+            if (rm && r_ < p.tilesN) {
+                tm = p.tilesM - 1;
+                tn = r_;
+            } else {
+                tn = p.tilesN - 1;
+                tm = r_ - (rm ? p.tilesN : 0);
+            }
+        }
+    }
     const int ks = blockIdx.y;
-    const int b = blockIdx.z;
     const int m0 = tm * BM;
     const int n0 = tn * BN;
     const int kbeg = ks * p.kchunk;
@@ -449,6 +474,71 @@ __global__ void splitk_reduce_kernel(const GemmParams p, int batch) {
         double v = p.alpha * s;
         if (p.beta != 0.0) v += p.beta * (*dst);
         *dst = v;
+    }
+}
+
+// kind 2: rank-K update with small K and N (<= 64): the n^5 "dressing" terms
+//   C[m, n] (+)= alpha * sum_k A[m, k] * B[k, n],   M ~ n^3 rows, K, N ~ n.
+// These move 24 bytes per C element for ~2K flops: HBM-bound.  One thread owns one
+// row: its A row lives in registers, B (K x N, a few KB) is broadcast from shared
+// memory, C is read-modify-written once, coalesced across the warp when the row
+// index is the contiguous one (it is for every term of the residual).
+template <int KMAX>
+__global__ void __launch_bounds__(256, 2) rankk_kernel(const GemmParams p, int blocks_per_cta) {
+    __shared__ __align__(16) double Bs[KMAX][64];
+    __shared__ uint32_t aks[KMAX];
+    __shared__ uint32_t cns[64];
+    const int tid = threadIdx.x;
+    const int b = blockIdx.z;
+    const int npad = (p.N + 3) & ~3;
+    const double* A = p.A + (long long)b * p.bsA;
+    const double* B = p.B + (long long)b * p.bsB;
+    double* C = p.C + (long long)b * p.bsC;
+    // stage B (K x N) and the k / n offset tables once per CTA
+    for (int idx = tid; idx < KMAX * 64; idx += 256) {
+        int k = idx >> 6, n = idx & 63;
+        Bs[k][n] = (k < p.K && n < p.N) ? B[(size_t)p.bk[k] + p.bn[n]] : 0.0;
+    }
+    if (tid < KMAX) aks[tid] = (tid < p.K) ? p.ak[tid] : 0u;
+    if (tid < 64) cns[tid] = (tid < p.N) ? p.cn[tid] : 0u;
+    __syncthreads();
+    const bool rmw = p.beta != 0.0;
+    for (int it = 0; it < blocks_per_cta; ++it) {
+        const int m = (blockIdx.x * blocks_per_cta + it) * 256 + tid;
+        if (m >= p.M) break;
+        const double* Ar = A + p.am[m];
+        double* Cr = C + p.cm[m];
+        double a[KMAX];
+#pragma unroll
+        for (int k = 0; k < KMAX; ++k) a[k] = (k < p.K) ? Ar[aks[k]] : 0.0;
+        for (int n0 = 0; n0 < npad; n0 += 8) {
+            double old[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                old[j] = (rmw && n0 + j < p.N) ? Cr[cns[n0 + j]] : 0.0;
+            double acc[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] = 0.0;
+#pragma unroll
+            for (int k = 0; k < KMAX; ++k) {
+                const double2 b01 = *reinterpret_cast<const double2*>(&Bs[k][n0]);
+                const double2 b23 = *reinterpret_cast<const double2*>(&Bs[k][n0 + 2]);
+                const double2 b45 = *reinterpret_cast<const double2*>(&Bs[k][n0 + 4]);
+                const double2 b67 = *reinterpret_cast<const double2*>(&Bs[k][n0 + 6]);
+                acc[0] = fma(a[k], b01.x, acc[0]);
+                acc[1] = fma(a[k], b01.y, acc[1]);
+                acc[2] = fma(a[k], b23.x, acc[2]);
+                acc[3] = fma(a[k], b23.y, acc[3]);
+                acc[4] = fma(a[k], b45.x, acc[4]);
+                acc[5] = fma(a[k], b45.y, acc[5]);
+                acc[6] = fma(a[k], b67.x, acc[6]);
+                acc[7] = fma(a[k], b67.y, acc[7]);
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (n0 + j < p.N)
+                    Cr[cns[n0 + j]] = p.alpha * acc[j] + (rmw ? p.beta * old[j] : 0.0);
+        }
     }
 }
 

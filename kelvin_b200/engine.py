@@ -115,7 +115,7 @@ class Plan(object):
                                               _lib.stream_ptr(), ms)
                 for k in range(len(ops)):
                     o = ops[k]
-                    timings.append((int(o.kind), 2.0*o.M*o.N*o.K*o.batch if o.kind == 0 else 0.0,
+                    timings.append((int(o.kind), 2.0*o.M*o.N*o.K*o.batch if o.kind in (0, 2) else 0.0,
                                     float(ms[k])*1e-3, (int(o.M), int(o.N), int(o.K), int(o.batch),
                                                         int(o.tile), int(o.splitk),
                                                         int(o.a_mode), int(o.b_mode))))

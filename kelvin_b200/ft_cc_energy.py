@@ -41,8 +41,7 @@ def oovv_to_abij(eri):
 
 
 def _gvec(g, dev):
-    return torch.as_tensor(numpy.asarray(g, dtype=numpy.float64)).to(dev) \
-        if not isinstance(g, torch.Tensor) else g.to(device=dev, dtype=torch.float64)
+    return _lib.const_dev(g, dev)
 
 
 def energy_terms(terms1, terms2, g, dev):

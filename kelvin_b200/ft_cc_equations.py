@@ -22,11 +22,19 @@ from . import _lib, engine, plan as _plan, programs, quadrature
 _F_NAMES = ("oo", "ov", "vo", "vv")
 
 
+_chunk_cache = {}
+
+
 def _chunk_for(p, ng, dev):
-    """Largest tau chunk whose scratch fits in ~60% of the free HBM."""
-    per = max(1, p.tmp_bytes_per_point())
-    free, _ = torch.cuda.mem_get_info(dev)
-    return int(max(1, min(ng, (0.6*free)//per)))
+    """Largest tau chunk whose scratch fits in ~60% of the free HBM (decided once per
+    plan and grid size; scratch is kept by the plan afterwards)."""
+    key = (id(p), ng, dev.index)
+    if key not in _chunk_cache:
+        per = max(1, p.tmp_bytes_per_point())
+        free, _ = torch.cuda.mem_get_info(dev)
+        have = 0 if p._tmp is None else p._tmp_nb*per
+        _chunk_cache[key] = int(max(1, min(ng, (0.6*(free + have))//per)))
+    return _chunk_cache[key]
 
 
 # ---------------------------------------------------------------------------
@@ -361,8 +369,7 @@ def rdm_assembly_plan(mode, sizes):
 def _gsum(X, g, dev):
     """sum_y g[y] X[y]  (kelvin/ft_cc_equations.py:713,737)."""
     lib = _lib.load()
-    gd = torch.as_tensor(g, dtype=torch.float64).to(dev) if not isinstance(g, torch.Tensor) \
-        else g.to(device=dev, dtype=torch.float64)
+    gd = _lib.const_dev(g, dev)
     out = torch.empty(tuple(X.shape[1:]), dtype=torch.float64, device=dev)
     rc = lib.kb200_gsum(X.shape[0], out.numel(), _lib.ptr(X), _lib.ptr(gd), _lib.ptr(out),
                         _lib.stream_ptr())

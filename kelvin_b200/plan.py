@@ -314,6 +314,7 @@ N_SM = 148
 # CTA tile used for large contractions (see kb200.cu: tile ids); overridable for experiments
 import os as _os
 BIG_TILE = int(_os.environ.get("KB200_BIG_TILE", "2"))
+RANKK = int(_os.environ.get("KB200_RANKK", "1"))
 _TILE_BN = {0: 128, 1: 32, 2: 128, 3: 128, 4: 64, 5: 64}
 _TILE_BM = {0: 128, 1: 128, 2: 128, 3: 128, 4: 128, 5: 64}
 
@@ -425,13 +426,23 @@ class Lowered(object):
         sa, sb = self._stride_map(na, la), self._stride_map(nb, lb)
         a_mode = 0 if la[-1] in K else 1
         b_mode = 0 if lb[-1] in K else 1
-        if a_mode == 0:
-            K = self._order(K, sa, sb)
-        elif b_mode == 0:
-            K = self._order(K, sb, sa)
+        # order of the contracted composite index: follow the operand that wants to be
+        # read contiguously along k; if both do, favour the tau-batched one (it streams
+        # from HBM once, whereas a tau-independent integral block stays L2-resident and
+        # tolerates a strided gather)
+        if a_mode == 0 and b_mode == 0:
+            a_first = not (bs(nb) != 0 and bs(na) == 0)
         else:
-            K = self._order(K, sa, sb)
-        M = self._order(M, sa, sc) if a_mode == 1 else self._order(M, sc, sa)
+            a_first = (a_mode == 0) or (b_mode != 0)
+        K = self._order(K, sa, sb) if a_first else self._order(K, sb, sa)
+        # HBM-bound rank-K update (small K and N, ~n^3 rows): the streaming SIMT kernel owns
+        # one C row per thread, so C (2/3 of the traffic) must be contiguous along the rows
+        rankk = (RANKK and size(K) <= 64 and size(N) <= 64 and size(M) >= 4096
+                 and lc[-1] in M)
+        if rankk:
+            M = self._order(M, sc, sa)
+        else:
+            M = self._order(M, sa, sc) if a_mode == 1 else self._order(M, sc, sa)
         N = self._order(N, sb, sc) if b_mode == 1 else self._order(N, sc, sb)
         d.kind = 0
         d.a, d.b = self.slot_index[na], self.slot_index[nb]
@@ -441,7 +452,10 @@ class Lowered(object):
         d.tBk, d.tBn = tab(K, sb), tab(N, sb)
         d.tCm, d.tCn = tab(M, sc), tab(N, sc)
         d.a_mode, d.b_mode = a_mode, b_mode
-        if d.N <= 32:
+        if rankk:
+            d.kind = 2
+            d.tile = 0
+        elif d.N <= 32:
             d.tile = 1 if d.M > 64 else 5
         elif d.N <= 64:
             d.tile = 5

@@ -157,8 +157,7 @@ def d_ft_quad(ng, beta, quad):
 # device integration
 # ---------------------------------------------------------------------------
 def _small(x, dev):
-    return torch.as_tensor(numpy.asarray(x, dtype=numpy.float64)).to(dev) \
-        if not isinstance(x, torch.Tensor) else x.to(device=dev, dtype=torch.float64).contiguous()
+    return _lib.const_dev(x, dev)
 
 
 def int_tbar(ng, tbar, ti, D, G, out=None, mode=None, rows=None):

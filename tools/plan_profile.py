@@ -45,6 +45,8 @@ def main():
     for dt, kind, fl, meta, txt in rows:
         if kind == 1:
             key = "permute"
+        elif kind == 2:
+            key = "rank-k update (kind 2)"
         elif fl >= 0.5*2*ng*m**6:
             key = "gemm m^6"
         elif meta[5] > 1:
