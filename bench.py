@@ -32,6 +32,18 @@ WORKLOADS = {
 T_, MU_, L_ = 0.5, 7.0, 1.942
 
 
+def _traffic(workload, world):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture
+    (profiles/r1_traffic.json), or None when no capture matches this configuration."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))["gemm_tab_kernel"]
+        if t["workload"] == workload and t["n_gpus"] == world:
+            return t["bytes_per_launch"]
+    except Exception:
+        pass
+    return None
+
+
 def algorithmic_flops(m, ng):
     """F_T of SURVEY.md 8(d): ng*(64 m^6 + 120 m^5), unrestricted formulation."""
     return ng*(64.0*m**6 + 120.0*m**5)
@@ -284,7 +296,7 @@ def main():
                 "avg_launch_s": dt_big/max(1, len(big)),
                 "gemm_share_of_plan": sum(d for _, d in gemm)/max(1e-12, sum(x[2] for x in tim)),
                 "plan_s": sum(x[2] for x in tim),
-                "traffic": None}
+                "traffic": _traffic(args.workload, world)}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -12,7 +12,7 @@ import torch
 from .plan import kb200_op
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libkb200.so")
+LIB_PATH = os.environ.get("KB200_LIB", os.path.join(_HERE, "libkb200.so"))
 
 _lib = None
 

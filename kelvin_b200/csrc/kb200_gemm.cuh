@@ -311,9 +311,15 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, MINB)
     const bool full = (mval == (1u << MI) - 1u) && (nval == (1u << NI) - 1u);
     for (int kt = 0; kt < nk; ++kt) {
         cp_async_wait<STAGES - 2>();
+#ifndef KB200_EXP_NOSYNC
         __syncthreads();
+#endif
         const int nxt = kt + STAGES - 1;
+#ifdef KB200_EXP_NOLOAD
+        const bool do_load = false;
+#else
         const bool do_load = nxt < nk;
+#endif
         la.advance_k();
         lb.advance_k();
         if (nxt + 1 < nk) {
