@@ -28,7 +28,10 @@ class Plan(object):
         self.outputs = [s for s in outputs if s in self.shapes]
         preset = list(self.inputs) + list(preset_outputs)
         self.low = _plan.Lowered(rops, self.shapes, self.batched, preset)
-        self.tmp_slots = [s for s in self.shapes if s not in self.inputs and s not in self.outputs]
+        self.derived = self.low.derived
+        self.tmp_slots = [s for s in self.shapes if s not in self.inputs and s not in self.outputs
+                          and s not in self.derived]
+        self._derived_bufs = {}
         self._dev_tables = None
         self._tmp = None
         self._tmp_nb = 0
@@ -90,6 +93,12 @@ class Plan(object):
                     or not t.is_contiguous():
                 raise Exception("plan %s: slot %s expects contiguous cuda float64 %s, got %s %s"
                                 % (self.name, s, want, tuple(t.shape), t.dtype))
+        for name, (src, perm) in self.derived.items():
+            st = tensors[src]
+            key = (st.data_ptr(), st._version)
+            have = self._derived_bufs.get(name)
+            if have is None or have[0] != key:
+                self._derived_bufs[name] = (key, permute_copy(st, perm))
         y0 = 0
         while y0 < ng:
             nb = min(nb_max, ng - y0)
@@ -100,6 +109,8 @@ class Plan(object):
             for k, s in enumerate(names):
                 if s in self._tmp:
                     ptrs[k] = self._tmp[s].data_ptr()
+                elif s in self.derived:
+                    ptrs[k] = self._derived_bufs[s][1].data_ptr()
                 else:
                     t = tensors[s]
                     off = y0*t.stride(0)*8 if self.batched[s] else 0
@@ -124,6 +135,25 @@ class Plan(object):
 
     def n_ops(self):
         return len(self.low.descs)
+
+
+_perm_plans = {}
+
+
+def permute_copy(src, perm):
+    """dst = src.permute(perm), materialised with the kb200 permuted-axpby kernel."""
+    letters = "abcdefgh"[:src.dim()]
+    key = (tuple(src.shape), tuple(perm))
+    if key not in _perm_plans:
+        dst_letters = "".join(letters[p] for p in perm)
+        op = _plan.ROp(("dst", dst_letters), 1.0, [("src", letters)])
+        shapes = {"src": tuple(src.shape), "dst": tuple(src.shape[p] for p in perm)}
+        _perm_plans[key] = Plan([op], "g", None, ["src"], ["dst"], name="permute",
+                                shapes=shapes, batched={"src": False, "dst": False})
+    p = _perm_plans[key]
+    dst = torch.empty(p.shapes["dst"], dtype=torch.float64, device=src.device)
+    p.run({"src": src.contiguous(), "dst": dst}, 1)
+    return dst
 
 
 _cache = {}

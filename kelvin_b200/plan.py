@@ -315,6 +315,11 @@ N_SM = 148
 import os as _os
 BIG_TILE = int(_os.environ.get("KB200_BIG_TILE", "2"))
 RANKK = int(_os.environ.get("KB200_RANKK", "1"))
+# re-laid-out integral copies for long-K contractions: measured neutral at m = 33 (the
+# split-K class is latency-, not gather-bound), so off by default
+DERIVE = int(_os.environ.get("KB200_DERIVE", "0"))
+LONGK_MIN = 4096      # contracted length from which the long-K path (derived layouts) is used
+RANKK_MIN_M = 4096    # rows from which the rank-K streaming kernel is used
 _TILE_BN = {0: 128, 1: 32, 2: 128, 3: 128, 4: 64, 5: 64}
 _TILE_BM = {0: 128, 1: 128, 2: 128, 3: 128, 4: 128, 5: 64}
 
@@ -333,6 +338,7 @@ class Lowered(object):
         self.slot_shapes = slot_shapes
         self.batched = batched
         self.bank = TableBank()
+        self.derived = OrderedDict()   # derived slot -> (source slot, axis permutation)
         self.descs = []
         self.flops = 0.0          # per tau point, executed (2*M*N*K)
         written = set(preset)
@@ -358,6 +364,23 @@ class Lowered(object):
 
     def _stride_map(self, slot, ls):
         return dict(zip(ls, _strides(self.slot_shapes[slot])))
+
+    def _derive(self, slot, letters, new_letters):
+        """Register a re-laid-out copy of a tau-independent integral block:
+        new[new_letters] = slot[letters].  Materialised once per integral tensor by the
+        engine (it is constant over iterations and grid points)."""
+        perm = tuple(letters.index(l) for l in new_letters)
+        if perm == tuple(range(len(perm))):
+            return slot
+        name = "%s@%s" % (slot, "".join(str(p) for p in perm))
+        if name not in self.derived:
+            self.derived[name] = (slot, perm)
+            shp = self.slot_shapes[slot]
+            self.slot_shapes[name] = tuple(shp[p] for p in perm)
+            self.batched[name] = False
+            self.slot_index[name] = len(self.slot_names)
+            self.slot_names.append(name)
+        return name
 
     @staticmethod
     def _order(group, primary, secondary):
@@ -424,6 +447,21 @@ class Lowered(object):
             (na, la), (nb, lb) = (nb, lb), (na, la)
             M, N = N, M
         sa, sb = self._stride_map(na, la), self._stride_map(nb, lb)
+        # long-K contraction into a tiny output (F_vv / F_oo builds, singles residual, their
+        # adjoints): both operands are n^4 tensors reduced over three indices.  The amplitude
+        # operand streams from HBM in its natural order; the integral operand is replaced by
+        # a copy laid out [row][k in the same order], so both sides are read contiguously.
+        if DERIVE and size(M) <= 64 and size(N) <= 64 and size(K) >= LONGK_MIN \
+                and is_integral_slot(na) != is_integral_slot(nb):
+            if is_integral_slot(na):
+                K = sorted(K, key=lambda l: -sb[l])
+                new = "".join(M) + "".join(K)
+                na, la = self._derive(na, la, new), new
+            else:
+                K = sorted(K, key=lambda l: -sa[l])
+                new = "".join(N) + "".join(K)
+                nb, lb = self._derive(nb, lb, new), new
+            sa, sb = self._stride_map(na, la), self._stride_map(nb, lb)
         a_mode = 0 if la[-1] in K else 1
         b_mode = 0 if lb[-1] in K else 1
         # order of the contracted composite index: follow the operand that wants to be
@@ -437,7 +475,7 @@ class Lowered(object):
         K = self._order(K, sa, sb) if a_first else self._order(K, sb, sa)
         # HBM-bound rank-K update (small K and N, ~n^3 rows): the streaming SIMT kernel owns
         # one C row per thread, so C (2/3 of the traffic) must be contiguous along the rows
-        rankk = (RANKK and size(K) <= 64 and size(N) <= 64 and size(M) >= 4096
+        rankk = (RANKK and size(K) <= 64 and size(N) <= 64 and size(M) >= RANKK_MIN_M
                  and lc[-1] in M)
         if rankk:
             M = self._order(M, sc, sa)
@@ -490,7 +528,7 @@ _INT_SLOT = re.compile(r"^(I|Ia|Ib|Iabab|F|Fa|Fb)\.")
 
 def is_integral_slot(slot):
     """True for the caller-supplied dressed-integral slots (not their adjoints)."""
-    return (not slot.endswith("~")) and _INT_SLOT.match(slot) is not None
+    return (not slot.endswith("~")) and ("@" not in slot) and _INT_SLOT.match(slot) is not None
 
 
 def slot_shapes(rops, mode, sizes):

@@ -12,6 +12,9 @@ def run_lowered(low, arrays, nbatch):
     """arrays: slot name -> ndarray; batched slots have a leading tau axis."""
     ops = low.finalize(nbatch)
     tabs = low.tables.astype(numpy.int64)
+    arrays = dict(arrays)
+    for nm, (src, perm) in low.derived.items():
+        arrays[nm] = numpy.ascontiguousarray(arrays[src].transpose(perm))
     flat = {}
     for nm in low.slot_names:
         a = arrays[nm]

@@ -145,3 +145,26 @@ def test_rdm_plan_u_all_spin_blocks():
         ref = [sum(gw[y]*getattr(ocq, "uccsd_1rdm_" + nm)(*args[y])[k] for y in range(ng)) for k in (0, 1)]
         assert numpy.abs(summed["Fa.%s~" % leaf].T - ref[0]).max() < 1e-12
         assert numpy.abs(summed["Fb.%s~" % leaf].T - ref[1]).max() < 1e-12
+
+
+def test_small_shape_paths_are_exercised(monkeypatch):
+    """Lower the size thresholds so that the derived-layout (long-K) and rank-K code paths
+    of the lowering are exercised at test sizes; results must not change."""
+    monkeypatch.setattr(plan, "DERIVE", 1)
+    monkeypatch.setattr(plan, "LONGK_MIN", 8)
+    monkeypatch.setattr(plan, "RANKK_MIN_M", 8)
+    na, nb, ng = 4, 3, 2
+    ints, amps = util.random_u(na, nb, ng, seed=11)
+    Fa, Fb, Ia, Ib, Iabab = ints
+    sizes = {("v", "a"): na, ("o", "a"): na, ("v", "b"): nb, ("o", "b"): nb}
+    names = ("t1.a", "t1.b", "t2.aa", "t2.ab", "t2.bb")
+    rops = plan.expand(programs.stanton(-1.0), programs.tensor_defs(), "u")
+    arr, low = _run(rops, "u", sizes, dict(zip(names, amps)),
+                    {"Fa": Fa, "Fb": Fb, "Ia": Ia, "Ib": Ib, "Iabab": Iabab}, ng)
+    assert len(low.derived) > 0
+    assert any(d.kind == 2 for d in low.descs)
+    for y in range(ng):
+        r = ocq.u_stanton_terms(*ints, (amps[0][y], amps[1][y]), (amps[2][y], amps[3][y], amps[4][y]))
+        ref = (-Fa.vo - r[0], -Fb.vo - r[1], -Ia.vvoo - r[2], -Iabab.vvoo - r[3], -Ib.vvoo - r[4])
+        for nm, rr in zip(("o1.a", "o1.b", "o2.aa", "o2.ab", "o2.bb"), ref):
+            assert numpy.abs(arr[nm][y] - rr).max() < 1e-12
