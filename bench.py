@@ -298,6 +298,26 @@ def main():
                 "plan_s": sum(x[2] for x in tim),
                 "traffic": _traffic(args.workload, world)}
 
+    # ---- auxiliary: one Lambda iteration (reverse sweep, intermediates cached), N = 1 only
+    lam = None
+    if world == 1:
+        Ts = solver.old
+        Ls = ft_cc_equations.uccsd_lambda_guess(Fa, Fb, Ia, Ib, Iabab, Ts[0], Ts[1], beta, ng)
+
+        def lam_step(Lc):
+            return ft_cc_equations.uccsd_lambda_opt(Fa, Fb, Ia, Ib, Iabab, *Ts, *Lc, *Ds, ti, ng, g, G, beta)
+        for _ in range(2):
+            Ls = lam_step(Ls)
+        torch.cuda.synchronize()
+        ev0.record()
+        nl = 3
+        for _ in range(nl):
+            Ls = lam_step(Ls)
+        ev1.record()
+        torch.cuda.synchronize()
+        lam = ev0.elapsed_time(ev1)*1e-3/nl
+        del Ls
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
@@ -321,7 +341,9 @@ def main():
                        "cache": "working set (amplitudes+integrals+intermediates) >> 126 MB L2",
                        "algorithmic_tflop_per_step": fl/1e12,
                        "fp64_tflops_whole_step": fl/t_step/1e12,
-                       "published_cpu_s_per_iter_unknown_hw": 321.4 if norb == 33 else None},
+                       "published_cpu_s_per_iter_unknown_hw": 321.4 if norb == 33 else None,
+                       "lambda_s_per_iteration": lam,
+                       "lambda_algorithmic_tflop": ng*92.0*norb**6/1e12},
             "e2e": {"value": t_e2e, "unit": "s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 160},
             "gpu_launches": launches,
             "clocks": clocks,

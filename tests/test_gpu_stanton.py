@@ -60,3 +60,30 @@ def test_u_equals_g_on_spin_packed_inputs(built):
     assert numpy.abs(u[2].cpu().numpy() - g2[:, :na, :na, :na, :na]).max() < 1e-11*sc
     assert numpy.abs(u[3].cpu().numpy() - g2[:, :na, na:, :na, na:]).max() < 1e-11*sc
     assert numpy.abs(u[4].cpu().numpy() - g2[:, na:, na:, na:, na:]).max() < 1e-11*sc
+
+
+def test_tau_sharded_step_equals_reference_loop(built):
+    """The bench / multi-GPU step object (world size 1) reproduces one iteration of the
+    reference loop (kelvin/cc_utils.py:274-305): energy and residual as logged."""
+    from kelvin_b200 import cc_utils, ft_utils, parallel, quadrature
+    from kelvin_b200.ueg_system import UEGSystem
+    T, mu, ng = 0.5, 7.0, 6
+    s = UEGSystem(T, 1.942, 30.0, mu=mu, norb=7, orbtype='u')
+    beta = 1.0/T
+    ea, eb = s.u_energies_tot()
+    ti, g, G = quadrature.ft_quad(ng, beta, 'lin')
+    ints = cc_utils.uft_integrals(s, ea, eb, beta, mu)
+    Ds = (ft_utils.D1(ea, ea), ft_utils.D1(eb, eb), ft_utils.D2(ea, ea),
+          ft_utils.D2u(ea, eb, ea, eb), ft_utils.D2(eb, eb))
+    oints = odrv.uft_integrals(s, ea, eb, beta, mu)
+    oD = [d.cpu().numpy() for d in Ds]
+    amps = odrv.mp2_guess_u(*oints, *oD, ti, ng, G)
+    solver = parallel.TauShardedUCCSD(*ints, Ds, g, G, beta, ng, ti)
+    solver.set_amplitudes(*amps)
+    E1, r1 = solver.step(0.3)
+    E2, r2 = solver.step(0.3)
+    conv = {"econv": 0.0, "tconv": 0.0, "max_iter": 2, "damp": 0.3}
+    _, _, _, hist = odrv.ft_ucc_iter(*amps, *oints, *oD, g, G, beta, ng, ti, conv)
+    assert abs(E1 - hist[0][0]) < 1e-12 and abs(E2 - hist[1][0]) < 1e-12
+    assert abs(r1 - hist[0][1]) < 1e-10*max(1.0, hist[0][1])
+    assert abs(r2 - hist[1][1]) < 1e-10*max(1.0, hist[1][1])
