@@ -141,3 +141,24 @@ def test_empty_and_bad_inputs(built):
         quadrature.ft_quad(4, 1.0, 'nope')
     out = quadrature.int_tbar(4, numpy.zeros((4, 0, 3)), ti, numpy.zeros((0, 3)), G)
     assert out.shape == (4, 0, 3)
+
+
+def test_contraction_wave_split_k(built):
+    """Few-CTA big-tile contraction: the wave-quantisation split-K path (deterministic
+    workspace reduction) gives the same result as einsum."""
+    from kelvin_b200 import engine, plan
+    rng = numpy.random.default_rng(8)
+    dims = dict(a=12, b=13, i=12, j=13, e=24, f=25)
+    A = rng.standard_normal((2,) + tuple(dims[l] for l in "abef"))
+    B = rng.standard_normal((2,) + tuple(dims[l] for l in "efij"))
+    C0 = rng.standard_normal((2,) + tuple(dims[l] for l in "abij"))
+    ops = [plan.ROp(("C", "abij"), 0.5, [("A", "abef"), ("B", "efij")])]
+    shapes = {"C": C0.shape[1:], "A": A.shape[1:], "B": B.shape[1:]}
+    p = engine.Plan(ops, "g", None, ["A", "B"], ["C"], preset_outputs=["C"], shapes=shapes,
+                    batched={"C": True, "A": True, "B": True})
+    arr = p.low.finalize(2)
+    assert arr[0].splitk > 1
+    t = {"A": _dev(A), "B": _dev(B), "C": _dev(C0)}
+    p.run(t, 2)
+    ref = C0 + 0.5*numpy.einsum("yabef,yefij->yabij", A, B)
+    assert numpy.abs(t["C"].cpu().numpy() - ref).max() < 1e-11*numpy.abs(ref).max()
