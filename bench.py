@@ -270,7 +270,7 @@ def main():
             tim = []
             p.run(t, nloc, timings=tim)
         gemm = [(fl, dt) for kind, fl, dt, meta in tim if kind == 0]
-        big = [(fl, dt, meta) for kind, fl, dt, meta in tim if kind == 0 and meta[5] == 1
+        big = [(fl, dt, meta) for kind, fl, dt, meta in tim if kind == 0
                and fl >= 0.5*2.0*nloc*norb**6]
         fl_big = sum(x[0] for x in big)
         dt_big = sum(x[1] for x in big)

@@ -517,13 +517,14 @@ class Lowered(object):
                 target = 4 * N_SM if o.tile == 5 else 2 * N_SM
                 if ctas < target // 2 and o.K >= 512:
                     o.splitk = int(min(max(1, -(-target // ctas)), max(1, o.K // 128)))
-                elif o.tile in (0, 2) and ctas < 3 * N_SM and o.K >= 512:
+                elif o.tile in (0, 2) and ctas <= 2 * N_SM and o.K >= 512:
                     # few waves of one-CTA-per-SM tiles (small tau batches on a sharded run):
                     # pick the split that minimises wave quantisation, charging the
-                    # deterministic reduction pass ~6 % of a wave per extra split
+                    # deterministic reduction pass ~10 % of a wave per extra split (measured: splitting
+                    # a 3-wave launch does not pay)
                     best, bests = None, 1
                     for sk in (1, 2, 3, 4):
-                        cost = -(-ctas * sk // N_SM) / float(sk) + 0.06 * (sk - 1)
+                        cost = -(-ctas * sk // N_SM) / float(sk) + 0.10 * (sk - 1)
                         if best is None or cost < best - 1e-9:
                             best, bests = cost, sk
                     o.splitk = bests
