@@ -79,8 +79,10 @@ int kb200_plan_run_timed(const kb200_op* ops /*host*/, int nops,
  *   out[y,p] = sum_x G[y,x] * w(y,x,p) * tbar[x,p],
  *   w = exp(D[p]*(ti[x]-ti[y])) for x<y, 1 otherwise   (quirk Q4).
  * n = elements per grid point.  ti[ng], G[ng*ng] row-major, D[n].
- * mode 0: one exp per (y,x) pair, exactly the reference's formula;
- * mode 1: ng-1 exps per element, weights built as running products.
+ * mode bit 0 = 0: one exp per (y,x) pair, exactly the reference's formula;
+ *            = 1: ng-1 exps per element, weights built as running products.
+ * mode bit 1 (+2): caller guarantees G[y,x] == 0 for x > y (true for every rule of
+ *            kelvin/quadrature.py); the kernel then skips the upper triangle.
  * ------------------------------------------------------------------------ */
 int kb200_int_tbar(int ng, int64_t n, const double* tbar, const double* D,
                    const double* ti, const double* G, double* out, int mode, void* stream);

@@ -80,7 +80,8 @@ template <int MODE>
 __global__ void __launch_bounds__(INT_THREADS)
     int_tbar_kernel(int ng, long long n, const double* __restrict__ tbar,
                     const double* __restrict__ D, const double* __restrict__ ti,
-                    const double* __restrict__ G, double* __restrict__ out, int y0, int y1) {
+                    const double* __restrict__ G, double* __restrict__ out, int y0, int y1,
+                    int lower) {
     extern __shared__ double sm[];
     double* tb = sm;
     double* E = sm + (size_t)ng * INT_THREADS;
@@ -112,7 +113,8 @@ __global__ void __launch_bounds__(INT_THREADS)
                     if (gw != 0.0) acc += gw * w * tb[x * INT_THREADS + tx];
                 }
             }
-            for (int x = y; x < ng; ++x) {
+            const int xend = lower ? y + 1 : ng;     // lower-triangular G: only x == y is left
+            for (int x = y; x < xend; ++x) {
                 double gw = __ldg(Gy + x);
                 if (gw != 0.0) acc += gw * tb[x * INT_THREADS + tx];
             }
@@ -131,7 +133,7 @@ __global__ void __launch_bounds__(INT_THREADS)
     int_L_kernel(int ng, long long n, Dims4 dm, const double* __restrict__ L,
                  const double* __restrict__ D, const double* __restrict__ ti,
                  const double* __restrict__ g, const double* __restrict__ G,
-                 double* __restrict__ out, int s0, int s1) {
+                 double* __restrict__ out, int s0, int s1, int lower) {
     extern __shared__ double sm[];
     double* lb = sm;
     double* E = sm + (size_t)ng * INT_THREADS;
@@ -149,11 +151,11 @@ __global__ void __launch_bounds__(INT_THREADS)
         bool act = p < n;
         double d = 0.0;
         if (act) {
-            long long r = p;
-            int i3 = (int)(r % dm.d[3]); r /= dm.d[3];
-            int i2 = (int)(r % dm.d[2]); r /= dm.d[2];
-            int i1 = (int)(r % dm.d[1]); r /= dm.d[1];
-            int i0 = (int)r;
+            unsigned r = (unsigned)p;               // n < 2^31 (checked on the host)
+            unsigned i3 = r % (unsigned)dm.d[3]; r /= (unsigned)dm.d[3];
+            unsigned i2 = r % (unsigned)dm.d[2]; r /= (unsigned)dm.d[2];
+            unsigned i1 = r % (unsigned)dm.d[1]; r /= (unsigned)dm.d[1];
+            unsigned i0 = r;
             d = D[i0 * dm.s[0] + i1 * dm.s[1] + i2 * dm.s[2] + i3 * dm.s[3]];
         }
         for (int y = 0; y < ng; ++y) lb[y * INT_THREADS + tx] = act ? L[(size_t)y * n + p] : 0.0;
@@ -161,7 +163,7 @@ __global__ void __launch_bounds__(INT_THREADS)
             for (int k = 1; k < ng; ++k) E[k * INT_THREADS + tx] = exp(d * (tis[k - 1] - tis[k]));
         for (int s = s0; s < s1; ++s) {
             double acc = 0.0;
-            for (int y = 0; y < s; ++y) {
+            for (int y = lower ? s : 0; y < s; ++y) {   // G[y,s] with y < s is the upper triangle
                 double gw = gs[y] * __ldg(G + (size_t)y * ng + s);
                 if (gw != 0.0) acc += gw * lb[y * INT_THREADS + tx];
             }
@@ -196,11 +198,11 @@ __global__ void __launch_bounds__(RED_THREADS)
     double acc[1] = {0.0};
     for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < n;
          p += (long long)gridDim.x * blockDim.x) {
-        long long r = p;
-        int j = (int)(r % nob); r /= nob;
-        int i = (int)(r % noa); r /= noa;
-        int bb = (int)(r % nvb); r /= nvb;
-        int a = (int)r;
+        unsigned r = (unsigned)p;                  // n < 2^31 (checked on the host)
+        unsigned j = r % (unsigned)nob; r /= (unsigned)nob;
+        unsigned i = r % (unsigned)noa; r /= (unsigned)noa;
+        unsigned bb = r % (unsigned)nvb; r /= (unsigned)nvb;
+        unsigned a = r;
         double s = 0.0;
         for (int y = 0; y < ng; ++y) {
             double v = c2 * T2[(size_t)y * n + p];
@@ -257,11 +259,11 @@ __global__ void dress4_kernel(int d0, int d1, int d2, int d3, const double* __re
     const long long n = (long long)d0 * d1 * d2 * d3;
     for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < n;
          p += (long long)gridDim.x * blockDim.x) {
-        long long r = p;
-        int l = (int)(r % d3); r /= d3;
-        int k = (int)(r % d2); r /= d2;
-        int j = (int)(r % d1); r /= d1;
-        int i = (int)r;
+        unsigned r = (unsigned)p;                  // n < 2^31 (checked on the host)
+        unsigned l = r % (unsigned)d3; r /= (unsigned)d3;
+        unsigned k = r % (unsigned)d2; r /= (unsigned)d2;
+        unsigned j = r % (unsigned)d1; r /= (unsigned)d1;
+        unsigned i = r;
         out[p] = eri[p] * s0[i] * s1[j] * s2[k] * s3[l];
     }
 }
@@ -319,11 +321,11 @@ __global__ void __launch_bounds__(RED_THREADS)
     double acc = 0.0;
     for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < inner;
          p += (long long)gridDim.x * blockDim.x) {
-        long long r = p;
-        int i4 = (int)(r % q.d[3]); r /= q.d[3];
-        int i3 = (int)(r % q.d[2]); r /= q.d[2];
-        int i2 = (int)(r % q.d[1]); r /= q.d[1];
-        int i1 = (int)r;
+        unsigned r = (unsigned)p;                  // inner < 2^31 (checked on the host)
+        unsigned i4 = r % (unsigned)q.d[3]; r /= (unsigned)q.d[3];
+        unsigned i3 = r % (unsigned)q.d[2]; r /= (unsigned)q.d[2];
+        unsigned i2 = r % (unsigned)q.d[1]; r /= (unsigned)q.d[1];
+        unsigned i1 = r;
         acc += Ak[i1 * q.sa[1] + i2 * q.sa[2] + i3 * q.sa[3] + i4 * q.sa[4]] *
                Bk[i1 * q.sb[1] + i2 * q.sb[2] + i3 * q.sb[3] + i4 * q.sb[4]];
     }
@@ -421,6 +423,7 @@ int kb200_dot_keep(int nkeep, const int32_t dims[4], const int64_t sA[5], const 
         q.d[i] = dims[i];
         inner *= dims[i];
     }
+    if (inner >= (1LL << 31)) return fail(-1, "dot_keep: inner extent too large");
     for (int i = 0; i < 5; ++i) {
         q.sa[i] = sA[i];
         q.sb[i] = sB[i];
@@ -583,6 +586,10 @@ int kb200_int_tbar(int ng, int64_t n, const double* tbar, const double* D, const
 
 int kb200_int_tbar_rows(int ng, int64_t n, const double* tbar, const double* D, const double* ti,
                         const double* G, double* out, int y0, int y1, int mode, void* stream) {
+    // mode bit 1 (value 2): the caller guarantees G[y,x] == 0 for x > y (every quadrature of
+    // kelvin/quadrature.py), which lets the kernel skip scanning the upper triangle
+    const int lower = (mode & 2) ? 1 : 0;
+    mode &= 1;
     if (ng <= 0 || n < 0 || y0 < 0 || y1 > ng || y0 > y1) return fail(-1, "int_tbar: bad size");
     if (y0 == y1) return 0;
     if (n == 0) return 0;
@@ -592,10 +599,10 @@ int kb200_int_tbar_rows(int ng, int64_t n, const double* tbar, const double* D, 
     int grid = grid_for(n, INT_THREADS, 148 * 8);
     if (mode == 1) {
         cudaFuncSetAttribute(int_tbar_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        int_tbar_kernel<1><<<grid, INT_THREADS, smem, st>>>(ng, n, tbar, D, ti, G, out, y0, y1);
+        int_tbar_kernel<1><<<grid, INT_THREADS, smem, st>>>(ng, n, tbar, D, ti, G, out, y0, y1, lower);
     } else {
         cudaFuncSetAttribute(int_tbar_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        int_tbar_kernel<0><<<grid, INT_THREADS, smem, st>>>(ng, n, tbar, D, ti, G, out, y0, y1);
+        int_tbar_kernel<0><<<grid, INT_THREADS, smem, st>>>(ng, n, tbar, D, ti, G, out, y0, y1, lower);
     }
     KB_CHECK_LAUNCH("int_tbar_kernel");
     return 0;
@@ -610,6 +617,8 @@ int kb200_int_L(int ng, const int32_t dims[4], const int64_t dstride[4], const d
 int kb200_int_L_rows(int ng, const int32_t dims[4], const int64_t dstride[4], const double* L,
                      const double* D, const double* ti, const double* g, const double* G,
                      double* out, int s0, int s1, int mode, void* stream) {
+    const int lower = (mode & 2) ? 1 : 0;
+    mode &= 1;
     if (ng <= 0 || s0 < 0 || s1 > ng || s0 > s1) return fail(-1, "int_L: bad size");
     if (s0 == s1) return 0;
     Dims4 dm;
@@ -620,16 +629,17 @@ int kb200_int_L_rows(int ng, const int32_t dims[4], const int64_t dstride[4], co
         dm.s[i] = dstride[i];
         n *= dims[i];
     }
+    if (n >= (1LL << 31)) return fail(-1, "int_L: block too large");
     cudaStream_t st = (cudaStream_t)stream;
     size_t smem = ((size_t)ng * INT_THREADS * (mode == 1 ? 2 : 1) + 2 * ng) * 8;
     if (smem > 227 * 1024) return fail(-1, "int_L: ng too large for shared memory");
     int grid = grid_for(n, INT_THREADS, 148 * 8);
     if (mode == 1) {
         cudaFuncSetAttribute(int_L_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        int_L_kernel<1><<<grid, INT_THREADS, smem, st>>>(ng, n, dm, L, D, ti, g, G, out, s0, s1);
+        int_L_kernel<1><<<grid, INT_THREADS, smem, st>>>(ng, n, dm, L, D, ti, g, G, out, s0, s1, lower);
     } else {
         cudaFuncSetAttribute(int_L_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        int_L_kernel<0><<<grid, INT_THREADS, smem, st>>>(ng, n, dm, L, D, ti, g, G, out, s0, s1);
+        int_L_kernel<0><<<grid, INT_THREADS, smem, st>>>(ng, n, dm, L, D, ti, g, G, out, s0, s1, lower);
     }
     KB_CHECK_LAUNCH("int_L_kernel");
     return 0;
@@ -640,6 +650,7 @@ int kb200_energy_pair(int ng, int nva, int nvb, int noa, int nob, const double* 
                       double c2, double c11, double* out, double* scratch, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     long long n = (long long)nva * nvb * noa * nob;
+    if (n <= 0 || n >= (1LL << 31)) return fail(-1, "energy_pair: bad dims");
     int grid = grid_for(n, RED_THREADS, RED_BLOCKS);
     if ((T1x == nullptr) != (T1y == nullptr)) return fail(-1, "energy_pair: T1x/T1y");
     energy_pair_kernel<<<grid, RED_THREADS, 0, st>>>(ng, nva, nvb, noa, nob, T2, T1x, T1y, Iabij, g,
@@ -676,7 +687,7 @@ int kb200_dress4(const int32_t d[4], const double* eri, const double* s0, const 
                  const double* s2, const double* s3, double* out, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     long long n = (long long)d[0] * d[1] * d[2] * d[3];
-    if (n <= 0) return fail(-1, "dress4: bad dims");
+    if (n <= 0 || n >= (1LL << 31)) return fail(-1, "dress4: bad dims");
     dress4_kernel<<<grid_for(n, 256), 256, 0, st>>>(d[0], d[1], d[2], d[3], eri, s0, s1, s2, s3, out);
     KB_CHECK_LAUNCH("dress4_kernel");
     return 0;

@@ -160,6 +160,16 @@ def _small(x, dev):
     return _lib.const_dev(x, dev)
 
 
+def _mode_bits(G, mode):
+    """Kernel mode word: bit 0 = product-form weights, bit 1 = G is lower triangular."""
+    m = INT_MODE if mode is None else mode
+    if not isinstance(G, torch.Tensor):
+        Gn = numpy.asarray(G)
+        if not numpy.any(numpy.triu(Gn, 1)):
+            m |= 2
+    return m
+
+
 def int_tbar(ng, tbar, ti, D, G, out=None, mode=None, rows=None):
     """out[y] = sum_x G[y,x] * exp(D*(ti[x]-ti[y]))_{x<y} * tbar[x]
     for any amplitude rank (kelvin/quadrature.py:292-317).  rows=(y0, y1)
@@ -177,8 +187,7 @@ def int_tbar(ng, tbar, ti, D, G, out=None, mode=None, rows=None):
     n = D.numel()
     tid, Gd = _small(ti, dev), _small(G, dev)
     rc = lib.kb200_int_tbar_rows(ng, n, _lib.ptr(tbar), _lib.ptr(D), _lib.ptr(tid), _lib.ptr(Gd),
-                                 _lib.ptr(out), y0, y1, INT_MODE if mode is None else mode,
-                                 _lib.stream_ptr())
+                                 _lib.ptr(out), y0, y1, _mode_bits(G, mode), _lib.stream_ptr())
     _lib.check(rc, "kb200_int_tbar")
     return out
 
@@ -218,7 +227,7 @@ def int_L(ng, Lold, ti, D, g, G, out=None, mode=None, rows=None):
     tid, gd, Gd = _small(ti, dev), _small(g, dev), _small(G, dev)
     rc = lib.kb200_int_L_rows(ng, cd, cs, _lib.ptr(Lold), _lib.ptr(D), _lib.ptr(tid),
                               _lib.ptr(gd), _lib.ptr(Gd), _lib.ptr(out), s0, s1,
-                              INT_MODE if mode is None else mode, _lib.stream_ptr())
+                              _mode_bits(G, mode), _lib.stream_ptr())
     _lib.check(rc, "kb200_int_L")
     return out
 
