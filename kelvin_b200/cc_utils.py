@@ -392,3 +392,38 @@ def on_response(leaves, ints, spin_of_leaf):
             res = _lib.dot_keep(A, la, B, lb, l, alpha=w, out=out, beta=0.0 if out is None else 1.0)
             acc[key] = res
     return acc
+
+
+def _add_pair(rdm2, A, B, fac, exchange):
+    """rdm2[p,q,r,s] += fac*A[p,r]*B[q,s]; with exchange also rdm2[p,q,s,r] -= fac*A[p,r]*B[q,s]."""
+    X = fac*A[:, None, :, None]*B[None, :, None, :]
+    rdm2 += X
+    if exchange:
+        rdm2 -= X.transpose(2, 3)
+
+
+def g_full_rdm2(fo, n1rdm, rdm2):
+    """Mean-field and mixed parts of the full 2-RDM, added in place (kelvin/cc_utils.py:2018-2024)."""
+    dev = rdm2.device
+    d = torch.diag(torch.as_tensor(fo, dtype=torch.float64)).to(dev)
+    _add_pair(rdm2, d, d, 1.0, True)
+    _add_pair(rdm2, d, n1rdm, 0.5, True)
+    _add_pair(rdm2, n1rdm, d, 0.5, True)
+
+
+def u_full_rdm2(foa, fob, n1rdm, rdm2):
+    """kelvin/cc_utils.py:2036-2053.  The reference's bb exchange term pairs diag(fob) with
+    diag(foa) (:2045); kept as is, identical for spin-symmetric occupations."""
+    dev = rdm2[0].device
+    da = torch.diag(torch.as_tensor(foa, dtype=torch.float64)).to(dev)
+    db = torch.diag(torch.as_tensor(fob, dtype=torch.float64)).to(dev)
+    _add_pair(rdm2[0], da, da, 1.0, True)
+    _add_pair(rdm2[0], da, n1rdm[0], 0.5, True)
+    _add_pair(rdm2[0], n1rdm[0], da, 0.5, True)
+    _add_pair(rdm2[1], db, db, 1.0, False)
+    rdm2[1] -= (db[:, None, :, None]*da[None, :, None, :]).transpose(2, 3)
+    _add_pair(rdm2[1], db, n1rdm[1], 0.5, True)
+    _add_pair(rdm2[1], n1rdm[1], db, 0.5, True)
+    _add_pair(rdm2[2], da, db, 1.0, False)
+    _add_pair(rdm2[2], da, n1rdm[1], 0.5, False)
+    _add_pair(rdm2[2], n1rdm[0], db, 0.5, False)

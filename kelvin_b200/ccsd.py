@@ -77,6 +77,8 @@ class ccsd(object):
         self.n1rdm = None
         self.n2rdm = None
         self.r1rdm = None
+        self.rorbo = None
+        self.rorbv = None
         self._ints = None
 
     # ------------------------------------------------------------------
@@ -372,6 +374,143 @@ class ccsd(object):
         acc = cc_utils.on_response(self._leaf_list(), None, self._spin_of_leaf)
         self.rono = [tA - 0.5*c(acc[("o", "a")])*fva, tB - 0.5*c(acc[("o", "b")])*fvb]
         self.ronv = [0.5*c(acc[("v", "a")])*foa, 0.5*c(acc[("v", "b")])*fob]
+
+    # ------------------------------------------------------------------
+    # orbital-energy response and relaxed 1-RDM (kelvin/ccsd.py:1494-1577, 1828-1959)
+    # ------------------------------------------------------------------
+    def _rorb_traces(self, pairs, no, nv):
+        """sum_y g_y <L_y, T_y> with one index kept, for the (L, T, weight, occ letters,
+        vir letters) tuples of one spin; returns (occ vector, vir vector) on the host."""
+        dev = pairs[0][0].device
+        o = torch.zeros(no, dtype=torch.float64, device=dev)
+        v = torch.zeros(nv, dtype=torch.float64, device=dev)
+        for L, Tg, w, okeep, vkeep in pairs:
+            ll, lt = ("yia", "yai") if L.dim() == 3 else ("yijab", "yabij")
+            for k in okeep:
+                _lib.dot_keep(L, ll, Tg, lt, k, alpha=w, out=o, beta=1.0)
+            for k in vkeep:
+                _lib.dot_keep(L, ll, Tg, lt, k, alpha=w, out=v, beta=1.0)
+        return o.cpu().numpy(), v.cpu().numpy()
+
+    def _tau_weighted_stanton(self):
+        """Residual pass with G[i,j]*(tau_j - tau_i) and the result scaled by g_y
+        (kelvin/ccsd.py:1519-1534, 1867-1888)."""
+        ti, ng = self.ti, self.ngrid
+        Gnew = self.G.copy()
+        for i in range(ng):
+            for j in range(ng):
+                Gnew[i, j] *= (ti[j] - ti[i])
+        if self.sys.has_u():
+            ea, eb, Ds, (Fa, Fb, Ia, Ib, Iabab) = self._u_setup()
+            t1, t2 = ft_cc_equations.uccsd_stanton(
+                Fa, Fb, Ia, Ib, Iabab, *self.T1, *self.T2, *Ds, ti, ng, Gnew)
+            Tt = list(t1) + list(t2)
+        else:
+            en, D1, D2, F, I = self._g_setup()
+            Tt = list(ft_cc_equations.ccsd_stanton(F, I, self.T1, self.T2, D1, D2, ti, ng, Gnew))
+        gdev = _lib.const_dev(self.g, Tt[0].device)
+        for X in Tt:
+            X.mul_(gdev.view((ng,) + (1,)*(X.dim() - 1)))
+        return Tt
+
+    def _g_ft_rorb(self):
+        """kelvin/ccsd.py:1494-1545."""
+        Tt = self._tau_weighted_stanton()
+        L1, L2 = _lib.as_dev(self.L1), _lib.as_dev(self.L2)
+        n = L1.shape[1]
+        s = -1.0/self.beta
+        o, v = self._rorb_traces([(L1, Tt[0], s, "i", "a"), (L2, Tt[1], 0.25*s, "ij", "ab")], n, n)
+        self.rorbo = -o
+        self.rorbv = v
+
+    def _u_ft_rorb(self):
+        """kelvin/ccsd.py:1828-1918."""
+        Tt = self._tau_weighted_stanton()
+        L1a, L1b = (_lib.as_dev(x) for x in self.L1)
+        L2aa, L2ab, L2bb = (_lib.as_dev(x) for x in self.L2)
+        na, nb = L1a.shape[1], L1b.shape[1]
+        s = -1.0/self.beta
+        oa, va = self._rorb_traces([(L1a, Tt[0], s, "i", "a"), (L2aa, Tt[2], 0.25*s, "ij", "ab"),
+                                    (L2ab, Tt[3], s, "i", "a")], na, na)
+        ob, vb = self._rorb_traces([(L1b, Tt[1], s, "i", "a"), (L2bb, Tt[4], 0.25*s, "ij", "ab"),
+                                    (L2ab, Tt[3], s, "j", "b")], nb, nb)
+        self.rorbo = [-oa, -ob]
+        self.rorbv = [va, vb]
+
+    def _grel_ft_1rdm(self):
+        """kelvin/ccsd.py:1547-1577."""
+        if self.dia is None:
+            self._g_ft_1rdm()
+        if self.P2 is None:
+            self._g_ft_2rdm()
+        (fo, fv), = self._occ()
+        self._g_ft_ron()
+        self._g_ft_rorb()
+        rdji = numpy.diag(self.rono) + numpy.diag(self.ron1) + numpy.diag(self.rorbo) + numpy.diag(fo)
+        rdba = numpy.diag(self.ronv) + numpy.diag(self.rorbv)
+        self.r1rdm = rdji + rdba
+
+    def _urel_ft_1rdm(self):
+        """kelvin/ccsd.py:1920-1959."""
+        if self.dia is None:
+            self._u_ft_1rdm()
+        if self.P2 is None:
+            self._u_ft_2rdm()
+        self._u_ft_ron()
+        self._u_ft_rorb()
+        (foa, fva), (fob, fvb) = self._occ()
+        fo = (foa, fob)
+        self.r1rdm = [numpy.diag(self.rono[k] + self.ron1[k] + self.rorbo[k] + fo[k]
+                                 + self.ronv[k] + self.rorbv[k]) for k in (0, 1)]
+
+    def full_1rdm(self, relax=False):
+        """Full (HF + correlation) 1-RDM as NumPy arrays (kelvin/ccsd.py:1961-2006)."""
+        c = lambda x: x.cpu().numpy()  # noqa: E731
+        if self.sys.orbtype == 'u':
+            if relax:
+                if self.r1rdm is None:
+                    self._urel_ft_1rdm()
+                n1 = [c(x) for x in self.n1rdm]
+                return [self.r1rdm[k] + (n1[k] - numpy.diag(n1[k].diagonal())) for k in (0, 1)]
+            if self.n1rdm is None:
+                self._u_ft_1rdm()
+            (foa, fva), (fob, fvb) = self._occ()
+            return [c(self.n1rdm[0]) + numpy.diag(foa), c(self.n1rdm[1]) + numpy.diag(fob)]
+        elif self.sys.orbtype == 'g':
+            if relax:
+                if self.r1rdm is None:
+                    self._grel_ft_1rdm()
+                n1 = c(self.n1rdm)
+                return self.r1rdm + (n1 - numpy.diag(n1.diagonal()))
+            if self.n1rdm is None:
+                self._g_ft_1rdm()
+            (fo, fv), = self._occ()
+            return c(self.n1rdm) + numpy.diag(fo)
+        raise Exception("orbital type " + self.sys.orbtype + " is not implemented for 1rdm")
+
+    def full_2rdm(self, relax=False):
+        """Full 2-RDM (device tensors; kelvin/ccsd.py:2008-2053)."""
+        if relax:
+            raise Exception("Rexalex 2-RDM is not implemented")
+        if self.sys.orbtype == 'u':
+            if self.n1rdm is None:
+                self._u_ft_1rdm()
+            if self.n2rdm is None:
+                self._u_ft_2rdm()
+            (foa, fva), (fob, fvb) = self._occ()
+            rdm2 = [x.clone() for x in self.n2rdm]
+            cc_utils.u_full_rdm2(foa, fob, self.n1rdm, rdm2)
+            return rdm2
+        elif self.sys.orbtype == 'g':
+            if self.n1rdm is None:
+                self._g_ft_1rdm()
+            if self.n2rdm is None:
+                self._g_ft_2rdm()
+            (fo, fv), = self._occ()
+            rdm2 = self.n2rdm.clone()
+            cc_utils.g_full_rdm2(fo, self.n1rdm, rdm2)
+            return rdm2
+        raise Exception("orbital type " + self.sys.orbtype + " is not implemented for 1rdm")
 
     # ------------------------------------------------------------------
     # derivative through the quadrature weights (kelvin/ccsd.py:1075-1148, 1150-1260)

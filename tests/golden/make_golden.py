@@ -98,6 +98,19 @@ def run_fixture(name, sysm, **kw):
     cc.compute_ESN()
     out = dict(Etot=Etot, Ecc=Ecc, E=cc.E, S=cc.S, N=cc.N, E0=cc.E0, E1=cc.E1, Ecc_=cc.Ecc,
                N0=cc.N0, N1=cc.N1, Ncc=cc.Ncc, S0=cc.S0, S1=cc.S1, Scc=cc.Scc)
+    full1 = cc.full_1rdm()
+    rel1 = cc.full_1rdm(relax=True)       # kelvin/ccsd.py:1961-2006 (runs _{g,u}_ft_rorb)
+    full2 = cc.full_2rdm()                # kelvin/ccsd.py:2008-2053
+    if sysm.has_u():
+        for k in (0, 1):
+            out["full1rdm%d" % k] = full1[k]
+            out["rel1rdm%d" % k] = rel1[k]
+            out["rorbo%d" % k] = cc.rorbo[k]
+            out["rorbv%d" % k] = cc.rorbv[k]
+        for k in (0, 1, 2):
+            out["full2rdm%d" % k] = full2[k]
+    else:
+        out.update(full1rdm=full1, rel1rdm=rel1, rorbo=cc.rorbo, rorbv=cc.rorbv, full2rdm=full2)
     if sysm.has_u():
         for k, nm in enumerate(("T1a", "T1b")):
             out[nm] = cc.T1[k]

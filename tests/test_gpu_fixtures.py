@@ -63,6 +63,19 @@ def _run_u(sysm, ref, **kw):
     for b, tup in enumerate(cc.P2):
         for k, P in enumerate(tup):
             assert _rel(P, ref["P2_%d_%d" % (b, k)]) < 1e-8, (b, k)
+    # relaxed / full density matrices (kelvin/ccsd.py:1828-2053)
+    full1 = cc.full_1rdm()
+    rel1 = cc.full_1rdm(relax=True)
+    full2 = cc.full_2rdm()
+    for k in (0, 1):
+        assert _rel(full1[k], ref["full1rdm%d" % k]) < 1e-8
+        assert _rel(rel1[k], ref["rel1rdm%d" % k]) < 1e-8
+        assert numpy.abs(cc.rorbo[k] - ref["rorbo%d" % k]).max() < 1e-9
+        assert numpy.abs(cc.rorbv[k] - ref["rorbv%d" % k]).max() < 1e-9
+    for k in (0, 1, 2):
+        assert _rel(full2[k], ref["full2rdm%d" % k]) < 1e-8
+    # trace of the relaxed 1-RDM is the particle number (kelvin/tests/test_ft_cc_relden.py:36-43)
+    assert abs(numpy.trace(cc.r1rdm[0]) + numpy.trace(cc.r1rdm[1]) - cc.N) < 1e-10
 
 
 def test_ueg7_u_full_path(built):
@@ -98,3 +111,10 @@ def test_ueg7_g_full_path(built):
     assert numpy.abs(cc.ronv - ref["ronv"]).max() < 1e-9
     for b, P in enumerate(cc.P2):
         assert _rel(P, ref["P2_%d" % b]) < 1e-8, b
+    assert _rel(cc.full_1rdm(), ref["full1rdm"]) < 1e-8
+    assert _rel(cc.full_1rdm(relax=True), ref["rel1rdm"]) < 1e-8
+    assert numpy.abs(cc.rorbo - ref["rorbo"]).max() < 1e-9
+    assert numpy.abs(cc.rorbv - ref["rorbv"]).max() < 1e-9
+    assert _rel(cc.full_2rdm(), ref["full2rdm"]) < 1e-8
+    # kelvin/tests/test_ft_cc_relden.py:36-43: tr(relaxed 1-RDM) == N
+    assert abs(numpy.trace(cc.r1rdm) - cc.N) < 1e-12
