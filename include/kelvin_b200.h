@@ -139,6 +139,21 @@ int kb200_dress4(const int32_t d[4] /*host*/, const double* eri, const double* s
 int kb200_dress2(int n0, int n1, const double* f, const double* e, const double* s0,
                  const double* s1, double* out, void* stream);
 
+/* ------------------------------------------------------------------------
+ * Active-space (athresh) index subsets.  Replaces the numpy.ix_ gathers of
+ * kelvin/cc_utils.py:825-938 (ft_active_integrals / uft_active_integrals) and the
+ * numpy.ix_ scatters of :1469-1503,1568-1625 (g/u_n2rdm_full_active):
+ *   gather4:      out[i0,i1,i2,i3]  = src[sum_k idx_k[i_k]*src_stride[k]] * prod_k scale_k[i_k]
+ *   scatter4_add: dst[sum_k idx_k[i_k]*dst_stride[k]] += alpha * src[i0,i1,i2,i3] * prod_k scale_k[i_k]
+ * d[], strides and the two pointer arrays are host arrays; idx_k (int32) / scale_k are device
+ * vectors of length d[k], nullptr meaning identity / 1.  Index lists must not repeat entries. */
+int kb200_gather4(const int32_t d[4], const int64_t src_stride[4], const double* src,
+                  const int32_t* const idx[4], const double* const scale[4], double* out,
+                  void* stream);
+int kb200_scatter4_add(const int32_t d[4], const int64_t dst_stride[4], const double* src,
+                       const int32_t* const idx[4], const double* const scale[4], double alpha,
+                       double* dst, void* stream);
+
 /* out[y,p] = sum over nothing: weighted grid sums used by the RDM drivers
  * (kelvin/ft_cc_equations.py:713,737): out[p] = sum_y g[y]*X[y,p]. */
 int kb200_gsum(int ng, int64_t n, const double* X, const double* g, double* out, void* stream);

@@ -20,7 +20,7 @@ EXPORTS = (
     "kb200_version", "kb200_last_error", "kb200_launch_count", "kb200_launch_count_reset",
     "kb200_plan_workspace_bytes", "kb200_plan_run", "kb200_plan_run_timed", "kb200_int_tbar", "kb200_int_L", "kb200_int_tbar_rows", "kb200_int_L_rows",
     "kb200_reduce_scratch_doubles", "kb200_energy_pair", "kb200_dot_g", "kb200_damp_norms",
-    "kb200_dress4", "kb200_dress2", "kb200_gsum", "kb200_scale_by", "kb200_dot_keep",
+    "kb200_dress4", "kb200_dress2", "kb200_gather4", "kb200_scatter4_add", "kb200_gsum", "kb200_scale_by", "kb200_dot_keep",
 )
 
 
@@ -64,6 +64,10 @@ def load():
     lib.kb200_damp_norms.argtypes = [i64, vp, vp, dbl, vp, vp, vp]
     lib.kb200_dress4.argtypes = [ctypes.POINTER(i32), vp, vp, vp, vp, vp, vp, vp]
     lib.kb200_dress2.argtypes = [ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, vp, vp]
+    lib.kb200_gather4.argtypes = [ctypes.POINTER(i32), ctypes.POINTER(i64), vp,
+                                  ctypes.POINTER(vp), ctypes.POINTER(vp), vp, vp]
+    lib.kb200_scatter4_add.argtypes = [ctypes.POINTER(i32), ctypes.POINTER(i64), vp,
+                                       ctypes.POINTER(vp), ctypes.POINTER(vp), dbl, vp, vp]
     lib.kb200_dot_keep.argtypes = [ctypes.c_int, ctypes.POINTER(i32), ctypes.POINTER(i64),
                                    ctypes.POINTER(i64), vp, vp, dbl, dbl, vp, vp, vp]
     lib.kb200_gsum.argtypes = [ctypes.c_int, i64, vp, vp, vp, vp]
@@ -158,3 +162,43 @@ def dot_keep(A, la, B, lb, keep, alpha=1.0, out=None, beta=0.0):
                             ptr(reduce_scratch(dev)), stream_ptr())
     check(rc, "kb200_dot_keep")
     return out
+
+
+def _ptr_array(xs):
+    return (ctypes.c_void_p*4)(*[None if x is None else x.data_ptr() for x in xs])
+
+
+def index_dev(idx, dev):
+    """int32 device copy of a host index list."""
+    import numpy
+    return torch.as_tensor(numpy.asarray(idx, dtype=numpy.int32)).to(dev)
+
+
+def gather4(src, idx, scale, out_shape):
+    """out[i0..i3] = src[idx0[i0], .., idx3[i3]] * prod scale_k[i_k]; idx_k / scale_k are device
+    vectors or None (identity / 1).  kb200_gather4."""
+    lib = load()
+    out = torch.empty(tuple(out_shape), dtype=torch.float64, device=src.device)
+    if out.numel() == 0:
+        return out
+    d = (ctypes.c_int32*4)(*out_shape)
+    st = (ctypes.c_int64*4)(*src.stride())
+    rc = lib.kb200_gather4(d, st, ptr(src), _ptr_array(idx), _ptr_array(scale), ptr(out), stream_ptr())
+    check(rc, "kb200_gather4")
+    return out
+
+
+def scatter4_add(dst, src, idx, scale=(None,)*4, alpha=1.0, perm=(0, 1, 2, 3)):
+    """dst.permute(perm)[idx0[i0], .., idx3[i3]] += alpha * src[i0..i3] * prod scale_k[i_k].
+    kb200_scatter4_add."""
+    lib = load()
+    if src.numel() == 0:
+        return dst
+    src = src.contiguous()
+    d = (ctypes.c_int32*4)(*src.shape)
+    dstride = dst.stride()
+    st = (ctypes.c_int64*4)(*[dstride[p] for p in perm])
+    rc = lib.kb200_scatter4_add(d, st, ptr(src), _ptr_array(idx), _ptr_array(scale), alpha,
+                                ptr(dst), stream_ptr())
+    check(rc, "kb200_scatter4_add")
+    return dst

@@ -95,6 +95,73 @@ def uft_integrals(sys, ea, eb, beta, mu):
     return Fa, Fb, Ia, Ib, Iabab
 
 
+def _sub2(X, rows, cols, dev):
+    r = torch.as_tensor(numpy.asarray(rows, dtype=numpy.int64)).to(dev)
+    c = torch.as_tensor(numpy.asarray(cols, dtype=numpy.int64)).to(dev)
+    return X.index_select(0, r).index_select(1, c).contiguous()
+
+
+class _Space(object):
+    """Index list + sqrt(occupation) dressing vector of one (o|v, spin) active set."""
+    def __init__(self, idx, f, dev):
+        self.host = list(idx)
+        self.idx = _lib.index_dev(idx, dev)
+        self.s = _vec(numpy.sqrt(numpy.asarray(f, dtype=numpy.float64)), dev)
+        self.n = len(self.host)
+
+
+def _active_F(fmo, en, so, sv, dev):
+    """Dressed F - diag(e) restricted to the active sets (kelvin/cc_utils.py:836-840)."""
+    n = fmo.shape[0]
+    one = torch.ones(n, dtype=torch.float64, device=dev)
+    base = _dress2(fmo, _vec(en, dev), one, one)
+    sp = {"o": so, "v": sv}
+    blocks = []
+    for p in ("oo", "ov", "vo", "vv"):
+        a, b = sp[p[0]], sp[p[1]]
+        blocks.append((_sub2(base, a.host, b.host, dev)*a.s[:, None]*b.s[None, :]).contiguous())
+    return one_e_blocks(*blocks)
+
+
+def _active_I(eri, spaces, names, cls):
+    """spaces: per index position a dict {'o': _Space, 'v': _Space}."""
+    out = {}
+    for p in names:
+        sel = [spaces[k][p[k]] for k in range(4)]
+        out[p] = _lib.gather4(eri, [x.idx for x in sel], [x.s for x in sel], [x.n for x in sel])
+    return cls(**out)
+
+
+def ft_active_integrals(sys, en, focc, fvir, iocc, ivir):
+    """Dressed integrals with small occupations excluded (kelvin/cc_utils.py:825-859):
+    block[p,q,r,s] = <P Q||R S> * sqrt(f) ..., P = iocc[p] / ivir[p]."""
+    dev = _lib.device()
+    so, sv = _Space(iocc, focc, dev), _Space(ivir, fvir, dev)
+    F = _active_F(_lib.as_dev(sys.g_fock_tot(), dev), en, so, sv, dev)
+    eri = _lib.as_dev(sys.g_aint_tot(), dev)
+    sp = {"o": so, "v": sv}
+    return F, _active_I(eri, [sp]*4, two_e_blocks.names, two_e_blocks)
+
+
+def uft_active_integrals(sys, ea, eb, foa, fva, fob, fvb, iocca, ivira, ioccb, ivirb):
+    """Unrestricted version (kelvin/cc_utils.py:862-938)."""
+    dev = _lib.device()
+    sa = {"o": _Space(iocca, foa, dev), "v": _Space(ivira, fva, dev)}
+    sb = {"o": _Space(ioccb, fob, dev), "v": _Space(ivirb, fvb, dev)}
+    fa, fb = sys.u_fock_tot()
+    Fa = _active_F(_lib.as_dev(fa, dev), ea, sa["o"], sa["v"], dev)
+    Fb = _active_F(_lib.as_dev(fb, dev), eb, sb["o"], sb["v"], dev)
+    eriA, eriB, eriAB = sys.u_aint_tot()
+    same = eriB is eriA
+    eriA = _lib.as_dev(eriA, dev)
+    eriB = eriA if same else _lib.as_dev(eriB, dev)
+    eriAB = _lib.as_dev(eriAB, dev)
+    Ia = _active_I(eriA, [sa]*4, two_e_blocks.names, two_e_blocks)
+    Ib = _active_I(eriB, [sb]*4, two_e_blocks.names, two_e_blocks)
+    Iabab = _active_I(eriAB, [sa, sb, sa, sb], two_e_blocks_full.names, two_e_blocks_full)
+    return Fa, Fb, Ia, Ib, Iabab
+
+
 # ---------------------------------------------------------------------------
 # amplitude updates
 # ---------------------------------------------------------------------------
@@ -355,6 +422,59 @@ def u_n2rdm_full(beta, sfoa, sfva, sfob, sfvb, P2):
     ab -= sc(P2[4][4], pats[4], "baab").permute(1, 0, 2, 3)
     ab += sc(P2[4][5], pats[4], "baba").permute(1, 0, 3, 2)
     return (out[0], out[1], ab)
+
+
+_P2_PATS = ("vvvv", "vovv", "vvvo", "oovv", "vovo", "vvoo", "oovo", "ovoo", "oooo")
+_ID, _S01, _S23, _S0123 = (0, 1, 2, 3), (1, 0, 2, 3), (0, 1, 3, 2), (1, 0, 3, 2)
+# antisymmetric images of each same-spin block: (sign, destination axis of each source axis)
+_P2_IMAGES = {0: ((1, _ID),), 1: ((1, _ID), (-1, _S01)), 2: ((1, _ID), (-1, _S23)), 3: ((1, _ID),),
+              4: ((1, _ID), (-1, _S23), (-1, _S01), (1, _S0123)), 5: ((1, _ID),),
+              6: ((1, _ID), (-1, _S23)), 7: ((1, _ID), (-1, _S01)), 8: ((1, _ID),)}
+
+
+def _scatter_block(dst, P, pat, spaces, beta, sign, perm):
+    sel = [spaces[k][pat[k]] for k in range(4)]
+    _lib.scatter4_add(dst, P, [x.idx for x in sel], [x.s for x in sel], alpha=sign/beta, perm=perm)
+
+
+def _n2rdm_same_spin_active(beta, n, sp, blocks, dev):
+    n2 = torch.zeros((n,)*4, dtype=torch.float64, device=dev)
+    for k, P in enumerate(blocks):
+        for sign, perm in _P2_IMAGES[k]:
+            _scatter_block(n2, P, _P2_PATS[k], [sp]*4, beta, sign, perm)
+    return n2
+
+
+def g_n2rdm_full_active(beta, n, iocc, ivir, sfo, sfv, P2):
+    """Normal-ordered 2-RDM in the full orbital space from active-space P blocks
+    (kelvin/cc_utils.py:1469-1503); sfo/sfv are the sqrt-occupations of the active sets."""
+    dev = P2[0].device
+    sp = {"o": _Space(iocc, numpy.asarray(sfo)**2, dev), "v": _Space(ivir, numpy.asarray(sfv)**2, dev)}
+    sp["o"].s, sp["v"].s = _vec(sfo, dev), _vec(sfv, dev)
+    return _n2rdm_same_spin_active(beta, n, sp, P2, dev)
+
+
+def u_n2rdm_full_active(beta, na, nb, iocca, ivira, ioccb, ivirb, sfoa, sfva, sfob, sfvb, P2):
+    """kelvin/cc_utils.py:1568-1625."""
+    dev = P2[0][0].device
+
+    def space(io, iv, so, sv):
+        sp = {"o": _Space(io, numpy.asarray(so)**2, dev), "v": _Space(iv, numpy.asarray(sv)**2, dev)}
+        sp["o"].s, sp["v"].s = _vec(so, dev), _vec(sv, dev)
+        return sp
+    sa, sb = space(iocca, ivira, sfoa, sfva), space(ioccb, ivirb, sfob, sfvb)
+    aa = _n2rdm_same_spin_active(beta, na, sa, [P2[b][0] for b in range(9)], dev)
+    bb = _n2rdm_same_spin_active(beta, nb, sb, [P2[b][1] for b in range(9)], dev)
+    ab = torch.zeros((na, nb, na, nb), dtype=torch.float64, device=dev)
+    abab, baba = [sa, sb, sa, sb], [sb, sa, sb, sa]
+    for b in range(9):
+        _scatter_block(ab, P2[b][2], _P2_PATS[b], abab, beta, 1.0, _ID)
+    for b in (1, 2, 6, 7):
+        _scatter_block(ab, P2[b][3], _P2_PATS[b], baba, beta, 1.0, _S0123)
+    _scatter_block(ab, P2[4][3], _P2_PATS[4], [sa, sb, sb, sa], beta, -1.0, _S23)
+    _scatter_block(ab, P2[4][4], _P2_PATS[4], [sb, sa, sa, sb], beta, -1.0, _S01)
+    _scatter_block(ab, P2[4][5], _P2_PATS[4], baba, beta, 1.0, _S0123)
+    return (aa, bb, ab)
 
 
 def g_Fd_on(Fd, ndia, ndba, ndji, ndai):

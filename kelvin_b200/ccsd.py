@@ -6,7 +6,8 @@ Drop-in for the finite-temperature path of ``kelvin.ccsd.ccsd``
 same saved attributes (T1, T2, L1, L2, G0, G1, Gcc, Gtot, dia, dba, dji, dai,
 P2, n1rdm, n2rdm, rono, ronv, ron1) and the same log lines.  Amplitudes are
 CUDA float64 tensors.  Zero-temperature CCSD, ``rt_iter='point'`` and
-``athresh>0`` are outside this path and raise.
+are outside this path and raise; ``athresh>0`` (active-space truncation,
+kelvin/ccsd.py:642-660,745-785) runs the same kernels on rectangular no != nv blocks.
 """
 import logging
 import time
@@ -42,8 +43,6 @@ class ccsd(object):
         self.rt_iter = rt_iter
         if not self.finite_T:
             raise Exception("kelvin_b200.ccsd implements the finite-temperature path only (T > 0)")
-        if self.athresh > 0.0:
-            raise Exception("athresh > 0 (active-space truncation) is not on the B200 path yet")
         if not self.singles:
             raise Exception("singles=False (CCD) is outside the B200 FT-CCSD path")
         self.realtime = True
@@ -80,6 +79,7 @@ class ccsd(object):
         self.rorbo = None
         self.rorbv = None
         self._ints = None
+        self._act = None
 
     # ------------------------------------------------------------------
     def run(self, T1=None, T2=None):
@@ -96,24 +96,74 @@ class ccsd(object):
                 "max_iter": self.max_iter, "damp": self.damp}
 
     # -- dressed integrals, built once per (T, mu) and kept on the device --
+    def _active(self):
+        """Active sets of the occupation-threshold truncation, one dict per spin with
+        fo, fv (all orbitals), focc, fvir, iocc, ivir (entries with f > athresh); with
+        athresh == 0 every orbital is in both sets (kelvin/ccsd.py:642-660, 745-785)."""
+        if self._act is None:
+            beta, mu = self.beta, self.mu
+            ens = self.sys.u_energies_tot() if self.sys.has_u() else (self.sys.g_energies_tot(),)
+            act = []
+            for e in ens:
+                fo, fv = ft_utils.ff(beta, e, mu), ft_utils.ffv(beta, e, mu)
+                iocc = [i for i, x in enumerate(fo) if x > self.athresh]
+                ivir = [i for i, x in enumerate(fv) if x > self.athresh]
+                act.append(dict(e=e, n=e.shape[0], fo=fo, fv=fv, iocc=iocc, ivir=ivir,
+                                focc=fo[iocc], fvir=fv[ivir]))
+            self._act = act
+        return self._act
+
+    def _log_active(self):
+        act = self._active()
+        if len(act) == 1:
+            a = act[0]
+            logging.info("FT-CCSD orbital info:")
+            for nm, v in (("nocc", len(a["iocc"])), ("nvir", len(a["ivir"])),
+                          ("nact", len(a["iocc"]) + len(a["ivir"]) - a["n"])):
+                logging.info('  {}: {:d}'.format(nm, v))
+        else:
+            logging.info("FT-UCCSD orbital info:")
+            for sp, a in zip("ab", act):
+                for nm, v in (("nocc", len(a["iocc"])), ("nvir", len(a["ivir"])),
+                              ("nact", len(a["iocc"]) + len(a["ivir"]) - a["n"])):
+                    logging.info('  {}{}: {:d}'.format(nm, sp, v))
+
     def _g_setup(self):
         if self._ints is None or self._ints[0] != "g":
             en = self.sys.g_energies_tot()
-            D1 = ft_utils.D1(en, en)
-            D2 = ft_utils.D2(en, en)
-            F, I = cc_utils.ft_integrals(self.sys, en, self.beta, self.mu)
+            if self.athresh > 0.0:
+                a, = self._active()
+                ev, eo = en[a["ivir"]], en[a["iocc"]]
+                D1 = ft_utils.D1(ev, eo)
+                D2 = ft_utils.D2(ev, eo)
+                F, I = cc_utils.ft_active_integrals(
+                    self.sys, en, a["focc"], a["fvir"], a["iocc"], a["ivir"])
+            else:
+                D1 = ft_utils.D1(en, en)
+                D2 = ft_utils.D2(en, en)
+                F, I = cc_utils.ft_integrals(self.sys, en, self.beta, self.mu)
             self._ints = ("g", en, D1, D2, F, I)
         return self._ints[1:]
 
     def _u_setup(self):
         if self._ints is None or self._ints[0] != "u":
             ea, eb = self.sys.u_energies_tot()
-            D1a = ft_utils.D1(ea, ea)
-            D1b = ft_utils.D1(eb, eb)
-            D2aa = ft_utils.D2(ea, ea)
-            D2ab = ft_utils.D2u(ea, eb, ea, eb)
-            D2bb = ft_utils.D2(eb, eb)
-            Fa, Fb, Ia, Ib, Iabab = cc_utils.uft_integrals(self.sys, ea, eb, self.beta, self.mu)
+            if self.athresh > 0.0:
+                a, b = self._active()
+                eva, eoa = ea[a["ivir"]], ea[a["iocc"]]
+                evb, eob = eb[b["ivir"]], eb[b["iocc"]]
+                Fa, Fb, Ia, Ib, Iabab = cc_utils.uft_active_integrals(
+                    self.sys, ea, eb, a["focc"], a["fvir"], b["focc"], b["fvir"],
+                    a["iocc"], a["ivir"], b["iocc"], b["ivir"])
+            else:
+                eva = eoa = ea
+                evb = eob = eb
+                Fa, Fb, Ia, Ib, Iabab = cc_utils.uft_integrals(self.sys, ea, eb, self.beta, self.mu)
+            D1a = ft_utils.D1(eva, eoa)
+            D1b = ft_utils.D1(evb, eob)
+            D2aa = ft_utils.D2(eva, eoa)
+            D2ab = ft_utils.D2u(eva, evb, eoa, eob)
+            D2bb = ft_utils.D2(evb, eob)
             self._ints = ("u", ea, eb, (D1a, D1b, D2aa, D2ab, D2bb), (Fa, Fb, Ia, Ib, Iabab))
         return self._ints[1:]
 
@@ -130,6 +180,8 @@ class ccsd(object):
         E0 = ft_mp.mp0(g0) + En
         E1 = self.sys.get_mp1()
         E01 = E0 + E1
+        if self.athresh > 0.0:
+            self._log_active()
 
         if T1in is not None and T2in is not None:
             T1old, T2old = T1in, T2in
@@ -165,6 +217,8 @@ class ccsd(object):
         E0 = ft_mp.ump0(g0[0], g0[1]) + En
         E1 = self.sys.get_mp1()
         E01 = E0 + E1
+        if self.athresh > 0.0:
+            self._log_active()
 
         if T1in is not None and T2in is not None:
             T1aold, T1bold = T1in
@@ -255,13 +309,30 @@ class ccsd(object):
         b = torch.as_tensor(s1, dtype=torch.float64).to(dev)
         return d*a[:, None]*b[None, :]
 
+    def _pad2(self, X, rows, cols, n):
+        """X scattered into an n x n zero matrix at (rows, cols) (the numpy.ix_ updates of
+        kelvin/ccsd.py:1381-1385)."""
+        if len(rows) == n and len(cols) == n:
+            return X
+        dev = X.device
+        out = torch.zeros((n, n), dtype=torch.float64, device=dev)
+        r = torch.as_tensor(numpy.asarray(rows, dtype=numpy.int64)).to(dev)
+        c = torch.as_tensor(numpy.asarray(cols, dtype=numpy.int64)).to(dev)
+        out[r[:, None], c[None, :]] = X
+        return out
+
+    def _n1rdm_total(self, a, ndia, ndba, ndji, ndai):
+        n, io, iv = a["n"], a["iocc"], a["ivir"]
+        return (self._pad2(ndia, io, iv, n) + self._pad2(ndba, iv, iv, n)
+                + self._pad2(ndji, io, io, n) + self._pad2(ndai, iv, io, n))/self.beta
+
     def _g_ft_1rdm(self):
         """kelvin/ccsd.py:1333-1387."""
         if self.L2 is None:
             self._ft_ccsd_lambda()
         en, D1, D2, F, I = self._g_setup()
-        (fo, fv), = self._occ()
-        sfo, sfv = numpy.sqrt(fo), numpy.sqrt(fv)
+        a, = self._active()
+        sfo, sfv = numpy.sqrt(a["focc"]), numpy.sqrt(a["fvir"])
         pia, pba, pji, pai = ft_cc_equations.ccsd_1rdm(
             self.T1, self.T2, self.L1, self.L2, D1, D2, self.ti, self.ngrid, self.g, self.G)
         self.dia, self.dba, self.dji, self.dai = pia, pba, pji, pai
@@ -269,44 +340,55 @@ class ccsd(object):
         self.ndba = self._nd(pba, sfv, sfv)
         self.ndji = self._nd(pji, sfo, sfo)
         self.ndai = self._nd(pai, sfv, sfo)
-        self.n1rdm = (self.ndia + self.ndba + self.ndji + self.ndai)/self.beta
+        self.n1rdm = self._n1rdm_total(a, self.ndia, self.ndba, self.ndji, self.ndai)
 
     def _g_ft_2rdm(self):
         """kelvin/ccsd.py:1389-1432."""
         if self.L2 is None:
             self._ft_ccsd_lambda()
         en, D1, D2, F, I = self._g_setup()
-        (fo, fv), = self._occ()
+        a, = self._active()
+        sfo, sfv = numpy.sqrt(a["focc"]), numpy.sqrt(a["fvir"])
         self.P2 = ft_cc_equations.ccsd_2rdm(
             self.T1, self.T2, self.L1, self.L2, D1, D2, self.ti, self.ngrid, self.g, self.G)
-        self.n2rdm = cc_utils.g_n2rdm_full(self.beta, numpy.sqrt(fo), numpy.sqrt(fv), self.P2)
+        if self.athresh > 0.0:
+            self.n2rdm = cc_utils.g_n2rdm_full_active(
+                self.beta, a["n"], a["iocc"], a["ivir"], sfo, sfv, self.P2)
+        else:
+            self.n2rdm = cc_utils.g_n2rdm_full(self.beta, sfo, sfv, self.P2)
 
     def _u_ft_1rdm(self):
         """kelvin/ccsd.py:1579-1665."""
         if self.L2 is None:
             self._ft_uccsd_lambda()
         ea, eb, Ds, ints = self._u_setup()
-        (foa, fva), (fob, fvb) = self._occ()
+        act = self._active()
         sq = numpy.sqrt
         pia, pba, pji, pai = ft_cc_equations.uccsd_1rdm(
             *self.T1, *self.T2, *self.L1, *self.L2, *Ds, self.ti, self.ngrid, self.g, self.G)
         self.dia, self.dba, self.dji, self.dai = pia, pba, pji, pai
-        so, sv = (sq(foa), sq(fob)), (sq(fva), sq(fvb))
+        so, sv = [sq(a["focc"]) for a in act], [sq(a["fvir"]) for a in act]
         self.ndia = tuple(self._nd(pia[k], so[k], sv[k]) for k in (0, 1))
         self.ndba = tuple(self._nd(pba[k], sv[k], sv[k]) for k in (0, 1))
         self.ndji = tuple(self._nd(pji[k], so[k], so[k]) for k in (0, 1))
         self.ndai = tuple(self._nd(pai[k], sv[k], so[k]) for k in (0, 1))
-        self.n1rdm = [(self.ndia[k] + self.ndba[k] + self.ndji[k] + self.ndai[k])/self.beta
-                      for k in (0, 1)]
+        self.n1rdm = [self._n1rdm_total(act[k], self.ndia[k], self.ndba[k], self.ndji[k],
+                                        self.ndai[k]) for k in (0, 1)]
 
     def _u_ft_2rdm(self):
         """kelvin/ccsd.py:1667-1729."""
         ea, eb, Ds, ints = self._u_setup()
-        (foa, fva), (fob, fvb) = self._occ()
+        a, b = self._active()
         sq = numpy.sqrt
         self.P2 = ft_cc_equations.uccsd_2rdm(
             *self.T1, *self.T2, *self.L1, *self.L2, *Ds, self.ti, self.ngrid, self.g, self.G)
-        self.n2rdm = cc_utils.u_n2rdm_full(self.beta, sq(foa), sq(fva), sq(fob), sq(fvb), self.P2)
+        if self.athresh > 0.0:
+            self.n2rdm = cc_utils.u_n2rdm_full_active(
+                self.beta, a["n"], b["n"], a["iocc"], a["ivir"], b["iocc"], b["ivir"],
+                sq(a["focc"]), sq(a["fvir"]), sq(b["focc"]), sq(b["fvir"]), self.P2)
+        else:
+            self.n2rdm = cc_utils.u_n2rdm_full(self.beta, sq(a["focc"]), sq(a["fvir"]),
+                                               sq(b["focc"]), sq(b["fvir"]), self.P2)
 
     # ------------------------------------------------------------------
     # occupation-number response (kelvin/ccsd.py:1434-1492, 1731-1826)
@@ -350,30 +432,47 @@ class ccsd(object):
             return "b"
         return "a" if pos % 2 == 0 else "b"
 
+    def _padded_nd(self, a, k):
+        """(ndia, ndba, ndji, ndai) of one spin as host arrays in the full orbital space;
+        zero rows/columns outside the active sets make g_Fd_on equal to the reference's
+        g_Fd_on_active / u_Fd_on_active (kelvin/cc_utils.py:1636-1645, 1709-1743)."""
+        n, io, iv = a["n"], a["iocc"], a["ivir"]
+        pick = (lambda x: x) if k is None else (lambda x: x[k])
+        return (self._pad2(pick(self.ndia), io, iv, n).cpu().numpy(),
+                self._pad2(pick(self.ndba), iv, iv, n).cpu().numpy(),
+                self._pad2(pick(self.ndji), io, io, n).cpu().numpy(),
+                self._pad2(pick(self.ndai), iv, io, n).cpu().numpy())
+
     def _g_ft_ron(self):
         """kelvin/ccsd.py:1434-1492."""
-        (fo, fv), = self._occ()
+        a, = self._active()
         self.ron1 = self.sys.g_mp1_den()
         Fd = self.sys.g_fock_d_den()
         c = lambda x: x.cpu().numpy()  # noqa: E731
-        rono = cc_utils.g_Fd_on(Fd, c(self.ndia), c(self.ndba), c(self.ndji), c(self.ndai))
+        rono = cc_utils.g_Fd_on(Fd, *self._padded_nd(a, None))
         acc = cc_utils.on_response(self._leaf_list(), None, self._spin_of_leaf)
-        self.rono = rono - 0.5*c(acc[("o", "g")])*fv
-        self.ronv = 0.5*c(acc[("v", "g")])*fo
+        ronv = numpy.zeros_like(rono)
+        io, iv = a["iocc"], a["ivir"]
+        rono[io] -= 0.5*c(acc[("o", "g")])*a["fv"][io]
+        ronv[iv] += 0.5*c(acc[("v", "g")])*a["fo"][iv]
+        self.rono, self.ronv = rono, ronv
 
     def _u_ft_ron(self):
         """kelvin/ccsd.py:1731-1826."""
-        (foa, fva), (fob, fvb) = self._occ()
+        act = self._active()
         mp1da, mp1db = self.sys.u_mp1_den()
         self.ron1 = [mp1da, mp1db]
         Fdaa, Fdab, Fdbb, Fdba = self.sys.u_fock_d_den()
         c = lambda x: x.cpu().numpy()  # noqa: E731
-        cc2 = lambda t: (c(t[0]), c(t[1]))  # noqa: E731
-        tA, tB = cc_utils.u_Fd_on(Fdaa, Fdab, Fdba, Fdbb, cc2(self.ndia), cc2(self.ndba),
-                                  cc2(self.ndji), cc2(self.ndai))
+        nda, ndb = self._padded_nd(act[0], 0), self._padded_nd(act[1], 1)
+        tA, tB = cc_utils.u_Fd_on(Fdaa, Fdab, Fdba, Fdbb, *zip(nda, ndb))
         acc = cc_utils.on_response(self._leaf_list(), None, self._spin_of_leaf)
-        self.rono = [tA - 0.5*c(acc[("o", "a")])*fva, tB - 0.5*c(acc[("o", "b")])*fvb]
-        self.ronv = [0.5*c(acc[("v", "a")])*foa, 0.5*c(acc[("v", "b")])*fob]
+        rono, ronv = [tA, tB], [numpy.zeros_like(tA), numpy.zeros_like(tB)]
+        for k, sp in enumerate("ab"):
+            io, iv = act[k]["iocc"], act[k]["ivir"]
+            rono[k][io] -= 0.5*c(acc[("o", sp)])*act[k]["fv"][io]
+            ronv[k][iv] += 0.5*c(acc[("v", sp)])*act[k]["fo"][iv]
+        self.rono, self.ronv = rono, ronv
 
     # ------------------------------------------------------------------
     # orbital-energy response and relaxed 1-RDM (kelvin/ccsd.py:1494-1577, 1828-1959)
@@ -417,25 +516,30 @@ class ccsd(object):
         """kelvin/ccsd.py:1494-1545."""
         Tt = self._tau_weighted_stanton()
         L1, L2 = _lib.as_dev(self.L1), _lib.as_dev(self.L2)
-        n = L1.shape[1]
+        a, = self._active()
         s = -1.0/self.beta
-        o, v = self._rorb_traces([(L1, Tt[0], s, "i", "a"), (L2, Tt[1], 0.25*s, "ij", "ab")], n, n)
-        self.rorbo = -o
-        self.rorbv = v
+        o, v = self._rorb_traces([(L1, Tt[0], s, "i", "a"), (L2, Tt[1], 0.25*s, "ij", "ab")],
+                                 L1.shape[1], L1.shape[2])
+        self.rorbo, self.rorbv = numpy.zeros(a["n"]), numpy.zeros(a["n"])
+        self.rorbo[a["iocc"]] -= o
+        self.rorbv[a["ivir"]] += v
 
     def _u_ft_rorb(self):
         """kelvin/ccsd.py:1828-1918."""
         Tt = self._tau_weighted_stanton()
         L1a, L1b = (_lib.as_dev(x) for x in self.L1)
         L2aa, L2ab, L2bb = (_lib.as_dev(x) for x in self.L2)
-        na, nb = L1a.shape[1], L1b.shape[1]
+        act = self._active()
         s = -1.0/self.beta
         oa, va = self._rorb_traces([(L1a, Tt[0], s, "i", "a"), (L2aa, Tt[2], 0.25*s, "ij", "ab"),
-                                    (L2ab, Tt[3], s, "i", "a")], na, na)
+                                    (L2ab, Tt[3], s, "i", "a")], L1a.shape[1], L1a.shape[2])
         ob, vb = self._rorb_traces([(L1b, Tt[1], s, "i", "a"), (L2bb, Tt[4], 0.25*s, "ij", "ab"),
-                                    (L2ab, Tt[3], s, "j", "b")], nb, nb)
-        self.rorbo = [-oa, -ob]
-        self.rorbv = [va, vb]
+                                    (L2ab, Tt[3], s, "j", "b")], L1b.shape[1], L1b.shape[2])
+        self.rorbo = [numpy.zeros(a["n"]) for a in act]
+        self.rorbv = [numpy.zeros(a["n"]) for a in act]
+        for k, (o, v) in enumerate(((oa, va), (ob, vb))):
+            self.rorbo[k][act[k]["iocc"]] -= o
+            self.rorbv[k][act[k]["ivir"]] += v
 
     def _grel_ft_1rdm(self):
         """kelvin/ccsd.py:1547-1577."""
@@ -463,6 +567,14 @@ class ccsd(object):
         self.r1rdm = [numpy.diag(self.rono[k] + self.ron1[k] + self.rorbo[k] + fo[k]
                                  + self.ronv[k] + self.rorbv[k]) for k in (0, 1)]
 
+    def _focc_padded(self):
+        """Occupations with the entries outside the active occupied set zeroed: adding
+        diag() of these over all orbitals equals the reference's numpy.ix_(iocc, iocc)
+        updates (kelvin/ccsd.py:1975-1983, cc_utils.py:2027-2073).  The reference's g
+        branch adds the untruncated diag(fo) into the iocc block (ccsd.py:2001), which only
+        works when nothing is truncated; the truncated vector is used here."""
+        return [numpy.where(a["fo"] > self.athresh, a["fo"], 0.0) for a in self._active()]
+
     def full_1rdm(self, relax=False):
         """Full (HF + correlation) 1-RDM as NumPy arrays (kelvin/ccsd.py:1961-2006)."""
         c = lambda x: x.cpu().numpy()  # noqa: E731
@@ -474,7 +586,7 @@ class ccsd(object):
                 return [self.r1rdm[k] + (n1[k] - numpy.diag(n1[k].diagonal())) for k in (0, 1)]
             if self.n1rdm is None:
                 self._u_ft_1rdm()
-            (foa, fva), (fob, fvb) = self._occ()
+            foa, fob = self._focc_padded()
             return [c(self.n1rdm[0]) + numpy.diag(foa), c(self.n1rdm[1]) + numpy.diag(fob)]
         elif self.sys.orbtype == 'g':
             if relax:
@@ -484,7 +596,7 @@ class ccsd(object):
                 return self.r1rdm + (n1 - numpy.diag(n1.diagonal()))
             if self.n1rdm is None:
                 self._g_ft_1rdm()
-            (fo, fv), = self._occ()
+            fo, = self._focc_padded()
             return c(self.n1rdm) + numpy.diag(fo)
         raise Exception("orbital type " + self.sys.orbtype + " is not implemented for 1rdm")
 
@@ -497,7 +609,7 @@ class ccsd(object):
                 self._u_ft_1rdm()
             if self.n2rdm is None:
                 self._u_ft_2rdm()
-            (foa, fva), (fob, fvb) = self._occ()
+            foa, fob = self._focc_padded()
             rdm2 = [x.clone() for x in self.n2rdm]
             cc_utils.u_full_rdm2(foa, fob, self.n1rdm, rdm2)
             return rdm2
@@ -506,7 +618,7 @@ class ccsd(object):
                 self._g_ft_1rdm()
             if self.n2rdm is None:
                 self._g_ft_2rdm()
-            (fo, fv), = self._occ()
+            fo, = self._focc_padded()
             rdm2 = self.n2rdm.clone()
             cc_utils.g_full_rdm2(fo, self.n1rdm, rdm2)
             return rdm2

@@ -268,6 +268,58 @@ __global__ void dress4_kernel(int d0, int d1, int d2, int d3, const double* __re
     }
 }
 
+// Index-subset variants for the active-space (athresh) path: every axis may carry an index
+// list (device int32, nullptr = identity) into a larger strided array.
+struct Sub4 {
+    int d[4];
+    long long st[4];
+    const int* idx[4];
+    const double* sc[4];
+};
+
+__global__ void gather4_kernel(Sub4 q, const double* __restrict__ src, double* __restrict__ out) {
+    const long long n = (long long)q.d[0] * q.d[1] * q.d[2] * q.d[3];
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < n;
+         p += (long long)gridDim.x * blockDim.x) {
+        unsigned r = (unsigned)p;
+        unsigned i[4];
+        i[3] = r % (unsigned)q.d[3]; r /= (unsigned)q.d[3];
+        i[2] = r % (unsigned)q.d[2]; r /= (unsigned)q.d[2];
+        i[1] = r % (unsigned)q.d[1]; r /= (unsigned)q.d[1];
+        i[0] = r;
+        long long off = 0;
+        double f = 1.0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            off += (long long)(q.idx[k] ? q.idx[k][i[k]] : (int)i[k]) * q.st[k];
+            if (q.sc[k]) f *= q.sc[k][i[k]];
+        }
+        out[p] = src[off] * f;
+    }
+}
+
+__global__ void scatter4_add_kernel(Sub4 q, double alpha, const double* __restrict__ src,
+                                    double* __restrict__ dst) {
+    const long long n = (long long)q.d[0] * q.d[1] * q.d[2] * q.d[3];
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < n;
+         p += (long long)gridDim.x * blockDim.x) {
+        unsigned r = (unsigned)p;
+        unsigned i[4];
+        i[3] = r % (unsigned)q.d[3]; r /= (unsigned)q.d[3];
+        i[2] = r % (unsigned)q.d[2]; r /= (unsigned)q.d[2];
+        i[1] = r % (unsigned)q.d[1]; r /= (unsigned)q.d[1];
+        i[0] = r;
+        long long off = 0;
+        double f = alpha;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            off += (long long)(q.idx[k] ? q.idx[k][i[k]] : (int)i[k]) * q.st[k];
+            if (q.sc[k]) f *= q.sc[k][i[k]];
+        }
+        dst[off] += src[p] * f;      // index lists hold distinct entries: no two threads collide
+    }
+}
+
 __global__ void dress2_kernel(int n0, int n1, const double* __restrict__ f,
                               const double* __restrict__ e, const double* __restrict__ s0,
                               const double* __restrict__ s1, double* __restrict__ out) {
@@ -690,6 +742,42 @@ int kb200_dress4(const int32_t d[4], const double* eri, const double* s0, const 
     if (n <= 0 || n >= (1LL << 31)) return fail(-1, "dress4: bad dims");
     dress4_kernel<<<grid_for(n, 256), 256, 0, st>>>(d[0], d[1], d[2], d[3], eri, s0, s1, s2, s3, out);
     KB_CHECK_LAUNCH("dress4_kernel");
+    return 0;
+}
+
+static int fill_sub4(Sub4& q, const int32_t d[4], const int64_t st[4], const int32_t* const idx[4],
+                     const double* const sc[4]) {
+    long long n = 1;
+    for (int k = 0; k < 4; ++k) {
+        if (d[k] <= 0) return -1;
+        q.d[k] = d[k];
+        q.st[k] = st[k];
+        q.idx[k] = idx ? idx[k] : nullptr;
+        q.sc[k] = sc ? sc[k] : nullptr;
+        n *= d[k];
+    }
+    return n < (1LL << 31) ? 0 : -1;
+}
+
+int kb200_gather4(const int32_t d[4], const int64_t src_stride[4], const double* src,
+                  const int32_t* const idx[4], const double* const scale[4], double* out,
+                  void* stream) {
+    Sub4 q;
+    if (fill_sub4(q, d, src_stride, idx, scale)) return fail(-1, "gather4: bad dims");
+    long long n = (long long)d[0] * d[1] * d[2] * d[3];
+    gather4_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(q, src, out);
+    KB_CHECK_LAUNCH("gather4_kernel");
+    return 0;
+}
+
+int kb200_scatter4_add(const int32_t d[4], const int64_t dst_stride[4], const double* src,
+                       const int32_t* const idx[4], const double* const scale[4], double alpha,
+                       double* dst, void* stream) {
+    Sub4 q;
+    if (fill_sub4(q, d, dst_stride, idx, scale)) return fail(-1, "scatter4_add: bad dims");
+    long long n = (long long)d[0] * d[1] * d[2] * d[3];
+    scatter4_add_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(q, alpha, src, dst);
+    KB_CHECK_LAUNCH("scatter4_add_kernel");
     return 0;
 }
 

@@ -316,19 +316,21 @@ _U2 = {  # spin-block slices of each g 2-RDM block type, in the tuple order of
 
 
 def _u_rdm(name, T1a, T1b, T2aa, T2ab, T2bb, L1a, L1b, L2aa, L2ab, L2bb):
-    na = T1a.shape[0]
+    nva, noa = T1a.shape
     t1, t2 = _t_to_spin(T1a, T1b, T2aa, T2ab, T2bb)
     l1, l2 = _l_to_spin(L1a, L1b, L2aa, L2ab, L2bb)
-    key = ("u", T1a.shape, float(T1a.ravel()[0]), float(T2ab.ravel()[-1]),
+    key = ("u", T1a.shape, T1b.shape, float(T1a.ravel()[0]), float(T2ab.ravel()[-1]),
            float(L1a.ravel()[0]), float(L2ab.ravel()[-1]), float(L2bb.ravel()[1]))
     if _rdm_cache.get("ukey") != key:
         _rdm_cache["ukey"] = key
         _rdm_cache["uval"] = dict(_rdm_all(t1, t2, l1, l2))
     P = _rdm_cache["uval"][name]
+    # alpha/beta ranges of every axis: virtual letters split at nva, occupied letters at noa
+    cut = [nva if c in "abcd" else noa for c in name]
+    sl = [(slice(0, n), slice(n, None)) for n in cut]
     if P.ndim == 2:
-        return P[:na, :na].copy(), P[na:, na:].copy()
-    sl = (slice(0, na), slice(na, None))
-    return tuple(P[sl[s[0]], sl[s[1]], sl[s[2]], sl[s[3]]].copy() for s in _U2[name])
+        return P[sl[0][0], sl[1][0]].copy(), P[sl[0][1], sl[1][1]].copy()
+    return tuple(P[sl[0][s[0]], sl[1][s[1]], sl[2][s[2]], sl[3][s[3]]].copy() for s in _U2[name])
 
 
 def _mku(name):

@@ -57,6 +57,27 @@ def test_stanton_plan_u_rectangular():
             assert numpy.abs(arr[nm][y] - rr).max() < 1e-12
 
 
+def test_plans_g_active_space_shapes():
+    """no != nv (athresh > 0, kelvin/ccsd.py:642-660): residual and Lambda plans on
+    rectangular blocks against the oracle."""
+    no, nv, ng = 3, 5, 2
+    F, I, t1, t2, l1, l2 = util.random_g_rect(no, nv, ng, seed=11)
+    sizes = {"o": no, "v": nv}
+    rops = plan.expand(programs.stanton(-1.0), programs.tensor_defs(), "g")
+    arr, _ = _run(rops, "g", sizes, {"t1": t1, "t2": t2}, {"F": F, "I": I}, ng)
+    inter, rest = programs.lambda_rops("g", -1.0)
+    lar, _ = _run(inter + rest, "g", sizes, {"t1": t1, "t2": t2, "l1": l1, "l2": l2},
+                  {"F": F, "I": I}, ng)
+    for y in range(ng):
+        R1, R2 = ocq.stanton_terms(F, I, t1[y], t2[y])
+        assert numpy.abs(arr["o1"][y] - (-F.vo - R1)).max() < 1e-12
+        assert numpy.abs(arr["o2"][y] - (-I.vvoo - R2)).max() < 1e-12
+        d1, d2 = ocq.lambda_terms(F, I, l1[y], l2[y], t1[y], t2[y])
+        r1 = -d1 - F.ov - numpy.einsum('jiba,bj->ia', I.oovv, t1[y])
+        assert numpy.abs(lar["lo1"][y] - r1).max() < 1e-12
+        assert numpy.abs(lar["lo2"][y] - (-d2 - I.oovv)).max() < 1e-12
+
+
 def test_u_plan_has_32_block_gemms():
     """32 Sz-allowed m^6 block GEMMs per residual (64 m^6 flops)."""
     m = 6

@@ -27,6 +27,27 @@ def random_g(n, ng, seed=0, scale=0.3):
     return F, I, t1, t2
 
 
+def random_g_rect(no, nv, ng, seed=0, scale=0.3):
+    """As random_g with no != nv (active-space truncation, kelvin/ccsd.py:642-660)."""
+    rng = numpy.random.default_rng(seed)
+    dim = {"o": no, "v": nv}
+    F = cqc.one_e_blocks(*[rng.standard_normal((dim[p[0]], dim[p[1]])) for p in ("oo", "ov", "vo", "vv")])
+    blocks = {}
+    for p in cqc.two_e_blocks.names:
+        x = rng.standard_normal(tuple(dim[c] for c in p))
+        if p[0] == p[1]:
+            x = x - x.transpose(1, 0, 2, 3)
+        if p[2] == p[3]:
+            x = x - x.transpose(0, 1, 3, 2)
+        blocks[p] = numpy.ascontiguousarray(x)
+    I = cqc.two_e_blocks(**blocks)
+    t1 = scale*rng.standard_normal((ng, nv, no))
+    t2 = numpy.ascontiguousarray(scale*asym(rng.standard_normal((ng, nv, nv, no, no))))
+    l1 = rng.standard_normal((ng, no, nv))
+    l2 = numpy.ascontiguousarray(asym(rng.standard_normal((ng, no, no, nv, nv))))
+    return F, I, t1, t2, l1, l2
+
+
 def random_u(na, nb, ng, seed=1, scale=0.3):
     """Random unrestricted inputs whose 34 integral blocks are distinct but
     mutually consistent (one underlying <pq|rs> per spin case, dressed with
