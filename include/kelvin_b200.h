@@ -54,6 +54,9 @@ typedef struct kb200_op {
     int32_t b_mode;        /* 0: B gathers contiguously along k, 1: along n    */
     int32_t tile;          /* CTA tile id: 0 128x128, 1 128x32, 5 64x64 (see kb200.cu) */
     int32_t splitk;        /* >=1; >1 uses the workspace + deterministic reduce */
+    int32_t group;         /* kind 0: this op and the next group-1 ops (same tile/a_mode/b_mode,
+                              splitk 1, mutually independent) share one launch; 0/1 = alone */
+    int32_t reserved;
 } kb200_op;
 
 /* Bytes of workspace kb200_plan_run needs for these ops (split-K partials). */

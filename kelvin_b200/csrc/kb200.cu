@@ -414,7 +414,7 @@ int grid_for(long long n, int threads, int cap = 148 * 16) {
 // GEMM dispatch
 // ---------------------------------------------------------------------------
 template <int WMs, int WNs, int WM, int WN, int AM, int BM_, int ST, bool ILV, int MINB>
-int launch_gemm_inst(const kb200::GemmParams& p, int batch, cudaStream_t st) {
+int launch_gemm_inst(const kb200::GemmGroup& grp, int splitk, cudaStream_t st) {
     using namespace kb200;
     constexpr int BMt = WMs * WM, BNt = WNs * WN, NT = WMs * WNs * 32;
     constexpr int smem = ST * (TileLoader<BMt, NT, AM>::STAGE + TileLoader<BNt, NT, BM_>::STAGE) * 8;
@@ -425,18 +425,18 @@ int launch_gemm_inst(const kb200::GemmParams& p, int batch, cudaStream_t st) {
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(gemm)");
         configured = true;
     }
-    dim3 grid(p.tilesM * p.tilesN * batch, p.splitk, 1);
-    kern<<<grid, NT, smem, st>>>(p);
+    dim3 grid(grp.fend[grp.n - 1] + grp.rend[grp.n - 1], splitk, 1);
+    kern<<<grid, NT, smem, st>>>(grp);
     KB_CHECK_LAUNCH("gemm_tab_kernel");
     return 0;
 }
 
 template <int WMs, int WNs, int WM, int WN, int ST, bool ILV, int MINB = 1>
-int launch_gemm_modes(const kb200::GemmParams& p, int batch, int am, int bm, cudaStream_t st) {
-    if (am == 0 && bm == 0) return launch_gemm_inst<WMs, WNs, WM, WN, 0, 0, ST, ILV, MINB>(p, batch, st);
-    if (am == 0 && bm == 1) return launch_gemm_inst<WMs, WNs, WM, WN, 0, 1, ST, ILV, MINB>(p, batch, st);
-    if (am == 1 && bm == 0) return launch_gemm_inst<WMs, WNs, WM, WN, 1, 0, ST, ILV, MINB>(p, batch, st);
-    return launch_gemm_inst<WMs, WNs, WM, WN, 1, 1, ST, ILV, MINB>(p, batch, st);
+int launch_gemm_modes(const kb200::GemmGroup& p, int splitk, int am, int bm, cudaStream_t st) {
+    if (am == 0 && bm == 0) return launch_gemm_inst<WMs, WNs, WM, WN, 0, 0, ST, ILV, MINB>(p, splitk, st);
+    if (am == 0 && bm == 1) return launch_gemm_inst<WMs, WNs, WM, WN, 0, 1, ST, ILV, MINB>(p, splitk, st);
+    if (am == 1 && bm == 0) return launch_gemm_inst<WMs, WNs, WM, WN, 1, 0, ST, ILV, MINB>(p, splitk, st);
+    return launch_gemm_inst<WMs, WNs, WM, WN, 1, 1, ST, ILV, MINB>(p, splitk, st);
 }
 
 // tile ids: 0 = 128x128, 8 warps (64x32 warp tiles), interleaved loads
@@ -512,44 +512,70 @@ static int run_plan_impl(const kb200_op* ops, int nops, const uint32_t* tables,
         if (o.a < 0 || o.a >= nslots || o.c < 0 || o.c >= nslots) return fail(-1, "plan: bad slot");
         if (o.M <= 0 || o.N <= 0 || o.batch <= 0) return fail(-1, "plan: empty op");
         if (o.kind == 0) {
-            if (o.b < 0 || o.b >= nslots || o.K <= 0) return fail(-1, "plan: bad contraction");
-            kb200::GemmParams p;
-            p.A = slots[o.a] + o.a_off;
-            p.B = slots[o.b] + o.b_off;
-            p.C = slots[o.c] + o.c_off;
-            p.am = tables + o.tAm; p.ak = tables + o.tAk;
-            p.bk = tables + o.tBk; p.bn = tables + o.tBn;
-            p.cm = tables + o.tCm; p.cn = tables + o.tCn;
-            p.M = o.M; p.N = o.N; p.K = o.K;
-            p.splitk = o.splitk < 1 ? 1 : o.splitk;
-            int nkt = (o.K + kb200::BK - 1) / kb200::BK;
-            if (p.splitk > nkt) p.splitk = nkt;
-            p.kchunk = ((nkt + p.splitk - 1) / p.splitk) * kb200::BK;
-            p.splitk = (o.K + p.kchunk - 1) / p.kchunk;
-            p.bsA = o.bsA; p.bsB = o.bsB; p.bsC = o.bsC;
-            p.alpha = o.alpha; p.beta = o.beta;
-            p.partial = workspace;
+            // a group leader carries the number of consecutive, mutually independent ops of the
+            // same kernel configuration that share its launch
+            int ng = o.group > 1 ? o.group : 1;
+            if (ng > kb200::MAX_GROUP || i + ng > nops) return fail(-1, "plan: bad group");
+            kb200::GemmGroup grp;
+            grp.n = ng;
             int BMt = tile_bm(o.tile), BNt = tile_bn(o.tile);
-            p.tilesM = (o.M + BMt - 1) / BMt;
-            p.tilesN = (o.N + BNt - 1) / BNt;
-            p.batch = o.batch;
+            int fsum = 0, rsum = 0;
+            for (int m = 0; m < ng; ++m) {
+                const kb200_op& q = ops[i + m];
+                if (q.kind != 0 || q.tile != o.tile || q.a_mode != o.a_mode || q.b_mode != o.b_mode ||
+                    (ng > 1 && q.splitk > 1))
+                    return fail(-1, "plan: inconsistent group");
+                if (q.a < 0 || q.a >= nslots || q.c < 0 || q.c >= nslots || q.b < 0 || q.b >= nslots ||
+                    q.K <= 0 || q.M <= 0 || q.N <= 0 || q.batch <= 0)
+                    return fail(-1, "plan: bad contraction");
+                kb200::GemmParams& p = grp.p[m];
+                p.A = slots[q.a] + q.a_off;
+                p.B = slots[q.b] + q.b_off;
+                p.C = slots[q.c] + q.c_off;
+                p.am = tables + q.tAm; p.ak = tables + q.tAk;
+                p.bk = tables + q.tBk; p.bn = tables + q.tBn;
+                p.cm = tables + q.tCm; p.cn = tables + q.tCn;
+                p.M = q.M; p.N = q.N; p.K = q.K;
+                p.splitk = q.splitk < 1 ? 1 : q.splitk;
+                int nkt = (q.K + kb200::BK - 1) / kb200::BK;
+                if (p.splitk > nkt) p.splitk = nkt;
+                p.kchunk = ((nkt + p.splitk - 1) / p.splitk) * kb200::BK;
+                p.splitk = (q.K + p.kchunk - 1) / p.kchunk;
+                p.bsA = q.bsA; p.bsB = q.bsB; p.bsC = q.bsC;
+                p.alpha = q.alpha; p.beta = q.beta;
+                p.partial = workspace;
+                p.tilesM = (q.M + BMt - 1) / BMt;
+                p.tilesN = (q.N + BNt - 1) / BNt;
+                p.batch = q.batch;
+                int fm = p.tilesM - ((q.M % BMt) ? 1 : 0), fn = p.tilesN - ((q.N % BNt) ? 1 : 0);
+                fsum += fm * fn * q.batch;
+                rsum += (p.tilesM * p.tilesN - fm * fn) * q.batch;
+                grp.fend[m] = fsum;
+                grp.rend[m] = rsum;
+            }
+            for (int m = ng; m < kb200::MAX_GROUP; ++m) {
+                grp.p[m] = grp.p[0];
+                grp.fend[m] = fsum;
+                grp.rend[m] = rsum;
+            }
+            const kb200::GemmParams& p = grp.p[0];
             if (p.splitk > 1) {
                 int64_t need = (int64_t)o.batch * p.splitk * (int64_t)o.M * o.N * 8;
                 if (workspace == nullptr || need > workspace_bytes) return fail(-1, "plan: workspace too small");
             }
             int rc;
             if (o.tile == 0)
-                rc = launch_gemm_modes<2, 4, 64, 32, 4, true>(p, o.batch, o.a_mode, o.b_mode, st);
+                rc = launch_gemm_modes<2, 4, 64, 32, 4, true>(grp, p.splitk, o.a_mode, o.b_mode, st);
             else if (o.tile == 1)
-                rc = launch_gemm_modes<8, 1, 16, 32, 4, true>(p, o.batch, o.a_mode, o.b_mode, st);
+                rc = launch_gemm_modes<8, 1, 16, 32, 4, true>(grp, p.splitk, o.a_mode, o.b_mode, st);
             else if (o.tile == 2)
-                rc = launch_gemm_modes<4, 4, 32, 32, 4, true>(p, o.batch, o.a_mode, o.b_mode, st);
+                rc = launch_gemm_modes<4, 4, 32, 32, 4, true>(grp, p.splitk, o.a_mode, o.b_mode, st);
             else if (o.tile == 3)
-                rc = launch_gemm_modes<2, 4, 64, 32, 4, false>(p, o.batch, o.a_mode, o.b_mode, st);
+                rc = launch_gemm_modes<2, 4, 64, 32, 4, false>(grp, p.splitk, o.a_mode, o.b_mode, st);
             else if (o.tile == 4)
-                rc = launch_gemm_modes<4, 2, 32, 32, 3, true, 2>(p, o.batch, o.a_mode, o.b_mode, st);
+                rc = launch_gemm_modes<4, 2, 32, 32, 3, true, 2>(grp, p.splitk, o.a_mode, o.b_mode, st);
             else if (o.tile == 5)
-                rc = launch_gemm_modes<2, 2, 32, 32, 3, true, 3>(p, o.batch, o.a_mode, o.b_mode, st);
+                rc = launch_gemm_modes<2, 2, 32, 32, 3, true, 3>(grp, p.splitk, o.a_mode, o.b_mode, st);
             else
                 return fail(-1, "plan: unknown tile id");
             if (rc) return rc;
@@ -558,6 +584,16 @@ static int run_plan_impl(const kb200_op* ops, int nops, const uint32_t* tables,
                 kb200::splitk_reduce_kernel<<<grid_for(total, 256), 256, 0, st>>>(p, o.batch);
                 KB_CHECK_LAUNCH("splitk_reduce_kernel");
             }
+            if (ev) {
+                // the group's time is recorded on its leader; the other members read 0
+                cudaEventRecord(ev[2 * i + 1], st);
+                for (int m = 1; m < ng; ++m) {
+                    cudaEventRecord(ev[2 * (i + m)], st);
+                    cudaEventRecord(ev[2 * (i + m) + 1], st);
+                }
+            }
+            i += ng - 1;
+            continue;
         } else if (o.kind == 2) {
             if (o.b < 0 || o.b >= nslots || o.K <= 0 || o.K > 64 || o.N > 64)
                 return fail(-1, "plan: bad rank-k op");

@@ -43,6 +43,17 @@ struct GemmParams {
     int batch;
 };
 
+// Up to KB200_MAX_GROUP independent contractions of one kernel configuration share a launch:
+// at m = 33 a single block GEMM is 5.5 waves of CTAs, a group of four 21.9, so the idle tail of
+// the last wave is paid once per group instead of once per contraction.
+constexpr int MAX_GROUP = 4;
+struct GemmGroup {
+    GemmParams p[MAX_GROUP];
+    int fend[MAX_GROUP];         // running end of the full-tile CTA ranges of the members
+    int rend[MAX_GROUP];         // same for the ragged-tile CTAs (these come last in the grid)
+    int n;
+};
+
 __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc, bool valid) {
     unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
     int sz = valid ? 8 : 0;
@@ -213,7 +224,7 @@ struct TileLoader {
 template <int WARPS_M, int WARPS_N, int WM, int WN, int AMODE, int BMODE, int STAGES, bool ILV,
           int MINB>
 __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, MINB)
-    gemm_tab_kernel(const GemmParams p) {
+    gemm_tab_kernel(const __grid_constant__ GemmGroup grp) {
     constexpr int BM = WARPS_M * WM;
     constexpr int BN = WARPS_N * WN;
     constexpr int NT = WARPS_M * WARPS_N * 32;
@@ -234,22 +245,37 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, MINB)
     const int g = lane >> 2;
     const int t = lane & 3;
 
-    // CTA order: batch-major over the full tiles (CTAs that run together share one
-    // batch's operands in L2), then the ragged -- cheaper -- edge tiles of all batches,
-    // so the final partial wave is filled with the short CTAs.
+    // CTA order: member by member, batch-major over the full tiles (CTAs that run together
+    // share one batch's operands in L2), then the ragged -- cheaper -- edge tiles of all
+    // members and batches, so the final partial wave is filled with the short CTAs.
+    int mi = 0;
+    int f_ = blockIdx.x;
+    bool in_full;
+    {
+        const int total_full = grp.fend[grp.n - 1];
+        in_full = f_ < total_full;
+        if (in_full) {
+            while (f_ >= grp.fend[mi]) ++mi;
+            if (mi) f_ -= grp.fend[mi - 1];
+        } else {
+            f_ -= total_full;
+            while (f_ >= grp.rend[mi]) ++mi;
+            if (mi) f_ -= grp.rend[mi - 1];
+        }
+    }
+    const GemmParams& p = grp.p[mi];
     int b, tm, tn;
     {
         const int rm = (p.M % BM) ? 1 : 0, rn = (p.N % BN) ? 1 : 0;
         const int fm = p.tilesM - rm, fn = p.tilesN - rn;
         const int nf = fm * fn, nr = p.tilesM * p.tilesN - nf;
-        const int f_ = blockIdx.x;
-        if (f_ < nf * p.batch) {
+        if (in_full) {
             b = f_ / nf;
             const int t_ = f_ - b * nf;
             tm = t_ % fm;
             tn = t_ / fm;
         } else {
-            const int g_ = f_ - nf * p.batch;
+            const int g_ = f_;
             b = g_ / nr;
             const int r_ = g_ - b * nr;
             if (rm && r_ < p.tilesN) {

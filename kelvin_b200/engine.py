@@ -124,12 +124,24 @@ class Plan(object):
                 rc = lib.kb200_plan_run_timed(ops, len(ops), _lib.ptr(tables), ptrs, len(names),
                                               _lib.ptr(self._ws) if wsb > 0 else None, wsb,
                                               _lib.stream_ptr(), ms)
+                # a launch group reports its time on the leader: share it among the members
+                k = 0
+                while k < len(ops):
+                    gs = int(ops[k].group)
+                    if ops[k].kind == 0 and gs > 1:
+                        share = float(ms[k])/gs
+                        for j in range(k, k + gs):
+                            ms[j] = share
+                        k += gs
+                    else:
+                        k += 1
                 for k in range(len(ops)):
                     o = ops[k]
                     timings.append((int(o.kind), 2.0*o.M*o.N*o.K*o.batch if o.kind in (0, 2) else 0.0,
                                     float(ms[k])*1e-3, (int(o.M), int(o.N), int(o.K), int(o.batch),
                                                         int(o.tile), int(o.splitk),
-                                                        int(o.a_mode), int(o.b_mode))))
+                                                        int(o.a_mode), int(o.b_mode),
+                                                        int(o.group) if o.kind == 0 else 1)))
             _lib.check(rc, "kb200_plan_run(%s)" % self.name)
             y0 += nb
 

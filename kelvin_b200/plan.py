@@ -87,9 +87,20 @@ class TDef(object):
              'int1'  Fock block F.xy          (u: Fa.xy / Fb.xy)
              'int2'  ERI block  I.wxyz        (u: Ia / Ib / Iabab.<pattern>)
        role: 'in' (caller supplies), 'out' (caller supplies, accumulated into),
-             'tmp' (plan-owned scratch); batched: has a leading tau index."""
-    def __init__(self, name, kind, role, batched, spaces):
+             'tmp' (plan-owned scratch); batched: has a leading tau index.
+       canon: for a 'gen4' scratch tensor stored in another index order, the storage positions
+             of the canonical <p q | r s> order (Sz conservation: spin(p)+spin(q) = spin(r)+spin(s))."""
+    def __init__(self, name, kind, role, batched, spaces, canon=None):
         self.name, self.kind, self.role, self.batched, self.spaces = name, kind, role, batched, spaces
+        self.canon = canon
+        assert canon is None or kind == "gen4"
+
+
+def _canon(td, xs):
+    """xs (letters or spins in storage order) -> canonical order."""
+    if td.canon is None or len(xs) != 4:
+        return list(xs)
+    return [xs[c] for c in td.canon]
 
 
 SPIN4 = ("aaaa", "bbbb", "abab", "baba", "abba", "baab")
@@ -103,10 +114,12 @@ def resolve_u(td, letters, spins):
         if td.kind == "int1":
             return ("F%s.%s" % (s[0], td.name.split(".")[1]), letters, 1.0)
         return (td.name + "." + s[0], letters, 1.0)
+    if td.kind == "gen4":
+        s = "".join(_canon(td, spins))
+        assert s in SPIN4, s
+        return (td.name + "." + s, letters, 1.0)
     assert s in SPIN4, s
     p, q, r, t = letters
-    if td.kind == "gen4":
-        return (td.name + "." + s, letters, 1.0)
     if td.kind == "amp2":
         if s == "aaaa":
             return (td.name + ".aa", letters, 1.0)
@@ -143,6 +156,14 @@ def canonical_out_blocks(td, nidx):
         return (("a", "a"), ("b", "b"))
     if td.kind == "amp2":
         return (tuple("aaaa"), tuple("abab"), tuple("bbbb"))
+    if td.canon is not None:
+        out = []
+        for s in SPIN4:
+            st = [None]*4
+            for k, c in enumerate(td.canon):
+                st[c] = s[k]
+            out.append(tuple(st))
+        return tuple(out)
     return tuple(tuple(s) for s in SPIN4)
 
 
@@ -206,8 +227,8 @@ def expand(stmts, tdefs, mode):
                 for k, l in enumerate(summed):
                     spin[l] = "a" if not (code >> k) & 1 else "b"
                 ok = True
-                for (_, ls) in st.ins:
-                    if not sz_ok([spin[l] for l in ls]):
+                for td, (_, ls) in zip(tds[1:], st.ins):
+                    if not sz_ok(_canon(td, [spin[l] for l in ls])):
                         ok = False
                         break
                 if not ok:
@@ -273,7 +294,8 @@ class kb200_op(ctypes.Structure):
                 ("tBn", ctypes.c_int64), ("tCm", ctypes.c_int64), ("tCn", ctypes.c_int64),
                 ("alpha", ctypes.c_double), ("beta", ctypes.c_double),
                 ("a_mode", ctypes.c_int32), ("b_mode", ctypes.c_int32),
-                ("tile", ctypes.c_int32), ("splitk", ctypes.c_int32)]
+                ("tile", ctypes.c_int32), ("splitk", ctypes.c_int32),
+                ("group", ctypes.c_int32), ("reserved", ctypes.c_int32)]
 
 
 def _strides(shape):
@@ -320,6 +342,9 @@ RANKK = int(_os.environ.get("KB200_RANKK", "1"))
 DERIVE = int(_os.environ.get("KB200_DERIVE", "0"))
 LONGK_MIN = 4096      # contracted length from which the long-K path (derived layouts) is used
 RANKK_MIN_M = 4096    # rows from which the rank-K streaming kernel is used
+# independent contractions of one kernel configuration launched together (kb200_gemm.cuh
+# MAX_GROUP); 1 disables grouping and keeps the program order
+MAX_GROUP = int(_os.environ.get("KB200_GROUP", "4"))
 _TILE_BN = {0: 128, 1: 32, 2: 128, 3: 128, 4: 64, 5: 64}
 _TILE_BM = {0: 128, 1: 128, 2: 128, 3: 128, 4: 128, 5: 64}
 
@@ -350,6 +375,94 @@ class Lowered(object):
                     raise ValueError("slot %s read before it is written: %r" % (slot, op))
             self.descs.append(self._lower(op, beta))
         self.tables = self.bank.buffer()
+        self.groups = [[k] for k in range(len(self.descs))]
+        if MAX_GROUP > 1:
+            self._schedule()
+
+    # -- launch grouping -----------------------------------------------------
+    def _groupable(self, d):
+        """Large-tile contractions: one launch is only a few waves of CTAs."""
+        return d.kind == 0 and d.tile in (0, 2) and d.K >= 512
+
+    def _schedule(self):
+        """Reorder the ops along their dependency DAG so that independent large contractions
+        of the same kernel configuration become adjacent, and record them as launch groups.
+        Read-after-write, write-after-write and write-after-read orders on every slot are
+        kept, so each output sees its accumulations in the program order (bit-identical
+        results); scratch slots are never aliased, so no liveness changes."""
+        n = len(self.descs)
+        reads, writes = [], []
+        for d in self.descs:
+            r = {d.a}
+            if d.kind != 1:
+                r.add(d.b)
+            if d.beta != 0.0:
+                r.add(d.c)
+            reads.append(r)
+            writes.append(d.c)
+        npred = [0]*n
+        succ = [[] for _ in range(n)]
+        last_write = {}
+        readers = {}
+        for i in range(n):
+            pre = set()
+            for s_ in reads[i]:
+                if s_ in last_write:
+                    pre.add(last_write[s_])
+            w = writes[i]
+            if w in last_write:
+                pre.add(last_write[w])
+            for j in readers.get(w, ()):
+                pre.add(j)
+            pre.discard(i)
+            for j in pre:
+                succ[j].append(i)
+            npred[i] = len(pre)
+            for s_ in reads[i]:
+                readers.setdefault(s_, []).append(i)
+            last_write[w] = i
+            readers[w] = []
+        ready = sorted(i for i in range(n) if npred[i] == 0)
+        order, groups = [], []
+
+        def retire(i):
+            for j in succ[i]:
+                npred[j] -= 1
+                if npred[j] == 0:
+                    ready.append(j)
+
+        while ready:
+            ready.sort()
+            small = [i for i in ready if not self._groupable(self.descs[i])]
+            if small:
+                # cheap ops first, in program order: they unlock more large contractions
+                i = small[0]
+                ready.remove(i)
+                groups.append([len(order)])
+                order.append(i)
+                retire(i)
+                continue
+            lead = self.descs[ready[0]]
+            sig = (lead.tile, lead.a_mode, lead.b_mode)
+            grp = [i for i in ready
+                   if (self.descs[i].tile, self.descs[i].a_mode, self.descs[i].b_mode) == sig]
+            # one slot may be accumulated into by only one member of a launch
+            seen, pick = set(), []
+            for i in grp:
+                if writes[i] in seen or len(pick) == MAX_GROUP:
+                    continue
+                seen.add(writes[i])
+                pick.append(i)
+            groups.append(list(range(len(order), len(order) + len(pick))))
+            for i in pick:
+                ready.remove(i)
+                order.append(i)
+            for i in pick:
+                retire(i)
+        assert len(order) == n
+        self.descs = [self.descs[i] for i in order]
+        self.rops = [self.rops[i] for i in order]
+        self.groups = groups
 
     # -- helpers ---------------------------------------------------------
     def _dims(self, op):
@@ -505,9 +618,12 @@ class Lowered(object):
     def finalize(self, nbatch):
         """Set the tau batch and the split-K factors; return the ctypes array."""
         arr = (kb200_op * len(self.descs))()
+        lead_size = {g[0]: len(g) for g in self.groups}
+        gsize_of = {k: len(g) for g in self.groups for k in g}
         for k, d in enumerate(self.descs):
             ctypes.memmove(ctypes.byref(arr[k]), ctypes.byref(d), ctypes.sizeof(kb200_op))
             o = arr[k]
+            o.group = lead_size.get(k, 0)
             o.batch = nbatch if (o.bsC != 0 or o.bsA != 0 or (o.kind == 0 and o.bsB != 0)) else 1
             if o.batch > 1 and o.bsC == 0:
                 raise ValueError("batched operands reduce into an unbatched output")
@@ -515,6 +631,8 @@ class Lowered(object):
                 bm, bn = _TILE_BM[o.tile], _TILE_BN[o.tile]
                 ctas = ((o.M + bm - 1) // bm) * ((o.N + bn - 1) // bn) * o.batch
                 target = 4 * N_SM if o.tile == 5 else 2 * N_SM
+                if gsize_of[k] > 1:
+                    continue                      # launched with its group: never split
                 if ctas < target // 2 and o.K >= 512:
                     o.splitk = int(min(max(1, -(-target // ctas)), max(1, o.K // 128)))
                 elif o.tile in (0, 2) and ctas <= 2 * N_SM and o.K >= 512:

@@ -16,8 +16,8 @@ _INT2 = ("vvvv", "vvvo", "vovv", "vvoo", "vovo", "oovv", "vooo", "ooov", "oooo")
 def tensor_defs():
     T = {}
 
-    def add(name, kind, role, batched, spaces):
-        T[name] = TDef(name, kind, role, batched, spaces)
+    def add(name, kind, role, batched, spaces, canon=None):
+        T[name] = TDef(name, kind, role, batched, spaces, canon)
     for xy in ("oo", "ov", "vo", "vv"):
         add("F." + xy, "int1", "in", False, xy)
     for pat in _INT2:
@@ -36,7 +36,9 @@ def tensor_defs():
     add("Woooo", "amp2", "tmp", True, "oooo")
     add("Wvvvv", "amp2", "tmp", True, "vvvv")
     add("Wovvo", "gen4", "tmp", True, "ovvo")
-    add("t2x", "gen4", "tmp", True, "vvoo")
+    # stored [b,j,n,f]: the contracted pair (n,f) is contiguous with f innermost, the same
+    # inner index as I.oovv[mnef], so neither operand of the W_ovvo build gathers with a stride
+    add("t2x", "gen4", "tmp", True, "voov", canon=(3, 0, 1, 2))
     add("Z", "gen4", "tmp", True, "vooo")
     add("rg", "gen4", "tmp", True, "vvoo")
     return T
@@ -67,12 +69,12 @@ Wvvvv[abef] += 1 I.vvvv[abef]
 Wvvvv[abef] += -1 I.vovv[amef] t1[bm]
 Wvvvv[abef] += 1 I.vovv[bmef] t1[am]
 Wvvvv[abef] += 0.25 I.oovv[mnef] tau[abmn]
-t2x[fbjn] += 0.5 t2[fbjn]
-t2x[fbjn] += 1 t1[fj] t1[bn]
+t2x[bjnf] += 0.5 t2[fbjn]
+t2x[bjnf] += 1 t1[fj] t1[bn]
 Wovvo[mbej] += -1 I.vovo[bmej]
 Wovvo[mbej] += -1 I.vovv[bmef] t1[fj]
 Wovvo[mbej] += 1 I.ooov[mnje] t1[bn]
-Wovvo[mbej] += -1 I.oovv[mnef] t2x[fbjn]
+Wovvo[mbej] += -1 I.oovv[mnef] t2x[bjnf]
 Xvv[be] += 1 Fvv[be]
 Xvv[be] += -0.5 t1[bm] Fov[me]
 Xoo[mj] += 1 Foo[mj]

@@ -62,7 +62,8 @@ def main():
     for k, (n, dt, fl) in sorted(cls.items(), key=lambda x: -x[1][1]):
         print("%-22s n=%3d  %8.3f ms  %5.1f%%  %7.2f TF" % (k, n, dt*1e3, 100*dt/tot, fl/max(dt, 1e-12)/1e12))
     print()
-    for dt, kind, fl, meta, txt in sorted(rows, key=lambda r: -r[0])[:70]:
+    top = int(sys.argv[4]) if len(sys.argv) > 4 else 70
+    for dt, kind, fl, meta, txt in sorted(rows, key=lambda r: -r[0])[:top]:
         print("%7.1f us k%d M=%6d N=%5d K=%6d b=%2d tile=%d sk=%2d am=%d bm=%d %6.2f TF  %s" %
               (dt*1e6, kind, meta[0], meta[1], meta[2], meta[3], meta[4], meta[5], meta[6], meta[7],
                fl/max(dt, 1e-12)/1e12, txt[:70]))
