@@ -56,7 +56,7 @@ typedef struct kb200_op {
     int32_t splitk;        /* >=1; >1 uses the workspace + deterministic reduce */
     int32_t group;         /* kind 0: this op and the next group-1 ops (same tile/a_mode/b_mode,
                               splitk 1, mutually independent) share one launch; 0/1 = alone */
-    int32_t reserved;
+    int32_t reserved;      /* tile 7: bit 0 = rows (not columns) of C are the contiguous direction */
 } kb200_op;
 
 /* Bytes of workspace kb200_plan_run needs for these ops (split-K partials). */

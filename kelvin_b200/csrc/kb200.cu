@@ -1,6 +1,12 @@
 // kb200.cu -- C ABI + streaming kernels of the B200-native FT-CCSD hot path.
 // See include/kelvin_b200.h for the contract and the reference call sites.
 #include "../../include/kelvin_b200.h"
+#ifndef KB200_LK_NW
+#define KB200_LK_NW 4
+#endif
+#ifndef KB200_LK_MINB
+#define KB200_LK_MINB 2
+#endif
 #include "kb200_gemm.cuh"
 
 #include <atomic>
@@ -439,6 +445,58 @@ int launch_gemm_modes(const kb200::GemmGroup& p, int splitk, int am, int bm, cud
     return launch_gemm_inst<WMs, WNs, WM, WN, 1, 1, ST, ILV, MINB>(p, splitk, st);
 }
 
+constexpr int LK_NW = KB200_LK_NW;       // warps per CTA of the long-K kernel
+constexpr int LK_MINB = KB200_LK_MINB;   // CTAs per SM it is compiled for
+
+template <int T, int AM, int BM_>
+int launch_longk_inst(const kb200::GemmParams& p, cudaStream_t st) {
+    using namespace kb200;
+    constexpr int NT = LK_NW * 32;
+    constexpr int smem = LK_STAGES * (LongKLoader<8 * T, AM, NT>::STAGE + LongKLoader<8 * T, BM_, NT>::STAGE) * 8;
+    auto kern = longk_kernel<T, AM, BM_, LK_NW, LK_MINB>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(longk)");
+        configured = true;
+    }
+    dim3 grid(p.splitk, p.batch, 1);
+    kern<<<grid, NT, smem, st>>>(p);
+    KB_CHECK_LAUNCH("longk_kernel");
+    return 0;
+}
+
+template <int T>
+int launch_longk_modes(const kb200::GemmParams& p, int am, int bm, cudaStream_t st) {
+    if (am == 0 && bm == 0) return launch_longk_inst<T, 0, 0>(p, st);
+    if (am == 0 && bm == 1) return launch_longk_inst<T, 0, 1>(p, st);
+    if (am == 1 && bm == 0) return launch_longk_inst<T, 1, 0>(p, st);
+    return launch_longk_inst<T, 1, 1>(p, st);
+}
+
+template <int KT, int NI>
+int launch_skinny(const kb200::GemmParams& p, int a_mode, int c_mode, cudaStream_t st) {
+    using namespace kb200;
+    constexpr int smem = SkinnyCfg<KT, NI>::SMEM;
+    auto kern = skinny_kernel<KT, NI>;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(skinny)");
+        configured = true;
+    }
+    // one CTA per SM over all batches; every CTA stages B once and its warps walk 8-row tiles
+    int ntiles = (p.M + 7) / 8;
+    int gx = 148 / p.batch;            // never more CTAs than SMs: a second wave would double the time
+    int maxgx = (ntiles + SK_WARPS - 1) / SK_WARPS;
+    if (gx > maxgx) gx = maxgx;
+    if (gx < 1) gx = 1;
+    dim3 grid(gx, p.batch, 1);
+    kern<<<grid, SK_WARPS * 32, smem, st>>>(p, a_mode, c_mode);
+    KB_CHECK_LAUNCH("skinny_kernel");
+    return 0;
+}
+
 // tile ids: 0 = 128x128, 8 warps (64x32 warp tiles), interleaved loads
 //           1 = 128x32,  8 warps (16x32)
 //           2 = 128x128, 16 warps (32x32 warp tiles), interleaved loads
@@ -446,6 +504,8 @@ int launch_gemm_modes(const kb200::GemmGroup& p, int splitk, int am, int bm, cud
 //           4 = 128x64,  8 warps (32x32 warp tiles), 2 CTAs/SM
 //           5 = 64x64,   4 warps (32x32 warp tiles), 3 stages, several CTAs/SM: bandwidth-bound
 //               shapes (skinny N, or tiny outputs with long split K)
+//           6 = whole output (<= 40x40) per CTA, split over K only (longk_kernel)
+//           7 = skinny streaming update, K, N <= 40, 8 rows per warp (skinny_kernel)
 int tile_bm(int tile) { return tile == 5 ? 64 : 128; }
 int tile_bn(int tile) { return tile == 1 ? 32 : ((tile == 4 || tile == 5) ? 64 : 128); }
 
@@ -576,7 +636,23 @@ static int run_plan_impl(const kb200_op* ops, int nops, const uint32_t* tables,
                 rc = launch_gemm_modes<4, 2, 32, 32, 3, true, 2>(grp, p.splitk, o.a_mode, o.b_mode, st);
             else if (o.tile == 5)
                 rc = launch_gemm_modes<2, 2, 32, 32, 3, true, 3>(grp, p.splitk, o.a_mode, o.b_mode, st);
-            else
+            else if (o.tile == 6) {
+                if (ng != 1 || o.M > 40 || o.N > 40) return fail(-1, "plan: bad long-K op");
+                if (o.M <= 24 && o.N <= 24)
+                    rc = launch_longk_modes<3>(p, o.a_mode, o.b_mode, st);
+                else
+                    rc = launch_longk_modes<5>(p, o.a_mode, o.b_mode, st);
+            } else if (o.tile == 7) {
+                if (ng != 1 || o.K > 40 || o.N > 40 || p.splitk != 1) return fail(-1, "plan: bad skinny op");
+                // reserved bit 0: consecutive rows of C are adjacent in memory (else its columns are)
+                const int cmode = o.reserved & 1;
+                if (o.K <= 20 && o.N <= 24)
+                    rc = launch_skinny<5, 3>(p, o.a_mode, cmode, st);
+                else if (o.K <= 36)
+                    rc = launch_skinny<9, 5>(p, o.a_mode, cmode, st);
+                else
+                    rc = launch_skinny<10, 5>(p, o.a_mode, cmode, st);
+            } else
                 return fail(-1, "plan: unknown tile id");
             if (rc) return rc;
             if (p.splitk > 1) {

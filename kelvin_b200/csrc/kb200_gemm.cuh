@@ -489,6 +489,406 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, MINB)
     }
 }
 
+// ---------------------------------------------------------------------------
+// Long-K contraction into a tiny output (tile id 6):
+//   C[m, n] (+)= alpha * sum_k A[m, k] * B[k, n],   M, N <= 8*T (T = 3 or 5), K ~ n^3.
+// These are the F_vv / F_oo builds, the singles residual and their adjoints: one operand is an
+// n^4 tensor streamed once from HBM, the output is n^2.  The 128x128 / 64x64 tiles waste
+// 3/4 of their DMMAs here; this kernel holds the whole (padded) output in the accumulators
+// of every warp and splits the K range instead: grid = (splitk, batch), each CTA walks its
+// K chunk in stages of 32, warp w owns the k4-step w of every stage (25 DMMAs for 10
+// fragment loads), the eight partial outputs are tree-reduced through shared memory and
+// the CTA result goes to the split-K workspace (deterministic reduction as for tile 0..5).
+// ---------------------------------------------------------------------------
+constexpr int LK_BK = 32;
+constexpr int LK_STAGES = 4;
+
+template <int R, int MODE, int NT>
+struct LongKLoader {
+    static constexpr int LDK = LK_BK + 4;
+    static constexpr int LDR = R + 4;
+    static constexpr int STAGE = (MODE == 0) ? R * LDK : LK_BK * LDR;
+    static constexpr int ITERS = (R * LK_BK) / NT;
+    static constexpr int NKV = (MODE == 0) ? 1 : ITERS;   // distinct k offsets a thread needs per stage
+    static_assert((R * LK_BK) % NT == 0 && NT % LK_BK == 0, "tile must divide the CTA");
+    // Element (row, kk) of a stage <- base[rowtab[row] + ktab[k0 + kk]].  A thread's (row, kk)
+    // assignments are the same in every stage; its k offsets for the next stage are fetched one
+    // stage ahead (prefetch/advance) so that no cp.async waits on a table load.
+    const double* base;
+    const uint32_t* ktab;
+    uint32_t roff[ITERS];
+    int kk[NKV];
+    int dst[ITERS];
+    unsigned rmask;
+    uint32_t kcur[NKV], knxt[NKV];
+
+    __device__ __forceinline__ void init(const double* base_, const uint32_t* __restrict__ rowtab,
+                                         int nrows, const uint32_t* ktab_, int tid) {
+        base = base_;
+        ktab = ktab_;
+        rmask = 0;
+#pragma unroll
+        for (int it = 0; it < ITERS; ++it) {
+            const int e = it * NT + tid;
+            const int row = (MODE == 0) ? e / LK_BK : e % R;
+            const int k_ = (MODE == 0) ? e % LK_BK : e / R;
+            if (MODE == 0) {
+                if (it == 0) kk[0] = k_;
+            } else {
+                kk[it] = k_;
+            }
+            dst[it] = (MODE == 0) ? row * LDK + k_ : k_ * LDR + row;
+            const bool v = row < nrows;
+            roff[it] = v ? __ldg(rowtab + row) : 0u;
+            rmask |= (v ? 1u : 0u) << it;
+        }
+#pragma unroll
+        for (int v = 0; v < NKV; ++v) kcur[v] = knxt[v] = 0xffffffffu;
+    }
+    __device__ __forceinline__ void prefetch(int k0, int kend) {
+#pragma unroll
+        for (int v = 0; v < NKV; ++v) {
+            const int k = k0 + kk[v];
+            knxt[v] = (k < kend) ? __ldg(ktab + k) : 0xffffffffu;
+        }
+    }
+    __device__ __forceinline__ void advance() {
+#pragma unroll
+        for (int v = 0; v < NKV; ++v) kcur[v] = knxt[v];
+    }
+    __device__ __forceinline__ void issue(uint32_t stage_u) const {
+#pragma unroll
+        for (int it = 0; it < ITERS; ++it) {
+            const uint32_t ko = kcur[(MODE == 0) ? 0 : it];
+            const bool valid = ((rmask >> it) & 1u) && (ko != 0xffffffffu);
+            const double* src = valid ? base + (size_t)roff[it] + ko : base;
+            unsigned sa = stage_u + dst[it] * 8;
+            int sz = valid ? 8 : 0;
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(sa), "l"(src), "r"(sz));
+        }
+    }
+    __device__ __forceinline__ static double frag(const double* stage, int r, int k_) {
+        return (MODE == 0) ? stage[r * LDK + k_] : stage[k_ * LDR + r];
+    }
+};
+
+template <int T, int AMODE, int BMODE, int NW, int MINB>
+__global__ void __launch_bounds__(NW * 32, MINB) longk_kernel(const GemmParams p) {
+    constexpr int R = 8 * T;
+    constexpr int NT = NW * 32;
+    constexpr int KSTEPS = (LK_BK / 4) / NW;      // k4-steps of a stage owned by one warp
+    static_assert((LK_BK / 4) % NW == 0, "warps must divide the k4-steps of a stage");
+    using LA = LongKLoader<R, AMODE, NT>;
+    using LB = LongKLoader<R, BMODE, NT>;
+    extern __shared__ double smem[];
+    double* As = smem;
+    double* Bs = smem + LK_STAGES * LA::STAGE;
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    const int g = lane >> 2;
+    const int t = lane & 3;
+    const int ks = blockIdx.x;
+    const int b = blockIdx.y;
+    const int kbeg = ks * p.kchunk;
+    const int kend = min(p.K, kbeg + p.kchunk);
+    const int nk = (kend - kbeg + LK_BK - 1) / LK_BK;
+
+    LA la;
+    LB lb;
+    la.init(p.A + (long long)b * p.bsA, p.am, p.M, p.ak, tid);
+    lb.init(p.B + (long long)b * p.bsB, p.bn, p.N, p.bk, tid);
+    const uint32_t As_u = (uint32_t)__cvta_generic_to_shared(As);
+    const uint32_t Bs_u = (uint32_t)__cvta_generic_to_shared(Bs);
+
+    double acc[T][T][2];
+#pragma unroll
+    for (int i = 0; i < T; ++i)
+#pragma unroll
+        for (int j = 0; j < T; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    la.prefetch(kbeg, kend);
+    lb.prefetch(kbeg, kend);
+#pragma unroll
+    for (int s = 0; s < LK_STAGES - 1; ++s) {
+        la.advance();
+        lb.advance();
+        la.prefetch(kbeg + (s + 1) * LK_BK, kend);
+        lb.prefetch(kbeg + (s + 1) * LK_BK, kend);
+        if (s < nk) {
+            la.issue(As_u + s * LA::STAGE * 8);
+            lb.issue(Bs_u + s * LB::STAGE * 8);
+        }
+        cp_async_commit();
+    }
+    for (int kt = 0; kt < nk; ++kt) {
+        cp_async_wait<LK_STAGES - 2>();
+        __syncthreads();
+        const int nxt = kt + LK_STAGES - 1;
+        la.advance();
+        lb.advance();
+        if (nxt + 1 < nk) {
+            la.prefetch(kbeg + (nxt + 1) * LK_BK, kend);
+            lb.prefetch(kbeg + (nxt + 1) * LK_BK, kend);
+        }
+        if (nxt < nk) {
+            la.issue(As_u + (nxt % LK_STAGES) * LA::STAGE * 8);
+            lb.issue(Bs_u + (nxt % LK_STAGES) * LB::STAGE * 8);
+        }
+        cp_async_commit();
+        const double* as = As + (kt % LK_STAGES) * LA::STAGE;
+        const double* bs = Bs + (kt % LK_STAGES) * LB::STAGE;
+#pragma unroll
+        for (int q = 0; q < KSTEPS; ++q) {
+            const int k4 = q * NW + warp;
+            double af[T], bf[T];
+#pragma unroll
+            for (int i = 0; i < T; ++i) af[i] = LA::frag(as, i * 8 + g, k4 * 4 + t);
+#pragma unroll
+            for (int j = 0; j < T; ++j) bf[j] = LB::frag(bs, j * 8 + g, k4 * 4 + t);
+#pragma unroll
+            for (int i = 0; i < T; ++i)
+#pragma unroll
+                for (int j = 0; j < T; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        }
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+
+    // tree reduction of the per-warp partial outputs (deterministic order)
+    double2* red = reinterpret_cast<double2*>(smem);
+#pragma unroll
+    for (int half = NW / 2; half >= 1; half >>= 1) {
+        if (warp >= half && warp < 2 * half) {
+#pragma unroll
+            for (int i = 0; i < T; ++i)
+#pragma unroll
+                for (int j = 0; j < T; ++j)
+                    red[((warp - half) * T * T + i * T + j) * 32 + lane] =
+                        make_double2(acc[i][j][0], acc[i][j][1]);
+        }
+        __syncthreads();
+        if (warp < half) {
+#pragma unroll
+            for (int i = 0; i < T; ++i)
+#pragma unroll
+                for (int j = 0; j < T; ++j) {
+                    const double2 v = red[(warp * T * T + i * T + j) * 32 + lane];
+                    acc[i][j][0] += v.x;
+                    acc[i][j][1] += v.y;
+                }
+        }
+        __syncthreads();
+    }
+    if (warp != 0) return;
+    if (p.splitk == 1) {
+        double* C = p.C + (long long)b * p.bsC;
+#pragma unroll
+        for (int i = 0; i < T; ++i) {
+            const int row = i * 8 + g;
+            if (row >= p.M) continue;
+            const uint32_t ro = p.cm[row];
+#pragma unroll
+            for (int j = 0; j < T; ++j)
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    const int col = j * 8 + 2 * t + c;
+                    if (col < p.N) {
+                        double* dst = C + ro + p.cn[col];
+                        double v = p.alpha * acc[i][j][c];
+                        if (p.beta != 0.0) v += p.beta * (*dst);
+                        *dst = v;
+                    }
+                }
+        }
+    } else {
+        double* P = p.partial + ((size_t)b * p.splitk + ks) * (size_t)p.M * p.N;
+#pragma unroll
+        for (int i = 0; i < T; ++i) {
+            const int row = i * 8 + g;
+            if (row >= p.M) continue;
+#pragma unroll
+            for (int j = 0; j < T; ++j)
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    const int col = j * 8 + 2 * t + c;
+                    if (col < p.N) P[(size_t)row * p.N + col] = acc[i][j][c];
+                }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Skinny streaming contraction (tile id 7): the n^5 "dressing" terms
+//   C[m, n] (+)= alpha * sum_k A[m, k] * B[k, n],   M ~ n^3 rows,  K <= 4*KT,  N <= 8*NI (<= 40).
+// 24 bytes of HBM traffic per C element for ~2K flops: bandwidth-bound, every A and C element is
+// touched exactly once, so nothing is staged except B (K x N, a few KB, once per CTA).
+// One warp owns 8 rows at a time: its A fragments come straight from global memory into the
+// DMMA operand registers (4 consecutive k per row = one 32-byte sector), B fragments from shared
+// memory, C is read-modify-written in the accumulator layout.  No barriers in the row loop;
+// latency is hidden by 16 resident warps per SM.
+// ---------------------------------------------------------------------------
+constexpr int SK_STAGES = 4;
+constexpr int SK_WARPS = 8;
+
+template <int KT, int NI>
+struct SkinnyCfg {
+    static constexpr int KPAD = KT * 4;
+    // pitches with conflict-free fragment reads (see LongKLoader / TileLoader)
+    static constexpr int AP = (KPAD % 16 == 4 || KPAD % 16 == 12) ? KPAD : KPAD + 4;
+    static constexpr int CP = NI * 8;
+    static constexpr int STAGE = 8 * AP + 8 * CP + 8;          // doubles: A tile, C tile, 8 row offsets (+pad)
+    static constexpr int BP = AP;
+    static constexpr int SMEM = (NI * 8 * BP + SK_WARPS * SK_STAGES * STAGE) * 8;
+};
+
+template <int KT, int NI>
+__global__ void __launch_bounds__(SK_WARPS * 32, 1) skinny_kernel(const GemmParams p, int a_mode, int c_mode) {
+    using Cfg = SkinnyCfg<KT, NI>;
+    constexpr int KPAD = Cfg::KPAD, AP = Cfg::AP, CP = Cfg::CP, BP = Cfg::BP;
+    constexpr int AIT = (8 * KPAD) / 32;       // cp.async per lane for the A tile (= KT)
+    constexpr int CIT = (8 * CP) / 32;         // ... for the C tile (= 2 NI)
+    extern __shared__ double smem[];
+    double* Bs = smem;                                         // [NI*8][BP], k contiguous
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+    const int g = lane >> 2;
+    const int t = lane & 3;
+    const int b = blockIdx.y;
+    const double* __restrict__ A = p.A + (long long)b * p.bsA;
+    const double* __restrict__ B = p.B + (long long)b * p.bsB;
+    double* __restrict__ C = p.C + (long long)b * p.bsC;
+    double* wst = smem + NI * 8 * BP + warp * SK_STAGES * Cfg::STAGE;   // this warp's stages
+
+    for (int idx = tid; idx < NI * 8 * KPAD; idx += SK_WARPS * 32) {
+        const int n = idx / KPAD, k = idx - n * KPAD;
+        Bs[n * BP + k] = (n < p.N && k < p.K) ? B[(size_t)p.bk[k] + p.bn[n]] : 0.0;
+    }
+    // per-lane constants of the copy pattern (the same in every tile): source offset along k / n,
+    // destination slot, source lane of the row offset
+    uint32_t a_ko[AIT];
+    int a_dst[AIT];
+    int a_row[AIT];
+#pragma unroll
+    for (int i = 0; i < AIT; ++i) {
+        const int e = i * 32 + lane;
+        const int row = a_mode ? (e & 7) : e / KPAD;
+        const int k = a_mode ? (e >> 3) : e - row * KPAD;
+        a_ko[i] = (k < p.K) ? __ldg(p.ak + k) : 0xffffffffu;
+        a_dst[i] = (row * AP + k) * 8;
+        a_row[i] = row;
+    }
+    // accumulator-layout column offsets (epilogue) and C-tile copy pattern
+    uint32_t cno[NI][2];
+#pragma unroll
+    for (int j = 0; j < NI; ++j)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            const int col = j * 8 + 2 * t + c;
+            cno[j][c] = (col < p.N) ? __ldg(p.cn + col) : 0xffffffffu;
+        }
+    __syncthreads();
+    // B fragments stay in registers for the whole kernel
+    double bf[KT][NI];
+#pragma unroll
+    for (int k4 = 0; k4 < KT; ++k4)
+#pragma unroll
+        for (int j = 0; j < NI; ++j) bf[k4][j] = Bs[(j * 8 + g) * BP + k4 * 4 + t];
+
+    const bool rmw = p.beta != 0.0;
+    const int ntiles = (p.M + 7) >> 3;
+    const int stride = gridDim.x * SK_WARPS;
+    const int first = blockIdx.x * SK_WARPS + warp;
+
+    // row offsets of a tile: lanes 0-7 hold am[row], lanes 8-15 cm[row] (fetched one tile ahead)
+    auto fetch_rows = [&](int mt) -> uint32_t {
+        const int row = mt * 8 + (lane & 7);
+        if (mt >= ntiles || row >= p.M || lane >= 16) return 0xffffffffu;
+        return __ldg((lane < 8 ? p.am : p.cm) + row);
+    };
+    auto issue = [&](int mt, int s, uint32_t rows) {
+        if (mt >= ntiles) return;
+        double* st = wst + s * Cfg::STAGE;
+        const uint32_t st_u = (uint32_t)__cvta_generic_to_shared(st);
+        uint32_t* roffs = reinterpret_cast<uint32_t*>(st + 8 * AP + 8 * CP);
+        if (lane >= 8 && lane < 16) roffs[lane - 8] = rows;           // C row offsets for the epilogue
+#pragma unroll
+        for (int i = 0; i < AIT; ++i) {
+            const uint32_t ro = __shfl_sync(0xffffffffu, rows, a_row[i]);
+            const bool v = (ro != 0xffffffffu) && (a_ko[i] != 0xffffffffu);
+            const double* src = v ? A + (size_t)ro + a_ko[i] : A;
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(st_u + a_dst[i]), "l"(src),
+                         "r"(v ? 8 : 0));
+        }
+        if (rmw) {
+            // old C values in the accumulator layout: lane (g, t) fetches its own 2 NI elements
+            const uint32_t ro = __shfl_sync(0xffffffffu, rows, 8 + g);
+#pragma unroll
+            for (int j = 0; j < NI; ++j)
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    const bool v = (ro != 0xffffffffu) && (cno[j][c] != 0xffffffffu);
+                    const double* src = v ? C + (size_t)ro + cno[j][c] : C;
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(
+                                     st_u + (8 * AP + g * CP + j * 8 + 2 * t + c) * 8),
+                                 "l"(src), "r"(v ? 8 : 0));
+                }
+        }
+    };
+    (void)c_mode;
+    (void)CIT;
+
+    uint32_t rows_next = fetch_rows(first);
+#pragma unroll
+    for (int s = 0; s < SK_STAGES - 1; ++s) {
+        const uint32_t rows = rows_next;
+        rows_next = fetch_rows(first + (s + 1) * stride);
+        issue(first + s * stride, s, rows);
+        cp_async_commit();
+    }
+    int it = 0;
+    for (int mt = first; mt < ntiles; mt += stride, ++it) {
+        cp_async_wait<SK_STAGES - 2>();
+        __syncwarp();
+        {
+            const uint32_t rows = rows_next;
+            rows_next = fetch_rows(mt + SK_STAGES * stride);
+            issue(mt + (SK_STAGES - 1) * stride, (it + SK_STAGES - 1) % SK_STAGES, rows);
+            cp_async_commit();
+        }
+        const double* st = wst + (it % SK_STAGES) * Cfg::STAGE;
+        const double* as = st + g * AP + t;
+        const double* cs = st + 8 * AP + g * CP + 2 * t;
+        const uint32_t* roffs = reinterpret_cast<const uint32_t*>(st + 8 * AP + 8 * CP);
+        double acc[NI][2];
+#pragma unroll
+        for (int j = 0; j < NI; ++j) acc[j][0] = acc[j][1] = 0.0;
+#pragma unroll
+        for (int k4 = 0; k4 < KT; ++k4) {
+            const double af = as[k4 * 4];
+#pragma unroll
+            for (int j = 0; j < NI; ++j) dmma884(acc[j][0], acc[j][1], af, bf[k4][j]);
+        }
+        const uint32_t ro = roffs[g];
+        if (ro != 0xffffffffu) {
+            double* Cr = C + ro;
+#pragma unroll
+            for (int j = 0; j < NI; ++j)
+#pragma unroll
+                for (int c = 0; c < 2; ++c)
+                    if (cno[j][c] != 0xffffffffu) {
+                        double v = p.alpha * acc[j][c];
+                        if (rmw) v += p.beta * cs[j * 8 + c];
+                        Cr[cno[j][c]] = v;
+                    }
+        }
+        __syncwarp();
+    }
+    cp_async_wait<0>();
+}
+
 // deterministic split-K reduction + scatter
 __global__ void splitk_reduce_kernel(const GemmParams p, int batch) {
     size_t mn = (size_t)p.M * p.N;

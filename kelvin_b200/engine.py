@@ -42,7 +42,8 @@ class Plan(object):
 
     # -- device state ------------------------------------------------------
     def _tables(self, dev):
-        if self._dev_tables is None or self._dev_tables.device != dev:
+        if self._dev_tables is None or self._dev_tables.device != dev \
+                or self._dev_tables.numel() != self.low.tables.size:
             # uint32 payload carried in an int32 tensor (bit pattern preserved)
             self._dev_tables = torch.from_numpy(self.low.tables.view("int32").copy()).to(dev)
         return self._dev_tables
@@ -84,7 +85,6 @@ class Plan(object):
         dev = _lib.device()
         nb_max = ng if chunk is None else max(1, min(int(chunk), ng))
         self._ensure_tmp(nb_max, dev)
-        tables = self._tables(dev)
         names = self.low.slot_names
         for s in self.inputs + self.outputs:
             t = tensors[s]
@@ -103,6 +103,7 @@ class Plan(object):
         while y0 < ng:
             nb = min(nb_max, ng - y0)
             ops, wsb = self._ops_for(nb)
+            tables = self._tables(dev)        # after finalize: it may add (batch-folded) tables
             if wsb > 0 and (self._ws is None or self._ws.numel()*8 < wsb or self._ws.device != dev):
                 self._ws = torch.empty((wsb + 7)//8, dtype=torch.float64, device=dev)
             ptrs = (ctypes.c_void_p*len(names))()

@@ -319,7 +319,7 @@ class TableBank(object):
         off = numpy.zeros((1,), dtype=numpy.int64)
         for d, s in dims_strides:
             off = (off[:, None] + (numpy.arange(d, dtype=numpy.int64) * s)[None, :]).reshape(-1)
-        assert off.max(initial=0) < 2 ** 32
+        assert off.max(initial=0) < 2 ** 32 - 1      # 0xffffffff marks 'no element' in the kernels
         start = self.pos
         self.chunks.append(off.astype(numpy.uint32))
         self.pos += off.size
@@ -337,16 +337,21 @@ N_SM = 148
 import os as _os
 BIG_TILE = int(_os.environ.get("KB200_BIG_TILE", "2"))
 RANKK = int(_os.environ.get("KB200_RANKK", "1"))
-# re-laid-out integral copies for long-K contractions: measured neutral at m = 33 (the
-# split-K class is latency-, not gather-bound), so off by default
-DERIVE = int(_os.environ.get("KB200_DERIVE", "0"))
+# re-laid-out integral copies for long-K contractions, so that both operands of the
+# whole-output-per-CTA kernel (tile 6) stream contiguously along k
+DERIVE = int(_os.environ.get("KB200_DERIVE", "1"))
+# fold the tau batch into the N index of matrix-vector-like contractions with a tau-independent
+# (integral) A operand: the integral block is then read once instead of once per grid point
+FOLD = int(_os.environ.get("KB200_FOLD", "1"))
 LONGK_MIN = 4096      # contracted length from which the long-K path (derived layouts) is used
 RANKK_MIN_M = 4096    # rows from which the rank-K streaming kernel is used
 # independent contractions of one kernel configuration launched together (kb200_gemm.cuh
 # MAX_GROUP); 1 disables grouping and keeps the program order
 MAX_GROUP = int(_os.environ.get("KB200_GROUP", "4"))
-_TILE_BN = {0: 128, 1: 32, 2: 128, 3: 128, 4: 64, 5: 64}
-_TILE_BM = {0: 128, 1: 128, 2: 128, 3: 128, 4: 128, 5: 64}
+LONGK_TILE = int(_os.environ.get("KB200_LONGK", "1"))
+SKINNY_TILE = int(_os.environ.get("KB200_SKINNY", "1"))
+_TILE_BN = {0: 128, 1: 32, 2: 128, 3: 128, 4: 64, 5: 64, 6: 40, 7: 40}
+_TILE_BM = {0: 128, 1: 128, 2: 128, 3: 128, 4: 128, 5: 64, 6: 40, 7: 8}
 
 
 class Lowered(object):
@@ -365,6 +370,7 @@ class Lowered(object):
         self.bank = TableBank()
         self.derived = OrderedDict()   # derived slot -> (source slot, axis permutation)
         self.descs = []
+        self._nfold = {}          # id(desc) -> N-index (dim, stride) lists on B and C (batch folding)
         self.flops = 0.0          # per tau point, executed (2*M*N*K)
         written = set(preset)
         for op in rops:
@@ -582,7 +588,11 @@ class Lowered(object):
         # from HBM once, whereas a tau-independent integral block stays L2-resident and
         # tolerates a strided gather)
         if a_mode == 0 and b_mode == 0:
-            a_first = not (bs(nb) != 0 and bs(na) == 0)
+            # (a nominal 8 grid points for a batched operand: a batched vector against an
+            # integral matrix still follows the matrix)
+            ea = size(M) * (8 if bs(na) != 0 else 1)
+            eb = size(N) * (8 if bs(nb) != 0 else 1)
+            a_first = ea >= eb
         else:
             a_first = (a_mode == 0) or (b_mode != 0)
         K = self._order(K, sa, sb) if a_first else self._order(K, sb, sa)
@@ -603,9 +613,15 @@ class Lowered(object):
         d.tBk, d.tBn = tab(K, sb), tab(N, sb)
         d.tCm, d.tCn = tab(M, sc), tab(N, sc)
         d.a_mode, d.b_mode = a_mode, b_mode
-        if rankk:
+        self._nfold[id(d)] = ([(dims[l], sb[l]) for l in N], [(dims[l], sc[l]) for l in N])
+        if SKINNY_TILE and d.K <= 40 and d.N <= 40 and d.M >= RANKK_MIN_M:
+            d.tile = 7       # skinny streaming update (DMMA, 8 rows per warp)
+            d.reserved = 1 if lc[-1] in M else 0
+        elif rankk:
             d.kind = 2
             d.tile = 0
+        elif LONGK_TILE and d.M <= 40 and d.N <= 40 and d.K >= 2048:
+            d.tile = 6       # whole output per CTA, split over K only
         elif d.N <= 32:
             d.tile = 1 if d.M > 64 else 5
         elif d.N <= 64:
@@ -627,12 +643,35 @@ class Lowered(object):
             o.batch = nbatch if (o.bsC != 0 or o.bsA != 0 or (o.kind == 0 and o.bsB != 0)) else 1
             if o.batch > 1 and o.bsC == 0:
                 raise ValueError("batched operands reduce into an unbatched output")
+            if FOLD and o.kind == 0 and o.batch > 1 and o.bsA == 0 and o.bsB != 0 \
+                    and o.N * o.batch <= 32 and o.tile != 6 and gsize_of[k] == 1:
+                nB, nC = self._nfold[id(d)]
+                o.tBn = self.bank.get([(o.batch, o.bsB)] + nB)
+                o.tCn = self.bank.get([(o.batch, o.bsC)] + nC)
+                o.N = o.N * o.batch
+                o.batch, o.bsB, o.bsC = 1, 0, 0
+                o.tile = 1 if o.M > 64 else 5
             if o.kind == 0:
                 bm, bn = _TILE_BM[o.tile], _TILE_BN[o.tile]
                 ctas = ((o.M + bm - 1) // bm) * ((o.N + bn - 1) // bn) * o.batch
                 target = 4 * N_SM if o.tile == 5 else 2 * N_SM
                 if gsize_of[k] > 1:
                     continue                      # launched with its group: never split
+                if o.tile == 7:
+                    continue
+                if o.tile == 6:
+                    # grid = (splitk, batch): fill whole waves of one-CTA-per-SM with K chunks
+                    # of at least 8 stages
+                    best = 1
+                    for w in (1, 2, 3, 4):
+                        sk = max(1, (w * N_SM) // o.batch)
+                        if o.K // sk < 256:
+                            break
+                        best = sk
+                        if sk * o.batch >= 0.97 * w * N_SM:
+                            break
+                    o.splitk = best
+                    continue
                 if ctas < target // 2 and o.K >= 512:
                     o.splitk = int(min(max(1, -(-target // ctas)), max(1, o.K // 128)))
                 elif o.tile in (0, 2) and ctas <= 2 * N_SM and o.K >= 512:
@@ -646,6 +685,7 @@ class Lowered(object):
                         if best is None or cost < best - 1e-9:
                             best, bests = cost, sk
                     o.splitk = bests
+        self.tables = self.bank.buffer()      # batch folding may have added tables
         return arr
 
 

@@ -162,3 +162,57 @@ def test_contraction_wave_split_k(built):
     p.run(t, 2)
     ref = C0 + 0.5*numpy.einsum("yabef,yefij->yabij", A, B)
     assert numpy.abs(t["C"].cpu().numpy() - ref).max() < 1e-11*numpy.abs(ref).max()
+
+
+@pytest.mark.parametrize("dims,nb", [
+    (dict(e=33, a=31, m=9, n=8, f=33), 3),        # T=5 tile, K=2376: one K chunk per batch
+    (dict(e=19, a=17, m=11, n=10, f=19), 3),      # T=3 tile
+    (dict(e=33, a=33, m=33, n=33, f=33), 2),      # ESN33 shape, split over K
+    (dict(e=40, a=1, m=16, n=16, f=9), 2),        # N = 1 column
+])
+def test_contraction_long_k_tiny_output(built, dims, nb):
+    """Tile 6 (longk_kernel): whole <= 40x40 output per CTA, K split across CTAs, all four
+    operand-contiguity modes; F_vv/F_oo-build shapes of kelvin/ft_cc_equations.py:96-164."""
+    from kelvin_b200 import engine, plan
+    rng = numpy.random.default_rng(12)
+    for la, lb in (("emnf", "afmn"), ("mnfe", "afmn"), ("emnf", "fmna"), ("mnfe", "fmna")):
+        A = rng.standard_normal(tuple(dims[l] for l in la))             # integral-like, unbatched
+        B = rng.standard_normal((nb,) + tuple(dims[l] for l in lb))
+        C0 = rng.standard_normal((nb, dims["a"], dims["e"]))
+        ops = [plan.ROp(("C", "ae"), -0.5, [("A", la), ("B", lb)])]
+        shapes = {"C": C0.shape[1:], "A": A.shape, "B": B.shape[1:]}
+        p = engine.Plan(ops, "g", None, ["A", "B"], ["C"], preset_outputs=["C"], shapes=shapes,
+                        batched={"C": True, "A": False, "B": True})
+        arr = p.low.finalize(nb)
+        assert arr[0].tile == 6
+        if dims["m"] == 33:
+            assert arr[0].splitk > 1
+        t = {"A": _dev(A), "B": _dev(B), "C": _dev(C0)}
+        p.run(t, nb)
+        ref = C0 - 0.5*numpy.einsum("%s,y%s->yae" % (la, lb), A, B)
+        assert numpy.abs(t["C"].cpu().numpy() - ref).max() < 1e-11*numpy.abs(ref).max(), (la, lb)
+
+
+@pytest.mark.parametrize("k,n", [(33, 33), (19, 19), (40, 40), (36, 7), (5, 40)])
+def test_contraction_skinny_streaming(built, k, n):
+    """Tile 7 (skinny_kernel): n^5 dressing terms, M ~ n^3 rows against a small K x N matrix,
+    every operand/output contiguity combination, accumulate and overwrite."""
+    from kelvin_b200 import engine, plan
+    rng = numpy.random.default_rng(21)
+    dims = dict(a=17, e=16, f=17, m=k, b=n)
+    nb = 2
+    for la, lb, lc in (("amef", "bm", "abef"), ("aefm", "mb", "abef"), ("amef", "mb", "aefb"),
+                       ("aefm", "bm", "aefb")):
+        A = rng.standard_normal((nb,) + tuple(dims[l] for l in la))
+        B = rng.standard_normal((nb,) + tuple(dims[l] for l in lb))
+        C0 = rng.standard_normal((nb,) + tuple(dims[l] for l in lc))
+        for preset in (True, False):
+            ops = [plan.ROp(("C", lc), -1.5, [("A", la), ("B", lb)])]
+            shapes = {"C": C0.shape[1:], "A": A.shape[1:], "B": B.shape[1:]}
+            p = engine.Plan(ops, "g", None, ["A", "B"], ["C"], preset_outputs=["C"] if preset else [],
+                            shapes=shapes, batched={"C": True, "A": True, "B": True})
+            assert p.low.finalize(nb)[0].tile == 7
+            t = {"A": _dev(A), "B": _dev(B), "C": _dev(C0)}
+            p.run(t, nb)
+            ref = -1.5*numpy.einsum("y%s,y%s->y%s" % (la, lb, lc), A, B) + (C0 if preset else 0.0)
+            assert numpy.abs(t["C"].cpu().numpy() - ref).max() < 1e-11*numpy.abs(ref).max(), (la, lb, lc)

@@ -169,11 +169,18 @@ def test_rdm_plan_u_all_spin_blocks():
 
 
 def test_small_shape_paths_are_exercised(monkeypatch):
-    """Lower the size thresholds so that the derived-layout (long-K) and rank-K code paths
-    of the lowering are exercised at test sizes; results must not change."""
+    """Lower the size thresholds so that the derived-layout (long-K), skinny-streaming,
+    rank-K and batch-folding code paths of the lowering are exercised at test sizes; results
+    must not change."""
     monkeypatch.setattr(plan, "DERIVE", 1)
     monkeypatch.setattr(plan, "LONGK_MIN", 8)
     monkeypatch.setattr(plan, "RANKK_MIN_M", 8)
+    _small_paths(monkeypatch, skinny=1)
+    _small_paths(monkeypatch, skinny=0)
+
+
+def _small_paths(monkeypatch, skinny):
+    monkeypatch.setattr(plan, "SKINNY_TILE", skinny)
     na, nb, ng = 4, 3, 2
     ints, amps = util.random_u(na, nb, ng, seed=11)
     Fa, Fb, Ia, Ib, Iabab = ints
@@ -183,7 +190,12 @@ def test_small_shape_paths_are_exercised(monkeypatch):
     arr, low = _run(rops, "u", sizes, dict(zip(names, amps)),
                     {"Fa": Fa, "Fb": Fb, "Ia": Ia, "Ib": Ib, "Iabab": Iabab}, ng)
     assert len(low.derived) > 0
-    assert any(d.kind == 2 for d in low.descs)
+    if skinny:
+        assert any(d.tile == 7 for d in low.descs)
+    else:
+        assert any(d.kind == 2 for d in low.descs)
+    assert any(o.batch == 1 and o.N == ng*d.N for o, d in zip(low.finalize(ng), low.descs)
+               if d.kind == 0 and d.bsB != 0 and d.bsA == 0)       # tau batch folded into N
     for y in range(ng):
         r = ocq.u_stanton_terms(*ints, (amps[0][y], amps[1][y]), (amps[2][y], amps[3][y], amps[4][y]))
         ref = (-Fa.vo - r[0], -Fb.vo - r[1], -Ia.vvoo - r[2], -Iabab.vvoo - r[3], -Ib.vvoo - r[4])
