@@ -43,7 +43,11 @@ void kb200_launch_count_reset(void);
  * ------------------------------------------------------------------------ */
 typedef struct kb200_op {
     int32_t kind;          /* 0 contraction (DMMA GEMM), 1 permuted axpby,
-                              2 contraction with K,N <= 64 (streaming rank-K update) */
+                              2 contraction with K,N <= 64 (streaming rank-K update),
+                              3 one term of a fused elementwise sum
+                                C = beta*C + sum_t alpha_t X_t[tAm[m]+tAk[n]] * Y_t[tBk[m]+tBn[n]]
+                                (a = X, b = Y or -1; `group` consecutive entries, same C/M/N;
+                                 beta of the first entry applies, a_mode = read X m-fast) */
     int32_t a, b, c;       /* tensor slot numbers (b unused for kind 1)        */
     int64_t a_off, b_off, c_off;   /* constant element offsets inside the slot */
     int32_t M, N, K, batch;

@@ -696,6 +696,47 @@ static int run_plan_impl(const kb200_op* ops, int nops, const uint32_t* tables,
             else
                 kb200::rankk_kernel<64><<<grid, 256, 0, st>>>(p, per);
             KB_CHECK_LAUNCH("rankk_kernel");
+        } else if (o.kind == 3) {
+            int ng = o.group > 1 ? o.group : 1;
+            if (ng > kb200::EW_MAX_TERMS || i + ng > nops) return fail(-1, "plan: bad fused group");
+            kb200::EwParams q;
+            q.nterms = ng;
+            q.C = slots[o.c] + o.c_off;
+            q.cm = tables + o.tCm; q.cn = tables + o.tCn;
+            q.bsC = o.bsC; q.beta = o.beta; q.M = o.M; q.N = o.N;
+            for (int m = 0; m < ng; ++m) {
+                const kb200_op& r = ops[i + m];
+                if (r.kind != 3 || r.c != o.c || r.M != o.M || r.N != o.N || r.tCm != o.tCm ||
+                    r.tCn != o.tCn || r.a < 0 || r.a >= nslots || r.b >= nslots)
+                    return fail(-1, "plan: inconsistent fused group");
+                kb200::EwTerm& t = q.t[m];
+                t.X = slots[r.a] + r.a_off;
+                t.xm = tables + r.tAm; t.xn = tables + r.tAk;
+                t.bsX = r.bsA;
+                if (r.b >= 0) {
+                    t.Y = slots[r.b] + r.b_off;
+                    t.ym = tables + r.tBk; t.yn = tables + r.tBn;
+                    t.bsY = r.bsB;
+                } else {
+                    t.Y = nullptr; t.ym = t.yn = nullptr; t.bsY = 0;
+                }
+                t.alpha = r.alpha;
+                t.transposed = r.a_mode;
+            }
+            for (int m = ng; m < kb200::EW_MAX_TERMS; ++m) q.t[m] = q.t[0];
+            dim3 grid((o.M + 31) / 32, (o.N + 31) / 32, o.batch);
+            if (grid.y > 65535) return fail(-1, "plan: fused N too large");
+            kb200::fused_ew_kernel<<<grid, 256, 0, st>>>(q);
+            KB_CHECK_LAUNCH("fused_ew_kernel");
+            if (ev) {
+                cudaEventRecord(ev[2 * i + 1], st);
+                for (int m = 1; m < ng; ++m) {
+                    cudaEventRecord(ev[2 * (i + m)], st);
+                    cudaEventRecord(ev[2 * (i + m) + 1], st);
+                }
+            }
+            i += ng - 1;
+            continue;
         } else if (o.kind == 1) {
             kb200::PermParams p;
             p.A = slots[o.a] + o.a_off;

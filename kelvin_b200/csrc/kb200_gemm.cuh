@@ -974,6 +974,98 @@ __global__ void __launch_bounds__(256, 2) rankk_kernel(const GemmParams p, int b
     }
 }
 
+// kind 3: fused index-permuted sums and outer products (no contracted index)
+//   C[cm[m]+cn[n]] = beta*C + sum_t alpha_t * X_t[xm_t[m]+xn_t[n]] * (Y_t ? Y_t[ym_t[m]+yn_t[n]] : 1)
+// e.g. tau = t2 + t1 x t1 - t1 x t1, the four antisymmetric images rg[abij] - rg[baij] - ...,
+// the drivers.  One pass over C instead of one read-modify-write pass per term.  n runs over
+// the last (contiguous) one or two indices of C, m over the others, one CTA per 32 x 32 tile.
+// A term whose big operand is contiguous along the fastest m letter instead is read m-fast
+// and transposed through shared memory.
+constexpr int EW_MAX_TERMS = 6;
+struct EwTerm {
+    const double* X;
+    const double* Y;                           // nullptr: no second factor
+    const uint32_t* xm;
+    const uint32_t* xn;
+    const uint32_t* ym;
+    const uint32_t* yn;
+    long long bsX, bsY;
+    double alpha;
+    int transposed;
+};
+struct EwParams {
+    EwTerm t[EW_MAX_TERMS];
+    int nterms;
+    double* C;
+    const uint32_t* cm;
+    const uint32_t* cn;
+    long long bsC;
+    double beta;
+    int M, N;
+};
+
+__global__ void __launch_bounds__(256) fused_ew_kernel(const __grid_constant__ EwParams p) {
+    __shared__ double tile[32][33];
+    const int tx = threadIdx.x & 31;
+    const int ty = threadIdx.x >> 5;   // 0..7
+    const int m0 = blockIdx.x * 32;
+    const int n0 = blockIdx.y * 32;
+    const int b = blockIdx.z;
+    const int n = n0 + tx;             // n-fast role: this thread's column, rows ty + 8 i
+    const int mt = m0 + tx;            // m-fast role: this thread's row, columns ty + 8 i
+    const bool nv = n < p.N, mv = mt < p.M;
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int t = 0; t < p.nterms; ++t) {
+        const EwTerm& q = p.t[t];
+        const double* X = q.X + (long long)b * q.bsX;
+        const double* Y = q.Y ? q.Y + (long long)b * q.bsY : nullptr;
+        if (!q.transposed) {
+            const uint32_t xo = nv ? __ldg(q.xn + n) : 0u;
+            const uint32_t yo = (nv && Y) ? __ldg(q.yn + n) : 0u;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int m = m0 + ty + 8 * i;
+                if (nv && m < p.M) {
+                    double v = q.alpha * X[(size_t)__ldg(q.xm + m) + xo];
+                    if (Y) v *= Y[(size_t)__ldg(q.ym + m) + yo];
+                    acc[i] += v;
+                }
+            }
+        } else {
+            const uint32_t xo = mv ? __ldg(q.xm + mt) : 0u;
+            const uint32_t yo = (mv && Y) ? __ldg(q.ym + mt) : 0u;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int nl = ty + 8 * i;
+                const int nn = n0 + nl;
+                double v = 0.0;
+                if (mv && nn < p.N) {
+                    v = q.alpha * X[(size_t)xo + __ldg(q.xn + nn)];
+                    if (Y) v *= Y[(size_t)yo + __ldg(q.yn + nn)];
+                }
+                tile[tx][nl] = v;
+            }
+            __syncthreads();
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[i] += tile[ty + 8 * i][tx];
+            __syncthreads();
+        }
+    }
+    if (nv) {
+        double* C = p.C + (long long)b * p.bsC + __ldg(p.cn + n);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int m = m0 + ty + 8 * i;
+            if (m < p.M) {
+                double* dst = C + __ldg(p.cm + m);
+                double v = acc[i];
+                if (p.beta != 0.0) v += p.beta * (*dst);
+                *dst = v;
+            }
+        }
+    }
+}
+
 // kind 1: C[b][cm[m]+cn[n]] = beta*C + alpha*A[b][am[m]+ak[n]]  (32x32 smem transpose tile)
 struct PermParams {
     const double* A;

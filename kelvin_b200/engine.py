@@ -129,7 +129,7 @@ class Plan(object):
                 k = 0
                 while k < len(ops):
                     gs = int(ops[k].group)
-                    if ops[k].kind == 0 and gs > 1:
+                    if ops[k].kind in (0, 3) and gs > 1:
                         share = float(ms[k])/gs
                         for j in range(k, k + gs):
                             ms[j] = share
@@ -142,7 +142,7 @@ class Plan(object):
                                     float(ms[k])*1e-3, (int(o.M), int(o.N), int(o.K), int(o.batch),
                                                         int(o.tile), int(o.splitk),
                                                         int(o.a_mode), int(o.b_mode),
-                                                        int(o.group) if o.kind == 0 else 1)))
+                                                        int(o.group) if o.kind in (0, 3) else 1)))
             _lib.check(rc, "kb200_plan_run(%s)" % self.name)
             y0 += nb
 

@@ -348,6 +348,9 @@ RANKK_MIN_M = 4096    # rows from which the rank-K streaming kernel is used
 # independent contractions of one kernel configuration launched together (kb200_gemm.cuh
 # MAX_GROUP); 1 disables grouping and keeps the program order
 MAX_GROUP = int(_os.environ.get("KB200_GROUP", "4"))
+# consecutive index-permuted sums / outer products into one output fused into one pass (kind 3)
+FUSE_EW = int(_os.environ.get("KB200_FUSE", "1"))
+EW_MAX_TERMS = 6
 LONGK_TILE = int(_os.environ.get("KB200_LONGK", "1"))
 SKINNY_TILE = int(_os.environ.get("KB200_SKINNY", "1"))
 _TILE_BN = {0: 128, 1: 32, 2: 128, 3: 128, 4: 64, 5: 64, 6: 40, 7: 40}
@@ -371,6 +374,7 @@ class Lowered(object):
         self.derived = OrderedDict()   # derived slot -> (source slot, axis permutation)
         self.descs = []
         self._nfold = {}          # id(desc) -> N-index (dim, stride) lists on B and C (batch folding)
+        self._src = {}            # id(desc) -> (resolved op, beta)
         self.flops = 0.0          # per tau point, executed (2*M*N*K)
         written = set(preset)
         for op in rops:
@@ -379,11 +383,83 @@ class Lowered(object):
             for slot, _ in op.ins:
                 if slot not in written:
                     raise ValueError("slot %s read before it is written: %r" % (slot, op))
-            self.descs.append(self._lower(op, beta))
+            d = self._lower(op, beta)
+            self._src[id(d)] = (op, beta)
+            self.descs.append(d)
         self.tables = self.bank.buffer()
         self.groups = [[k] for k in range(len(self.descs))]
         if MAX_GROUP > 1:
             self._schedule()
+            self.tables = self.bank.buffer()
+
+    # -- fused elementwise chains (kind 3) -------------------------------------
+    def _is_ew(self, d):
+        """Index-permuted copy/sum or outer product: no contracted index, output not read."""
+        if not FUSE_EW:
+            return False
+        op, _ = self._src[id(d)]
+        out = set(op.out[1])
+        return all(set(ls) <= out for _, ls in op.ins) and all(sl != op.out[0] for sl, _ in op.ins)
+
+    def _lower_fused(self, items):
+        """items: [(op, beta)] writing one slot, in program order -> kind-3 descriptors."""
+        cslot = items[0][0].out[0]
+        shp = self.slot_shapes[cslot]
+        nd = len(shp)
+        stc = _strides(shp)
+        numel = lambda sl: int(numpy.prod(self.slot_shapes[sl]))  # noqa: E731
+        bs = lambda sl: numel(sl) if self.batched[sl] else 0      # noqa: E731
+        terms = []
+        votes = {}
+        for op, beta in items:
+            pos = {l: k for k, l in enumerate(op.out[1])}
+            ins = sorted(op.ins, key=lambda x: -numel(x[0]))       # X = the larger operand
+            strides = []
+            for sl, ls in ins:
+                st = [0]*nd
+                for l, v in zip(ls, _strides(self.slot_shapes[sl])):
+                    st[pos[l]] = v
+                strides.append(st)
+            xs, xl = ins[0]
+            fast = pos[xl[-1]]
+            big = numel(xs) > 16384
+            if big and fast != nd - 1:
+                votes[fast] = votes.get(fast, 0) + 1
+            terms.append((op, beta, ins, strides, fast, big))
+        winner = max(votes, key=lambda a: votes[a]) if votes else None
+        # n runs over the last index of C, or the last two when that keeps every big operand
+        # readable along its own contiguous index
+        n_axes = [nd - 1]
+        if nd >= 3 and winner != nd - 2 and shp[nd - 1] < 64:
+            n_axes = [nd - 2, nd - 1]
+        m_axes = [a for a in range(nd) if a not in n_axes]
+        if winner is not None and winner in m_axes:
+            m_axes.remove(winner)
+            m_axes.append(winner)
+        tabm = lambda st: self.bank.get([(shp[a], st[a]) for a in m_axes])    # noqa: E731
+        tabn = lambda st: self.bank.get([(shp[a], st[a]) for a in n_axes])    # noqa: E731
+        M = int(numpy.prod([shp[a] for a in m_axes])) if m_axes else 1
+        out = []
+        for k, (op, beta, ins, strides, fast, big) in enumerate(terms):
+            d = kb200_op()
+            d.kind = 3
+            d.a = self.slot_index[ins[0][0]]
+            d.b = self.slot_index[ins[1][0]] if len(ins) > 1 else -1
+            d.c = self.slot_index[cslot]
+            d.M, d.N, d.K, d.batch, d.splitk = M, int(numpy.prod([shp[a] for a in n_axes])), 1, 1, 1
+            d.bsA = bs(ins[0][0])
+            d.bsB = bs(ins[1][0]) if len(ins) > 1 else 0
+            d.bsC = bs(cslot)
+            d.tAm, d.tAk = tabm(strides[0]), tabn(strides[0])
+            if len(ins) > 1:
+                d.tBk, d.tBn = tabm(strides[1]), tabn(strides[1])
+            d.tCm, d.tCn = tabm(stc), tabn(stc)
+            d.alpha = op.coef
+            d.beta = beta if k == 0 else 1.0
+            d.a_mode = 1 if (big and winner is not None and fast == winner and winner in m_axes) else 0
+            self._src[id(d)] = (op, d.beta)
+            out.append(d)
+        return out
 
     # -- launch grouping -----------------------------------------------------
     def _groupable(self, d):
@@ -429,7 +505,7 @@ class Lowered(object):
             last_write[w] = i
             readers[w] = []
         ready = sorted(i for i in range(n) if npred[i] == 0)
-        order, groups = [], []
+        order, groups, chains = [], [], []
 
         def retire(i):
             for j in succ[i]:
@@ -444,9 +520,22 @@ class Lowered(object):
                 # cheap ops first, in program order: they unlock more large contractions
                 i = small[0]
                 ready.remove(i)
-                groups.append([len(order)])
-                order.append(i)
+                chain = [i]
                 retire(i)
+                if self._is_ew(self.descs[i]):
+                    # following elementwise updates of the same output join its pass
+                    while len(chain) < EW_MAX_TERMS:
+                        cand = [j for j in ready if writes[j] == writes[i] and self._is_ew(self.descs[j])]
+                        if not cand:
+                            break
+                        j = min(cand)
+                        ready.remove(j)
+                        chain.append(j)
+                        retire(j)
+                    if len(chain) > 1 or self.descs[i].kind == 0:
+                        chains.append(list(range(len(order), len(order) + len(chain))))
+                groups.append(list(range(len(order), len(order) + len(chain))))
+                order.extend(chain)
                 continue
             lead = self.descs[ready[0]]
             sig = (lead.tile, lead.a_mode, lead.b_mode)
@@ -469,6 +558,12 @@ class Lowered(object):
         self.descs = [self.descs[i] for i in order]
         self.rops = [self.rops[i] for i in order]
         self.groups = groups
+        for pos in chains:
+            fused = self._lower_fused([self._src[id(self.descs[k])] for k in pos])
+            for k, d in zip(pos, fused):
+                self.flops -= 2.0 * self.descs[k].M * self.descs[k].N * self.descs[k].K \
+                    if self.descs[k].kind == 0 else 0.0
+                self.descs[k] = d
 
     # -- helpers ---------------------------------------------------------
     def _dims(self, op):
@@ -640,7 +735,7 @@ class Lowered(object):
             ctypes.memmove(ctypes.byref(arr[k]), ctypes.byref(d), ctypes.sizeof(kb200_op))
             o = arr[k]
             o.group = lead_size.get(k, 0)
-            o.batch = nbatch if (o.bsC != 0 or o.bsA != 0 or (o.kind == 0 and o.bsB != 0)) else 1
+            o.batch = nbatch if (o.bsC != 0 or o.bsA != 0 or (o.kind in (0, 3) and o.bsB != 0)) else 1
             if o.batch > 1 and o.bsC == 0:
                 raise ValueError("batched operands reduce into an unbatched output")
             if FOLD and o.kind == 0 and o.batch > 1 and o.bsA == 0 and o.bsB != 0 \

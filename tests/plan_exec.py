@@ -31,6 +31,16 @@ def run_lowered(low, arrays, nbatch):
             if o.kind == 1:
                 an = tabs[o.tAk:o.tAk + o.N]
                 val = A[(o.a_off + b * o.bsA + am[:, None] + an[None, :]).reshape(-1)]
+            elif o.kind == 3:
+                # one term of a fused elementwise sum; entries after the first carry beta = 1,
+                # so running them one after the other equals the fused pass
+                an = tabs[o.tAk:o.tAk + o.N]
+                val = A[(o.a_off + b * o.bsA + am[:, None] + an[None, :]).reshape(-1)]
+                if o.b >= 0:
+                    Y = flat[low.slot_names[o.b]]
+                    ym = tabs[o.tBk:o.tBk + o.M]
+                    yn = tabs[o.tBn:o.tBn + o.N]
+                    val = val * Y[(o.b_off + b * o.bsB + ym[:, None] + yn[None, :]).reshape(-1)]
             else:
                 B = flat[low.slot_names[o.b]]
                 ak = tabs[o.tAk:o.tAk + o.K]

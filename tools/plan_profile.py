@@ -45,6 +45,12 @@ def main():
     for dt, kind, fl, meta, txt in rows:
         if kind == 1:
             key = "permute"
+        elif kind == 3:
+            key = "fused elementwise (kind 3)"
+        elif kind == 0 and meta[4] == 7:
+            key = "skinny streaming (tile 7)"
+        elif kind == 0 and meta[4] == 6:
+            key = "long-K tiny output (tile 6)"
         elif kind == 2:
             key = "rank-k update (kind 2)"
         elif fl >= 0.5*2*ng*m**6:
