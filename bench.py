@@ -234,6 +234,16 @@ def main():
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     t_step = float(tt.item())/K
 
+    # ---- optional per-phase breakdown of the sharded step (diagnostics, outside the timed region)
+    phases = None
+    if os.environ.get("KB200_PHASES"):
+        solver.phase_ms = {}
+        for _ in range(3):
+            solver.step(0.0)
+        phases = {k: v/3.0 for k, v in solver.phase_ms.items()}
+        solver.phase_ms = None
+        print("rank %d phases (ms/step): %s" % (rank, json.dumps(phases)), flush=True)
+
     # ---- end-to-end: host amplitudes in pinned memory -> device -> iterate -> E,res to host
     host = [x.cpu().pin_memory() for x in solver.old]
     h2d = sum(x.numel()*8 for x in host)

@@ -65,6 +65,7 @@ class TauShardedUCCSD(object):
         self.stats = torch.zeros(20, dtype=torch.float64, device=self.dev)
         self.old = None
         self._gather = None
+        self.phase_ms = None      # set to {} to collect per-phase device times (diagnostics)
 
     # -- amplitudes ---------------------------------------------------------
     def set_amplitudes(self, T1a, T1b, T2aa, T2ab, T2bb):
@@ -96,18 +97,30 @@ class TauShardedUCCSD(object):
         lib = _lib.load()
         ng, nloc = self.ng, self.nloc
         Fa, Fb, Ia, Ib, Iabab = self.ints
+        marks = []
+
+        def mark(name):
+            if self.phase_ms is not None:
+                ev = torch.cuda.Event(enable_timing=True)
+                ev.record()
+                marks.append((name, ev))
+        mark("start")
         if nloc > 0:
             bars = ft_cc_equations.uccsd_stanton_bar(Fa, Fb, Ia, Ib, Iabab, *self.old)
         else:
             bars = [torch.zeros((0,) + tuple(d.shape), dtype=torch.float64, device=self.dev)
                     for d in self.Ds]
         self.stats.zero_()
+        mark("residual")
         new = []
+        fulls = [self._allgather_rows(bars[k]) for k in range(5)]
+        mark("all-gather")
         for k in range(5):
-            full = self._allgather_rows(bars[k])
             if nloc > 0:
-                new.append(quadrature.int_tbar(ng, full[:ng], self.ti, self.Ds[k], self.G,
+                new.append(quadrature.int_tbar(ng, fulls[k][:ng], self.ti, self.Ds[k], self.G,
                                                rows=(self.y0, self.y1)))
+        fulls = None
+        mark("integrate")
         if nloc > 0:
             scratch = _lib.reduce_scratch(self.dev)
             for k in range(5):
@@ -124,9 +137,15 @@ class TauShardedUCCSD(object):
                  (T2bb, T1b, T1b, self.abij[2], 0.25, 0.5)],
                 self.g[self.y0:self.y1], self.dev)
             self.stats[15:20] = parts
+        mark("damp+energy")
         if self.world > 1:
             dist.all_reduce(self.stats, group=self.group)
         s = self.stats.cpu().numpy()
+        mark("all-reduce")
+        if self.phase_ms is not None:
+            torch.cuda.synchronize()
+            for (_, e0), (nm, e1) in zip(marks[:-1], marks[1:]):
+                self.phase_ms[nm] = self.phase_ms.get(nm, 0.0) + e0.elapsed_time(e1)
         n = numpy.sqrt(s[:15].reshape(5, 3))
         nl1 = n[0, 1] + 0.1 + n[1, 1]
         nl2 = n[2, 1] + 0.1 + n[3, 1] + n[4, 1]

@@ -755,16 +755,8 @@ class Lowered(object):
                 if o.tile == 7:
                     continue
                 if o.tile == 6:
-                    # grid = (splitk, batch): fill whole waves of one-CTA-per-SM with K chunks
-                    # of at least 8 stages
-                    best = 1
-                    for w in (1, 2, 3, 4):
-                        sk = max(1, (w * N_SM) // o.batch)
-                        if o.K // sk < 256:
-                            break
-                        best = sk
-                        if sk * o.batch >= 0.97 * w * N_SM:
-                            break
+                    # grid = (splitk, batch): one wave of two CTAs per SM, K chunks of >= 4 stages
+                    best = max(1, min((2 * N_SM) // o.batch, o.K // 128))
                     o.splitk = best
                     continue
                 if ctas < target // 2 and o.K >= 512:
