@@ -326,6 +326,24 @@ class TableBank(object):
         self.index[key] = start
         return start
 
+    def get_lt(self, dims_strides, px, py):
+        """As get(), keeping only the entries whose index at position px is smaller than the
+        one at position py (the x < y half of an antisymmetric contracted pair)."""
+        key = ("lt", px, py) + tuple(dims_strides)
+        if key in self.index:
+            return self.index[key]
+        dims = [d for d, _ in dims_strides]
+        grids = numpy.meshgrid(*[numpy.arange(d, dtype=numpy.int64) for d in dims], indexing="ij")
+        off = sum(g*s_ for g, (_, s_) in zip(grids, dims_strides))
+        keep = grids[px] < grids[py]
+        off = off[keep].reshape(-1)          # C order of the full index space, filtered
+        assert off.max(initial=0) < 2 ** 32 - 1
+        start = self.pos
+        self.chunks.append(off.astype(numpy.uint32))
+        self.pos += off.size
+        self.index[key] = start
+        return start
+
     def buffer(self):
         if not self.chunks:
             return numpy.zeros((1,), dtype=numpy.uint32)
@@ -350,6 +368,25 @@ RANKK_MIN_M = 4096    # rows from which the rank-K streaming kernel is used
 MAX_GROUP = int(_os.environ.get("KB200_GROUP", "4"))
 # consecutive index-permuted sums / outer products into one output fused into one pass (kind 3)
 FUSE_EW = int(_os.environ.get("KB200_FUSE", "1"))
+# contracted index pairs in which both operands are antisymmetric are summed over x < y only
+# (twice the half sum): the same-spin ladder terms then do half the flops of the reference's
+# full double sum.  Relies on the amplitudes being antisymmetric, which the equations preserve.
+ANTISYM = int(_os.environ.get("KB200_ANTISYM", "1"))
+_AMP2_BASES = ("t2", "tau", "tauh", "Woooo", "Wvvvv", "l2")
+
+
+def antisym_pairs(slot):
+    """Index-position pairs under which the tensor in `slot` changes sign, known from its class
+    (programs.tensor_defs): same-spin amplitudes / ladder intermediates and same-spin
+    antisymmetrised integral blocks.  Adjoint and derived slots are not claimed."""
+    if "~" in slot or "@" in slot:
+        return ()
+    base, _, suf = slot.partition(".")
+    if base in ("I", "Ia", "Ib"):
+        return tuple(pq for pq in ((0, 1), (2, 3)) if suf[pq[0]] == suf[pq[1]])
+    if base in _AMP2_BASES and suf in ("", "aa", "bb"):
+        return ((0, 1), (2, 3))
+    return ()
 EW_MAX_TERMS = 6
 LONGK_TILE = int(_os.environ.get("KB200_LONGK", "1"))
 SKINNY_TILE = int(_os.environ.get("KB200_SKINNY", "1"))
@@ -704,8 +741,22 @@ class Lowered(object):
         d.a, d.b = self.slot_index[na], self.slot_index[nb]
         d.M, d.N, d.K = size(M), size(N), size(K)
         d.bsA, d.bsB = bs(na), bs(nb)
-        d.tAm, d.tAk = tab(M, sa), tab(K, sa)
-        d.tBk, d.tBn = tab(K, sb), tab(N, sb)
+        d.tAm, d.tBn = tab(M, sa), tab(N, sb)
+        half = None
+        if ANTISYM and len(K) >= 2:
+            for pa, qa in antisym_pairs(na):
+                x, y = la[pa], la[qa]
+                if x in K and y in K and any({lb[pb], lb[qb]} == {x, y} for pb, qb in antisym_pairs(nb)):
+                    half = (K.index(x), K.index(y))
+                    break
+        if half is not None and "@" not in na and "@" not in nb:
+            d.tAk = self.bank.get_lt([(dims[l], sa[l]) for l in K], *half)
+            d.tBk = self.bank.get_lt([(dims[l], sb[l]) for l in K], *half)
+            nx = dims[K[half[0]]]
+            d.K = size(K) // (nx * nx) * (nx * (nx - 1) // 2)
+            d.alpha = 2.0 * op.coef
+        else:
+            d.tAk, d.tBk = tab(K, sa), tab(K, sb)
         d.tCm, d.tCn = tab(M, sc), tab(N, sc)
         d.a_mode, d.b_mode = a_mode, b_mode
         self._nfold[id(d)] = ([(dims[l], sb[l]) for l in N], [(dims[l], sc[l]) for l in N])

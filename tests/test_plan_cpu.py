@@ -86,8 +86,10 @@ def test_u_plan_has_32_block_gemms():
     shapes = plan.slot_shapes(rops, "u", sizes)
     low = plan.Lowered(rops, shapes, {s: not plan.is_integral_slot(s) for s in shapes},
                        [s for s in shapes if plan.is_integral_slot(s)] + ["t1.a", "t1.b", "t2.aa", "t2.ab", "t2.bb"])
-    big = [d for d in low.descs if d.kind == 0 and d.M*d.N*d.K == m**6]
+    big = [d for d in low.descs if d.kind == 0 and d.M*d.N == m**4 and d.K >= m*(m - 1)//2]
     assert len(big) == 32
+    # the 8 same-spin ladder contractions sum their antisymmetric pair over x < y only
+    assert sum(1 for d in big if d.K == m*(m - 1)//2) == 8
     assert low.flops <= 64*m**6 + 200*m**5
 
 
