@@ -130,9 +130,11 @@ class Plan(object):
                 while k < len(ops):
                     gs = int(ops[k].group)
                     if ops[k].kind in (0, 3) and gs > 1:
-                        share = float(ms[k])/gs
+                        # in proportion to the members' work (flops; equal for elementwise terms)
+                        w = [float(ops[j].M)*ops[j].N*ops[j].K for j in range(k, k + gs)]
+                        tot = float(ms[k])
                         for j in range(k, k + gs):
-                            ms[j] = share
+                            ms[j] = tot*w[j - k]/sum(w)
                         k += gs
                     else:
                         k += 1

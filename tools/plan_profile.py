@@ -53,7 +53,7 @@ def main():
             key = "long-K tiny output (tile 6)"
         elif kind == 2:
             key = "rank-k update (kind 2)"
-        elif fl >= 0.5*2*ng*m**6:
+        elif fl >= 0.4*2*ng*m**6:
             key = "gemm m^6"
         elif meta[5] > 1:
             key = "gemm split-K"
