@@ -165,22 +165,23 @@ def uft_active_integrals(sys, ea, eb, foa, fva, fob, fvb, iocca, ivira, ioccb, i
 # ---------------------------------------------------------------------------
 # amplitude updates
 # ---------------------------------------------------------------------------
-def form_new_ampl(method, F, I, T1old, T2old, D1, D2, ti, ng, G):
+def form_new_ampl(method, F, I, T1old, T2old, D1, D2, ti, ng, G, t0_zero=False):
     """Form new amplitudes (kelvin/cc_utils.py:17-49).  CCSD only on this path."""
     if method == "CCSD":
-        return ft_cc_equations.ccsd_stanton(F, I, T1old, T2old, D1, D2, ti, ng, G)
+        return ft_cc_equations.ccsd_stanton(F, I, T1old, T2old, D1, D2, ti, ng, G,
+                                            t0_zero=t0_zero)
     if method in ("CCD", "LCCSD", "LCCD"):
         raise Exception("{} is outside the B200 FT-CCSD path".format(method))
     raise Exception("Unrecognized method keyword")
 
 
 def form_new_ampl_u(method, Fa, Fb, Ia, Ib, Iabab, T1aold, T1bold, T2aaold, T2abold, T2bbold,
-                    D1a, D1b, D2aa, D2ab, D2bb, ti, ng, G):
+                    D1a, D1b, D2aa, D2ab, D2bb, ti, ng, G, t0_zero=False):
     """Form new amplitudes, unrestricted (kelvin/cc_utils.py:52-86)."""
     if method == "CCSD":
         return ft_cc_equations.uccsd_stanton(
             Fa, Fb, Ia, Ib, Iabab, T1aold, T1bold, T2aaold, T2abold, T2bbold,
-            D1a, D1b, D2aa, D2ab, D2bb, ti, ng, G)
+            D1a, D1b, D2aa, D2ab, D2bb, ti, ng, G, t0_zero=t0_zero)
     raise Exception("Unrecognized method keyword for unrestricted calc")
 
 
@@ -225,8 +226,10 @@ def ft_cc_iter(method, T1old, T2old, F, I, D1, D2, g, G, beta, ng, ti, iprint, c
     nl2 = _norm(T2old) + 0.1
     Iabij = ft_cc_energy.oovv_to_abij(I.oovv)
     st = _Stats(2, dev)
+    # T[0] == 0 is preserved by the update (row 0 of G vanishes): skip that grid point
+    t0 = ft_cc_equations.t0_is_zero(G, (T1old, T2old))
     while i < max_iter and not converged:
-        T1, T2 = form_new_ampl(method, F, I, T1old, T2old, D1, D2, ti, ng, G)
+        T1, T2 = form_new_ampl(method, F, I, T1old, T2old, D1, D2, ti, ng, G, t0_zero=t0)
         # residuals, damping and new norms in one pass per tensor
         st.damp(0, T1old, T1, alpha)
         st.damp(1, T2old, T2, alpha)
@@ -265,10 +268,12 @@ def ft_ucc_iter(method, T1aold, T1bold, T2aaold, T2abold, T2bbold, Fa, Fb, Ia, I
     abij = (ft_cc_energy.oovv_to_abij(Ia.oovv), ft_cc_energy.oovv_to_abij(Iabab.oovv),
             ft_cc_energy.oovv_to_abij(Ib.oovv))
     st = _Stats(5, dev)
+    # T[0] == 0 is preserved by the update (row 0 of G vanishes): skip that grid point
+    t0 = ft_cc_equations.t0_is_zero(G, old)
     while i < max_iter and not converged:
         T1out, T2out = form_new_ampl_u(
             method, Fa, Fb, Ia, Ib, Iabab, old[0], old[1], old[2], old[3], old[4],
-            D1a, D1b, D2aa, D2ab, D2bb, ti, ng, G)
+            D1a, D1b, D2aa, D2ab, D2bb, ti, ng, G, t0_zero=t0)
         new = (T1out[0], T1out[1], T2out[0], T2out[1], T2out[2])
         for k in range(5):
             st.damp(k, old[k], new[k], alpha)

@@ -87,10 +87,45 @@ def _u_integral_slots(Fa, Fb, Ia, Ib, Iabab, dev, needed):
 # ---------------------------------------------------------------------------
 # amplitude equations
 # ---------------------------------------------------------------------------
-def ccsd_stanton_bar(F, I, T1old, T2old, fac=-1.0):
+def t0_is_zero(G, amps):
+    """True when the amplitudes at the first grid point (tau = 0) are exactly zero and
+    stay zero under the quadrature: row 0 of G vanishes (every rule of
+    kelvin/quadrature.py:215-235 integrates from tau_0 = 0), so T[0] = sum_x G[0,x] w T̄[x]
+    = 0 and T̄[0] = drivers + fac*StantonTerms(T = 0) = drivers.  The pointwise solver of the
+    reference uses the same fact (kelvin/cc_utils.py:205-208, "don't bother computing at
+    T = inf").  One device reduction; call it once per solve, not per iteration."""
+    import numpy
+    G = G.cpu().numpy() if isinstance(G, torch.Tensor) else numpy.asarray(G)
+    if G.shape[0] < 2 or numpy.any(G[0] != 0.0):
+        return False
+    for x in amps:
+        if x.shape[0] < 2 or float(x[0].abs().max()) != 0.0:
+            return False
+    return True
+
+
+def _run_rows(p, t, ins, outs, drivers, ng, dev, t0_zero):
+    """Run the residual plan over the grid points; with t0_zero the first point is not
+    evaluated (its amplitudes are exactly zero): T̄[0] = drivers."""
+    if not t0_zero:
+        p.run(t, ng, _chunk_for(p, ng, dev))
+        return
+    full = {nm: t[nm] for nm in tuple(ins) + tuple(outs)}
+    if ng > 1:
+        for nm in full:
+            t[nm] = full[nm][1:]
+        p.run(t, ng - 1, _chunk_for(p, ng - 1, dev))
+    for nm, d in zip(outs, drivers):
+        full[nm][0].copy_(d)
+        full[nm][0].neg_()
+        t[nm] = full[nm]
+
+
+def ccsd_stanton_bar(F, I, T1old, T2old, fac=-1.0, t0_zero=False):
     """T1bar, T2bar: drivers + fac*StantonTerms at every grid point, i.e. the
     state of T1new/T2new just before the integration at
-    kelvin/ft_cc_equations.py:109."""
+    kelvin/ft_cc_equations.py:109.  t0_zero: the caller guarantees T1old[0] = T2old[0] = 0
+    (see t0_is_zero); the first grid point then costs nothing."""
     dev = _lib.device()
     T1old = _lib.as_dev(T1old, dev)
     T2old = _lib.as_dev(T2old, dev)
@@ -98,43 +133,49 @@ def ccsd_stanton_bar(F, I, T1old, T2old, fac=-1.0):
     p = stanton_plan("g", _g_sizes(F), fac)
     t = _g_integral_slots(F, I, dev)
     t["t1"], t["t2"] = T1old, T2old
-    t["o1"] = torch.empty_like(T1old)
-    t["o2"] = torch.empty_like(T2old)
-    p.run(t, ng, _chunk_for(p, ng, dev))
-    return t["o1"], t["o2"]
+    o1 = t["o1"] = torch.empty_like(T1old)
+    o2 = t["o2"] = torch.empty_like(T2old)
+    _run_rows(p, t, ("t1", "t2"), ("o1", "o2"), (t["F.vo"], t["I.vvoo"]), ng, dev, t0_zero)
+    return o1, o2
 
 
-def ccsd_stanton(F, I, T1old, T2old, D1, D2, ti, ng, G):
+def ccsd_stanton(F, I, T1old, T2old, D1, D2, ti, ng, G, t0_zero=False):
     """Time-dependent CCSD iteration using Stanton-Gauss intermediates
     (kelvin/ft_cc_equations.py:96-113)."""
-    T1bar, T2bar = ccsd_stanton_bar(F, I, T1old, T2old)
+    T1bar, T2bar = ccsd_stanton_bar(F, I, T1old, T2old, t0_zero=t0_zero)
     T1new = quadrature.int_tbar1(ng, T1bar, ti, D1, G)
     T2new = quadrature.int_tbar2(ng, T2bar, ti, D2, G)
     return T1new, T2new
 
 
-def uccsd_stanton_bar(Fa, Fb, Ia, Ib, Iabab, T1aold, T1bold, T2aaold, T2abold, T2bbold, fac=-1.0):
+def uccsd_stanton_bar(Fa, Fb, Ia, Ib, Iabab, T1aold, T1bold, T2aaold, T2abold, T2bbold, fac=-1.0,
+                      t0_zero=False):
     dev = _lib.device()
     ins = [_lib.as_dev(x, dev) for x in (T1aold, T1bold, T2aaold, T2abold, T2bbold)]
     ng = ins[0].shape[0]
     p = stanton_plan("u", _u_sizes(Fa, Fb), fac)
     t = _u_integral_slots(Fa, Fb, Ia, Ib, Iabab, dev,
                           [s for s in p.inputs if _plan.is_integral_slot(s)])
-    for nm, x in zip(("t1.a", "t1.b", "t2.aa", "t2.ab", "t2.bb"), ins):
+    in_names = ("t1.a", "t1.b", "t2.aa", "t2.ab", "t2.bb")
+    out_names = ("o1.a", "o1.b", "o2.aa", "o2.ab", "o2.bb")
+    for nm, x in zip(in_names, ins):
         t[nm] = x
     outs = []
-    for nm, x in zip(("o1.a", "o1.b", "o2.aa", "o2.ab", "o2.bb"), ins):
+    for nm, x in zip(out_names, ins):
         t[nm] = torch.empty_like(x)
         outs.append(t[nm])
-    p.run(t, ng, _chunk_for(p, ng, dev))
+    drivers = None
+    if t0_zero:
+        drivers = [_lib.as_dev(x, dev) for x in (Fa.vo, Fb.vo, Ia.vvoo, Iabab.vvoo, Ib.vvoo)]
+    _run_rows(p, t, in_names, out_names, drivers, ng, dev, t0_zero)
     return tuple(outs)
 
 
 def uccsd_stanton(Fa, Fb, Ia, Ib, Iabab, T1aold, T1bold, T2aaold, T2abold,
-                  T2bbold, D1a, D1b, D2aa, D2ab, D2bb, ti, ng, G):
+                  T2bbold, D1a, D1b, D2aa, D2ab, D2bb, ti, ng, G, t0_zero=False):
     """Unrestricted CCSD iteration (kelvin/ft_cc_equations.py:130-164)."""
     b1a, b1b, b2aa, b2ab, b2bb = uccsd_stanton_bar(
-        Fa, Fb, Ia, Ib, Iabab, T1aold, T1bold, T2aaold, T2abold, T2bbold)
+        Fa, Fb, Ia, Ib, Iabab, T1aold, T1bold, T2aaold, T2abold, T2bbold, t0_zero=t0_zero)
     T1a = quadrature.int_tbar1(ng, b1a, ti, D1a, G)
     T1b = quadrature.int_tbar1(ng, b1b, ti, D1b, G)
     T2aa = quadrature.int_tbar2(ng, b2aa, ti, D2aa, G)

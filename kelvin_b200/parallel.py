@@ -64,6 +64,7 @@ class TauShardedUCCSD(object):
         self.fbT = _lib.as_dev(Fb.ov, self.dev).t().contiguous()
         self.stats = torch.zeros(20, dtype=torch.float64, device=self.dev)
         self.old = None
+        self.t0_zero = False      # T[0] == 0 on the rank that owns tau_0: that point is skipped
         self._gather = None
         self.phase_ms = None      # set to {} to collect per-phase device times (diagnostics)
 
@@ -72,9 +73,22 @@ class TauShardedUCCSD(object):
         """Full (ng, ...) amplitudes -> local shard (copied)."""
         self.old = [_lib.as_dev(x, self.dev)[self.y0:self.y1].clone().contiguous()
                     for x in (T1a, T1b, T2aa, T2ab, T2bb)]
+        self._check_t0(None)
 
-    def set_local_amplitudes(self, local):
+    def set_local_amplitudes(self, local, t0_zero=None):
+        """t0_zero: None = look at the data (one device reduction + sync); True/False = the
+        caller's knowledge of whether the amplitudes at tau_0 vanish (only read on the rank
+        that owns tau_0)."""
         self.old = [_lib.as_dev(x, self.dev).contiguous() for x in local]
+        self._check_t0(t0_zero)
+
+    def _check_t0(self, known):
+        if self.y0 != 0 or self.nloc < 1 or self.ng < 2 or numpy.any(self.G[0] != 0.0):
+            self.t0_zero = False
+        elif known is not None:
+            self.t0_zero = bool(known)
+        else:
+            self.t0_zero = all(float(x[0].abs().max()) == 0.0 for x in self.old)
 
     def full_amplitudes(self):
         """All-gather the local shards into full (ng, ...) tensors."""
@@ -106,7 +120,8 @@ class TauShardedUCCSD(object):
                 marks.append((name, ev))
         mark("start")
         if nloc > 0:
-            bars = ft_cc_equations.uccsd_stanton_bar(Fa, Fb, Ia, Ib, Iabab, *self.old)
+            bars = ft_cc_equations.uccsd_stanton_bar(Fa, Fb, Ia, Ib, Iabab, *self.old,
+                                                     t0_zero=self.t0_zero)
         else:
             bars = [torch.zeros((0,) + tuple(d.shape), dtype=torch.float64, device=self.dev)
                     for d in self.Ds]

@@ -87,3 +87,32 @@ def test_tau_sharded_step_equals_reference_loop(built):
     assert abs(E1 - hist[0][0]) < 1e-12 and abs(E2 - hist[1][0]) < 1e-12
     assert abs(r1 - hist[0][1]) < 1e-10*max(1.0, hist[0][1])
     assert abs(r2 - hist[1][1]) < 1e-10*max(1.0, hist[1][1])
+
+
+def test_tau0_shortcut(built):
+    """With T[0] == 0 the residual at the first grid point is the bare driver; the
+    shortcut (t0_zero=True: that point is not evaluated) gives what the full evaluation gives."""
+    from kelvin_b200 import ft_cc_equations
+    ng = 4
+    ints, amps = util.random_u(6, 5, ng, seed=5)
+    amps = [a.copy() for a in amps]
+    for a in amps:
+        a[0] = 0.0
+    ti, g, G = odrv.simpsons(ng, 0.9)
+    assert ft_cc_equations.t0_is_zero(G, [__import__("torch").as_tensor(a) for a in amps])
+    full = ft_cc_equations.uccsd_stanton_bar(*ints, *amps)
+    fast = ft_cc_equations.uccsd_stanton_bar(*ints, *amps, t0_zero=True)
+    Fa, Fb, Ia, Ib, Iabab = ints
+    for got, ref, drv in zip(fast, full, (Fa.vo, Fb.vo, Ia.vvoo, Iabab.vvoo, Ib.vvoo)):
+        ref = ref.cpu().numpy()
+        assert numpy.array_equal(got[0].cpu().numpy(), -drv)
+        assert numpy.abs(ref[0] + drv).max() < 1e-13*numpy.abs(drv).max()
+        assert _relerr(got, ref) < 1e-12
+    F, I, t1, t2 = util.random_g(7, 3, seed=3)
+    t1[0] = 0.0
+    t2[0] = 0.0
+    f1, f2 = ft_cc_equations.ccsd_stanton_bar(F, I, t1, t2)
+    s1, s2 = ft_cc_equations.ccsd_stanton_bar(F, I, t1, t2, t0_zero=True)
+    assert _relerr(s1, f1.cpu().numpy()) < 1e-12
+    assert _relerr(s2, f2.cpu().numpy()) < 1e-12
+    assert numpy.array_equal(s2[0].cpu().numpy(), -I.vvoo)

@@ -154,3 +154,23 @@ def test_tau_allgather_gloo_world2(ng):
         p.join(timeout=60)
     for rank, ok, tot in res:
         assert ok and tot == ng
+
+
+def test_t0_is_zero_predicate():
+    """The tau_0 shortcut is only taken when row 0 of G vanishes and every amplitude block is
+    exactly zero at the first grid point."""
+    import torch
+    from kelvin_b200 import ft_cc_equations, quadrature
+    for quad in ("lin", "ln", "sin", "quad", "cub"):
+        ti, g, G = quadrature.ft_quad(6, 2.0, quad)
+        assert numpy.all(G[0] == 0.0), quad
+    ti, g, G = quadrature.ft_quad(6, 2.0, "lin")
+    a = torch.zeros(6, 3, 3, dtype=torch.float64)
+    b = torch.randn(6, 3, 3, 3, 3, dtype=torch.float64)
+    assert not ft_cc_equations.t0_is_zero(G, (a, b))
+    b[0] = 0.0
+    assert ft_cc_equations.t0_is_zero(G, (a, b))
+    G2 = G.copy()
+    G2[0, 0] = 1e-3
+    assert not ft_cc_equations.t0_is_zero(G2, (a, b))
+    assert not ft_cc_equations.t0_is_zero(G[:1, :1], (a[:1], b[:1]))
