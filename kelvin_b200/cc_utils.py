@@ -15,7 +15,7 @@ import time
 import numpy
 import torch
 
-from . import _lib, ft_cc_energy, ft_cc_equations, ft_utils
+from . import _lib, ft_cc_energy, ft_cc_equations, ft_utils, quadrature
 from .ov_blocks import one_e_blocks, two_e_blocks, two_e_blocks_full
 
 
@@ -166,12 +166,16 @@ def uft_active_integrals(sys, ea, eb, foa, fva, fob, fvb, iocca, ivira, ioccb, i
 # amplitude updates
 # ---------------------------------------------------------------------------
 def form_new_ampl(method, F, I, T1old, T2old, D1, D2, ti, ng, G, t0_zero=False):
-    """Form new amplitudes (kelvin/cc_utils.py:17-49).  CCSD only on this path."""
+    """Form new amplitudes (kelvin/cc_utils.py:17-49)."""
     if method == "CCSD":
         return ft_cc_equations.ccsd_stanton(F, I, T1old, T2old, D1, D2, ti, ng, G,
                                             t0_zero=t0_zero)
-    if method in ("CCD", "LCCSD", "LCCD"):
-        raise Exception("{} is outside the B200 FT-CCSD path".format(method))
+    if method == "CCD":
+        return T1old, ft_cc_equations.ccd_simple(F, I, T2old, D2, ti, ng, G)
+    if method == "LCCSD":
+        return ft_cc_equations.lccsd_simple(F, I, T1old, T2old, D1, D2, ti, ng, G)
+    if method == "LCCD":
+        return T1old, ft_cc_equations.lccd_simple(F, I, T2old, D2, ti, ng, G)
     raise Exception("Unrecognized method keyword")
 
 
@@ -297,10 +301,105 @@ def ft_ucc_iter(method, T1aold, T1bold, T2aaold, T2abold, T2bbold, Fa, Fb, Ia, I
     return Eold, (old[0], old[1]), (old[2], old[3], old[4])
 
 
+def form_new_ampl_extrap(ig, method, F, I, T1, T2, T1bar, T2bar, D1, D2, ti, ng, G):
+    """kelvin/cc_utils.py:89-96."""
+    if method == "CCSD":
+        return ft_cc_equations.ccsd_stanton_single(
+            ig, F, I, T1, T2, T1bar, T2bar, D1, D2, ti, ng, G)
+    raise Exception("Unrecognized method keyword")
+
+
+def form_new_ampl_extrap_u(ig, method, Fa, Fb, Ia, Ib, Iabab,
+                           T1a, T1b, T2aa, T2ab, T2bb, T1bara, T1barb,
+                           T2baraa, T2barab, T2barbb, D1a, D1b,
+                           D2aa, D2ab, D2bb, ti, ng, G):
+    """kelvin/cc_utils.py:98-108."""
+    if method == "CCSD":
+        return ft_cc_equations.uccsd_stanton_single(
+            ig, Fa, Fb, Ia, Ib, Iabab, T1a, T1b, T2aa, T2ab, T2bb, T1bara, T1barb,
+            T2baraa, T2barab, T2barbb, D1a, D1b, D2aa, D2ab, D2bb, ti, ng, G)
+    raise Exception("Unrecognized method keyword")
+
+
+def _pointwise(method, drivers, Ds, single, G, ng, ti, conv_options, nres1):
+    """Shared body of ft_cc_iter_extrap / ft_ucc_iter_extrap (kelvin/cc_utils.py:176-242,
+    320-411): march through the grid points; at each one start from the linear extrapolation
+    of the two previous points and iterate the single-point update to convergence.
+    drivers: F.vo / I.vvoo blocks; single(ig, amps_at_ig, bars) -> new amplitudes at ig;
+    nres1: how many of the blocks are singles (their residuals use nl1)."""
+    thresh = conv_options["tconv"]
+    max_iter = conv_options["max_iter"]
+    alpha = conv_options["damp"]
+    dev = _lib.device()
+    drivers = [_lib.as_dev(x, dev) for x in drivers]
+    nb = len(drivers)
+    bars = [torch.zeros((ng,) + tuple(d.shape), dtype=torch.float64, device=dev) for d in drivers]
+    news = [torch.zeros_like(b) for b in bars]
+    st = _Stats(nb, dev)
+    for ig in range(ng):
+        if ig == 0:
+            for b, d in zip(bars, drivers):
+                b[0].copy_(d).neg_()
+            continue  # don't bother computing at T = inf
+        elif ig == 1:
+            for k in range(nb):
+                bars[k][ig].copy_(drivers[k]).neg_()
+                news[k][ig].copy_(quadrature.int_tbar(ng, bars[k], ti, Ds[k], G,
+                                                        rows=(ig, ig + 1))[0])
+        else:
+            # linear extrapolation: T[ig] = T[ig-1] + (T[ig-2] - T[ig-1])*fac
+            fac = (ti[ig] - ti[ig - 1])/(ti[ig - 2] - ti[ig - 1])
+            for k in range(nb):
+                news[k][ig].copy_(news[k][ig - 1])
+                st.damp(k, news[k][ig], news[k][ig - 2], 1.0 - fac)
+        converged = False
+        nl1 = math.sqrt(float(news[0][ig].numel()))
+        nl2 = math.sqrt(float(news[nres1][ig].numel()))
+        logging.info("Time point {}".format(ig))
+        i = 0
+        while i < max_iter and not converged:
+            out = single(ig, [x[ig] for x in news], bars)
+            for k in range(nb):
+                st.damp(k, news[k][ig], out[k], alpha)
+            s = numpy.sqrt(st.read()[:, 0])
+            res1 = float(sum(s[:nres1]))/nl1
+            res2 = float(sum(s[nres1:]))/nl2
+            logging.info(' %2d  %.4E' % (i + 1, res1 + res2))
+            i = i + 1
+            if res1 + res2 < thresh:
+                converged = True
+    return news
+
+
+def ft_cc_iter_extrap(method, F, I, D1, D2, g, G, beta, ng, ti, iprint, conv_options):
+    """Pointwise-extrapolated FT-CCSD solver, general spin orbitals
+    (kelvin/cc_utils.py:176-242).  Returns (T1, T2)."""
+    def single(ig, amps, bars):
+        return form_new_ampl_extrap(ig, method, F, I, amps[0], amps[1], bars[0], bars[1],
+                                    D1, D2, ti, ng, G)
+    T1, T2 = _pointwise(method, (F.vo, I.vvoo), (D1, D2), single, G, ng, ti, conv_options, 1)
+    return T1, T2
+
+
+def ft_ucc_iter_extrap(method, Fa, Fb, Ia, Ib, Iabab, D1a, D1b, D2aa, D2ab, D2bb,
+                       g, G, beta, ng, ti, iprint, conv_options):
+    """Pointwise-extrapolated FT-UCCSD solver (kelvin/cc_utils.py:320-411).
+    Returns ((T1a, T1b), (T2aa, T2ab, T2bb))."""
+    def single(ig, amps, bars):
+        t1, t2 = form_new_ampl_extrap_u(ig, method, Fa, Fb, Ia, Ib, Iabab, *amps, *bars,
+                                        D1a, D1b, D2aa, D2ab, D2bb, ti, ng, G)
+        return (t1[0], t1[1], t2[0], t2[1], t2[2])
+    out = _pointwise(method, (Fa.vo, Fb.vo, Ia.vvoo, Iabab.vvoo, Ib.vvoo),
+                     (D1a, D1b, D2aa, D2ab, D2bb), single, G, ng, ti, conv_options, 2)
+    return (out[0], out[1]), (out[2], out[3], out[4])
+
+
 def ft_lambda_iter(method, L1old, L2old, T1, T2, F, I, D1, D2, g, G, beta, ng, ti, iprint,
                    conv_options):
-    """Fixed-point FT-CCSD Lambda loop (kelvin/cc_utils.py:414-480)."""
-    if method != "CCSD":
+    """Fixed-point FT-CCSD Lambda loop (kelvin/cc_utils.py:414-480); method = CCSD, CCD,
+    LCCSD or LCCD (:441-456)."""
+    from .programs import METHODS
+    if method not in METHODS:
         raise Exception("Unrecognized method keyword")
     tbeg = time.time()
     dev = _lib.device()
@@ -315,8 +414,18 @@ def ft_lambda_iter(method, L1old, L2old, T1, T2, F, I, D1, D2, g, G, beta, ng, t
     nl2 = _norm(L2old) + 0.1
     st = _Stats(2, dev)
     while i < max_iter and not converged:
-        L1, L2 = ft_cc_equations.ccsd_lambda_opt(
-            F, I, T1, T2, L1old, L2old, D1, D2, ti, ng, g, G, beta)
+        if method == "LCCSD":
+            L1, L2 = ft_cc_equations.lccsd_lambda_simple(
+                F, I, T1, T2, L1old, L2old, D1, D2, ti, ng, g, G, beta)
+        elif method == "LCCD":
+            L1 = L1old
+            L2 = ft_cc_equations.lccd_lambda_simple(F, I, T2, L2old, D2, ti, ng, g, G, beta)
+        elif method == "CCSD":
+            L1, L2 = ft_cc_equations.ccsd_lambda_opt(
+                F, I, T1, T2, L1old, L2old, D1, D2, ti, ng, g, G, beta)
+        else:
+            L1 = L1old
+            L2 = ft_cc_equations.ccd_lambda_simple(F, I, T2, L2old, D2, ti, ng, g, G, beta)
         st.damp(0, L1old, L1, alpha)
         st.damp(1, L2old, L2, alpha)
         s = st.read()

@@ -5,9 +5,11 @@ Drop-in for the finite-temperature path of ``kelvin.ccsd.ccsd``
 (Omega_tot, Omega_cc), ``compute_ESN()`` setting E/S/N and their pieces, the
 same saved attributes (T1, T2, L1, L2, G0, G1, Gcc, Gtot, dia, dba, dji, dai,
 P2, n1rdm, n2rdm, rono, ronv, ron1) and the same log lines.  Amplitudes are
-CUDA float64 tensors.  Zero-temperature CCSD, ``rt_iter='point'`` and
-are outside this path and raise; ``athresh>0`` (active-space truncation,
-kelvin/ccsd.py:642-660,745-785) runs the same kernels on rectangular no != nv blocks.
+CUDA float64 tensors.  Zero-temperature CCSD is outside this path and raises.
+``rt_iter='point'`` (pointwise-extrapolated solver, kelvin/cc_utils.py:176-242,320-411) and
+``singles=False`` (FT-CCD, general spin orbitals as in the reference) run on the same
+kernels; ``athresh>0`` (active-space truncation, kelvin/ccsd.py:642-660,745-785) runs them
+on rectangular no != nv blocks.
 """
 import logging
 import time
@@ -43,8 +45,6 @@ class ccsd(object):
         self.rt_iter = rt_iter
         if not self.finite_T:
             raise Exception("kelvin_b200.ccsd implements the finite-temperature path only (T > 0)")
-        if not self.singles:
-            raise Exception("singles=False (CCD) is outside the B200 FT-CCSD path")
         self.realtime = True
         if not sys.verify(self.T, self.mu):
             raise Exception("Sytem temperature inconsistent with CC temp")
@@ -85,8 +85,6 @@ class ccsd(object):
     def run(self, T1=None, T2=None):
         """Run CCSD calculation (kelvin/ccsd.py:109-126)."""
         logging.info('Running CCSD at an electronic temperature of %f K' % ft_utils.HtoK(self.T))
-        if self.rt_iter[0] != 'a' and T2 is None:
-            raise Exception("rt_iter='point' is outside the B200 FT-CCSD path")
         if self.sys.has_u():
             return self._ft_uccsd(T1in=T1, T2in=T2)
         return self._ft_ccsd(T1in=T1, T2in=T2)
@@ -183,19 +181,35 @@ class ccsd(object):
         if self.athresh > 0.0:
             self._log_active()
 
-        if T1in is not None and T2in is not None:
-            T1old, T2old = T1in, T2in
-        else:
-            # MP2 guess: integrate the bare drivers (kelvin/ccsd.py:676-688)
-            T1old = quadrature.int_tbar1(ng, (-F.vo).expand(ng, -1, -1).contiguous(), ti, D1, G)
-            T2old = quadrature.int_tbar2(
-                ng, (-I.vvoo).expand(ng, -1, -1, -1, -1).contiguous(), ti, D2, G)
-        E2 = ft_cc_energy.ft_cc_energy(T1old, T2old, F.ov, I.oovv, g, self.beta_max, Qterm=False)
-        logging.info('MP2 Energy: {:.10f}'.format(E2))
+        method = "CCSD" if self.singles else "CCD"
+        if self.rt_iter[0] == 'a' or T2in is not None:
+            if self.rt_iter[0] != 'a':
+                logging.warning("Converngece scheme ({}) is being ignored.".format(self.rt_iter))
+            if T1in is not None and T2in is not None:
+                T1old = T1in if self.singles else torch.zeros_like(_lib.as_dev(T1in))
+                T2old = T2in
+            else:
+                # MP2 guess: integrate the bare drivers (kelvin/ccsd.py:676-688)
+                if self.singles:
+                    T1old = quadrature.int_tbar1(
+                        ng, (-F.vo).expand(ng, -1, -1).contiguous(), ti, D1, G)
+                else:
+                    T1old = torch.zeros((ng,) + tuple(F.vo.shape), dtype=torch.float64,
+                                        device=F.vo.device)
+                T2old = quadrature.int_tbar2(
+                    ng, (-I.vvoo).expand(ng, -1, -1, -1, -1).contiguous(), ti, D2, G)
+            E2 = ft_cc_energy.ft_cc_energy(T1old, T2old, F.ov, I.oovv, g, self.beta_max,
+                                           Qterm=False)
+            logging.info('MP2 Energy: {:.10f}'.format(E2))
 
-        Eccn, T1, T2 = cc_utils.ft_cc_iter(
-            "CCSD", T1old, T2old, F, I, D1, D2, g, G, self.beta_max, ng, ti, self.iprint,
-            self._conv_options())
+            Eccn, T1, T2 = cc_utils.ft_cc_iter(
+                method, T1old, T2old, F, I, D1, D2, g, G, self.beta_max, ng, ti, self.iprint,
+                self._conv_options())
+        else:
+            T1, T2 = cc_utils.ft_cc_iter_extrap(
+                method, F, I, D1, D2, g, G, self.beta_max, ng, ti, self.iprint,
+                self._conv_options())
+            Eccn = ft_cc_energy.ft_cc_energy(T1, T2, F.ov, I.oovv, g, self.beta_max)
 
         self.T1 = T1
         self.T2 = T2
@@ -220,27 +234,47 @@ class ccsd(object):
         if self.athresh > 0.0:
             self._log_active()
 
-        if T1in is not None and T2in is not None:
-            T1aold, T1bold = T1in
-            T2aaold, T2abold, T2bbold = T2in
+        # as in the reference, the unrestricted loops know CCSD only: singles=False raises
+        # "Unrecognized method keyword for unrestricted calc" (kelvin/cc_utils.py:84)
+        method = "CCSD" if self.singles else "CCD"
+        if self.rt_iter[0] == 'a' or T2in is not None:
+            if self.rt_iter[0] != 'a':
+                logging.warning("Converngece scheme ({}) is being ignored.".format(self.rt_iter))
+            if T1in is not None and T2in is not None:
+                T1aold, T1bold = T1in
+                if not self.singles:
+                    T1aold = torch.zeros_like(_lib.as_dev(T1aold))
+                    T1bold = torch.zeros_like(_lib.as_dev(T1bold))
+                T2aaold, T2abold, T2bbold = T2in
+            else:
+                def rep(x):
+                    return (-x).expand(*((ng,) + (-1,)*x.dim())).contiguous()
+                if self.singles:
+                    T1aold = quadrature.int_tbar1(ng, rep(Fa.vo), ti, D1a, G)
+                    T1bold = quadrature.int_tbar1(ng, rep(Fb.vo), ti, D1b, G)
+                else:
+                    T1aold = torch.zeros_like(rep(Fa.vo))
+                    T1bold = torch.zeros_like(rep(Fb.vo))
+                T2aaold = quadrature.int_tbar2(ng, rep(Ia.vvoo), ti, D2aa, G)
+                T2abold = quadrature.int_tbar2(ng, rep(Iabab.vvoo), ti, D2ab, G)
+                T2bbold = quadrature.int_tbar2(ng, rep(Ib.vvoo), ti, D2bb, G)
+
+            E2 = ft_cc_energy.ft_ucc_energy(
+                T1aold, T1bold, T2aaold, T2abold, T2bbold, Fa.ov, Fb.ov,
+                Ia.oovv, Ib.oovv, Iabab.oovv, g, self.beta_max, Qterm=False)
+            logging.info('MP2 Energy: {:.10f}'.format(E2))
+
+            Eccn, T1, T2 = cc_utils.ft_ucc_iter(
+                method, T1aold, T1bold, T2aaold, T2abold, T2bbold, Fa, Fb, Ia, Ib, Iabab,
+                D1a, D1b, D2aa, D2ab, D2bb, g, G, self.beta_max, ng, ti, self.iprint,
+                self._conv_options())
         else:
-            def rep(x):
-                return (-x).expand(*((ng,) + (-1,)*x.dim())).contiguous()
-            T1aold = quadrature.int_tbar1(ng, rep(Fa.vo), ti, D1a, G)
-            T1bold = quadrature.int_tbar1(ng, rep(Fb.vo), ti, D1b, G)
-            T2aaold = quadrature.int_tbar2(ng, rep(Ia.vvoo), ti, D2aa, G)
-            T2abold = quadrature.int_tbar2(ng, rep(Iabab.vvoo), ti, D2ab, G)
-            T2bbold = quadrature.int_tbar2(ng, rep(Ib.vvoo), ti, D2bb, G)
-
-        E2 = ft_cc_energy.ft_ucc_energy(
-            T1aold, T1bold, T2aaold, T2abold, T2bbold, Fa.ov, Fb.ov,
-            Ia.oovv, Ib.oovv, Iabab.oovv, g, self.beta_max, Qterm=False)
-        logging.info('MP2 Energy: {:.10f}'.format(E2))
-
-        Eccn, T1, T2 = cc_utils.ft_ucc_iter(
-            "CCSD", T1aold, T1bold, T2aaold, T2abold, T2bbold, Fa, Fb, Ia, Ib, Iabab,
-            D1a, D1b, D2aa, D2ab, D2bb, g, G, self.beta_max, ng, ti, self.iprint,
-            self._conv_options())
+            T1, T2 = cc_utils.ft_ucc_iter_extrap(
+                method, Fa, Fb, Ia, Ib, Iabab, D1a, D1b, D2aa, D2ab, D2bb,
+                g, G, self.beta_max, ng, ti, self.iprint, self._conv_options())
+            Eccn = ft_cc_energy.ft_ucc_energy(
+                T1[0], T1[1], T2[0], T2[1], T2[2], Fa.ov, Fb.ov,
+                Ia.oovv, Ib.oovv, Iabab.oovv, g, self.beta_max)
 
         self.T1 = T1
         self.T2 = T2
@@ -256,14 +290,22 @@ class ccsd(object):
         ng, ti, G, g = self.ngrid, self.ti, self.G, self.g
         en, D1, D2, F, I = self._g_setup()
         if L2 is None and L1 is None:
-            L1old, L2old = ft_cc_equations.ccsd_lambda_guess(F, I, self.T1, self.beta_max, ng)
+            if self.singles:
+                L1old, L2old = ft_cc_equations.ccsd_lambda_guess(F, I, self.T1, self.beta_max, ng)
+            else:
+                # the reference's zero singles guess has no grid axis (kelvin/ccsd.py:930); here
+                # it is (ng, no, nv) so that the response densities accept it
+                L2old = ft_cc_equations.ccd_lambda_guess(I, self.beta_max, ng)
+                L1old = torch.zeros((ng,) + tuple(F.ov.shape), dtype=torch.float64,
+                                    device=L2old.device)
         elif L1 is not None and L2 is not None:
             L1old, L2old = L1, L2
         else:
             # the reference allocates a mis-shaped zero guess here (quirk Q8); refuse instead
             raise Exception("provide both L1 and L2 (or neither) as Lambda guess")
         L1, L2 = cc_utils.ft_lambda_iter(
-            "CCSD", L1old, L2old, self.T1, self.T2, F, I, D1, D2, g, G, self.beta_max, ng, ti,
+            "CCSD" if self.singles else "CCD", L1old, L2old, self.T1, self.T2, F, I, D1, D2, g, G,
+            self.beta_max, ng, ti,
             self.iprint, self._conv_options())
         self.L1 = L1
         self.L2 = L2

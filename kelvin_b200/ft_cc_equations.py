@@ -184,6 +184,46 @@ def uccsd_stanton(Fa, Fb, Ia, Ib, Iabab, T1aold, T1bold, T2aaold, T2abold,
     return (T1a, T1b), (T2aa, T2ab, T2bb)
 
 
+def _store_row(bar, ig, row):
+    """bar[ig] = row for a device tensor or a NumPy array (the reference updates the caller's
+    T̄ buffers in place, kelvin/ft_cc_equations.py:122-123)."""
+    if isinstance(bar, torch.Tensor):
+        bar[ig].copy_(row)
+    else:
+        bar[ig] = row.cpu().numpy()
+
+
+def ccsd_stanton_single(ig, F, I, T1old, T2old, T1bar, T2bar, D1, D2, ti, ng, G):
+    """Amplitude update at the single grid point ig (pointwise solver,
+    kelvin/ft_cc_equations.py:116-127): T1old/T2old are the amplitudes AT that point,
+    T1bar/T2bar the (ng, ...) residual buffers, whose row ig is overwritten."""
+    dev = _lib.device()
+    b1, b2 = ccsd_stanton_bar(F, I, _lib.as_dev(T1old, dev)[None], _lib.as_dev(T2old, dev)[None])
+    _store_row(T1bar, ig, b1[0])
+    _store_row(T2bar, ig, b2[0])
+    T1new = quadrature.int_tbar1_single(ng, ig, T1bar, ti, D1, G)
+    T2new = quadrature.int_tbar2_single(ng, ig, T2bar, ti, D2, G)
+    return T1new, T2new
+
+
+def uccsd_stanton_single(ig, Fa, Fb, Ia, Ib, Iabab, T1a, T1b, T2aa, T2ab,
+                         T2bb, T1bara, T1barb, T2baraa, T2barab, T2barbb,
+                         D1a, D1b, D2aa, D2ab, D2bb, ti, ng, G):
+    """Unrestricted single-point update (kelvin/ft_cc_equations.py:167-192)."""
+    dev = _lib.device()
+    bars = uccsd_stanton_bar(Fa, Fb, Ia, Ib, Iabab,
+                             *[_lib.as_dev(x, dev)[None] for x in (T1a, T1b, T2aa, T2ab, T2bb)])
+    bufs = (T1bara, T1barb, T2baraa, T2barab, T2barbb)
+    for buf, b in zip(bufs, bars):
+        _store_row(buf, ig, b[0])
+    T1newa = quadrature.int_tbar1_single(ng, ig, T1bara, ti, D1a, G)
+    T1newb = quadrature.int_tbar1_single(ng, ig, T1barb, ti, D1b, G)
+    T2newaa = quadrature.int_tbar2_single(ng, ig, T2baraa, ti, D2aa, G)
+    T2newab = quadrature.int_tbar2_single(ng, ig, T2barab, ti, D2ab, G)
+    T2newbb = quadrature.int_tbar2_single(ng, ig, T2barbb, ti, D2bb, G)
+    return (T1newa, T1newb), (T2newaa, T2newab, T2newbb)
+
+
 # ---------------------------------------------------------------------------
 # Lambda equations
 # ---------------------------------------------------------------------------
@@ -337,6 +377,118 @@ def uccsd_lambda_opt(Fa, Fb, Ia, Ib, Iabab, T1aold, T1bold, T2aaold, T2abold,
     else:
         pf.run(t, ng, _chunk_for(pf, ng, dev))
     return tuple(outs)
+
+
+# ---------------------------------------------------------------------------
+# CCD / LCCSD / LCCD switches (general spin orbitals, as in the reference)
+# ---------------------------------------------------------------------------
+def _variant_plan(method, sizes, fac=-1.0):
+    key = ("residual", method, tuple(sorted(sizes.items(), key=str)), fac)
+
+    def build():
+        rops = _plan.expand(programs.residual_program(method, fac), programs.tensor_defs(), "g")
+        s1 = programs.has_singles(method)
+        ins = ("t1", "t2") if s1 else ("t2",)
+        outs = ("o1", "o2") if s1 else ("o2",)
+        return engine.Plan(rops, "g", sizes, ins, outs, name=method.lower() + "-g")
+    return engine.cached(key, build)
+
+
+def _variant_bar(method, F, I, T1old, T2old):
+    dev = _lib.device()
+    T2old = _lib.as_dev(T2old, dev)
+    ng = T2old.shape[0]
+    p = _variant_plan(method, _g_sizes(F))
+    t = {k: v for k, v in _g_integral_slots(F, I, dev).items() if k in p.shapes}
+    t["t2"] = T2old
+    t["o2"] = torch.empty_like(T2old)
+    if programs.has_singles(method):
+        t["t1"] = _lib.as_dev(T1old, dev)
+        t["o1"] = torch.empty_like(t["t1"])
+    p.run(t, ng, _chunk_for(p, ng, dev))
+    return t.get("o1"), t["o2"]
+
+
+def lccd_simple(F, I, T2old, D2, ti, ng, G):
+    """Time-dependent linearized coupled cluster doubles (LCCD) iteration
+    (kelvin/ft_cc_equations.py:11-24)."""
+    return quadrature.int_tbar2(ng, _variant_bar("LCCD", F, I, None, T2old)[1], ti, D2, G)
+
+
+def lccsd_simple(F, I, T1old, T2old, D1, D2, ti, ng, G):
+    """Time-dependent linearized coupled cluster singles and doubles (LCCSD) iteration
+    (kelvin/ft_cc_equations.py:27-45)."""
+    b1, b2 = _variant_bar("LCCSD", F, I, T1old, T2old)
+    return quadrature.int_tbar1(ng, b1, ti, D1, G), quadrature.int_tbar2(ng, b2, ti, D2, G)
+
+
+def ccd_simple(F, I, T2old, D2, ti, ng, G):
+    """Time-dependent coupled cluster doubles (CCD) iteration
+    (kelvin/ft_cc_equations.py:48-62)."""
+    return quadrature.int_tbar2(ng, _variant_bar("CCD", F, I, None, T2old)[1], ti, D2, G)
+
+
+def _variant_lambda(method, F, I, T1old, T2old, L1int, L2int, ng, beta):
+    dev = _lib.device()
+    sizes = _g_sizes(F)
+    key = ("lambda-variant", method, tuple(sorted(sizes.items(), key=str)),
+           beta if method == "LCCD" else None)
+    s1 = programs.has_singles(method)
+
+    def build():
+        inter, rest = programs.lambda_rops("g", -1.0, method=method, beta=beta)
+        ins = ("t1", "t2", "l1", "l2") if s1 else ("t2", "l2")
+        outs = ("lo1", "lo2") if s1 else ("lo2",)
+        return engine.Plan(inter + rest, "g", sizes, ins, outs, name="lambda-" + method.lower())
+    p = engine.cached(key, build)
+    t = {k: v for k, v in _g_integral_slots(F, I, dev).items() if k in p.shapes}
+    T2old = _lib.as_dev(T2old, dev)
+    if "t2" in p.shapes:
+        t["t2"] = T2old
+    t["l2"] = L2int
+    t["lo2"] = torch.empty_like(L2int)
+    if s1:
+        if "t1" in p.shapes:
+            t["t1"] = _lib.as_dev(T1old, dev)
+        t["l1"] = L1int
+        t["lo1"] = torch.empty_like(L1int)
+    p.run(t, ng, _chunk_for(p, ng, dev))
+    return t.get("lo1"), t["lo2"]
+
+
+def lccd_lambda_simple(F, I, T2old, L2old, D2, ti, ng, g, G, beta):
+    """LCCD Lambda iteration (kelvin/ft_cc_equations.py:292-310); the energy term carries the
+    1/beta of the reference (:308)."""
+    L2int = quadrature.int_L2(ng, L2old, ti, D2, g, G)
+    return _variant_lambda("LCCD", F, I, None, T2old, None, L2int, ng, beta)[1]
+
+
+def lccsd_lambda_simple(F, I, T1old, T2old, L1old, L2old, D1, D2, ti, ng, g, G, beta):
+    """LCCSD Lambda iteration (kelvin/ft_cc_equations.py:313-340)."""
+    L1int = quadrature.int_L1(ng, L1old, ti, D1, g, G)
+    L2int = quadrature.int_L2(ng, L2old, ti, D2, g, G)
+    return _variant_lambda("LCCSD", F, I, T1old, T2old, L1int, L2int, ng, beta)
+
+
+def ccd_lambda_simple(F, I, T2old, L2old, D2, ti, ng, g, G, beta):
+    """CCD Lambda iteration (kelvin/ft_cc_equations.py:682-701)."""
+    L2int = quadrature.int_L2(ng, L2old, ti, D2, g, G)
+    return _variant_lambda("CCD", F, I, None, T2old, None, L2int, ng, beta)[1]
+
+
+def _rep_over_grid(x, ng, scale):
+    x = _lib.as_dev(x)
+    return (x*scale).expand(*((ng,) + (-1,)*x.dim())).contiguous()
+
+
+def ccd_lambda_guess(I, beta, ng):
+    """kelvin/ft_cc_equations.py:496-499."""
+    return _rep_over_grid(I.oovv, ng, 1.0/beta)
+
+
+def uccd_lambda_guess(Ia, Ib, Iabab, beta, ng):
+    """kelvin/ft_cc_equations.py:529-535."""
+    return tuple(_rep_over_grid(x.oovv, ng, 1.0/beta) for x in (Ia, Iabab, Ib))
 
 
 def ccsd_lambda_guess(F, I, T1old, beta, ng):

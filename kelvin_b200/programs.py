@@ -136,6 +136,77 @@ def stanton(fac=-1.0, drivers=True):
     return st
 
 
+# Terms of the residual that are linear in the amplitudes (LCCSD; LCCD = its t2-only part):
+# cqcpy's _S_S + _S_D and _D_S + _D_D as the reference combines them at
+# kelvin/ft_cc_equations.py:11-45.  This is the Jacobian of StantonTerms at T = 0 (checked against
+# the full polynomial in tests/test_plan_cpu.py).
+_LINEAR = """
+o1[ai] += 1 F.vv[ae] t1[ei]
+o1[ai] += -1 F.oo[mi] t1[am]
+o1[ai] += -1 I.vovo[anfi] t1[fn]
+o1[ai] += 1 F.ov[me] t2[aeim]
+o1[ai] += 0.5 I.vovv[amef] t2[efim]
+o1[ai] += -0.5 I.ooov[mnie] t2[aemn]
+o2[abij] += 1 t1[ei] I.vvvo[abej]
+o2[abij] += -1 t1[ej] I.vvvo[abei]
+o2[abij] += 1 t1[am] I.vooo[bmij]
+o2[abij] += -1 t1[bm] I.vooo[amij]
+o2[abij] += 1 t2[aeij] F.vv[be]
+o2[abij] += -1 t2[beij] F.vv[ae]
+o2[abij] += -1 t2[abim] F.oo[mj]
+o2[abij] += 1 t2[abjm] F.oo[mi]
+o2[abij] += 0.5 t2[abmn] I.oooo[mnij]
+o2[abij] += 0.5 t2[efij] I.vvvv[abef]
+rg[abij] += -1 t2[aeim] I.vovo[bmej]
+o2[abij] += 1 rg[abij]
+o2[abij] += -1 rg[baij]
+o2[abij] += -1 rg[abji]
+o2[abij] += 1 rg[baji]
+"""
+
+METHODS = ("CCSD", "CCD", "LCCSD", "LCCD")
+
+
+def has_singles(method):
+    return method in ("CCSD", "LCCSD")
+
+
+def _without_singles(stmts):
+    """t1 := 0: drop every statement that reads t1 or writes the singles residual, then
+    every intermediate nothing reads any more."""
+    kept = [st for st in stmts if st.out[0] != "o1" and all(nm != "t1" for nm, _ in st.ins)]
+    live = {"o2"}
+    out = []
+    for st in reversed(kept):
+        if st.out[0] in live:
+            out.append(st)
+            for nm, _ in st.ins:
+                live.add(nm)
+    out.reverse()
+    return out
+
+
+def residual_program(method, fac=-1.0, drivers=True):
+    """Statements of o = drivers + fac*R_method(t): CCSD = StantonTerms; CCD = the same with
+    t1 = 0 (cqcpy _D_D + _D_DD, kelvin/ft_cc_equations.py:48-62); LCCSD / LCCD = the linear
+    terms (kelvin/ft_cc_equations.py:11-45)."""
+    if method not in METHODS:
+        raise Exception("Unrecognized method keyword")
+    if method == "CCSD":
+        return stanton(fac, drivers)
+    if method == "CCD":
+        body = _parse_block(_INTERMEDIATES) + _parse_block(_RESIDUAL, fac)
+    else:
+        body = []
+        for st in _parse_block(_LINEAR):
+            if st.out[0] in ("o1", "o2"):
+                st.coef *= fac
+            body.append(st)
+    st = _parse_block(_DRIVERS) if drivers else []
+    st += body
+    return st if has_singles(method) else _without_singles(st)
+
+
 # ---------------------------------------------------------------------------
 # Lambda map = vector-Jacobian product of StantonTerms (SURVEY.md A.3)
 # ---------------------------------------------------------------------------
@@ -154,7 +225,7 @@ def _subst_in(op, table):
     return ROp(op.out, coef, ins, op.spin)
 
 
-def lambda_rops(mode, fac=-1.0):
+def lambda_rops(mode, fac=-1.0, method="CCSD", beta=None):
     """Resolved ops of cqcpy.cc_equations._Lambda_opt / _uccsd_Lambda_opt as the
     reference uses them (kelvin/ft_cc_equations.py:396-407, 437-456):
 
@@ -162,15 +233,24 @@ def lambda_rops(mode, fac=-1.0):
         lo2[i,j,a,b] = -I.oovv                     + fac * P(ij)P(ab) d<Lbar,R(t)>/d t2[a,b,i,j]
 
     with <L,R> = L1.R1 + 1/4 L2.R2 over spin orbitals.  Inputs: t1,t2 (amplitudes),
-    l1,l2 (time-integrated Lambda, o..v.. order); outputs lo1, lo2."""
+    l1,l2 (time-integrated Lambda, o..v.. order); outputs lo1, lo2.
+
+    method: the same construction on the CCD / LCCSD / LCCD residual (general spin orbitals
+    only, as in the reference) gives ccd_lambda_simple, lccsd_lambda_simple and
+    lccd_lambda_simple (kelvin/ft_cc_equations.py:682-701, 313-340, 292-310); without singles
+    there is no lo1, and LCCD scales its energy term by 1/beta as the reference does (:308)."""
     from .plan import ROp, adjoint, expand, is_integral_slot
     T = tensor_defs()
-    fwd = expand(stanton(1.0, drivers=False), T, mode)
+    fwd = expand(residual_program(method, 1.0, drivers=False), T, mode)
+    s1 = has_singles(method)
     if mode == "g":
-        outs1, outs2 = ["o1"], ["o2"]
-        seed = {"o1~": ("l1", (1, 0), 1.0), "o2~": ("l2", (2, 3, 0, 1), 0.25)}
-        t1s, t2s = [("t1", "lo1")], [("t2", "lo2", True)]
+        outs1, outs2 = (["o1"] if s1 else []), ["o2"]
+        seed = {"o2~": ("l2", (2, 3, 0, 1), 0.25)}
+        if s1:
+            seed["o1~"] = ("l1", (1, 0), 1.0)
+        t1s, t2s = ([("t1", "lo1")] if s1 else []), [("t2", "lo2", True)]
     else:
+        assert method == "CCSD", "the unrestricted loops know CCSD only (kelvin/cc_utils.py:84)"
         outs1, outs2 = ["o1.a", "o1.b"], ["o2.aa", "o2.ab", "o2.bb"]
         seed = {"o1.a~": ("l1.a", (1, 0), 1.0), "o1.b~": ("l1.b", (1, 0), 1.0),
                 "o2.aa~": ("l2.aa", (2, 3, 0, 1), 0.25), "o2.bb~": ("l2.bb", (2, 3, 0, 1), 0.25),
@@ -188,11 +268,15 @@ def lambda_rops(mode, fac=-1.0):
     from .plan import TDef
     Tl["lo1"] = TDef("lo1", "one", "out", True, "ov")
     Tl["lo2"] = TDef("lo2", "amp2", "out", True, "oovv")
-    eterm = expand(_parse_block("""
-        lo1[ia] += -1 F.ov[ia]
-        lo1[ia] += -1 I.oovv[jiba] t1[bj]
-        lo2[ijab] += -1 I.oovv[ijab]
-    """), Tl, mode)
+    if s1:
+        eterm = expand(_parse_block("""
+            lo1[ia] += -1 F.ov[ia]
+            lo1[ia] += -1 I.oovv[jiba] t1[bj]
+            lo2[ijab] += -1 I.oovv[ijab]
+        """), Tl, mode)
+    else:
+        eterm = expand(_parse_block("lo2[ijab] += -1 I.oovv[ijab]",
+                                    1.0/beta if method == "LCCD" else 1.0), Tl, mode)
 
     # scatter the amplitude adjoints into the outputs
     tail = []

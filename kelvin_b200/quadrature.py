@@ -202,6 +202,18 @@ def int_tbar2(ng, t2bar, ti, D2, G):
     return int_tbar(ng, t2bar, ti, D2, G)
 
 
+def int_tbar1_single(ng, ig, t1bar, ti, D1, G):
+    """Integrate t1bar with exponential factor at the single grid point ig
+    (kelvin/quadrature.py:348-357) = row ig of int_tbar1."""
+    return int_tbar(ng, t1bar, ti, D1, G, rows=(ig, ig + 1))[0]
+
+
+def int_tbar2_single(ng, ig, t2bar, ti, D2, G):
+    """Integrate t2bar with exponential factor at the single grid point ig
+    (kelvin/quadrature.py:360-369) = row ig of int_tbar2."""
+    return int_tbar(ng, t2bar, ti, D2, G, rows=(ig, ig + 1))[0]
+
+
 def int_L(ng, Lold, ti, D, g, G, out=None, mode=None, rows=None):
     """Lbar[s] = (1/g[s]) sum_y g[y] G[y,s] exp(D^T*(ti[s]-ti[y]))_{y>=s} L[y]
     with D indexed (v..,o..) and L indexed (o..,v..) (kelvin/quadrature.py:320-345)."""

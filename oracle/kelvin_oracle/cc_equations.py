@@ -150,6 +150,98 @@ def _Lambda_opt(L1, L2, F, I, L1old, L2old, T1old, T2old, fac=1.0):
 
 
 # ---------------------------------------------------------------------------
+# Term classes of cqcpy.cc_equations used by the CCD / LCCSD / LCCD switches
+# (kelvin/ft_cc_equations.py:11-62, 292-340, 682-701): "_X_Y..." = the part of the X (S/D)
+# residual that is homogeneous of degree one in each amplitude listed after the underscore.
+# They are extracted from the pinned polynomial stanton_terms (degree <= 4 in T, no
+# constant term) by exact finite combinations, not restated term by term:
+#   linear part   L(t) = [8(R(t) - R(-t)) - (R(2t) - R(-2t))]/12
+# (odd differences cancel the degree-2/4 parts, the 8:1 weights cancel the cubic one).
+# No reference golden pins these switches at finite temperature; they inherit the pin of the
+# full polynomial.
+# ---------------------------------------------------------------------------
+def _linear_part(fn, x):
+    r1, rm1 = fn(x), fn(-x)
+    r2, rm2 = fn(2.0*x), fn(-2.0*x)
+    return tuple((8.0*(a - b) - (c - d))/12.0 for a, b, c, d in zip(r1, rm1, r2, rm2))
+
+
+def _zeros1(F):
+    no, nv = F.ov.shape
+    return numpy.zeros((nv, no))
+
+
+def _zeros2(F):
+    no, nv = F.ov.shape
+    return numpy.zeros((nv, nv, no, no))
+
+
+def _S_S(T1, F, I, T1old, fac=1.0):
+    T1 += fac*_linear_part(lambda x: stanton_terms(F, I, x, _zeros2(F)), numpy.asarray(T1old))[0]
+
+
+def _D_S(T2, F, I, T1old, fac=1.0):
+    T2 += fac*_linear_part(lambda x: stanton_terms(F, I, x, _zeros2(F)), numpy.asarray(T1old))[1]
+
+
+def _S_D(T1, F, I, T2old, fac=1.0):
+    T1 += fac*_linear_part(lambda x: stanton_terms(F, I, _zeros1(F), x), numpy.asarray(T2old))[0]
+
+
+def _D_D(T2, F, I, T2old, fac=1.0):
+    T2 += fac*_linear_part(lambda x: stanton_terms(F, I, _zeros1(F), x), numpy.asarray(T2old))[1]
+
+
+def _D_DD(T2, F, I, T2old, fac=1.0):
+    """Quadratic part of R2(0, t2) (R2 is of degree two in t2 when t1 = 0)."""
+    t2 = numpy.asarray(T2old)
+    full = stanton_terms(F, I, _zeros1(F), t2)[1]
+    lin = _linear_part(lambda x: stanton_terms(F, I, _zeros1(F), x), t2)[1]
+    T2 += fac*(full - lin)
+
+
+def _zl1(F):
+    return numpy.zeros(F.ov.shape)
+
+
+def _zl2(F):
+    no, nv = F.ov.shape
+    return numpy.zeros((no, no, nv, nv))
+
+
+def _LS_LS(L1, F, I, L1old, fac=1.0):
+    L1 += fac*lambda_terms(F, I, L1old, _zl2(F), _zeros1(F), _zeros2(F))[0]
+
+
+def _LD_LS(L2, F, I, L1old, fac=1.0):
+    L2 += fac*lambda_terms(F, I, L1old, _zl2(F), _zeros1(F), _zeros2(F))[1]
+
+
+def _LS_LD(L1, F, I, L2old, fac=1.0):
+    L1 += fac*lambda_terms(F, I, _zl1(F), L2old, _zeros1(F), _zeros2(F))[0]
+
+
+def _LD_LD(L2, F, I, L2old, fac=1.0):
+    L2 += fac*lambda_terms(F, I, _zl1(F), L2old, _zeros1(F), _zeros2(F))[1]
+
+
+class _FI0(object):
+    pass
+
+
+def _LD_LDTD(L2, I, L2old, T2old, fac=1.0):
+    """Part of the doubles Lambda map linear in T2 (no F dependence: F drops out of the
+    difference)."""
+    F = _FI0()
+    no, nv = I.oovv.shape[0], I.oovv.shape[2]
+    F.oo, F.ov = numpy.zeros((no, no)), numpy.zeros((no, nv))
+    F.vo, F.vv = numpy.zeros((nv, no)), numpy.zeros((nv, nv))
+    a = lambda_terms(F, I, _zl1(F), L2old, _zeros1(F), T2old)[1]
+    b = lambda_terms(F, I, _zl1(F), L2old, _zeros1(F), _zeros2(F))[1]
+    L2 += fac*(a - b)
+
+
+# ---------------------------------------------------------------------------
 # RDM blocks (SURVEY.md A.4) -- derivative of phi w.r.t. zero-valued F/I
 # ---------------------------------------------------------------------------
 _rdm_cache = {}

@@ -160,6 +160,7 @@ def main():
     run_fixture("hubbard4_u", sysm, T=1.0, mu=0.3, iprint=0, max_iter=80, ngrid=8, quad='quad',
                 econv=1e-11, tconv=1e-9)
     active_fixtures()
+    variant_fixtures()
 
 
 def active_fixtures():
@@ -178,8 +179,41 @@ def active_fixtures():
                 econv=1e-11, tconv=1e-9, athresh=0.05)
 
 
+def variant_fixtures():
+    """Sibling solvers on the same kernels: the pointwise-extrapolated solver
+    (rt_iter='point', kelvin/cc_utils.py:176-242,320-411; parameters of
+    kelvin/tests/test_ft_ccsd.py:166-201 on a 6-point grid) and FT-CCD (singles=False,
+    general spin orbitals) with its Lambda solve."""
+    T, mu = 0.1, 0.1
+    out = {}
+    for orb in ("u", "g"):
+        ueg = UEGSystem(T, 2*numpy.pi, 1.2, mu=mu, norb=7, orbtype=orb)
+        cc = ccsd(ueg, T=T, mu=mu, iprint=0, max_iter=50, damp=0.2, tconv=1e-8, ngrid=6,
+                  rt_iter="point")
+        Etot, Ecc = cc.run()
+        out["point_%s_Etot" % orb], out["point_%s_Ecc" % orb] = Etot, Ecc
+        if orb == "u":
+            for k, nm in enumerate(("T1a", "T1b")):
+                out["point_u_" + nm] = cc.T1[k]
+            for k, nm in enumerate(("T2aa", "T2ab", "T2bb")):
+                out["point_u_" + nm] = cc.T2[k]
+        else:
+            out["point_g_T1"], out["point_g_T2"] = cc.T1, cc.T2
+        print("point", orb, Etot, Ecc)
+    ueg = UEGSystem(T, 2*numpy.pi, 1.2, mu=mu, norb=7, orbtype='g')
+    cc = ccsd(ueg, T=T, mu=mu, iprint=0, max_iter=80, damp=0.2, ngrid=6, econv=1e-11, tconv=1e-9,
+              singles=False)
+    Etot, Ecc = cc.run()
+    cc._ft_ccsd_lambda()
+    out.update(ccd_Etot=Etot, ccd_Ecc=Ecc, ccd_T1=cc.T1, ccd_T2=cc.T2, ccd_L2=cc.L2)
+    print("ccd", Etot, Ecc)
+    numpy.savez_compressed(os.path.join(HERE, "ueg7_variants.npz"), **out)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "active":
         active_fixtures()
+    elif len(sys.argv) > 1 and sys.argv[1] == "variants":
+        variant_fixtures()
     else:
         main()

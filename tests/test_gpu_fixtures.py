@@ -141,3 +141,114 @@ def test_hubbard4_u_active_space(built):
     assert ref["T1a"].shape == (8, 3, 2)
     _run_u(_hubbard4(0.5), ref, T=0.5, mu=0.3, iprint=0, max_iter=150, damp=0.2, ngrid=8,
            econv=1e-11, tconv=1e-9, athresh=0.05)
+
+
+# ---------------------------------------------------------------------------
+# sibling solvers on the same kernels; fixtures: make_golden.py variants
+# ---------------------------------------------------------------------------
+def _ueg7(orb):
+    from kelvin_b200.ueg_system import UEGSystem
+    return UEGSystem(0.1, 2*numpy.pi, 1.2, mu=0.1, norb=7, orbtype=orb)
+
+
+@pytest.mark.parametrize("orb", ["u", "g"])
+def test_pointwise_solver_fixture(built, orb):
+    """rt_iter='point' (kelvin/cc_utils.py:176-242,320-411): grid points converged one after
+    the other from linearly extrapolated guesses."""
+    from kelvin_b200.ccsd import ccsd
+    ref = _load("ueg7_variants")
+    cc = ccsd(_ueg7(orb), T=0.1, mu=0.1, iprint=0, max_iter=50, damp=0.2, tconv=1e-8, ngrid=6,
+              rt_iter="point")
+    Etot, Ecc = cc.run()
+    assert abs(Etot - float(ref["point_%s_Etot" % orb])) < 1e-10
+    assert abs(Ecc - float(ref["point_%s_Ecc" % orb])) < 1e-10
+    if orb == "u":
+        for k, nm in enumerate(("T1a", "T1b")):
+            assert _rel(cc.T1[k], ref["point_u_" + nm]) < 1e-9
+        for k, nm in enumerate(("T2aa", "T2ab", "T2bb")):
+            assert _rel(cc.T2[k], ref["point_u_" + nm]) < 1e-9
+    else:
+        assert _rel(cc.T1, ref["point_g_T1"]) < 1e-9
+        assert _rel(cc.T2, ref["point_g_T2"]) < 1e-9
+
+
+def test_pointwise_agrees_with_all_at_once(built):
+    """kelvin/tests/test_ft_ccsd.py:166-201: both convergence schemes reach the same Omega_cc."""
+    from kelvin_b200.ccsd import ccsd
+    kw = dict(T=0.1, mu=0.1, iprint=0, max_iter=50, damp=0.2, tconv=1e-8, ngrid=10)
+    E1 = ccsd(_ueg7("u"), **kw).run()[1]
+    E2 = ccsd(_ueg7("u"), rt_iter="point", **kw).run()[1]
+    assert abs(E1 - E2) < 1e-8
+
+
+def test_ccd_fixture(built):
+    """singles=False: FT-CCD amplitudes and Lambda (general spin orbitals); the unrestricted
+    loops refuse it with the reference's message (kelvin/cc_utils.py:84)."""
+    from kelvin_b200.ccsd import ccsd
+    ref = _load("ueg7_variants")
+    kw = dict(T=0.1, mu=0.1, iprint=0, max_iter=80, damp=0.2, ngrid=6, econv=1e-11, tconv=1e-9,
+              singles=False)
+    cc = ccsd(_ueg7("g"), **kw)
+    Etot, Ecc = cc.run()
+    assert abs(Etot - float(ref["ccd_Etot"])) < 1e-10
+    assert abs(Ecc - float(ref["ccd_Ecc"])) < 1e-10
+    assert float(cc.T1.abs().max()) == 0.0 and numpy.abs(ref["ccd_T1"]).max() == 0.0
+    assert _rel(cc.T2, ref["ccd_T2"]) < 1e-9
+    cc._ft_ccsd_lambda()
+    assert _rel(cc.L2, ref["ccd_L2"]) < 1e-8
+    assert float(cc.L1.abs().max()) == 0.0
+    with pytest.raises(Exception, match="Unrecognized method keyword for unrestricted calc"):
+        ccsd(_ueg7("u"), **kw).run()
+
+
+@pytest.mark.parametrize("method", ["CCD", "LCCSD", "LCCD"])
+def test_method_switches_vs_oracle(built, method):
+    """cc_utils.form_new_ampl / the Lambda maps for the CCD, LCCSD and LCCD keywords
+    (kelvin/cc_utils.py:32-47,441-454) against the oracle's term classes."""
+    import sys
+    sys.path.insert(0, os.path.join(HERE))
+    import util
+    from kelvin_oracle import cc_equations as ocq, cqc, driver as odrv
+    from kelvin_b200 import cc_utils, ft_cc_equations
+    no, nv, ng, beta = 5, 7, 3, 1.3
+    F, I, t1, t2, l1, l2 = util.random_g_rect(no, nv, ng, seed=31)
+    ev, eo = util.random_D(nv, 1), util.random_D(no, 2)
+    D1, D2 = cqc.D1(ev, eo), cqc.D2(ev, eo)
+    ti, g, G = odrv.simpsons(ng, beta)
+    T1, T2 = cc_utils.form_new_ampl(method, F, I, t1, t2, D1, D2, ti, ng, G)
+    r1 = numpy.stack([-F.vo]*ng)
+    r2 = numpy.stack([-I.vvoo]*ng)
+    L1i, L2i = odrv.int_L(ng, l1, ti, D1, g, G), odrv.int_L(ng, l2, ti, D2, g, G)
+    o1 = numpy.zeros_like(l1)
+    o2 = numpy.zeros_like(l2)
+    for y in range(ng):
+        if method in ("CCD", "LCCD"):
+            ocq._D_D(r2[y], F, I, t2[y], fac=-1.0)
+            ocq._LD_LD(o2[y], F, I, L2i[y], fac=-1.0)
+            if method == "CCD":
+                ocq._D_DD(r2[y], F, I, t2[y], fac=-1.0)
+                ocq._LD_LDTD(o2[y], I, L2i[y], t2[y], fac=-1.0)
+        else:
+            ocq._S_S(r1[y], F, I, t1[y], fac=-1.0)
+            ocq._S_D(r1[y], F, I, t2[y], fac=-1.0)
+            ocq._D_S(r2[y], F, I, t1[y], fac=-1.0)
+            ocq._D_D(r2[y], F, I, t2[y], fac=-1.0)
+            ocq._LS_LS(o1[y], F, I, L1i[y], fac=-1.0)
+            ocq._LS_LD(o1[y], F, I, L2i[y], fac=-1.0)
+            ocq._LD_LS(o2[y], F, I, L1i[y], fac=-1.0)
+            ocq._LD_LD(o2[y], F, I, L2i[y], fac=-1.0)
+            ocq._LS_TS(o1[y], I, t1[y], fac=-1.0)
+            o1[y] -= F.ov
+        o2[y] -= I.oovv/beta if method == "LCCD" else I.oovv
+    assert _rel(T2, odrv.int_tbar(ng, r2, ti, D2, G)) < 1e-11
+    if method == "LCCSD":
+        assert _rel(T1, odrv.int_tbar(ng, r1, ti, D1, G)) < 1e-11
+        L1, L2 = ft_cc_equations.lccsd_lambda_simple(F, I, t1, t2, l1, l2, D1, D2, ti, ng, g, G, beta)
+        assert _rel(L1, o1) < 1e-11
+    elif method == "CCD":
+        assert T1 is t1
+        L2 = ft_cc_equations.ccd_lambda_simple(F, I, t2, l2, D2, ti, ng, g, G, beta)
+    else:
+        assert T1 is t1
+        L2 = ft_cc_equations.lccd_lambda_simple(F, I, t2, l2, D2, ti, ng, g, G, beta)
+    assert _rel(L2, o2) < 1e-11

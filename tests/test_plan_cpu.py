@@ -203,3 +203,66 @@ def _small_paths(monkeypatch, skinny):
         ref = (-Fa.vo - r[0], -Fb.vo - r[1], -Ia.vvoo - r[2], -Iabab.vvoo - r[3], -Ib.vvoo - r[4])
         for nm, rr in zip(("o1.a", "o1.b", "o2.aa", "o2.ab", "o2.bb"), ref):
             assert numpy.abs(arr[nm][y] - rr).max() < 1e-12
+
+
+@pytest.mark.parametrize("method", ["CCD", "LCCSD", "LCCD"])
+def test_method_variants_g(method):
+    """CCD / LCCSD / LCCD residual and Lambda programs (kelvin/ft_cc_equations.py:11-62,
+    292-340, 682-701) against the oracle's term classes, rectangular no != nv."""
+    no, nv, ng, beta = 3, 4, 2, 1.7
+    F, I, t1, t2, l1, l2 = util.random_g_rect(no, nv, ng, seed=17)
+    sizes = {"o": no, "v": nv}
+    s1 = programs.has_singles(method)
+    ins = {"t1": t1, "t2": t2} if s1 else {"t2": t2}
+    rops = plan.expand(programs.residual_program(method, -1.0), programs.tensor_defs(), "g")
+    assert s1 or all(slot != "t1" for op in rops for slot, _ in op.ins)
+    arr, _ = _run(rops, "g", sizes, ins, {"F": F, "I": I}, ng)
+    lins = dict(ins)
+    lins["l2"] = l2
+    if s1:
+        lins["l1"] = l1
+    inter, rest = programs.lambda_rops("g", -1.0, method=method, beta=beta)
+    lar, _ = _run(inter + rest, "g", sizes, lins, {"F": F, "I": I}, ng)
+    for y in range(ng):
+        r1, r2 = -F.vo.copy(), -I.vvoo.copy()
+        o1, o2 = numpy.zeros((no, nv)), numpy.zeros((no, no, nv, nv))
+        if method == "CCD":
+            ocq._D_D(r2, F, I, t2[y], fac=-1.0)
+            ocq._D_DD(r2, F, I, t2[y], fac=-1.0)
+            ocq._LD_LD(o2, F, I, l2[y], fac=-1.0)
+            ocq._LD_LDTD(o2, I, l2[y], t2[y], fac=-1.0)
+            o2 -= I.oovv
+        elif method == "LCCD":
+            ocq._D_D(r2, F, I, t2[y], fac=-1.0)
+            ocq._LD_LD(o2, F, I, l2[y], fac=-1.0)
+            o2 -= I.oovv/beta
+        else:
+            ocq._S_S(r1, F, I, t1[y], fac=-1.0)
+            ocq._S_D(r1, F, I, t2[y], fac=-1.0)
+            ocq._D_S(r2, F, I, t1[y], fac=-1.0)
+            ocq._D_D(r2, F, I, t2[y], fac=-1.0)
+            ocq._LS_LS(o1, F, I, l1[y], fac=-1.0)
+            ocq._LS_LD(o1, F, I, l2[y], fac=-1.0)
+            ocq._LD_LS(o2, F, I, l1[y], fac=-1.0)
+            ocq._LD_LD(o2, F, I, l2[y], fac=-1.0)
+            o1 -= F.ov
+            o2 -= I.oovv
+            ocq._LS_TS(o1, I, t1[y], fac=-1.0)
+        sc = numpy.abs(r2).max()
+        assert numpy.abs(arr["o2"][y] - r2).max() < 1e-11*sc
+        assert numpy.abs(lar["lo2"][y] - o2).max() < 1e-11*numpy.abs(o2).max()
+        if s1:
+            assert numpy.abs(arr["o1"][y] - r1).max() < 1e-11*sc
+            assert numpy.abs(lar["lo1"][y] - o1).max() < 1e-11*numpy.abs(o1).max()
+        else:
+            assert "o1" not in arr and "lo1" not in lar
+
+
+def test_ccd_is_ccsd_with_zero_singles():
+    n, ng = 4, 2
+    F, I, t1, t2 = util.random_g(n, ng, seed=23)
+    rops = plan.expand(programs.residual_program("CCD", -1.0), programs.tensor_defs(), "g")
+    arr, _ = _run(rops, "g", {"o": n, "v": n}, {"t2": t2}, {"F": F, "I": I}, ng)
+    for y in range(ng):
+        R1, R2 = ocq.stanton_terms(F, I, numpy.zeros((n, n)), t2[y])
+        assert numpy.abs(arr["o2"][y] - (-I.vvoo - R2)).max() < 1e-12*numpy.abs(R2).max()
