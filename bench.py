@@ -234,6 +234,30 @@ def main():
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
     t_step = float(tt.item())/K
 
+    # ---- auxiliary: the same step without the closed-shell reduction (every beta block
+    # evaluated, all 32 block GEMMs per grid point), for a like-for-like flop count
+    t_general = None
+    closed = bool(solver.closed_shell)
+    fc = torch.tensor([1.0 if closed else 0.0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(fc, op=dist.ReduceOp.MAX)      # ranks without grid points report False
+    if fc.item() > 0:
+        solver.closed_shell = False
+        for _ in range(2):
+            solver.step(0.0)
+        barrier()
+        ev0.record()
+        for _ in range(K):
+            solver.step(0.0)
+        ev1.record()
+        barrier()
+        tg = torch.tensor([ev0.elapsed_time(ev1)*1e-3], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tg, op=dist.ReduceOp.MAX)
+        t_general = float(tg.item())/K
+        solver.closed_shell = closed
+        solver.step(0.0)
+
     # ---- optional per-phase breakdown of the sharded step (diagnostics, outside the timed region)
     phases = None
     if os.environ.get("KB200_PHASES"):
@@ -251,7 +275,7 @@ def main():
     def e2e_step():
         # the host copy is the solver's own state: whether T[0] vanishes is already known
         solver.set_local_amplitudes([x.to(dev, non_blocking=True) for x in host],
-                                    t0_zero=solver.t0_zero)
+                                    t0_zero=solver.t0_zero, closed_shell=solver.closed_shell)
         return solver.step(0.0)
     for _ in range(2):
         e2e_step()
@@ -269,14 +293,18 @@ def main():
     # ---- live roofline of the dominant kernel (DMMA contraction GEMM) --------
     roof = None
     if rank == 0:
-        p = ft_cc_equations.stanton_plan("u", ft_cc_equations._u_sizes(Fa, Fb), -1.0)
+        # the plan the step runs (closed-shell reduction when the inputs allow it)
+        p = ft_cc_equations.stanton_plan("u", ft_cc_equations._u_sizes(Fa, Fb), -1.0,
+                                         mirror=closed)
         t = ft_cc_equations._u_integral_slots(
             Fa, Fb, Ia, Ib, Iabab, dev, [s for s in p.inputs if _plan.is_integral_slot(s)])
         nloc = solver.nloc
         for nm, x in zip(("t1.a", "t1.b", "t2.aa", "t2.ab", "t2.bb"), solver.old):
-            t[nm] = x
+            if nm in p.shapes:
+                t[nm] = x
         for nm, x in zip(("o1.a", "o1.b", "o2.aa", "o2.ab", "o2.bb"), solver.old):
-            t[nm] = torch.empty_like(x)
+            if nm in p.shapes:
+                t[nm] = torch.empty_like(x)
         tim = []
         for _ in range(3):
             tim = []
@@ -321,7 +349,8 @@ def main():
         Ls = ft_cc_equations.uccsd_lambda_guess(Fa, Fb, Ia, Ib, Iabab, Ts[0], Ts[1], beta, ng)
 
         def lam_step(Lc):
-            return ft_cc_equations.uccsd_lambda_opt(Fa, Fb, Ia, Ib, Iabab, *Ts, *Lc, *Ds, ti, ng, g, G, beta)
+            return ft_cc_equations.uccsd_lambda_opt(Fa, Fb, Ia, Ib, Iabab, *Ts, *Lc, *Ds, ti, ng, g,
+                                                    G, beta, closed_shell=closed)
         for _ in range(2):
             Ls = lam_step(Ls)
         torch.cuda.synchronize()
@@ -351,7 +380,12 @@ def main():
         # tau_0 shortcut: T[0] = 0 identically (row 0 of G vanishes), so T̄[0] = drivers and that
         # grid point is not evaluated (SURVEY 8d allows it; the reference's own pointwise solver
         # does the same, kelvin/cc_utils.py:205-208).  TFLOP/s is quoted on the EXECUTED flops.
-        fl_exec = algorithmic_flops(norb, ng - 1) if t0 else fl
+        npts = ng - 1 if t0 else ng
+        fl_exec = algorithmic_flops(norb, npts)
+        if closed:
+            # executed 2*M*N*K of the reduced program (all contraction classes)
+            pc = ft_cc_equations.stanton_plan("u", ft_cc_equations._u_sizes(Fa, Fb), -1.0, mirror=True)
+            fl_exec = float(pc.flops_per_point)*npts
         line = {
             "metric": "ft_ccsd_seconds_per_amplitude_iteration", "value": t_step, "unit": "s",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": t_step*1e3,
@@ -363,6 +397,8 @@ def main():
                        "cache": "working set (amplitudes+integrals+intermediates) >> 126 MB L2",
                        "algorithmic_tflop_per_step": fl/1e12,
                        "tau0_shortcut": t0, "tau_points_evaluated": ng - 1 if t0 else ng,
+                       "closed_shell_reduction": closed,
+                       "general_path_s_per_iteration": t_general,
                        "executed_tflop_per_step": fl_exec/1e12,
                        "fp64_tflops_whole_step": fl_exec/t_step/1e12,
                        "published_cpu_s_per_iter_unknown_hw": 321.4 if norb == 33 else None,

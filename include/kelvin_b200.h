@@ -177,6 +177,16 @@ int kb200_dot_keep(int nkeep, const int32_t dims[4] /*host*/, const int64_t sA[5
 /* Elementwise X[y,p] *= D[p]  (kelvin/ccsd.py:1138-1139,1238-1242). */
 int kb200_scale_by(int ng, int64_t n, double* X, const double* D, void* stream);
 
+/* Symmetry defect of two strided 5-index views (element strides; unused leading dims = 1):
+ *   out[0] = max |X - Y|, out[1] = max |X|   (device doubles, overwritten).
+ * Used for the closed-shell test of unrestricted inputs: Fa == Fb, Ia == Ib,
+ * Iabab.wxyz[p,q,r,s] == Iabab.xwzy[q,p,s,r], T1a == T1b, T2aa == T2bb,
+ * T2ab[y,a,B,i,J] == T2ab[y,B,a,J,i] -- the condition under which kelvin's unrestricted
+ * loops (kelvin/cc_utils.py:245-317, 483-566) compute every beta block twice. */
+int kb200_max_absdiff(const int32_t dims[5] /*host*/, const int64_t sx[5] /*host*/,
+                      const int64_t sy[5] /*host*/, const double* X, const double* Y,
+                      double* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -21,6 +21,7 @@ EXPORTS = (
     "kb200_plan_workspace_bytes", "kb200_plan_run", "kb200_plan_run_timed", "kb200_int_tbar", "kb200_int_L", "kb200_int_tbar_rows", "kb200_int_L_rows",
     "kb200_reduce_scratch_doubles", "kb200_energy_pair", "kb200_dot_g", "kb200_damp_norms",
     "kb200_dress4", "kb200_dress2", "kb200_gather4", "kb200_scatter4_add", "kb200_gsum", "kb200_scale_by", "kb200_dot_keep",
+    "kb200_max_absdiff",
 )
 
 
@@ -72,6 +73,8 @@ def load():
                                    ctypes.POINTER(i64), vp, vp, dbl, dbl, vp, vp, vp]
     lib.kb200_gsum.argtypes = [ctypes.c_int, i64, vp, vp, vp, vp]
     lib.kb200_scale_by.argtypes = [ctypes.c_int, i64, vp, vp, vp]
+    lib.kb200_max_absdiff.argtypes = [ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(i64),
+                                      ctypes.POINTER(i64), vp, vp, vp, vp]
     for nm in EXPORTS:
         getattr(lib, nm)
     _lib = lib
@@ -137,6 +140,25 @@ def reduce_scratch(dev):
         n = load().kb200_reduce_scratch_doubles()
         _scratch[key] = torch.empty(int(n), dtype=torch.float64, device=dev)
     return _scratch[key]
+
+
+def max_absdiff(X, Y):
+    """(max |X - Y|, max |X|) of two CUDA float64 tensors of one shape (rank <= 5; strided /
+    permuted views are read in place).  Synchronises: use it for one-off checks."""
+    lib = load()
+    if tuple(X.shape) != tuple(Y.shape) or X.dim() > 5:
+        raise KB200Error("max_absdiff: shapes %s vs %s" % (tuple(X.shape), tuple(Y.shape)))
+    if X.numel() == 0:
+        return 0.0, 0.0
+    pad = 5 - X.dim()
+    dims = (ctypes.c_int32*5)(*([1]*pad + list(X.shape)))
+    sx = (ctypes.c_int64*5)(*([0]*pad + list(X.stride())))
+    sy = (ctypes.c_int64*5)(*([0]*pad + list(Y.stride())))
+    out = torch.empty(2, dtype=torch.float64, device=X.device)
+    rc = lib.kb200_max_absdiff(dims, sx, sy, ptr(X), ptr(Y), ptr(out), stream_ptr())
+    check(rc, "kb200_max_absdiff")
+    d, m = out.cpu().tolist()
+    return float(d), float(m)
 
 
 def dot_keep(A, la, B, lb, keep, alpha=1.0, out=None, beta=0.0):

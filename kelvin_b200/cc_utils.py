@@ -180,13 +180,29 @@ def form_new_ampl(method, F, I, T1old, T2old, D1, D2, ti, ng, G, t0_zero=False):
 
 
 def form_new_ampl_u(method, Fa, Fb, Ia, Ib, Iabab, T1aold, T1bold, T2aaold, T2abold, T2bbold,
-                    D1a, D1b, D2aa, D2ab, D2bb, ti, ng, G, t0_zero=False):
+                    D1a, D1b, D2aa, D2ab, D2bb, ti, ng, G, t0_zero=False, closed_shell=False):
     """Form new amplitudes, unrestricted (kelvin/cc_utils.py:52-86)."""
     if method == "CCSD":
         return ft_cc_equations.uccsd_stanton(
             Fa, Fb, Ia, Ib, Iabab, T1aold, T1bold, T2aaold, T2abold, T2bbold,
-            D1a, D1b, D2aa, D2ab, D2bb, ti, ng, G, t0_zero=t0_zero)
+            D1a, D1b, D2aa, D2ab, D2bb, ti, ng, G, t0_zero=t0_zero, closed_shell=closed_shell)
     raise Exception("Unrecognized method keyword for unrestricted calc")
+
+
+def _closed_shell(Fa, Fb, Ia, Ib, Iabab, Ds, *amp_sets):
+    """Integrals, denominators (D1a, D1b, D2aa, D2ab, D2bb) and every amplitude set mirror
+    symmetric?  (The denominators enter through the time integration that follows the
+    residual: with D1a != D1b equal residuals would still integrate to different amplitudes.)"""
+    if not ft_cc_equations.CLOSED_SHELL:
+        return False
+    dev = _lib.device()
+    D1a, D1b, D2aa, D2ab, D2bb = [_lib.as_dev(d, dev) for d in Ds]
+    same = ft_cc_equations._same
+    if not (same(D1a, D1b) and same(D2aa, D2bb) and same(D2ab, D2ab.permute(1, 0, 3, 2))):
+        return False
+    if not ft_cc_equations.closed_shell_integrals(Fa, Fb, Ia, Ib, Iabab):
+        return False
+    return all(ft_cc_equations.closed_shell_amplitudes(*a) for a in amp_sets)
 
 
 class _Stats(object):
@@ -274,10 +290,13 @@ def ft_ucc_iter(method, T1aold, T1bold, T2aaold, T2abold, T2bbold, Fa, Fb, Ia, I
     st = _Stats(5, dev)
     # T[0] == 0 is preserved by the update (row 0 of G vanishes): skip that grid point
     t0 = ft_cc_equations.t0_is_zero(G, old)
+    # closed shell (alpha == beta throughout, e.g. the UEG): the update preserves it, so the
+    # beta blocks are copies of the alpha ones and only the reduced program runs
+    cs = _closed_shell(Fa, Fb, Ia, Ib, Iabab, (D1a, D1b, D2aa, D2ab, D2bb), old)
     while i < max_iter and not converged:
         T1out, T2out = form_new_ampl_u(
             method, Fa, Fb, Ia, Ib, Iabab, old[0], old[1], old[2], old[3], old[4],
-            D1a, D1b, D2aa, D2ab, D2bb, ti, ng, G, t0_zero=t0)
+            D1a, D1b, D2aa, D2ab, D2bb, ti, ng, G, t0_zero=t0, closed_shell=cs)
         new = (T1out[0], T1out[1], T2out[0], T2out[1], T2out[2])
         for k in range(5):
             st.damp(k, old[k], new[k], alpha)
@@ -465,11 +484,13 @@ def ft_ulambda_iter(method, L1ain, L1bin, L2aain, L2abin, L2bbin, T1aold, T1bold
     nl1 = nrm[0] + nrm[1] + 0.1
     nl2 = nrm[2] + 0.1 + nrm[4] + 4*nrm[3]
     st = _Stats(5, dev)
+    cs = _closed_shell(Fa, Fb, Ia, Ib, Iabab, (D1a, D1b, D2aa, D2ab, D2bb),
+                       (T1aold, T1bold, T2aaold, T2abold, T2bbold), old)
     while i < max_iter and not converged:
         new = ft_cc_equations.uccsd_lambda_opt(
             Fa, Fb, Ia, Ib, Iabab, T1aold, T1bold, T2aaold, T2abold, T2bbold,
             old[0], old[1], old[2], old[3], old[4], D1a, D1b, D2aa, D2ab, D2bb,
-            ti, ng, g, G, beta)
+            ti, ng, g, G, beta, closed_shell=cs)
         for k in range(5):
             st.damp(k, old[k], new[k], alpha)
         new = None

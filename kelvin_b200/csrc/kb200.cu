@@ -359,6 +359,46 @@ __global__ void scale_by_kernel(int ng, long long n, double* __restrict__ X,
 }
 
 // ---------------------------------------------------------------------------
+// Symmetry defect of two strided views (closed-shell check of the unrestricted inputs):
+//   out[0] = max |X[i] - Y[i]|, out[1] = max |X[i]| over a 5-index box; out is zeroed by the
+//   caller.  Non-negative doubles order like their bit patterns, so the maxima are atomicMax
+//   on the unsigned image.
+// ---------------------------------------------------------------------------
+struct Box5 {
+    int d[5];
+    long long sx[5];
+    long long sy[5];
+};
+
+__global__ void max_absdiff_kernel(Box5 q, const double* __restrict__ X,
+                                   const double* __restrict__ Y, unsigned long long* out) {
+    const long long tot = (long long)q.d[0] * q.d[1] * q.d[2] * q.d[3] * q.d[4];
+    double md = 0.0, mx = 0.0;
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < tot;
+         p += (long long)gridDim.x * blockDim.x) {
+        long long r = p, ox = 0, oy = 0;
+#pragma unroll
+        for (int k = 4; k >= 0; --k) {
+            const long long i = r % q.d[k];
+            r /= q.d[k];
+            ox += i * q.sx[k];
+            oy += i * q.sy[k];
+        }
+        const double x = X[ox];
+        md = fmax(md, fabs(x - Y[oy]));
+        mx = fmax(mx, fabs(x));
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        md = fmax(md, __shfl_xor_sync(0xffffffffu, md, o));
+        mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMax(out, (unsigned long long)__double_as_longlong(md));
+        atomicMax(out + 1, (unsigned long long)__double_as_longlong(mx));
+    }
+}
+
+// ---------------------------------------------------------------------------
 // "keep one index" partial traces (cc_utils.py:1648-1685,1746-1895) and the
 // per-grid-point <L, T> pairings of ccsd.py:1121-1146,1214-1258:
 //   out[k] = beta*out[k] + alpha * sum_{i1..i4} A[k*sa0 + sum i_d*sa_d] * B[k*sb0 + sum i_d*sb_d]
@@ -957,6 +997,25 @@ int kb200_scale_by(int ng, int64_t n, double* X, const double* D, void* stream) 
     if (n <= 0) return fail(-1, "scale_by: bad size");
     scale_by_kernel<<<grid_for(n * ng, 256), 256, 0, st>>>(ng, n, X, D);
     KB_CHECK_LAUNCH("scale_by_kernel");
+    return 0;
+}
+
+int kb200_max_absdiff(const int32_t dims[5], const int64_t sx[5], const int64_t sy[5],
+                      const double* X, const double* Y, double* out, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    Box5 q;
+    long long tot = 1;
+    for (int k = 0; k < 5; ++k) {
+        if (dims[k] <= 0) return fail(-1, "max_absdiff: bad size");
+        q.d[k] = dims[k];
+        q.sx[k] = sx[k];
+        q.sy[k] = sy[k];
+        tot *= dims[k];
+    }
+    if (cudaMemsetAsync(out, 0, 2 * sizeof(double), st) != cudaSuccess)
+        return fail(-2, "max_absdiff: memset");
+    max_absdiff_kernel<<<grid_for(tot, 256), 256, 0, st>>>(q, X, Y, (unsigned long long*)out);
+    KB_CHECK_LAUNCH("max_absdiff_kernel");
     return 0;
 }
 

@@ -46,7 +46,7 @@ struct GemmParams {
 // Up to KB200_MAX_GROUP independent contractions of one kernel configuration share a launch:
 // at m = 33 a single block GEMM is 5.5 waves of CTAs, a group of four 21.9, so the idle tail of
 // the last wave is paid once per group instead of once per contraction.
-constexpr int MAX_GROUP = 4;
+constexpr int MAX_GROUP = 8;
 struct GemmGroup {
     GemmParams p[MAX_GROUP];
     int fend[MAX_GROUP];         // running end of the full-tile CTA ranges of the members

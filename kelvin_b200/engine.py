@@ -97,8 +97,10 @@ class Plan(object):
             st = tensors[src]
             key = (st.data_ptr(), st._version)
             have = self._derived_bufs.get(name)
-            if have is None or have[0] != key:
-                self._derived_bufs[name] = (key, permute_copy(st, perm))
+            # the entry keeps its source tensor alive, so an equal (address, version) can only
+            # be that same tensor (a freed tensor's address could be reused by another one)
+            if have is None or have[0] != key or have[2] is not st:
+                self._derived_bufs[name] = (key, permute_copy(st, perm), st)
         y0 = 0
         while y0 < ng:
             nb = min(nb_max, ng - y0)

@@ -15,6 +15,8 @@ tensors (inputs are never modified, as in the reference).  The per-grid-point
 loop of the reference (``for y in range(ng): cqcpy._Stanton(...)``) is replaced
 by one batched contraction plan over all grid points (kelvin_b200/plan.py).
 """
+import os
+
 import torch
 
 from . import _lib, engine, plan as _plan, programs, quadrature
@@ -51,8 +53,10 @@ def _u_sizes(Fa, Fb):
     return {("o", "a"): int(noa), ("v", "a"): int(nva), ("o", "b"): int(nob), ("v", "b"): int(nvb)}
 
 
-def stanton_plan(mode, sizes, fac=-1.0):
-    key = ("stanton", mode, tuple(sorted(sizes.items(), key=str)), fac)
+def stanton_plan(mode, sizes, fac=-1.0, mirror=False):
+    """mirror (u only): the closed-shell reduction of the program (plan.mirror_reduce): only the
+    alpha-leading block of every alpha <-> beta pair is evaluated."""
+    key = ("stanton", mode, tuple(sorted(sizes.items(), key=str)), fac, bool(mirror))
 
     def build():
         T = programs.tensor_defs()
@@ -62,8 +66,67 @@ def stanton_plan(mode, sizes, fac=-1.0):
         else:
             ins = ("t1.a", "t1.b", "t2.aa", "t2.ab", "t2.bb")
             outs = ("o1.a", "o1.b", "o2.aa", "o2.ab", "o2.bb")
-        return engine.Plan(rops, mode, sizes, ins, outs, name="stanton-" + mode)
+        if mirror:
+            assert mode == "u"
+            rops = _plan.mirror_reduce(rops)
+            ins = tuple(s for s in ins if _plan.mirror_rep(s) == s)
+            outs = tuple(s for s in outs if _plan.mirror_rep(s) == s)
+        return engine.Plan(rops, mode, sizes, ins, outs,
+                           name="stanton-" + mode + ("-closed" if mirror else ""))
     return engine.cached(key, build)
+
+
+# ---------------------------------------------------------------------------
+# closed-shell detection (unrestricted inputs whose alpha and beta halves coincide)
+# ---------------------------------------------------------------------------
+CLOSED_SHELL = int(os.environ.get("KB200_CLOSED_SHELL", "1"))
+CLOSED_SHELL_TOL = 1e-12
+
+
+def _same(x, y, tol=CLOSED_SHELL_TOL):
+    if tuple(x.shape) != tuple(y.shape):
+        return False
+    if x.data_ptr() == y.data_ptr() and x.stride() == y.stride():
+        return True
+    d, m = _lib.max_absdiff(x, y)
+    return d <= tol*m
+
+
+def closed_shell_integrals(Fa, Fb, Ia, Ib, Iabab):
+    """True when the dressed integrals are mirror symmetric: Fa == Fb, Ia == Ib and
+    Iabab.wxyz[p,q,r,s] == Iabab.xwzy[q,p,s,r] (to CLOSED_SHELL_TOL relative).  Checked on
+    the device (about forty reductions over the blocks): call once per solve."""
+    if not CLOSED_SHELL:
+        return False
+    dev = _lib.device()
+    ts = []
+    for nm in _F_NAMES:
+        ts += [_lib.as_dev(getattr(Fa, nm), dev), _lib.as_dev(getattr(Fb, nm), dev)]
+    for nm in programs._INT2:
+        ts += [_lib.as_dev(getattr(Ia, nm), dev), _lib.as_dev(getattr(Ib, nm), dev)]
+    from .ov_blocks import two_e_blocks_full
+    ab = {nm: _lib.as_dev(getattr(Iabab, nm), dev) for nm in two_e_blocks_full.names}
+    ok = all(_same(ts[k], ts[k + 1]) for k in range(0, len(ts), 2))
+    if ok:
+        for nm, x in ab.items():
+            img = nm[1] + nm[0] + nm[3] + nm[2]
+            if img < nm:
+                continue
+            if not _same(x, ab[img].permute(1, 0, 3, 2)):
+                ok = False
+                break
+    return ok
+
+
+def closed_shell_amplitudes(X1a, X1b, X2aa, X2ab, X2bb):
+    """True when X1a == X1b, X2aa == X2bb and X2ab[y,p,Q,r,S] == X2ab[y,Q,p,S,r]
+    (amplitudes or Lambda, to CLOSED_SHELL_TOL relative).  Three device reductions and one
+    synchronisation: call once per solve."""
+    if not CLOSED_SHELL:
+        return False
+    dev = _lib.device()
+    X1a, X1b, X2aa, X2ab, X2bb = [_lib.as_dev(x, dev) for x in (X1a, X1b, X2aa, X2ab, X2bb)]
+    return _same(X1a, X1b) and _same(X2aa, X2bb) and _same(X2ab, X2ab.permute(0, 2, 1, 4, 3))
 
 
 def _g_integral_slots(F, I, dev):
@@ -149,33 +212,40 @@ def ccsd_stanton(F, I, T1old, T2old, D1, D2, ti, ng, G, t0_zero=False):
 
 
 def uccsd_stanton_bar(Fa, Fb, Ia, Ib, Iabab, T1aold, T1bold, T2aaold, T2abold, T2bbold, fac=-1.0,
-                      t0_zero=False):
+                      t0_zero=False, closed_shell=False):
+    """closed_shell: the caller guarantees mirror-symmetric integrals and amplitudes
+    (closed_shell_integrals / closed_shell_amplitudes); the beta-leading blocks are then copies
+    of their alpha images and only the reduced program runs (plan.mirror_reduce)."""
     dev = _lib.device()
     ins = [_lib.as_dev(x, dev) for x in (T1aold, T1bold, T2aaold, T2abold, T2bbold)]
     ng = ins[0].shape[0]
-    p = stanton_plan("u", _u_sizes(Fa, Fb), fac)
+    p = stanton_plan("u", _u_sizes(Fa, Fb), fac, mirror=closed_shell)
     t = _u_integral_slots(Fa, Fb, Ia, Ib, Iabab, dev,
                           [s for s in p.inputs if _plan.is_integral_slot(s)])
     in_names = ("t1.a", "t1.b", "t2.aa", "t2.ab", "t2.bb")
     out_names = ("o1.a", "o1.b", "o2.aa", "o2.ab", "o2.bb")
-    for nm, x in zip(in_names, ins):
-        t[nm] = x
-    outs = []
-    for nm, x in zip(out_names, ins):
-        t[nm] = torch.empty_like(x)
-        outs.append(t[nm])
-    drivers = None
-    if t0_zero:
-        drivers = [_lib.as_dev(x, dev) for x in (Fa.vo, Fb.vo, Ia.vvoo, Iabab.vvoo, Ib.vvoo)]
-    _run_rows(p, t, in_names, out_names, drivers, ng, dev, t0_zero)
+    drivers = [Fa.vo, Fb.vo, Ia.vvoo, Iabab.vvoo, Ib.vvoo]
+    live = [k for k in range(5) if not closed_shell or k in (0, 2, 3)]
+    outs = [None]*5
+    for k in live:
+        t[in_names[k]] = ins[k]
+        outs[k] = t[out_names[k]] = torch.empty_like(ins[k])
+    drv = [_lib.as_dev(drivers[k], dev) for k in live] if t0_zero else None
+    _run_rows(p, t, [in_names[k] for k in live], [out_names[k] for k in live], drv, ng, dev,
+              t0_zero)
+    if closed_shell:
+        outs[1] = outs[0].clone()
+        outs[4] = outs[2].clone()
     return tuple(outs)
 
 
 def uccsd_stanton(Fa, Fb, Ia, Ib, Iabab, T1aold, T1bold, T2aaold, T2abold,
-                  T2bbold, D1a, D1b, D2aa, D2ab, D2bb, ti, ng, G, t0_zero=False):
+                  T2bbold, D1a, D1b, D2aa, D2ab, D2bb, ti, ng, G, t0_zero=False,
+                  closed_shell=False):
     """Unrestricted CCSD iteration (kelvin/ft_cc_equations.py:130-164)."""
     b1a, b1b, b2aa, b2ab, b2bb = uccsd_stanton_bar(
-        Fa, Fb, Ia, Ib, Iabab, T1aold, T1bold, T2aaold, T2abold, T2bbold, t0_zero=t0_zero)
+        Fa, Fb, Ia, Ib, Iabab, T1aold, T1bold, T2aaold, T2abold, T2bbold, t0_zero=t0_zero,
+        closed_shell=closed_shell)
     T1a = quadrature.int_tbar1(ng, b1a, ti, D1a, G)
     T1b = quadrature.int_tbar1(ng, b1b, ti, D1b, G)
     T2aa = quadrature.int_tbar2(ng, b2aa, ti, D2aa, G)
@@ -232,10 +302,14 @@ _U_L = ("l1.a", "l1.b", "l2.aa", "l2.ab", "l2.bb")
 _U_LO = ("lo1.a", "lo1.b", "lo2.aa", "lo2.ab", "lo2.bb")
 
 
-def lambda_plan(mode, sizes, fac=-1.0):
+def _reps(names):
+    return tuple(s for s in names if _plan.mirror_rep(s) == s)
+
+
+def lambda_plan(mode, sizes, fac=-1.0, mirror=False):
     """Plan of -J(T)^T.Lbar - (F.ov + <ji||ba>t, I.oovv): intermediates of the
     forward residual followed by its mechanically derived reverse sweep."""
-    key = ("lambda", mode, tuple(sorted(sizes.items(), key=str)), fac)
+    key = ("lambda", mode, tuple(sorted(sizes.items(), key=str)), fac, bool(mirror))
 
     def build():
         inter, rest = programs.lambda_rops(mode, fac)
@@ -243,23 +317,30 @@ def lambda_plan(mode, sizes, fac=-1.0):
             ins, outs = ("t1", "t2", "l1", "l2"), ("lo1", "lo2")
         else:
             ins, outs = _U_T + _U_L, _U_LO
-        return engine.Plan(inter + rest, mode, sizes, ins, outs, name="lambda-" + mode)
+        if mirror:
+            inter, rest = _plan.mirror_reduce(inter), _plan.mirror_reduce(rest)
+            ins, outs = _reps(ins), _reps(outs)
+        return engine.Plan(inter + rest, mode, sizes, ins, outs,
+                           name="lambda-" + mode + ("-closed" if mirror else ""))
     return engine.cached(key, build)
 
 
-def lambda_split_plans(mode, sizes, fac=-1.0):
+def lambda_split_plans(mode, sizes, fac=-1.0, mirror=False):
     """(prep, sweep): the amplitude-only forward intermediates (W_oooo, W_vvvv, W_ovvo,
     F_oo/vv/ov, tau ...) depend on T alone, which is fixed during the whole Lambda
     solve, so they are built once (prep) and every Lambda iteration runs only the
     reverse sweep (sweep) with the intermediates as inputs -- the 'cached W' cost
     model of SURVEY.md 8(d) (92 m^6 instead of 128 m^6 per grid point)."""
-    key = ("lambda-split", mode, tuple(sorted(sizes.items(), key=str)), fac)
+    key = ("lambda-split", mode, tuple(sorted(sizes.items(), key=str)), fac, bool(mirror))
 
     def build():
         inter, rest = programs.lambda_rops(mode, fac)
         tins = ("t1", "t2") if mode == "g" else _U_T
         lins = ("l1", "l2") if mode == "g" else _U_L
         louts = ("lo1", "lo2") if mode == "g" else _U_LO
+        if mirror:
+            inter, rest = _plan.mirror_reduce(inter), _plan.mirror_reduce(rest)
+            tins, lins, louts = _reps(tins), _reps(lins), _reps(louts)
         inter_slots = []
         for op in inter:
             if op.out[0] not in inter_slots:
@@ -278,18 +359,21 @@ def lambda_split_plans(mode, sizes, fac=-1.0):
     return engine.cached(key, build)
 
 
-_lam_cache = {"key": None, "val": None}
+_lam_cache = {"key": None, "val": None, "refs": None}
 
 
-def _lambda_intermediates(mode, sizes, ints_slots, tslots, ng, dev):
+def _lambda_intermediates(mode, sizes, ints_slots, tslots, ng, dev, mirror=False):
     """Forward intermediates for the current amplitudes, cached across Lambda iterations."""
-    prep, sweep = lambda_split_plans(mode, sizes)
-    key = (mode, ng, tuple((v.data_ptr(), v._version) for v in tslots.values()),
-           tuple((v.data_ptr(), v._version) for v in ints_slots.values()))
-    if _lam_cache["key"] == key:
+    prep, sweep = lambda_split_plans(mode, sizes, mirror=mirror)
+    # the cache entry keeps the key tensors alive: a live tensor's address cannot be handed to
+    # another tensor, so equal (address, version) means the very same, unmodified tensors
+    refs = list(tslots.values()) + list(ints_slots.values())
+    key = (mode, bool(mirror), ng, tuple((v.data_ptr(), v._version) for v in refs))
+    if _lam_cache["key"] == key and all(a is b for a, b in zip(_lam_cache["refs"], refs)):
         return _lam_cache["val"]
     _lam_cache["key"] = None
     _lam_cache["val"] = None
+    _lam_cache["refs"] = None
     need = sum(8*ng*int(torch.tensor(prep.shapes[s]).prod()) for s in prep.all_slots)
     free, _ = torch.cuda.mem_get_info(dev)
     if need > 0.5*free:
@@ -302,6 +386,7 @@ def _lambda_intermediates(mode, sizes, ints_slots, tslots, ng, dev):
     val = {s: t[s] for s in sweep.cached_slots}
     _lam_cache["key"] = key
     _lam_cache["val"] = val
+    _lam_cache["refs"] = refs
     return val
 
 
@@ -350,38 +435,39 @@ def ccsd_lambda_opt(F, I, T1old, T2old, L1old, L2old, D1, D2, ti, ng, g, G, beta
 
 def uccsd_lambda_opt(Fa, Fb, Ia, Ib, Iabab, T1aold, T1bold, T2aaold, T2abold,
                      T2bbold, L1aold, L1bold, L2aaold, L2abold, L2bbold, D1a,
-                     D1b, D2aa, D2ab, D2bb, ti, ng, g, G, beta):
-    """Unrestricted Lambda iteration (kelvin/ft_cc_equations.py:412-458)."""
+                     D1b, D2aa, D2ab, D2bb, ti, ng, g, G, beta, closed_shell=False):
+    """Unrestricted Lambda iteration (kelvin/ft_cc_equations.py:412-458).  closed_shell: as in
+    uccsd_stanton_bar (integrals, amplitudes and Lambda all mirror symmetric)."""
     dev = _lib.device()
     Ts = [_lib.as_dev(x, dev) for x in (T1aold, T1bold, T2aaold, T2abold, T2bbold)]
     assert(Ts[0].shape[0] == ng)
-    Ls = [quadrature.int_L(ng, L, ti, D, g, G) for L, D in
-          zip((L1aold, L1bold, L2aaold, L2abold, L2bbold), (D1a, D1b, D2aa, D2ab, D2bb))]
+    live = (0, 2, 3) if closed_shell else (0, 1, 2, 3, 4)
+    Lin = (L1aold, L1bold, L2aaold, L2abold, L2bbold)
+    Ds = (D1a, D1b, D2aa, D2ab, D2bb)
+    Ls = {k: quadrature.int_L(ng, Lin[k], ti, Ds[k], g, G) for k in live}
     sizes = _u_sizes(Fa, Fb)
-    pf = lambda_plan("u", sizes)
+    pf = lambda_plan("u", sizes, mirror=closed_shell)
     t = _u_integral_slots(Fa, Fb, Ia, Ib, Iabab, dev,
                           [s for s in pf.inputs if _plan.is_integral_slot(s)])
-    cached = _lambda_intermediates("u", sizes, t, dict(zip(_U_T, Ts)), ng, dev)
-    for nm, x in zip(_U_T, Ts):
-        t[nm] = x
-    for nm, x in zip(_U_L, Ls):
-        t[nm] = x
-    outs = []
-    for nm, x in zip(_U_LO, Ls):
-        t[nm] = torch.empty_like(x)
-        outs.append(t[nm])
+    cached = _lambda_intermediates("u", sizes, t, {_U_T[k]: Ts[k] for k in live}, ng, dev,
+                                   mirror=closed_shell)
+    outs = [None]*5
+    for k in live:
+        t[_U_T[k]] = Ts[k]
+        t[_U_L[k]] = Ls[k]
+        outs[k] = t[_U_LO[k]] = torch.empty_like(Ls[k])
     if cached is not None:
-        p = lambda_split_plans("u", sizes)[1]
+        p = lambda_split_plans("u", sizes, mirror=closed_shell)[1]
         t.update(cached)
         p.run({k: v for k, v in t.items() if k in p.shapes}, ng, _chunk_for(p, ng, dev))
     else:
         pf.run(t, ng, _chunk_for(pf, ng, dev))
+    if closed_shell:
+        outs[1] = outs[0].clone()
+        outs[4] = outs[2].clone()
     return tuple(outs)
 
 
-# ---------------------------------------------------------------------------
-# CCD / LCCSD / LCCD switches (general spin orbitals, as in the reference)
-# ---------------------------------------------------------------------------
 def _variant_plan(method, sizes, fac=-1.0):
     key = ("residual", method, tuple(sorted(sizes.items(), key=str)), fac)
 
@@ -570,7 +656,7 @@ def _gsum(X, g, dev):
     return out
 
 
-_rdm_cache = {"key": None, "val": None}
+_rdm_cache = {"key": None, "val": None, "refs": None}
 
 
 def _rdm_leaves(mode, Ts, Ls, Ds, ti, ng, g, G):
@@ -581,7 +667,8 @@ def _rdm_leaves(mode, Ts, Ls, Ds, ti, ng, g, G):
     Ls = [_lib.as_dev(x, dev) for x in Ls]
     key = (mode, ng, tuple((x.data_ptr(), x._version) for x in Ts + Ls),
            tuple(float(v) for v in g), float(ti[-1]))
-    if _rdm_cache["key"] == key:
+    refs = Ts + Ls          # kept alive by the cache entry (see _lambda_intermediates)
+    if _rdm_cache["key"] == key and all(a is b for a, b in zip(_rdm_cache["refs"], refs)):
         return _rdm_cache["val"]
     Lbar = [quadrature.int_L(ng, L, ti, D, g, G) for L, D in zip(Ls, Ds)]
     t = {}
@@ -609,6 +696,7 @@ def _rdm_leaves(mode, Ts, Ls, Ds, ti, ng, g, G):
     p.release()
     _rdm_cache["key"] = key
     _rdm_cache["val"] = (summed, lsum, sizes)
+    _rdm_cache["refs"] = refs
     return _rdm_cache["val"]
 
 

@@ -65,6 +65,7 @@ class TauShardedUCCSD(object):
         self.stats = torch.zeros(20, dtype=torch.float64, device=self.dev)
         self.old = None
         self.t0_zero = False      # T[0] == 0 on the rank that owns tau_0: that point is skipped
+        self.closed_shell = False  # alpha == beta inputs: the reduced (mirror) program runs
         self._gather = None
         self.phase_ms = None      # set to {} to collect per-phase device times (diagnostics)
 
@@ -74,13 +75,25 @@ class TauShardedUCCSD(object):
         self.old = [_lib.as_dev(x, self.dev)[self.y0:self.y1].clone().contiguous()
                     for x in (T1a, T1b, T2aa, T2ab, T2bb)]
         self._check_t0(None)
+        self._check_closed_shell()
 
-    def set_local_amplitudes(self, local, t0_zero=None):
-        """t0_zero: None = look at the data (one device reduction + sync); True/False = the
-        caller's knowledge of whether the amplitudes at tau_0 vanish (only read on the rank
-        that owns tau_0)."""
+    def set_local_amplitudes(self, local, t0_zero=None, closed_shell=None):
+        """t0_zero / closed_shell: None = look at the data (device reductions + sync);
+        True/False = the caller's knowledge of whether the amplitudes at tau_0 vanish (only
+        read on the rank that owns tau_0) / are mirror symmetric."""
         self.old = [_lib.as_dev(x, self.dev).contiguous() for x in local]
         self._check_t0(t0_zero)
+        if closed_shell is None:
+            self._check_closed_shell()
+        else:
+            self.closed_shell = bool(closed_shell)
+
+    def _check_closed_shell(self):
+        """Closed shell (alpha == beta integrals, denominators and local amplitudes): the update
+        preserves it.  Each rank decides for its own shard; the ranks need not agree."""
+        from . import cc_utils
+        self.closed_shell = self.nloc > 0 and cc_utils._closed_shell(
+            *self.ints, self.Ds, self.old)
 
     def _check_t0(self, known):
         if self.y0 != 0 or self.nloc < 1 or self.ng < 2 or numpy.any(self.G[0] != 0.0):
@@ -121,7 +134,8 @@ class TauShardedUCCSD(object):
         mark("start")
         if nloc > 0:
             bars = ft_cc_equations.uccsd_stanton_bar(Fa, Fb, Ia, Ib, Iabab, *self.old,
-                                                     t0_zero=self.t0_zero)
+                                                     t0_zero=self.t0_zero,
+                                                     closed_shell=self.closed_shell)
         else:
             bars = [torch.zeros((0,) + tuple(d.shape), dtype=torch.float64, device=self.dev)
                     for d in self.Ds]

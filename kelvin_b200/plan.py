@@ -257,6 +257,67 @@ def expand(stmts, tdefs, mode):
 
 
 # ---------------------------------------------------------------------------
+# closed-shell mirror reduction (unrestricted programs on alpha == beta inputs)
+# ---------------------------------------------------------------------------
+_FLIP = str.maketrans("ab", "ba")
+
+
+def mirror_slot(slot):
+    """The stored slot that holds the same numbers once alpha and beta are interchanged
+    (same index order), or None when the slot is its own mirror image (amp2 'ab' blocks,
+    whose 'ba' image is a transposed view of themselves) or has no stored image by name
+    (Iabab blocks: their images are other, transposed Iabab blocks)."""
+    bar = "~" if slot.endswith("~") else ""
+    base = slot[:-1] if bar else slot
+    pre, _, suf = base.partition(".")
+    if pre in ("Ia", "Ib", "Fa", "Fb"):
+        return pre[0] + pre[1].translate(_FLIP) + "." + suf + bar
+    if pre == "Iabab" or "@" in base:
+        return None
+    name, _, sp = base.rpartition(".")
+    if not name or not sp or set(sp) - set("ab"):
+        return None
+    fl = sp.translate(_FLIP)
+    if len(sp) == 2 and sp[0] != sp[1]:
+        return None
+    return name + "." + fl + bar
+
+
+def mirror_rep(slot):
+    """Representative of {slot, mirror_slot(slot)}: the alpha-leading one."""
+    m = mirror_slot(slot)
+    if m is None:
+        return slot
+    pre = slot.partition(".")[0]
+    if pre in ("Ib", "Fb"):
+        return m
+    if pre in ("Ia", "Fa"):
+        return slot
+    sp = slot.rstrip("~").rpartition(".")[2]
+    return slot if sp[0] == "a" else m
+
+
+def mirror_reduce(rops):
+    """Unrestricted program -> the ops a spin-symmetric (closed-shell) run needs.
+
+    The spin expansion is closed under the interchange alpha <-> beta: every op writing a
+    block X.s has a partner writing X.flip(s) with all spins flipped.  When every input is
+    mirror symmetric (Fa == Fb, Ia == Ib, Iabab.wxyz[p,q,r,s] == Iabab.xwzy[q,p,s,r],
+    T1a == T1b, T2aa == T2bb, T2ab[a,B,i,J] == T2ab[B,a,J,i]; na == nb) the partner computes
+    the same numbers, so only the alpha-leading block of each pair is evaluated and every
+    read of a beta-leading block is redirected to its image (same memory, same index order).
+    Blocks that are their own image (o2.ab, tau.ab, W_oooo.ab, ...) keep all their ops.
+    The caller copies the alpha outputs into the beta ones."""
+    out = []
+    for op in rops:
+        if mirror_rep(op.out[0]) != op.out[0]:
+            continue
+        ins = [(mirror_rep(sl), ls) for sl, ls in op.ins]
+        out.append(ROp(op.out, op.coef, ins, op.spin))
+    return out
+
+
+# ---------------------------------------------------------------------------
 # reverse mode (Lambda / RDM)
 # ---------------------------------------------------------------------------
 def adjoint(rops, wrt, seeds, bar=lambda s: s + "~"):

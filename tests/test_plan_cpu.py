@@ -266,3 +266,49 @@ def test_ccd_is_ccsd_with_zero_singles():
     for y in range(ng):
         R1, R2 = ocq.stanton_terms(F, I, numpy.zeros((n, n)), t2[y])
         assert numpy.abs(arr["o2"][y] - (-I.vvoo - R2)).max() < 1e-12*numpy.abs(R2).max()
+
+
+def _closed_inputs(n, ng, seed):
+    ints, amps, lam = util.random_u_closed(n, ng, seed=seed)
+    lam = [numpy.ascontiguousarray(lam[0].transpose(0, 2, 1)),
+           numpy.ascontiguousarray(lam[1].transpose(0, 2, 1)),
+           numpy.ascontiguousarray(lam[2].transpose(0, 3, 4, 1, 2)),
+           numpy.ascontiguousarray(lam[3].transpose(0, 3, 4, 1, 2)),
+           numpy.ascontiguousarray(lam[4].transpose(0, 3, 4, 1, 2))]
+    return ints, amps, lam
+
+
+def test_mirror_reduced_plans_on_closed_shell_inputs():
+    """plan.mirror_reduce: on alpha == beta inputs the reduced unrestricted residual and
+    Lambda programs (beta-leading blocks aliased to their alpha images) reproduce the
+    alpha and mixed blocks of the full programs."""
+    n, ng = 4, 2
+    ints, amps, lam = _closed_inputs(n, ng, 41)
+    Fa, Fb, Ia, Ib, Iabab = ints
+    src = {"Fa": Fa, "Fb": Fb, "Ia": Ia, "Ib": Ib, "Iabab": Iabab}
+    sizes = {("v", "a"): n, ("o", "a"): n, ("v", "b"): n, ("o", "b"): n}
+    tn = ("t1.a", "t1.b", "t2.aa", "t2.ab", "t2.bb")
+    ln = ("l1.a", "l1.b", "l2.aa", "l2.ab", "l2.bb")
+    full = plan.expand(programs.stanton(-1.0), programs.tensor_defs(), "u")
+    red = plan.mirror_reduce(full)
+    assert all(s == plan.mirror_rep(s) for op in red for s in [op.out[0]] + [x for x, _ in op.ins])
+    a_full, lf = _run(full, "u", sizes, dict(zip(tn, amps)), src, ng)
+    keep = {k: v for k, v in zip(tn, amps) if plan.mirror_rep(k) == k}
+    a_red, lr = _run(red, "u", sizes, keep, src, ng)
+    assert lr.flops < 0.62*lf.flops
+    for nm in ("o1.a", "o2.aa", "o2.ab"):
+        assert numpy.abs(a_red[nm] - a_full[nm]).max() < 1e-12*numpy.abs(a_full[nm]).max()
+    # what the caller copies is what the full program computes for the beta blocks
+    assert numpy.abs(a_full["o2.bb"] - a_full["o2.aa"]).max() < 1e-12*numpy.abs(a_full["o2.aa"]).max()
+    assert numpy.abs(a_full["o1.b"] - a_full["o1.a"]).max() < 1e-12*numpy.abs(a_full["o1.a"]).max()
+    ab = a_full["o2.ab"]
+    assert numpy.abs(ab - ab.transpose(0, 2, 1, 4, 3)).max() < 1e-12*numpy.abs(ab).max()
+    inter, rest = programs.lambda_rops("u", -1.0)
+    inputs = dict(zip(tn, amps))
+    inputs.update(zip(ln, lam))
+    l_full, _ = _run(inter + rest, "u", sizes, inputs, src, ng)
+    keep = {k: v for k, v in inputs.items() if plan.mirror_rep(k) == k}
+    l_red, _ = _run(plan.mirror_reduce(inter) + plan.mirror_reduce(rest), "u", sizes, keep, src, ng)
+    for nm in ("lo1.a", "lo2.aa", "lo2.ab"):
+        assert numpy.abs(l_red[nm] - l_full[nm]).max() < 1e-12*numpy.abs(l_full[nm]).max()
+    assert numpy.abs(l_full["lo2.bb"] - l_full["lo2.aa"]).max() < 1e-12*numpy.abs(l_full["lo2.aa"]).max()

@@ -77,6 +77,40 @@ def random_u(na, nb, ng, seed=1, scale=0.3):
     return (Fa, Fb, Ia, Ib, Iabab), (T1a, T1b, T2aa, T2ab, T2bb)
 
 
+def random_u_closed(n, ng, seed=1, scale=0.3):
+    """Random CLOSED-SHELL unrestricted inputs: one spatial <pq|rs> (symmetric under
+    particle exchange) for both spins, Fa == Fb, Ia == Ib, Iabab mirror symmetric,
+    T1a == T1b, T2aa == T2bb, T2ab[a,B,i,J] == T2ab[B,a,J,i]; plus Lambda-shaped partners."""
+    rng = numpy.random.default_rng(seed)
+    rnd = rng.standard_normal
+    V = rnd((n,)*4)
+    V = V + V.transpose(1, 0, 3, 2)
+    Vs = V - V.transpose(0, 1, 3, 2)
+    sc = {"o": rnd(n), "v": rnd(n)}
+
+    def dress(X, pat):
+        f = [sc[c] for c in pat]
+        return numpy.ascontiguousarray(numpy.einsum('pqrs,p,q,r,s->pqrs', X, *f))
+    Ia = cqc.two_e_blocks(**{p: dress(Vs, p) for p in cqc.two_e_blocks.names})
+    Ib = cqc.two_e_blocks(**{p: dress(Vs, p) for p in cqc.two_e_blocks.names})
+    Iabab = cqc.two_e_blocks_full(**{p: dress(V, p) for p in cqc.two_e_blocks_full.names})
+    f = rnd((n, n))
+
+    def dressF(pat):
+        return numpy.ascontiguousarray(numpy.einsum('pq,p,q->pq', f, sc[pat[0]], sc[pat[1]]))
+    Fa = cqc.one_e_blocks(*[dressF(p) for p in ("oo", "ov", "vo", "vv")])
+    Fb = cqc.one_e_blocks(*[dressF(p) for p in ("oo", "ov", "vo", "vv")])
+
+    def amps(sc_):
+        t1 = sc_*rnd((ng, n, n))
+        tab = sc_*rnd((ng, n, n, n, n))
+        tab = numpy.ascontiguousarray(tab + tab.transpose(0, 2, 1, 4, 3))
+        # the same-spin block of a closed-shell state is the antisymmetrised opposite-spin one
+        taa = numpy.ascontiguousarray(tab - tab.transpose(0, 2, 1, 3, 4))
+        return (t1, t1.copy(), taa, tab, taa.copy())
+    return (Fa, Fb, Ia, Ib, Iabab), amps(scale), amps(1.0)
+
+
 def random_D(n, seed=5):
     rng = numpy.random.default_rng(seed)
     e = numpy.sort(rng.uniform(0.0, 5.0, n))
