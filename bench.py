@@ -72,7 +72,7 @@ class ClockSampler(threading.Thread):
                     self.rows.append([x.strip() for x in out.split(",")])
             except Exception:
                 pass
-            self._halt.wait(0.2)
+            self._halt.wait(0.1)
 
     def stop(self):
         self._halt.set()
@@ -155,11 +155,11 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="kb200", choices=["kb200", "reference"])
     ap.add_argument("--workload", default="ueg_ft_ccsd_ESN33", choices=sorted(WORKLOADS))
-    ap.add_argument("--cpu-points", type=int, default=2,
+    ap.add_argument("--cpu-points", type=int, default=6,
                     help="grid points sampled by the CPU baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

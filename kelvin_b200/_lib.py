@@ -21,7 +21,7 @@ EXPORTS = (
     "kb200_plan_workspace_bytes", "kb200_plan_run", "kb200_plan_run_timed", "kb200_int_tbar", "kb200_int_L", "kb200_int_tbar_rows", "kb200_int_L_rows",
     "kb200_reduce_scratch_doubles", "kb200_energy_pair", "kb200_dot_g", "kb200_damp_norms",
     "kb200_dress4", "kb200_dress2", "kb200_gather4", "kb200_scatter4_add", "kb200_gsum", "kb200_scale_by", "kb200_dot_keep",
-    "kb200_max_absdiff",
+    "kb200_max_absdiff", "kb200_set_plan_streams",
 )
 
 
@@ -73,6 +73,7 @@ def load():
                                    ctypes.POINTER(i64), vp, vp, dbl, dbl, vp, vp, vp]
     lib.kb200_gsum.argtypes = [ctypes.c_int, i64, vp, vp, vp, vp]
     lib.kb200_scale_by.argtypes = [ctypes.c_int, i64, vp, vp, vp]
+    lib.kb200_set_plan_streams.argtypes = [ctypes.c_int]
     lib.kb200_max_absdiff.argtypes = [ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(i64),
                                       ctypes.POINTER(i64), vp, vp, vp, vp]
     for nm in EXPORTS:

@@ -10,6 +10,8 @@
 #include "kb200_gemm.cuh"
 
 #include <atomic>
+#include <cstdlib>
+#include <vector>
 #include <cstdio>
 #include <cstring>
 
@@ -603,11 +605,179 @@ int64_t kb200_plan_workspace_bytes(const kb200_op* ops, int nops) {
     return w;
 }
 
-static int run_plan_impl(const kb200_op* ops, int nops, const uint32_t* tables,
+
+// ---------------------------------------------------------------------------
+// Concurrent execution of a plan's independent launches.
+//
+// The plan arrives in a dependency-respecting order (plan.py: Lowered._schedule).  With one
+// stream every launch waits for the tail of the one before it: at small tau batches (tau-sharded
+// runs: 1-3 grid points per GPU) an m^6 launch is only 1-3 waves of CTAs and the ~100 small
+// kernels of a residual each fill a fraction of the machine.  Here the big contraction launches
+// alternate between two streams and everything else goes to a third; read-after-write,
+// write-after-write and write-after-read orders on every slot (and on the split-K workspace) are
+// enforced with events, so the arithmetic and its order per output are unchanged
+// (bit-identical results).  The caller's stream is stream 0; the side streams fork from it at
+// the start of the plan and join it at the end, so the call keeps stream semantics.
+// ---------------------------------------------------------------------------
+struct MultiStream {
+    static constexpr int NS = 3;
+    cudaStream_t s[NS] = {nullptr, nullptr, nullptr};
+    bool made = false;
+    std::vector<cudaEvent_t> pool;      // one event per launch of the current plan
+    int used = 0;
+    // per launch
+    std::vector<int> l_stream, l_seq;
+    // per slot (last entry = workspace)
+    std::vector<int> last_writer;               // launch id or -1
+    std::vector<int> last_reader;               // [slot*NS + stream] launch id or -1
+    int seq[NS];                                // launches issued per stream
+    int synced[NS][NS];                         // synced[S][T]: S has waited for T's launch seq <= this
+    int last_on[NS];                            // last launch id per stream
+    int nbig = 0;
+    cudaEvent_t fork_ev = nullptr;
+    bool forked[NS];
+
+    int init(cudaStream_t caller, int nslots) {
+        if (!made) {
+            for (int k = 1; k < NS; ++k)
+                if (cudaStreamCreateWithFlags(&s[k], cudaStreamNonBlocking) != cudaSuccess)
+                    return fail(-2, "plan: cannot create side stream");
+            if (cudaEventCreateWithFlags(&fork_ev, cudaEventDisableTiming) != cudaSuccess)
+                return fail(-2, "plan: cannot create event");
+            made = true;
+        }
+        s[0] = caller;
+        used = 0;
+        nbig = 0;
+        l_stream.clear();
+        l_seq.clear();
+        last_writer.assign(nslots + 1, -1);
+        last_reader.assign((size_t)(nslots + 1) * NS, -1);
+        for (int a = 0; a < NS; ++a) {
+            seq[a] = 0;
+            last_on[a] = -1;
+            forked[a] = (a == 0);
+            for (int b = 0; b < NS; ++b) synced[a][b] = 0;
+        }
+        if (cudaEventRecord(fork_ev, caller) != cudaSuccess) return fail(-2, "plan: fork record");
+        return 0;
+    }
+    int wait_for(int S, int launch) {
+        if (launch < 0) return 0;
+        const int T = l_stream[launch];
+        if (T == S || l_seq[launch] <= synced[S][T]) return 0;
+        if (cudaStreamWaitEvent(s[S], pool[launch], 0) != cudaSuccess)
+            return fail(-2, "plan: stream wait");
+        synced[S][T] = l_seq[launch];
+        return 0;
+    }
+    // stream for the launch made of ops[i .. i+n): inserts the waits it needs
+    int begin(const kb200_op* ops, int i, int n, int nslots, cudaStream_t* out) {
+        const kb200_op& o = ops[i];
+        const bool big = o.kind == 0 && (o.tile == 0 || o.tile == 2 || o.tile == 3);
+        const int S = big ? (nbig++ & 1) : 2;
+        if (!forked[S]) {
+            if (cudaStreamWaitEvent(s[S], fork_ev, 0) != cudaSuccess)
+                return fail(-2, "plan: fork wait");
+            forked[S] = true;
+        }
+        for (int m = 0; m < n; ++m) {
+            const kb200_op& q = ops[i + m];
+            int rd[3], nr = 0;
+            rd[nr++] = q.a;
+            if (q.kind != 1 && q.b >= 0) rd[nr++] = q.b;
+            if (q.beta != 0.0) rd[nr++] = q.c;
+            for (int k = 0; k < nr; ++k) {
+                if (rd[k] < 0 || rd[k] >= nslots) return fail(-1, "plan: bad slot");
+                if (wait_for(S, last_writer[rd[k]])) return -2;
+            }
+            int wr[2], nw = 0;
+            if (q.c < 0 || q.c >= nslots) return fail(-1, "plan: bad slot");
+            wr[nw++] = q.c;
+            if (op_workspace(q) > 0) wr[nw++] = nslots;          // split-K partials
+            for (int k = 0; k < nw; ++k) {
+                if (wait_for(S, last_writer[wr[k]])) return -2;
+                for (int T = 0; T < NS; ++T)
+                    if (wait_for(S, last_reader[(size_t)wr[k] * NS + T])) return -2;
+            }
+        }
+        *out = s[S];
+        return S;
+    }
+    int end(const kb200_op* ops, int i, int n, int nslots, int S) {
+        const int id = (int)l_stream.size();
+        if ((int)pool.size() <= id) {
+            cudaEvent_t e;
+            if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess)
+                return fail(-2, "plan: cannot create event");
+            pool.push_back(e);
+        }
+        if (cudaEventRecord(pool[id], s[S]) != cudaSuccess) return fail(-2, "plan: event record");
+        l_stream.push_back(S);
+        l_seq.push_back(++seq[S]);
+        last_on[S] = id;
+        for (int m = 0; m < n; ++m) {
+            const kb200_op& q = ops[i + m];
+            last_reader[(size_t)q.a * NS + S] = id;
+            if (q.kind != 1 && q.b >= 0) last_reader[(size_t)q.b * NS + S] = id;
+        }
+        for (int m = 0; m < n; ++m) {
+            const kb200_op& q = ops[i + m];
+            int wr[2], nw = 0;
+            wr[nw++] = q.c;
+            if (op_workspace(q) > 0) wr[nw++] = nslots;
+            for (int k = 0; k < nw; ++k) {
+                last_writer[wr[k]] = id;
+                for (int T = 0; T < NS; ++T) last_reader[(size_t)wr[k] * NS + T] = -1;
+            }
+        }
+        return 0;
+    }
+    // the caller's stream waits for everything issued on the side streams
+    int join() {
+        int rc = 0;
+        for (int T = 1; T < NS; ++T)
+            if (last_on[T] >= 0 &&
+                cudaStreamWaitEvent(s[0], pool[last_on[T]], 0) != cudaSuccess)
+                rc = fail(-2, "plan: join wait");
+        return rc;
+    }
+};
+
+static MultiStream g_ms[16];
+
+static int g_plan_streams = -1;
+
+static int plan_streams() {
+    if (g_plan_streams < 0) {
+        const char* e = getenv("KB200_STREAMS");
+        g_plan_streams = (e && atoi(e) == 1) ? 1 : 3;
+    }
+    return g_plan_streams;
+}
+
+int kb200_set_plan_streams(int n) {
+    const int old = plan_streams();
+    g_plan_streams = (n == 1) ? 1 : 3;
+    return old;
+}
+
+static int run_plan_body(const kb200_op* ops, int nops, const uint32_t* tables,
                          double* const* slots, int nslots, double* workspace,
-                         int64_t workspace_bytes, cudaStream_t st, cudaEvent_t* ev) {
+                         int64_t workspace_bytes, cudaStream_t st0, cudaEvent_t* ev,
+                         MultiStream* ms) {
+    int prev_i = -1, prev_n = 0, prev_S = 0;
     for (int i = 0; i < nops; ++i) {
         const kb200_op& o = ops[i];
+        cudaStream_t st = st0;
+        if (ms) {
+            if (prev_i >= 0 && ms->end(ops, prev_i, prev_n, nslots, prev_S)) return -2;
+            int n = ((o.kind == 0 || o.kind == 3) && o.group > 1) ? o.group : 1;
+            if (i + n > nops) return fail(-1, "plan: bad group");
+            int S = ms->begin(ops, i, n, nslots, &st);
+            if (S < 0) return S;
+            prev_i = i; prev_n = n; prev_S = S;
+        }
         if (ev) cudaEventRecord(ev[2 * i], st);
         if (o.a < 0 || o.a >= nslots || o.c < 0 || o.c >= nslots) return fail(-1, "plan: bad slot");
         if (o.M <= 0 || o.N <= 0 || o.batch <= 0) return fail(-1, "plan: empty op");
@@ -796,7 +966,24 @@ static int run_plan_impl(const kb200_op* ops, int nops, const uint32_t* tables,
         }
         if (ev) cudaEventRecord(ev[2 * i + 1], st);
     }
+    if (ms && prev_i >= 0 && ms->end(ops, prev_i, prev_n, nslots, prev_S)) return -2;
     return 0;
+}
+
+static int run_plan_impl(const kb200_op* ops, int nops, const uint32_t* tables,
+                         double* const* slots, int nslots, double* workspace,
+                         int64_t workspace_bytes, cudaStream_t st, cudaEvent_t* ev) {
+    MultiStream* ms = nullptr;
+    int dev = 0;
+    if (!ev && nops > 1 && plan_streams() > 1 && cudaGetDevice(&dev) == cudaSuccess && dev < 16) {
+        ms = &g_ms[dev];
+        if (ms->init(st, nslots)) return -2;
+    }
+    int rc = run_plan_body(ops, nops, tables, slots, nslots, workspace, workspace_bytes, st, ev, ms);
+    // join even after an error: nothing may stay in flight on the side streams unordered
+    if (ms && ms->join() && rc == 0) rc = -2;
+    if (ms && rc != 0) cudaDeviceSynchronize();
+    return rc;
 }
 
 int kb200_plan_run(const kb200_op* ops, int nops, const uint32_t* tables, double* const* slots,

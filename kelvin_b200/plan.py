@@ -426,7 +426,7 @@ LONGK_MIN = 4096      # contracted length from which the long-K path (derived la
 RANKK_MIN_M = 4096    # rows from which the rank-K streaming kernel is used
 # independent contractions of one kernel configuration launched together (kb200_gemm.cuh
 # MAX_GROUP); 1 disables grouping and keeps the program order
-MAX_GROUP = int(_os.environ.get("KB200_GROUP", "4"))
+MAX_GROUP = int(_os.environ.get("KB200_GROUP", "8"))
 # consecutive index-permuted sums / outer products into one output fused into one pass (kind 3)
 FUSE_EW = int(_os.environ.get("KB200_FUSE", "1"))
 # contracted index pairs in which both operands are antisymmetric are summed over x < y only

@@ -14,6 +14,7 @@ def main():
     norb = int(sys.argv[1]) if len(sys.argv) > 1 else 33
     ng = int(sys.argv[2]) if len(sys.argv) > 2 else 10
     which = sys.argv[3] if len(sys.argv) > 3 else "stanton"
+    closed = len(sys.argv) > 4 and sys.argv[4] == "closed"     # closed-shell (mirror) reduction
     T_, MU_, L_ = 0.5, 7.0, 1.942
     dev = _lib.device()
     beta = 1.0/T_
@@ -21,8 +22,8 @@ def main():
     ea, eb = sysm.u_energies_tot()
     Fa, Fb, Ia, Ib, Iabab = cc_utils.uft_integrals(sysm, ea, eb, beta, MU_)
     sizes = ft_cc_equations._u_sizes(Fa, Fb)
-    p = ft_cc_equations.stanton_plan("u", sizes, -1.0) if which == "stanton" else \
-        ft_cc_equations.lambda_plan("u", sizes, -1.0)
+    p = ft_cc_equations.stanton_plan("u", sizes, -1.0, mirror=closed) if which == "stanton" else \
+        ft_cc_equations.lambda_plan("u", sizes, -1.0, mirror=closed)
     t = ft_cc_equations._u_integral_slots(Fa, Fb, Ia, Ib, Iabab, dev,
                                           [s for s in p.inputs if _plan.is_integral_slot(s)])
     m = norb
@@ -68,7 +69,7 @@ def main():
     for k, (n, dt, fl) in sorted(cls.items(), key=lambda x: -x[1][1]):
         print("%-22s n=%3d  %8.3f ms  %5.1f%%  %7.2f TF" % (k, n, dt*1e3, 100*dt/tot, fl/max(dt, 1e-12)/1e12))
     print()
-    top = int(sys.argv[4]) if len(sys.argv) > 4 else 70
+    top = int(sys.argv[5]) if len(sys.argv) > 5 else (0 if closed else 70)
     for dt, kind, fl, meta, txt in sorted(rows, key=lambda r: -r[0])[:top]:
         print("%7.1f us k%d M=%6d N=%5d K=%6d b=%2d tile=%d sk=%2d am=%d bm=%d %6.2f TF  %s" %
               (dt*1e6, kind, meta[0], meta[1], meta[2], meta[3], meta[4], meta[5], meta[6], meta[7],
