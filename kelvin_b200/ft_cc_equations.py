@@ -212,10 +212,11 @@ def ccsd_stanton(F, I, T1old, T2old, D1, D2, ti, ng, G, t0_zero=False):
 
 
 def uccsd_stanton_bar(Fa, Fb, Ia, Ib, Iabab, T1aold, T1bold, T2aaold, T2abold, T2bbold, fac=-1.0,
-                      t0_zero=False, closed_shell=False):
+                      t0_zero=False, closed_shell=False, beta_copies=True):
     """closed_shell: the caller guarantees mirror-symmetric integrals and amplitudes
     (closed_shell_integrals / closed_shell_amplitudes); the beta-leading blocks are then copies
-    of their alpha images and only the reduced program runs (plan.mirror_reduce)."""
+    of their alpha images and only the reduced program runs (plan.mirror_reduce).
+    beta_copies=False returns None in their place (the caller copies later)."""
     dev = _lib.device()
     ins = [_lib.as_dev(x, dev) for x in (T1aold, T1bold, T2aaold, T2abold, T2bbold)]
     ng = ins[0].shape[0]
@@ -233,7 +234,7 @@ def uccsd_stanton_bar(Fa, Fb, Ia, Ib, Iabab, T1aold, T1bold, T2aaold, T2abold, T
     drv = [_lib.as_dev(drivers[k], dev) for k in live] if t0_zero else None
     _run_rows(p, t, [in_names[k] for k in live], [out_names[k] for k in live], drv, ng, dev,
               t0_zero)
-    if closed_shell:
+    if closed_shell and beta_copies:
         outs[1] = outs[0].clone()
         outs[4] = outs[2].clone()
     return tuple(outs)

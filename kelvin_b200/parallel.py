@@ -80,7 +80,8 @@ class TauShardedUCCSD(object):
     def set_local_amplitudes(self, local, t0_zero=None, closed_shell=None):
         """t0_zero / closed_shell: None = look at the data (device reductions + sync);
         True/False = the caller's knowledge of whether the amplitudes at tau_0 vanish (only
-        read on the rank that owns tau_0) / are mirror symmetric."""
+        read on the rank that owns tau_0) / are mirror symmetric (must then be the same on
+        every rank)."""
         self.old = [_lib.as_dev(x, self.dev).contiguous() for x in local]
         self._check_t0(t0_zero)
         if closed_shell is None:
@@ -90,10 +91,16 @@ class TauShardedUCCSD(object):
 
     def _check_closed_shell(self):
         """Closed shell (alpha == beta integrals, denominators and local amplitudes): the update
-        preserves it.  Each rank decides for its own shard; the ranks need not agree."""
+        preserves it.  The ranks must agree (the step gathers three blocks instead of five), so
+        the local verdicts are combined with a MIN all-reduce; a rank without grid points
+        abstains."""
         from . import cc_utils
-        self.closed_shell = self.nloc > 0 and cc_utils._closed_shell(
-            *self.ints, self.Ds, self.old)
+        ok = True if self.nloc == 0 else bool(cc_utils._closed_shell(*self.ints, self.Ds, self.old))
+        if self.world > 1:
+            f = torch.tensor([1.0 if ok else 0.0], dtype=torch.float64, device=self.dev)
+            dist.all_reduce(f, op=dist.ReduceOp.MIN, group=self.group)
+            ok = bool(f.item() > 0.5)
+        self.closed_shell = ok
 
     def _check_t0(self, known):
         if self.y0 != 0 or self.nloc < 1 or self.ng < 2 or numpy.any(self.G[0] != 0.0):
@@ -111,8 +118,11 @@ class TauShardedUCCSD(object):
         shp = tuple(local.shape[1:])
         if self.world == 1:
             return local
-        pad = torch.zeros((self.chunk,) + shp, dtype=torch.float64, device=local.device)
-        pad[:self.nloc] = local
+        if local.shape[0] == self.chunk:
+            pad = local                        # full shard: sent in place
+        else:
+            pad = torch.zeros((self.chunk,) + shp, dtype=torch.float64, device=local.device)
+            pad[:local.shape[0]] = local
         out = torch.empty((self.world*self.chunk,) + shp, dtype=torch.float64, device=local.device)
         dist.all_gather_into_tensor(out, pad, group=self.group)
         return out
@@ -132,32 +142,41 @@ class TauShardedUCCSD(object):
                 ev.record()
                 marks.append((name, ev))
         mark("start")
+        # closed shell: the beta blocks (T1b, T2bb) are copies of the alpha ones -- they are
+        # neither gathered nor integrated nor damped, only copied at the end
+        live = (0, 2, 3) if self.closed_shell else (0, 1, 2, 3, 4)
         if nloc > 0:
             bars = ft_cc_equations.uccsd_stanton_bar(Fa, Fb, Ia, Ib, Iabab, *self.old,
                                                      t0_zero=self.t0_zero,
-                                                     closed_shell=self.closed_shell)
+                                                     closed_shell=self.closed_shell,
+                                                     beta_copies=False)
         else:
             bars = [torch.zeros((0,) + tuple(d.shape), dtype=torch.float64, device=self.dev)
                     for d in self.Ds]
         self.stats.zero_()
         mark("residual")
-        new = []
-        fulls = [self._allgather_rows(bars[k]) for k in range(5)]
+        new = {}
+        fulls = {k: self._allgather_rows(bars[k]) for k in live}
         mark("all-gather")
-        for k in range(5):
+        for k in live:
             if nloc > 0:
-                new.append(quadrature.int_tbar(ng, fulls[k][:ng], self.ti, self.Ds[k], self.G,
-                                               rows=(self.y0, self.y1)))
+                new[k] = quadrature.int_tbar(ng, fulls[k][:ng], self.ti, self.Ds[k], self.G,
+                                             rows=(self.y0, self.y1))
         fulls = None
         mark("integrate")
         if nloc > 0:
             scratch = _lib.reduce_scratch(self.dev)
-            for k in range(5):
+            for k in live:
                 rc = lib.kb200_damp_norms(self.old[k].numel(), _lib.ptr(self.old[k]),
                                           _lib.ptr(new[k]), alpha,
                                           self.stats.data_ptr() + 24*k, _lib.ptr(scratch),
                                           _lib.stream_ptr())
                 _lib.check(rc, "kb200_damp_norms")
+            if self.closed_shell:
+                self.old[1].copy_(self.old[0])
+                self.old[4].copy_(self.old[2])
+                self.stats[3:6] = self.stats[0:3]
+                self.stats[12:15] = self.stats[6:9]
             T1a, T1b, T2aa, T2ab, T2bb = self.old
             parts = ft_cc_energy.energy_terms(
                 [(T1a, self.faT), (T1b, self.fbT)],
