@@ -298,13 +298,15 @@ def main():
                                          mirror=closed)
         t = ft_cc_equations._u_integral_slots(
             Fa, Fb, Ia, Ib, Iabab, dev, [s for s in p.inputs if _plan.is_integral_slot(s)])
-        nloc = solver.nloc
+        # the grid points the step evaluates (without tau_0 when the shortcut applies)
+        skip = 1 if (solver.t0_zero and solver.nloc > 1) else 0
+        nloc = solver.nloc - skip
         for nm, x in zip(("t1.a", "t1.b", "t2.aa", "t2.ab", "t2.bb"), solver.old):
             if nm in p.shapes:
-                t[nm] = x
+                t[nm] = x[skip:]
         for nm, x in zip(("o1.a", "o1.b", "o2.aa", "o2.ab", "o2.bb"), solver.old):
             if nm in p.shapes:
-                t[nm] = torch.empty_like(x)
+                t[nm] = torch.empty_like(x[skip:])
         tim = []
         for _ in range(3):
             tim = []
