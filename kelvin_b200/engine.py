@@ -60,8 +60,10 @@ class Plan(object):
     def _ensure_tmp(self, nb, dev):
         if self._tmp is not None and self._tmp_nb >= nb and self._tmp_dev == dev:
             return
-        self._tmp = {s: torch.empty((nb,) + tuple(self.shapes[s]), dtype=torch.float64, device=dev)
-                     for s in self.tmp_slots}
+        # triangle blocks (plan.antisym_outputs) must be zero outside the part the plan writes
+        self._tmp = {s: (torch.zeros if s.startswith(_plan.TRI_PREFIX) else torch.empty)(
+            (nb,) + tuple(self.shapes[s]), dtype=torch.float64, device=dev)
+            for s in self.tmp_slots}
         self._tmp_nb = nb
         self._tmp_dev = dev
 

@@ -71,6 +71,7 @@ def stanton_plan(mode, sizes, fac=-1.0, mirror=False):
             rops = _plan.mirror_reduce(rops)
             ins = tuple(s for s in ins if _plan.mirror_rep(s) == s)
             outs = tuple(s for s in outs if _plan.mirror_rep(s) == s)
+        rops = _plan.antisym_outputs(rops)
         return engine.Plan(rops, mode, sizes, ins, outs,
                            name="stanton-" + mode + ("-closed" if mirror else ""))
     return engine.cached(key, build)

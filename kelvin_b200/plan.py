@@ -27,10 +27,13 @@ from the resolved forward ops, so the g and u Lambda kernels are generated, not
 hand-written.
 """
 import ctypes
+import os
 import re
 from collections import OrderedDict
 
 import numpy
+
+_os_environ_get = os.environ.get
 
 VIRT = "abcdefgh"
 OCC = "ijklmnop"
@@ -176,10 +179,13 @@ def sz_ok(spins):
 
 class ROp(object):
     """Resolved op on concrete slots: out[letters] += coef * prod(ins)."""
-    __slots__ = ("out", "coef", "ins", "spin")
+    __slots__ = ("out", "coef", "ins", "spin", "tri")
 
-    def __init__(self, out, coef, ins, spin=None):
+    def __init__(self, out, coef, ins, spin=None, tri=None):
         self.out, self.coef, self.ins, self.spin = out, coef, ins, spin
+        # tri: pairs of output letters (x, y); only the elements with x < y are computed and
+        # written (see antisym_outputs)
+        self.tri = tri
 
     def __repr__(self):
         return "%s[%s] += %g %s" % (self.out[0], self.out[1], self.coef,
@@ -314,6 +320,65 @@ def mirror_reduce(rops):
             continue
         ins = [(mirror_rep(sl), ls) for sl, ls in op.ins]
         out.append(ROp(op.out, op.coef, ins, op.spin))
+    return out
+
+
+# ---------------------------------------------------------------------------
+# antisymmetric outputs: compute one triangle, add its four images
+# ---------------------------------------------------------------------------
+ANTISYM_OUT = int(_os_environ_get("KB200_ANTISYM_OUT", "1"))
+TRI_PREFIX = "Ptri"
+
+
+def _tri_candidate(op):
+    """((x, y), (u, v)) when the product of the two operands is antisymmetric under x <-> y
+    (a pair carried by the first operand) and under u <-> v (carried by the second) and these
+    four letters are the whole output: the same-spin ladder terms
+    tau[efij] W_vvvv[abef], tau[abmn] W_oooo[mnij] and the I.oovv.tau builds of W_oooo / W_vvvv."""
+    if len(op.ins) != 2 or len(op.out[1]) != 4 or op.tri is not None:
+        return None
+    (na, la), (nb, lb) = op.ins
+    lc = op.out[1]
+    pa = [(la[p], la[q]) for p, q in antisym_pairs(na) if la[p] in lc and la[q] in lc]
+    pb = [(lb[p], lb[q]) for p, q in antisym_pairs(nb) if lb[p] in lc and lb[q] in lc]
+    if len(pa) != 1 or len(pb) != 1 or set(pa[0]) | set(pb[0]) != set(lc):
+        return None
+    if len(set(pa[0]) | set(pb[0])) != 4:
+        return None
+    order = lambda pr: tuple(sorted(pr, key=lc.index))      # noqa: E731
+    return order(pa[0]), order(pb[0])
+
+
+def antisym_outputs(rops):
+    """Rewrite every contraction whose result is antisymmetric in two output index pairs
+
+        X[abij] += c A B      as      P[abij]  = c A B   restricted to a < b, i < j
+                                      X[abij] += P[abij] - P[baij] - P[abji] + P[baji]
+
+    P is a plan-owned scratch block that is zero outside the triangle (allocated zeroed; only the
+    triangle is ever written), so the four permuted adds -- one fused elementwise pass -- restore
+    the full antisymmetric contribution.  The contraction runs on m(m-1)/2 rows and columns
+    instead of m^2: with the x < y sum over the contracted pair (ANTISYM) a same-spin ladder
+    term does 1/8 of the reference's flops.  Relies on the operands being antisymmetric to
+    rounding, like ANTISYM."""
+    out, k = [], 0
+    for op in rops:
+        t = _tri_candidate(op) if ANTISYM_OUT else None
+        if t is None:
+            out.append(op)
+            continue
+        (x, y), (u, v) = t
+        ls = op.out[1]
+        suf = op.out[0].partition(".")[2]
+        slot = "%s%d%s" % (TRI_PREFIX, k, "." + suf if suf else "")
+        k += 1
+        out.append(ROp((slot, ls), op.coef, list(op.ins), op.spin, tri=((x, y), (u, v))))
+
+        def sw(s, p, q):
+            return s.translate(str.maketrans(p + q, q + p))
+        for pls, sg in ((ls, 1.0), (sw(ls, x, y), -1.0), (sw(ls, u, v), -1.0),
+                        (sw(sw(ls, x, y), u, v), 1.0)):
+            out.append(ROp(op.out, sg, [(slot, pls)], op.spin))
     return out
 
 
@@ -803,6 +868,23 @@ class Lowered(object):
         d.M, d.N, d.K = size(M), size(N), size(K)
         d.bsA, d.bsB = bs(na), bs(nb)
         d.tAm, d.tBn = tab(M, sa), tab(N, sb)
+        tri_m = tri_n = None
+        for x, y in (op.tri or ()):
+            if x in M and y in M and tri_m is None:
+                tri_m = (M.index(x), M.index(y))
+            elif x in N and y in N and tri_n is None:
+                tri_n = (N.index(x), N.index(y))
+            else:
+                raise ValueError("triangular output pair (%s,%s) straddles rows and columns: %r"
+                                 % (x, y, op))
+        if tri_m is not None:
+            d.tAm = self.bank.get_lt([(dims[l], sa[l]) for l in M], *tri_m)
+            nx = dims[M[tri_m[0]]]
+            d.M = size(M) // (nx * nx) * (nx * (nx - 1) // 2)
+        if tri_n is not None:
+            d.tBn = self.bank.get_lt([(dims[l], sb[l]) for l in N], *tri_n)
+            nx = dims[N[tri_n[0]]]
+            d.N = size(N) // (nx * nx) * (nx * (nx - 1) // 2)
         half = None
         if ANTISYM and len(K) >= 2:
             for pa, qa in antisym_pairs(na):
@@ -819,8 +901,14 @@ class Lowered(object):
         else:
             d.tAk, d.tBk = tab(K, sa), tab(K, sb)
         d.tCm, d.tCn = tab(M, sc), tab(N, sc)
+        if tri_m is not None:
+            d.tCm = self.bank.get_lt([(dims[l], sc[l]) for l in M], *tri_m)
+        if tri_n is not None:
+            d.tCn = self.bank.get_lt([(dims[l], sc[l]) for l in N], *tri_n)
         d.a_mode, d.b_mode = a_mode, b_mode
-        self._nfold[id(d)] = ([(dims[l], sb[l]) for l in N], [(dims[l], sc[l]) for l in N])
+        # (batch folding rebuilds the N tables from these lists: not for triangular columns)
+        self._nfold[id(d)] = None if tri_n is not None else \
+            ([(dims[l], sb[l]) for l in N], [(dims[l], sc[l]) for l in N])
         if SKINNY_TILE and d.K <= 40 and d.N <= 40 and d.M >= RANKK_MIN_M:
             d.tile = 7       # skinny streaming update (DMMA, 8 rows per warp)
             d.reserved = 1 if lc[-1] in M else 0
@@ -851,7 +939,8 @@ class Lowered(object):
             if o.batch > 1 and o.bsC == 0:
                 raise ValueError("batched operands reduce into an unbatched output")
             if FOLD and o.kind == 0 and o.batch > 1 and o.bsA == 0 and o.bsB != 0 \
-                    and o.N * o.batch <= 32 and o.tile != 6 and gsize_of[k] == 1:
+                    and o.N * o.batch <= 32 and o.tile != 6 and gsize_of[k] == 1 \
+                    and self._nfold.get(id(d)) is not None:
                 nB, nC = self._nfold[id(d)]
                 o.tBn = self.bank.get([(o.batch, o.bsB)] + nB)
                 o.tCn = self.bank.get([(o.batch, o.bsC)] + nC)

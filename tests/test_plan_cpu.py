@@ -22,6 +22,8 @@ def _run(rops, mode, sizes, inputs, src, ng):
             arrays[s] = numpy.ascontiguousarray(getattr(src[pre], pat))
         elif s in inputs:
             arrays[s] = numpy.ascontiguousarray(inputs[s])
+        elif s.startswith(plan.TRI_PREFIX):
+            arrays[s] = numpy.zeros((ng,) + shp)       # the engine allocates these zeroed
         else:
             arrays[s] = numpy.full((ng,) + shp, numpy.nan)
     run_lowered(low, arrays, ng)
@@ -312,3 +314,41 @@ def test_mirror_reduced_plans_on_closed_shell_inputs():
     for nm in ("lo1.a", "lo2.aa", "lo2.ab"):
         assert numpy.abs(l_red[nm] - l_full[nm]).max() < 1e-12*numpy.abs(l_full[nm]).max()
     assert numpy.abs(l_full["lo2.bb"] - l_full["lo2.aa"]).max() < 1e-12*numpy.abs(l_full["lo2.aa"]).max()
+
+
+@pytest.mark.parametrize("mode", ["g", "u", "closed"])
+def test_antisymmetric_outputs_triangle(mode):
+    """plan.antisym_outputs: the same-spin ladder terms are computed on the a<b, i<j triangle
+    only and expanded into their four images; residual unchanged."""
+    ng = 2
+    if mode == "g":
+        n = 5
+        F, I, t1, t2 = util.random_g(n, ng, seed=51)
+        sizes, src, ins = {"o": n, "v": n}, {"F": F, "I": I}, {"t1": t1, "t2": t2}
+        rops = plan.expand(programs.stanton(-1.0), programs.tensor_defs(), "g")
+        outs = ("o1", "o2")
+    else:
+        n = 4
+        if mode == "u":
+            ints, amps = util.random_u(n, n - 1, ng, seed=52)
+        else:
+            ints, amps, _ = util.random_u_closed(n, ng, seed=53)
+        Fa, Fb, Ia, Ib, Iabab = ints
+        nb = ints[1].ov.shape[0]
+        sizes = {("v", "a"): n, ("o", "a"): n, ("v", "b"): nb, ("o", "b"): nb}
+        src = {"Fa": Fa, "Fb": Fb, "Ia": Ia, "Ib": Ib, "Iabab": Iabab}
+        ins = dict(zip(("t1.a", "t1.b", "t2.aa", "t2.ab", "t2.bb"), amps))
+        rops = plan.expand(programs.stanton(-1.0), programs.tensor_defs(), "u")
+        outs = ("o1.a", "o1.b", "o2.aa", "o2.ab", "o2.bb")
+        if mode == "closed":
+            rops = plan.mirror_reduce(rops)
+            ins = {k: v for k, v in ins.items() if plan.mirror_rep(k) == k}
+            outs = tuple(s for s in outs if plan.mirror_rep(s) == s)
+    tri = plan.antisym_outputs(rops)
+    ntri = sum(1 for op in tri if op.tri is not None)
+    assert ntri == {"g": 4, "u": 8, "closed": 4}[mode]
+    ref, lref = _run(rops, mode if mode != "closed" else "u", sizes, ins, src, ng)
+    got, lgot = _run(tri, mode if mode != "closed" else "u", sizes, ins, src, ng)
+    assert lgot.flops < lref.flops
+    for nm in outs:
+        assert numpy.abs(got[nm] - ref[nm]).max() < 1e-12*numpy.abs(ref[nm]).max(), nm
