@@ -293,14 +293,15 @@ def main():
     # ---- live roofline of the dominant kernel (DMMA contraction GEMM) --------
     roof = None
     if rank == 0:
-        # the plan the step runs (closed-shell reduction when the inputs allow it)
-        p = ft_cc_equations.stanton_plan("u", ft_cc_equations._u_sizes(Fa, Fb), -1.0,
-                                         mirror=closed)
-        t = ft_cc_equations._u_integral_slots(
-            Fa, Fb, Ia, Ib, Iabab, dev, [s for s in p.inputs if _plan.is_integral_slot(s)])
-        # the grid points the step evaluates (without tau_0 when the shortcut applies)
+        # the plan the step runs (closed-shell reduction when the inputs allow it), on the grid
+        # points the step evaluates (without tau_0 when the shortcut applies)
         skip = 1 if (solver.t0_zero and solver.nloc > 1) else 0
         nloc = solver.nloc - skip
+        mrows = closed and nloc >= ft_cc_equations.MIRROR_ROWS_MIN_BATCH
+        p = ft_cc_equations.stanton_plan("u", ft_cc_equations._u_sizes(Fa, Fb), -1.0,
+                                         mirror=closed, mirror_rows=mrows)
+        t = ft_cc_equations._u_integral_slots(
+            Fa, Fb, Ia, Ib, Iabab, dev, [s for s in p.inputs if _plan.is_integral_slot(s)])
         for nm, x in zip(("t1.a", "t1.b", "t2.aa", "t2.ab", "t2.bb"), solver.old):
             if nm in p.shapes:
                 t[nm] = x[skip:]
@@ -386,7 +387,9 @@ def main():
         fl_exec = algorithmic_flops(norb, npts)
         if closed:
             # executed 2*M*N*K of the reduced program (all contraction classes)
-            pc = ft_cc_equations.stanton_plan("u", ft_cc_equations._u_sizes(Fa, Fb), -1.0, mirror=True)
+            pc = ft_cc_equations.stanton_plan(
+                "u", ft_cc_equations._u_sizes(Fa, Fb), -1.0, mirror=True,
+                mirror_rows=npts >= ft_cc_equations.MIRROR_ROWS_MIN_BATCH)
             fl_exec = float(pc.flops_per_point)*npts
         line = {
             "metric": "ft_ccsd_seconds_per_amplitude_iteration", "value": t_step, "unit": "s",

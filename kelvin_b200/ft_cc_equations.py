@@ -53,10 +53,18 @@ def _u_sizes(Fa, Fb):
     return {("o", "a"): int(noa), ("v", "a"): int(nva), ("o", "b"): int(nob), ("v", "b"): int(nvb)}
 
 
-def stanton_plan(mode, sizes, fac=-1.0, mirror=False):
+# tau batch from which the closed-shell program also halves the rows of its mirror-symmetric
+# opposite-spin ladder terms (plan.mirror_outputs): the extra launches (diagonal pass + mirrored
+# add per term) only pay once the contractions are several waves of CTAs long
+MIRROR_ROWS_MIN_BATCH = int(os.environ.get("KB200_MIRROR_ROWS_MIN_BATCH", "4"))
+
+
+def stanton_plan(mode, sizes, fac=-1.0, mirror=False, mirror_rows=False):
     """mirror (u only): the closed-shell reduction of the program (plan.mirror_reduce): only the
-    alpha-leading block of every alpha <-> beta pair is evaluated."""
-    key = ("stanton", mode, tuple(sorted(sizes.items(), key=str)), fac, bool(mirror))
+    alpha-leading block of every alpha <-> beta pair is evaluated; mirror_rows: additionally
+    plan.mirror_outputs."""
+    mirror_rows = bool(mirror and mirror_rows)
+    key = ("stanton", mode, tuple(sorted(sizes.items(), key=str)), fac, bool(mirror), mirror_rows)
 
     def build():
         T = programs.tensor_defs()
@@ -71,6 +79,8 @@ def stanton_plan(mode, sizes, fac=-1.0, mirror=False):
             rops = _plan.mirror_reduce(rops)
             ins = tuple(s for s in ins if _plan.mirror_rep(s) == s)
             outs = tuple(s for s in outs if _plan.mirror_rep(s) == s)
+            if mirror_rows:
+                rops = _plan.mirror_outputs(rops)
         rops = _plan.antisym_outputs(rops)
         return engine.Plan(rops, mode, sizes, ins, outs,
                            name="stanton-" + mode + ("-closed" if mirror else ""))
@@ -221,7 +231,9 @@ def uccsd_stanton_bar(Fa, Fb, Ia, Ib, Iabab, T1aold, T1bold, T2aaold, T2abold, T
     dev = _lib.device()
     ins = [_lib.as_dev(x, dev) for x in (T1aold, T1bold, T2aaold, T2abold, T2bbold)]
     ng = ins[0].shape[0]
-    p = stanton_plan("u", _u_sizes(Fa, Fb), fac, mirror=closed_shell)
+    neval = ng - 1 if (t0_zero and ng > 1) else ng
+    p = stanton_plan("u", _u_sizes(Fa, Fb), fac, mirror=closed_shell,
+                     mirror_rows=neval >= MIRROR_ROWS_MIN_BATCH)
     t = _u_integral_slots(Fa, Fb, Ia, Ib, Iabab, dev,
                           [s for s in p.inputs if _plan.is_integral_slot(s)])
     in_names = ("t1.a", "t1.b", "t2.aa", "t2.ab", "t2.bb")

@@ -383,6 +383,77 @@ def antisym_outputs(rops):
 
 
 # ---------------------------------------------------------------------------
+# closed shell: mirror-symmetric opposite-spin outputs, computed on half of their rows
+# ---------------------------------------------------------------------------
+MIRROR_OUT = int(_os_environ_get("KB200_MIRROR_OUT", "1"))
+_SELF_MIRROR_AMP = ("t2", "tau", "tauh", "Woooo", "Wvvvv", "o2")
+
+
+def _self_mirror(slot):
+    """Opposite-spin blocks that equal their own alpha <-> beta image, X[p,Q,r,S] == X[Q,p,S,r],
+    in a closed-shell (mirror_reduce'd) program: amplitude-like 'ab' blocks and the Iabab blocks
+    whose pattern is its own image."""
+    if "~" in slot or "@" in slot:
+        return False
+    base, _, suf = slot.partition(".")
+    if base == "Iabab":
+        return suf[0] == suf[1] and suf[2] == suf[3]
+    return base in _SELF_MIRROR_AMP and suf == "ab"
+
+
+def _mirror_candidate(op):
+    """(p, q): the leading output pair of an opposite-spin contraction X.ab[p,q,r,s] += A B whose
+    value is unchanged under the joint swap p <-> q, r <-> s: every operand is its own mirror
+    image and every operand's index pairs (0,1), (2,3) are {p,q}, {r,s} or the summed pair."""
+    if len(op.ins) != 2 or len(op.out[1]) != 4 or op.tri is not None:
+        return None
+    if not _self_mirror(op.out[0]) or not all(_self_mirror(sl) and len(ls) == 4 for sl, ls in op.ins):
+        return None
+    lc = op.out[1]
+    summed = set(l for _, ls in op.ins for l in ls) - set(lc)
+    pairs = [frozenset(lc[:2]), frozenset(lc[2:]), frozenset(summed)]
+    if len(summed) != 2:
+        return None
+    for _, ls in op.ins:
+        if frozenset(ls[:2]) not in pairs or frozenset(ls[2:]) not in pairs:
+            return None
+    # restrict the output pair carried by the FIRST operand: it becomes the row index of the
+    # contraction, so the diagonal pass (m rows x m^2 columns) runs on the big-tile kernel's
+    # ragged-row path instead of a 33-column GEMM
+    first = op.ins[0][1]
+    for pr in (lc[:2], lc[2:]):
+        if set(pr) <= set(first):
+            return pr[0], pr[1]
+    return None
+
+
+def mirror_outputs(rops):
+    """Closed-shell programs only (after mirror_reduce).  An opposite-spin ladder-type contraction
+    between self-mirror blocks gives a block with X[p,q,r,s] == X[q,p,s,r]:
+
+        X[pqrs] += c A B     becomes     P[pqrs]  = c A B   on the rows p < q   (P zero elsewhere)
+                                         X[pqrs] += P[pqrs] + P[qpsr]
+                                         X[pqrs] += c A B   on the rows p == q
+
+    i.e. m(m-1)/2 + m of the m^2 rows are contracted."""
+    out, k = [], 0
+    for op in rops:
+        t = _mirror_candidate(op) if MIRROR_OUT else None
+        if t is None:
+            out.append(op)
+            continue
+        p, q = t
+        ls = op.out[1]
+        slot = "%sm%d.ab" % (TRI_PREFIX, k)
+        k += 1
+        out.append(ROp((slot, ls), op.coef, list(op.ins), op.spin, tri=((p, q, "lt"),)))
+        out.append(ROp(op.out, 1.0, [(slot, ls)], op.spin))
+        out.append(ROp(op.out, 1.0, [(slot, ls[1] + ls[0] + ls[3] + ls[2])], op.spin))
+        out.append(ROp(op.out, op.coef, list(op.ins), op.spin, tri=((p, q, "eq"),)))
+    return out
+
+
+# ---------------------------------------------------------------------------
 # reverse mode (Lambda / RDM)
 # ---------------------------------------------------------------------------
 def adjoint(rops, wrt, seeds, bar=lambda s: s + "~"):
@@ -452,16 +523,17 @@ class TableBank(object):
         self.index[key] = start
         return start
 
-    def get_lt(self, dims_strides, px, py):
+    def get_lt(self, dims_strides, px, py, rel="lt"):
         """As get(), keeping only the entries whose index at position px is smaller than the
-        one at position py (the x < y half of an antisymmetric contracted pair)."""
-        key = ("lt", px, py) + tuple(dims_strides)
+        one at position py (the x < y half of an antisymmetric contracted pair); rel="eq" keeps
+        the diagonal x == y instead."""
+        key = (rel, px, py) + tuple(dims_strides)
         if key in self.index:
             return self.index[key]
         dims = [d for d, _ in dims_strides]
         grids = numpy.meshgrid(*[numpy.arange(d, dtype=numpy.int64) for d in dims], indexing="ij")
         off = sum(g*s_ for g, (_, s_) in zip(grids, dims_strides))
-        keep = grids[px] < grids[py]
+        keep = (grids[px] < grids[py]) if rel == "lt" else (grids[px] == grids[py])
         off = off[keep].reshape(-1)          # C order of the full index space, filtered
         assert off.max(initial=0) < 2 ** 32 - 1
         start = self.pos
@@ -869,22 +941,28 @@ class Lowered(object):
         d.bsA, d.bsB = bs(na), bs(nb)
         d.tAm, d.tBn = tab(M, sa), tab(N, sb)
         tri_m = tri_n = None
-        for x, y in (op.tri or ()):
+        for ent in (op.tri or ()):
+            x, y = ent[0], ent[1]
+            rel = ent[2] if len(ent) > 2 else "lt"
+            if dims[x] != dims[y]:
+                raise ValueError("restricted output pair (%s,%s) of unequal ranges: %r" % (x, y, op))
             if x in M and y in M and tri_m is None:
-                tri_m = (M.index(x), M.index(y))
+                tri_m = (M.index(x), M.index(y), rel)
             elif x in N and y in N and tri_n is None:
-                tri_n = (N.index(x), N.index(y))
+                tri_n = (N.index(x), N.index(y), rel)
             else:
-                raise ValueError("triangular output pair (%s,%s) straddles rows and columns: %r"
+                raise ValueError("restricted output pair (%s,%s) straddles rows and columns: %r"
                                  % (x, y, op))
+
+        def kept(grp, t):
+            nx = dims[grp[t[0]]]
+            return size(grp) // (nx * nx) * ((nx * (nx - 1) // 2) if t[2] == "lt" else nx)
         if tri_m is not None:
             d.tAm = self.bank.get_lt([(dims[l], sa[l]) for l in M], *tri_m)
-            nx = dims[M[tri_m[0]]]
-            d.M = size(M) // (nx * nx) * (nx * (nx - 1) // 2)
+            d.M = kept(M, tri_m)
         if tri_n is not None:
             d.tBn = self.bank.get_lt([(dims[l], sb[l]) for l in N], *tri_n)
-            nx = dims[N[tri_n[0]]]
-            d.N = size(N) // (nx * nx) * (nx * (nx - 1) // 2)
+            d.N = kept(N, tri_n)
         half = None
         if ANTISYM and len(K) >= 2:
             for pa, qa in antisym_pairs(na):

@@ -193,3 +193,20 @@ def test_multi_stream_plan_is_bit_identical(built, closed):
                 assert torch.equal(a, b)
     finally:
         lib.kb200_set_plan_streams(old)
+
+
+def test_closed_shell_mirror_rows(built):
+    """From MIRROR_ROWS_MIN_BATCH grid points on, the closed-shell program also contracts its
+    mirror-symmetric opposite-spin ladder terms on the rows p <= q only (plan.mirror_outputs),
+    and the same-spin ladder terms on the a<b, i<j triangle (plan.antisym_outputs)."""
+    from kelvin_b200 import ft_cc_equations as fe, plan as _plan
+    n, ng = 9, 5
+    assert ng >= fe.MIRROR_ROWS_MIN_BATCH
+    ints, amps, _ = util.random_u_closed(n, ng, seed=19)
+    full = fe.uccsd_stanton_bar(*ints, *amps)
+    red = fe.uccsd_stanton_bar(*ints, *amps, closed_shell=True)
+    p = fe.stanton_plan("u", fe._u_sizes(ints[0], ints[1]), -1.0, mirror=True, mirror_rows=True)
+    assert sum(1 for op in p.low.rops if op.tri is not None) == 12
+    assert any(s.startswith(_plan.TRI_PREFIX + "m") for s in p.shapes)
+    for got, ref in zip(red, full):
+        assert _relerr(got, ref.cpu().numpy()) < 1e-12

@@ -347,6 +347,10 @@ def test_antisymmetric_outputs_triangle(mode):
     tri = plan.antisym_outputs(rops)
     ntri = sum(1 for op in tri if op.tri is not None)
     assert ntri == {"g": 4, "u": 8, "closed": 4}[mode]
+    if mode == "closed":
+        # opposite-spin ladder terms on the rows p <= q only (p < q mirrored, p == q direct)
+        tri = plan.antisym_outputs(plan.mirror_outputs(rops))
+        assert sum(1 for op in tri if op.tri is not None) == 4 + 2*4
     ref, lref = _run(rops, mode if mode != "closed" else "u", sizes, ins, src, ng)
     got, lgot = _run(tri, mode if mode != "closed" else "u", sizes, ins, src, ng)
     assert lgot.flops < lref.flops

@@ -24,12 +24,22 @@ def main():
     ea, eb = sysm.u_energies_tot()
     Fa, Fb, Ia, Ib, Iabab = cc_utils.uft_integrals(sysm, ea, eb, beta, MU_)
     sizes = ft_cc_equations._u_sizes(Fa, Fb)
-    p = ft_cc_equations.stanton_plan("u", sizes, -1.0, mirror=closed)
+    rows = closed and os.environ.get("KB200_MIRROR_ROWS", "auto")
+    plans = {}
+
+    def plan_for(ng):
+        mr = bool(closed) and (ng >= ft_cc_equations.MIRROR_ROWS_MIN_BATCH if rows == "auto"
+                               else rows == "1")
+        if mr not in plans:
+            plans[mr] = ft_cc_equations.stanton_plan("u", sizes, -1.0, mirror=closed, mirror_rows=mr)
+        return plans[mr]
+    p = plan_for(max(ngs))
     ints = ft_cc_equations._u_integral_slots(Fa, Fb, Ia, Ib, Iabab, dev,
                                              [s for s in p.inputs if _plan.is_integral_slot(s)])
     print("streams=%s group=%s closed=%s" % (os.environ.get("KB200_STREAMS", "3"),
                                               os.environ.get("KB200_GROUP", "8"), closed))
     for ng in ngs:
+        p = plan_for(ng)
         t = dict(ints)
         for s in p.inputs + p.outputs:
             if s not in t:
