@@ -161,6 +161,7 @@ def main():
                 econv=1e-11, tconv=1e-9)
     active_fixtures()
     variant_fixtures()
+    pueg_fixture()
 
 
 def active_fixtures():
@@ -210,8 +211,27 @@ def variant_fixtures():
     numpy.savez_compressed(os.path.join(HERE, "ueg7_variants.npz"), **out)
 
 
+def pueg_fixture():
+    """Spin-polarised UEG (kelvin/pueg_system.py) with the parameters of
+    kelvin/tests/test_ft_ccsd.py:157-170 (pinned there: Omega_cc = -0.001403909274)."""
+    from kelvin.pueg_system import PUEGSystem
+    T, mu = 0.1, 0.1
+    s = PUEGSystem(T, 2*numpy.pi/numpy.sqrt(1.0), 1.2, mu=mu, norb=7)
+    out = dict(N=s.N, mp1=s.get_mp1(), en=s.g_energies_tot(), eri=s.g_aint_tot(), f=s.g_fock_tot(),
+               mp1den=s.g_mp1_den(), fdd=s.g_fock_d_den(), fdt=s.g_fock_d_tot(numpy.arange(7.0)),
+               dmp1=s.g_d_mp1(numpy.arange(7.0)))
+    cc = ccsd(s, T=T, mu=mu, iprint=0, max_iter=50, damp=0.2, ngrid=10)
+    Etot, Ecc = cc.run()
+    cc.compute_ESN()
+    out.update(Etot=Etot, Ecc=Ecc, E=cc.E, S=cc.S, N_=cc.N, T1=cc.T1, T2=cc.T2)
+    numpy.savez_compressed(os.path.join(HERE, "pueg7.npz"), **out)
+    print("pueg", Etot, Ecc, cc.E, cc.S, cc.N)
+
+
 if __name__ == "__main__":
-    if len(sys.argv) > 1 and sys.argv[1] == "active":
+    if len(sys.argv) > 1 and sys.argv[1] == "pueg":
+        pueg_fixture()
+    elif len(sys.argv) > 1 and sys.argv[1] == "active":
         active_fixtures()
     elif len(sys.argv) > 1 and sys.argv[1] == "variants":
         variant_fixtures()

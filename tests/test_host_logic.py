@@ -174,3 +174,37 @@ def test_t0_is_zero_predicate():
     G2[0, 0] = 1e-3
     assert not ft_cc_equations.t0_is_zero(G2, (a, b))
     assert not ft_cc_equations.t0_is_zero(G[:1, :1], (a[:1], b[:1]))
+
+
+def test_pueg_system_matches_reference_fixture():
+    """kelvin_b200.pueg_system.PUEGSystem against the arrays of the unmodified
+    kelvin/pueg_system.py (tests/golden/make_golden.py pueg), and -- through the CPU oracle
+    loop -- against the grand potential the reference pins for it
+    (kelvin/tests/test_ft_ccsd.py:27,157-170: -0.001403909274 to 1e-8)."""
+    from kelvin_b200.pueg_system import PUEGSystem
+    from kelvin_oracle import cqc, driver as odrv
+    ref = numpy.load(os.path.join(HERE, "golden", "pueg7.npz"))
+    T, mu = 0.1, 0.1
+    s = PUEGSystem(T, 2*numpy.pi, 1.2, mu=mu, norb=7)
+    assert s.has_g() and not s.has_u() and s.verify(T, mu) and not s.verify(T, 0.2)
+    assert s.N == float(ref["N"])
+    assert abs(s.get_mp1() - float(ref["mp1"])) < 1e-14
+    assert numpy.abs(s.g_energies_tot() - ref["en"]).max() == 0.0
+    assert numpy.abs(s.g_aint_tot() - ref["eri"]).max() == 0.0
+    assert numpy.abs(s.g_fock_tot() - ref["f"]).max() < 1e-14
+    assert numpy.abs(s.g_mp1_den() - ref["mp1den"]).max() < 1e-14
+    assert numpy.abs(s.g_fock_d_den() - ref["fdd"]).max() < 1e-14
+    assert numpy.abs(s.g_fock_d_tot(numpy.arange(7.0)) - ref["fdt"]).max() < 1e-14
+    assert abs(s.g_d_mp1(numpy.arange(7.0)) - float(ref["dmp1"])) < 1e-14
+    # the solve (CPU oracle loop, parameters of the reference test)
+    beta, ng = 1.0/T, 10
+    en = s.g_energies_tot()
+    ti, g, G = odrv.simpsons(ng, beta)
+    F, I = odrv.ft_integrals(s, en, beta, mu)
+    D1, D2 = cqc.D1(en, en), cqc.D2(en, en)
+    T1, T2 = odrv.mp2_guess_g(F, I, D1, D2, ti, ng, G)
+    conv = {"econv": 1e-8, "tconv": 1e-5, "max_iter": 50, "damp": 0.2}
+    Ecc, T1, T2, hist = odrv.ft_cc_iter(T1, T2, F, I, D1, D2, g, G, beta, ng, ti, conv)
+    assert abs(Ecc - float(ref["Ecc"])) < 1e-12
+    assert abs(Ecc - (-0.001403909274)) < 1e-8
+    assert numpy.abs(T2 - ref["T2"]).max() < 1e-10
