@@ -13,7 +13,6 @@ Prints ONE JSON line (rank 0).
 """
 import argparse
 import json
-import math
 import os
 import subprocess
 import sys

@@ -6,7 +6,6 @@ Drop-in for kelvin/ft_cc_energy.py:7-32 (``ft_cc_energy``) and :35-72
 temporary; here each term is one streaming reduction kernel
 (kb200_energy_pair / kb200_dot_g) with a deterministic two-pass sum.
 """
-import numpy
 import torch
 
 from . import _lib, engine, plan as _plan

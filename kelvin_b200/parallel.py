@@ -14,8 +14,6 @@ One process per GPU (torch.distributed, backend nccl; gloo on CPU for the
 host-logic tests).  With world_size == 1 this is exactly the loop body of
 kelvin/cc_utils.py:274-299.
 """
-import math
-
 import numpy
 import torch
 
