@@ -59,12 +59,14 @@ def _u_sizes(Fa, Fb):
 MIRROR_ROWS_MIN_BATCH = int(os.environ.get("KB200_MIRROR_ROWS_MIN_BATCH", "4"))
 
 
-def stanton_plan(mode, sizes, fac=-1.0, mirror=False, mirror_rows=False):
+def stanton_plan(mode, sizes, fac=-1.0, mirror=False, mirror_rows=False, singlet=False):
     """mirror (u only): the closed-shell reduction of the program (plan.mirror_reduce): only the
     alpha-leading block of every alpha <-> beta pair is evaluated; mirror_rows: additionally
-    plan.mirror_outputs."""
+    plan.mirror_outputs; singlet: additionally plan.singlet_reduce (not used by the loops yet)."""
     mirror_rows = bool(mirror and mirror_rows)
-    key = ("stanton", mode, tuple(sorted(sizes.items(), key=str)), fac, bool(mirror), mirror_rows)
+    singlet = bool(mirror and singlet)
+    key = ("stanton", mode, tuple(sorted(sizes.items(), key=str)), fac, bool(mirror), mirror_rows,
+           singlet)
 
     def build():
         T = programs.tensor_defs()
@@ -79,6 +81,8 @@ def stanton_plan(mode, sizes, fac=-1.0, mirror=False, mirror_rows=False):
             rops = _plan.mirror_reduce(rops)
             ins = tuple(s for s in ins if _plan.mirror_rep(s) == s)
             outs = tuple(s for s in outs if _plan.mirror_rep(s) == s)
+            if singlet:
+                rops = _plan.singlet_reduce(rops)
             if mirror_rows:
                 rops = _plan.mirror_outputs(rops)
         rops = _plan.antisym_outputs(rops)

@@ -356,3 +356,25 @@ def test_antisymmetric_outputs_triangle(mode):
     assert lgot.flops < lref.flops
     for nm in outs:
         assert numpy.abs(got[nm] - ref[nm]).max() < 1e-12*numpy.abs(ref[nm]).max(), nm
+
+
+def test_singlet_reduced_program():
+    """plan.singlet_reduce: for closed-shell inputs that satisfy T2aa = T2ab - T2ab(a<->b) the
+    same-spin doubles residual is the antisymmetrised opposite-spin one, so the program that
+    evaluates only o1.a and o2.ab reproduces all three residual blocks."""
+    n, ng = 4, 2
+    ints, amps, _ = util.random_u_closed(n, ng, seed=61)
+    assert numpy.abs(amps[2] - (amps[3] - amps[3].transpose(0, 2, 1, 3, 4))).max() == 0.0
+    Fa, Fb, Ia, Ib, Iabab = ints
+    src = {"Fa": Fa, "Fb": Fb, "Ia": Ia, "Ib": Ib, "Iabab": Iabab}
+    sizes = {("v", "a"): n, ("o", "a"): n, ("v", "b"): n, ("o", "b"): n}
+    ins = {"t1.a": amps[0], "t2.aa": amps[2], "t2.ab": amps[3]}
+    red = plan.mirror_reduce(plan.expand(programs.stanton(-1.0), programs.tensor_defs(), "u"))
+    sing = plan.singlet_reduce(red)
+    assert not any(op.out[0].startswith(("rg.aaaa", "Woooo.aa", "Wvvvv.aa")) for op in sing)
+    ref, lref = _run(plan.antisym_outputs(red), "u", sizes, ins, src, ng)
+    got, lgot = _run(plan.antisym_outputs(plan.mirror_outputs(sing)), "u", sizes,
+                     {k: v for k, v in ins.items()}, src, ng)
+    assert lgot.flops < 0.85*lref.flops
+    for nm in ("o1.a", "o2.aa", "o2.ab"):
+        assert numpy.abs(got[nm] - ref[nm]).max() < 1e-12*numpy.abs(ref[nm]).max(), nm
