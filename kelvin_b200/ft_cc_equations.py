@@ -59,14 +59,22 @@ def _u_sizes(Fa, Fb):
 MIRROR_ROWS_MIN_BATCH = int(os.environ.get("KB200_MIRROR_ROWS_MIN_BATCH", "4"))
 
 
-def stanton_plan(mode, sizes, fac=-1.0, mirror=False, mirror_rows=False, singlet=False):
+# sum/difference form of the paired closed-shell ring contractions (plan.sumdiff_pairs): built and
+# CPU-tested, off until it has had its GPU parity run
+SUMDIFF = int(os.environ.get("KB200_SUMDIFF", "0"))
+
+
+def stanton_plan(mode, sizes, fac=-1.0, mirror=False, mirror_rows=False, singlet=False,
+                 sumdiff=None):
     """mirror (u only): the closed-shell reduction of the program (plan.mirror_reduce): only the
     alpha-leading block of every alpha <-> beta pair is evaluated; mirror_rows: additionally
-    plan.mirror_outputs; singlet: additionally plan.singlet_reduce (not used by the loops yet)."""
+    plan.mirror_outputs; singlet / sumdiff: additionally plan.singlet_reduce /
+    plan.sumdiff_pairs (neither is used by the loops yet)."""
     mirror_rows = bool(mirror and mirror_rows)
     singlet = bool(mirror and singlet)
+    sumdiff = bool(mirror and (SUMDIFF if sumdiff is None else sumdiff))
     key = ("stanton", mode, tuple(sorted(sizes.items(), key=str)), fac, bool(mirror), mirror_rows,
-           singlet)
+           singlet, sumdiff)
 
     def build():
         T = programs.tensor_defs()
@@ -83,6 +91,8 @@ def stanton_plan(mode, sizes, fac=-1.0, mirror=False, mirror_rows=False, singlet
             outs = tuple(s for s in outs if _plan.mirror_rep(s) == s)
             if singlet:
                 rops = _plan.singlet_reduce(rops)
+            if sumdiff:
+                rops = _plan.sumdiff_pairs(rops)
             if mirror_rows:
                 rops = _plan.mirror_outputs(rops)
         rops = _plan.antisym_outputs(rops)

@@ -324,6 +324,104 @@ def mirror_reduce(rops):
 
 
 # ---------------------------------------------------------------------------
+# closed shell: sum/difference form of paired contractions
+# ---------------------------------------------------------------------------
+SUMDIFF_PREFIX = "Qsd"
+
+
+def sumdiff_pairs(rops):
+    """Closed-shell (mirror_reduce'd) programs contain quartets of contractions
+
+        Xa += c A1 B1     Xa += c A2 B2     Xb += c A1 B2     Xb += c A2 B1
+
+    with identical index patterns (the W_ovvo.aaaa / W_ovvo.abab builds from Ia.oovv, Iabab.oovv
+    and t2x.aaaa, t2x.abba; the ring contractions rg.aaaa / rg.abab from t2.aa, t2.ab and those
+    two W blocks).  Since Xa + Xb gets c (A1+A2)(B1+B2) and Xa - Xb gets c (A1-A2)(B1-B2), two
+    contractions do the work of four:
+
+        Ap = A1+A2, Am = A1-A2, Bp = B1+B2, Bm = B1-B2        (elementwise)
+        S = c Ap Bp,  D = c Am Bm                              (2 contractions)
+        Xa += S/2 + D/2,  Xb += S/2 - D/2                      (elementwise)
+
+    This is the singlet/triplet channel decomposition of the closed-shell ring terms.  The
+    rewrite is placed where the last member of the quartet stood and is only done when nothing in
+    between reads Xa/Xb or writes an operand.  NOT enabled by default (KB200_SUMDIFF=1): built and
+    CPU-tested in round 1, waiting for its GPU parity run."""
+    ops = list(rops)
+    k = 0
+    while True:
+        quartet = _find_quartet(ops)
+        if quartet is None:
+            return ops
+        i11, i22, i12, i21 = quartet
+        o11, o22, o12 = ops[i11], ops[i22], ops[i12]
+        (A1, la), (B1, lb) = o11.ins
+        A2, B2 = o22.ins[0][0], o22.ins[1][0]
+        Xa, Xb = o11.out, o12.out
+        c, spin = o11.coef, o11.spin
+        tag = "%s%d" % (SUMDIFF_PREFIX, k)
+        k += 1
+        Ap, Am, Bp, Bm, S, D = [tag + x for x in ("Ap", "Am", "Bp", "Bm", "S", "D")]
+        lc = Xa[1]
+        new = [ROp((Ap, la), 1.0, [(A1, la)], spin), ROp((Ap, la), 1.0, [(A2, la)], spin),
+               ROp((Am, la), 1.0, [(A1, la)], spin), ROp((Am, la), -1.0, [(A2, la)], spin),
+               ROp((Bp, lb), 1.0, [(B1, lb)], spin), ROp((Bp, lb), 1.0, [(B2, lb)], spin),
+               ROp((Bm, lb), 1.0, [(B1, lb)], spin), ROp((Bm, lb), -1.0, [(B2, lb)], spin),
+               ROp((S, lc), c, [(Ap, la), (Bp, lb)], spin),
+               ROp((D, lc), c, [(Am, la), (Bm, lb)], spin),
+               ROp(Xa, 0.5, [(S, lc)], spin), ROp(Xa, 0.5, [(D, lc)], spin),
+               ROp(Xb, 0.5, [(S, lc)], spin), ROp(Xb, -0.5, [(D, lc)], spin)]
+        last = max(quartet)
+        drop = set(quartet)
+        ops = [op for j, op in enumerate(ops[:last]) if j not in drop] + new + ops[last + 1:]
+
+
+def _find_quartet(ops):
+    def sig(op):
+        return (op.coef, op.out[1], op.ins[0][1], op.ins[1][1])
+    cand = [j for j, op in enumerate(ops) if len(op.ins) == 2 and op.tri is None
+            and len(op.out[1]) == 4 and not op.out[0].startswith(SUMDIFF_PREFIX)
+            and len(set(op.ins[0][1]) & set(op.ins[1][1])) == 2]
+    for x, i11 in enumerate(cand):
+        o11 = ops[i11]
+        for i22 in cand[x + 1:]:
+            o22 = ops[i22]
+            if o22.out[0] != o11.out[0] or sig(o22) != sig(o11):
+                continue
+            A1, B1 = o11.ins[0][0], o11.ins[1][0]
+            A2, B2 = o22.ins[0][0], o22.ins[1][0]
+            if A1 == A2 or B1 == B2:
+                continue
+            i12 = i21 = None
+            for j in cand:
+                o = ops[j]
+                if o.out[0] == o11.out[0] or sig(o) != sig(o11):
+                    continue
+                pair = (o.ins[0][0], o.ins[1][0])
+                if pair == (A1, B2):
+                    i12 = j
+                elif pair == (A2, B1):
+                    i21 = j
+            if i12 is None or i21 is None or ops[i12].out[0] != ops[i21].out[0]:
+                continue
+            q = (i11, i22, i12, i21)
+            lo, hi = min(q), max(q)
+            Xs = {o11.out[0], ops[i12].out[0]}
+            srcs = {A1, A2, B1, B2}
+            ok = True
+            for j in range(lo, hi + 1):
+                if j in q:
+                    continue
+                o = ops[j]
+                if o.out[0] in srcs or any(sl in Xs for sl, _ in o.ins):
+                    ok = False
+                    break
+            if ok:
+                return q
+    return None
+
+
+# ---------------------------------------------------------------------------
 # closed-shell singlet: the same-spin doubles residual from the opposite-spin one
 # ---------------------------------------------------------------------------
 def singlet_reduce(rops, o1="o1.a", o2ab="o2.ab", o2aa="o2.aa"):
