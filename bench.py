@@ -5,14 +5,21 @@
   python bench.py --impl reference --steps K --warmup W    # CPU restatement of the reference path
 
 A "step" is ONE FT-CCSD amplitude iteration of the unrestricted UEG benchmark
-(bench/ueg_ft_ccsd_ESN33.py: 33 plane waves, T=0.5, mu=7, L=1.942, ngrid=10):
-per-grid-point Stanton residual for all grid points, exp-weighted time
-integration, damping + residual norms, energy.  For N > 1 the imaginary-time
-grid is sharded over ranks (strong scaling: the job is fixed).
-Prints ONE JSON line (rank 0).
+(bench/ueg_ft_ccsd_ESN33.py: 33 plane waves, T=0.5, mu=7, L=1.942, ngrid=10) exactly as the
+loop of kelvin/cc_utils.py:274-305 runs it: per-grid-point Stanton residual for all grid
+points, exp-weighted time integration, damping + residual norms, energy.  For N > 1 the
+per-grid-point programs are dealt out over the ranks (kelvin_b200/parallel.py; strong scaling:
+the job is fixed).  Prints ONE JSON line (rank 0).
+
+Besides the step the line carries the four timings the reference logs for a full calculation
+(kelvin/cc_utils.py:170-171,477-478; kelvin/ccsd.py:150-154,160-163): time to convergence of
+the amplitude solve, of the Lambda solve (and per iteration), RDM construction, derivative --
+measured on a complete `ccsd(...).run()` + `.compute_ESN()` through the public API, from host
+NumPy inputs to host results, which is also the end-to-end (`e2e`) number.
 """
 import argparse
 import json
+import logging
 import os
 import subprocess
 import sys
@@ -23,23 +30,27 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    # name: (norb, ngrid, Emax)
-    "ueg_ft_ccsd_ESN19": (19, 10, 30.0),
-    "ueg_ft_ccsd_ESN33": (33, 10, 30.0),
-    "ueg57_ng16": (57, 16, 30.0),
+    # name: (kind, size, ngrid, Emax)
+    "ueg_ft_ccsd_ESN19": ("ueg", 19, 10, 30.0),
+    "ueg_ft_ccsd_ESN33": ("ueg", 33, 10, 30.0),
+    "ueg57_ng16": ("ueg", 57, 16, 30.0),
+    "ueg81_ng24": ("ueg", 81, 24, 35.0),
+    "hubbard32_ng40": ("hubbard", 32, 40, None),
 }
 T_, MU_, L_ = 0.5, 7.0, 1.942
+HUB_T = 1.0
 
 
 def _traffic(workload, world):
     """DRAM bytes per launch of the dominant kernel from the committed ncu capture
-    (profiles/r1_traffic.json), or None when no capture matches this configuration."""
-    try:
-        t = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))["gemm_tab_kernel"]
-        if t["workload"] == workload and t["n_gpus"] == world:
-            return t["bytes_per_launch"]
-    except Exception:
-        pass
+    (profiles/r2_traffic.json, else r1), or None when no capture matches this configuration."""
+    for nm in ("r2_traffic.json", "r1_traffic.json"):
+        try:
+            t = json.load(open(os.path.join(ROOT, "profiles", nm)))["gemm_tab_kernel"]
+            if t["workload"] == workload and t["n_gpus"] == world:
+                return t["bytes_per_launch"]
+        except Exception:
+            pass
     return None
 
 
@@ -88,69 +99,141 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.rows), "reasons": sorted(reasons)}
 
 
+class LogTimes(logging.Handler):
+    """Collects the timings the reference logs (same strings: kelvin/cc_utils.py:170-171,
+    477-478; kelvin/ccsd.py:153,162) and counts the iteration lines."""
+    def __init__(self):
+        super().__init__(level=logging.INFO)
+        self.t = {}
+        self.lines = []
+
+    def emit(self, record):
+        msg = record.getMessage()
+        self.lines.append(msg)
+        for key, tag in (("ccsd_s", "Total CCSD time:"), ("lambda_s", "Total CCSD Lambda time:"),
+                         ("rdm_s", "RDM construction time:"), ("derivative_s", "Total derivative time:")):
+            if msg.startswith(tag):
+                self.t[key] = float(msg[len(tag):].split()[0])
+
+    def iterations(self):
+        """(amplitude iterations, Lambda iterations): ' %2d  E  res' lines have three fields,
+        ' %2d  res' lines two."""
+        nt = nl = 0
+        for m in self.lines:
+            f = m.split()
+            if f and f[0].isdigit():
+                if len(f) == 3:
+                    nt += 1
+                elif len(f) == 2:
+                    nl += 1
+        return nt, nl
+
+
 # ---------------------------------------------------------------------------
-def cpu_port_step(m, ng, sample_points, threads):
-    """Time the oracle's Sz-blocked CPU restatement of one residual evaluation
-    on `sample_points` grid points; returns seconds per full iteration
-    (scaled by ng/sample_points) and the sample description."""
+def host_threads():
+    """All host cores, pinned explicitly: torchrun exports OMP_NUM_THREADS=1 to its workers and
+    NumPy's BLAS only reads the variable when it is first imported."""
+    return os.cpu_count() or 1
+
+
+def set_blas_threads(n):
+    """-> (context manager limiting every BLAS/OpenMP pool to n threads, description)."""
+    from threadpoolctl import threadpool_limits, threadpool_info
+    ctx = threadpool_limits(limits=n)
+    pools = sorted({"%s:%s" % (p.get("internal_api"), p.get("num_threads")) for p in threadpool_info()})
+    return ctx, pools
+
+
+def cpu_port_point(m, ng, ints, amps, w, y):
+    """Oracle Sz-blocked residual at ONE grid point -> seconds."""
+    from kelvin_oracle import spin_blocked as sb
+    t0 = time.time()
+    sb.u_stanton_terms(*ints, (amps[0][y], amps[1][y]), (amps[2][y], amps[3][y], amps[4][y]), wrapped=w)
+    return time.time() - t0
+
+
+def cpu_port_setup(m, npts):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import numpy
-    from kelvin_oracle import spin_blocked as sb, driver as odrv
+    from kelvin_oracle import spin_blocked as sb
     import util
-    ints, amps = util.random_u(m, m, sample_points, seed=0, scale=0.05)
-    w = sb.wrap_integrals(*ints)
-    t0 = time.time()
-    outs = []
-    for y in range(sample_points):
-        outs.append(sb.u_stanton_terms(*ints, (amps[0][y], amps[1][y]),
-                                       (amps[2][y], amps[3][y], amps[4][y]), wrapped=w))
-    t_res = time.time() - t0
-    # integration of the sampled points (exp-weighted quadrature, kelvin/quadrature.py:292-317)
+    ints, amps = util.random_u(m, m, npts, seed=0, scale=0.05)
+    return ints, amps, sb.wrap_integrals(*ints)
+
+
+def cpu_port_integration(m, ng):
+    """NumPy exp-weighted integration of the three T2 blocks of one iteration
+    (kelvin/quadrature.py:292-317) -> seconds."""
+    import numpy
+    from kelvin_oracle import driver as odrv
     e = numpy.linspace(0.1, 5.0, m)
     D2 = e[:, None, None, None] + e[None, :, None, None] - e[None, None, :, None] - e[None, None, None, :]
     ti, g, G = odrv.simpsons(ng, 1.0/T_)
-    tb = numpy.broadcast_to(outs[0][3][None], (ng,) + outs[0][3].shape)
+    tb = numpy.zeros((ng,) + D2.shape)
     t0 = time.time()
     odrv.int_tbar(ng, tb, ti, D2, G)
-    t_int = (time.time() - t0)*3.0          # three T2 blocks
-    return t_res*ng/sample_points + t_int, t_res, t_int
+    return (time.time() - t0)*3.0
 
 
 def run_reference(args):
-    """--impl reference: the CPU restatement of the reference path (oracle port)
-    on all host threads; one step = a bounded sample scaled to one iteration."""
+    """--impl reference: the CPU restatement of the reference path (oracle Sz-blocked port,
+    NumPy/BLAS) on all host threads.  Each step is a BOUNDED SAMPLE of one amplitude iteration:
+    the residual at ONE grid point (random amplitudes of the benchmark's shape) scaled to the
+    ng grid points, plus the measured NumPy integration of the three doubles blocks."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import torch
-    norb, ng, _ = WORKLOADS[args.workload]
-    threads = os.cpu_count() or 1
-    torch.set_num_threads(threads)
-    sample = max(1, min(ng, args.cpu_points))
-    for _ in range(max(0, min(args.warmup, 1))):
-        cpu_port_step(norb, ng, 1, threads)
-    ts = []
-    for _ in range(max(1, min(args.steps, 3))):
-        s_iter, _, _ = cpu_port_step(norb, ng, sample, threads)
-        ts.append(s_iter)
+    threads = host_threads()
+    for v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[v] = str(threads)          # before NumPy is imported in this process
+    kind, norb, ng, _ = WORKLOADS[args.workload]
+    ctx, pools = set_blas_threads(threads)
+    with ctx:
+        ints, amps, w = cpu_port_setup(norb, 2)
+        t_int = cpu_port_integration(norb, ng)
+        W, K = max(0, args.warmup), max(1, args.steps)
+        for k in range(W):
+            cpu_port_point(norb, ng, ints, amps, w, k % 2)
+        ts = [cpu_port_point(norb, ng, ints, amps, w, k % 2)*ng + t_int for k in range(K)]
     val = sum(ts)/len(ts)
     line = {
         "impl": "reference", "metric": "ft_ccsd_seconds_per_amplitude_iteration", "value": val,
-        "unit": "s", "n_gpus": args.gpus, "steps": len(ts), "warmup": min(args.warmup, 1),
+        "unit": "s", "n_gpus": args.gpus, "steps": K, "warmup": W,
         "ms_per_step": val*1e3, "higher_is_better": False, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": args.workload, "norb": norb, "ngrid": ng, "formulation": "u"},
         "cpu_baseline": {"value": val, "unit": "s", "cores": threads, "kind": "port",
-                         "sample": "oracle Sz-blocked NumPy/BLAS residual on %d of %d grid points "
-                                   "(random amplitudes of the benchmark's shape) + NumPy "
-                                   "integration, scaled to one iteration" % (sample, ng)},
+                         "blas_pools": pools,
+                         "sample": "per step: oracle Sz-blocked NumPy/BLAS residual at 1 of %d grid "
+                                   "points (random amplitudes of the benchmark's shape; all of the "
+                                   "reference's work: no tau_0 shortcut, no closed-shell reduction) x %d "
+                                   "+ NumPy integration of the three T2 blocks (%.2f s, measured once)"
+                                   % (ng, ng, t_int)},
         "e2e": {"value": val, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
 
 
 # ---------------------------------------------------------------------------
+def build_system(workload):
+    import numpy
+    kind, size, ng, emax = WORKLOADS[workload]
+    if kind == "ueg":
+        from kelvin_b200.ueg_system import UEGSystem
+        return UEGSystem(T_, L_, emax, mu=MU_, norb=size, orbtype='u'), T_, MU_, ng, \
+            "UEG T=0.5 mu=7 L=1.942", dict(max_iter=50, damp=0.0)
+    from kelvin_b200.hubbard_system import HubbardSystem, Hubbard1D
+    L = size
+    hub = Hubbard1D(L, 1.0, 1.0, boundary='p')
+    Oa, Ob = numpy.zeros(L), numpy.zeros(L)
+    Oa[0::2] = 1.0
+    Ob[1::2] = 1.0
+    s = HubbardSystem(HUB_T, hub, numpy.einsum('i,j->ij', Oa, Oa), numpy.einsum('i,j->ij', Ob, Ob),
+                      mu=0.0)
+    return s, HUB_T, 0.0, ng, "Hubbard1D L=%d t=1 U=1 periodic, Neel densities, T=%g mu=0" % (L, HUB_T), \
+        dict(max_iter=80, econv=1e-11)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -159,8 +242,10 @@ def main():
     ap.add_argument("--impl", default="kb200", choices=["kb200", "reference"])
     ap.add_argument("--workload", default="ueg_ft_ccsd_ESN33", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-points", type=int, default=6,
-                    help="grid points sampled by the CPU baseline")
+                    help="grid points sampled by the CPU baseline of the kb200 arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-full-solve", action="store_true",
+                    help="skip the run() + compute_ESN() timings (e2e is then null)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -181,34 +266,47 @@ def main():
         dist.barrier()
     from kelvin_b200 import _lib, cc_utils, ft_utils, parallel, quadrature, ft_cc_equations
     from kelvin_b200 import plan as _plan
-    from kelvin_b200.ueg_system import UEGSystem
+    from kelvin_b200.ccsd import ccsd
     lib = _lib.load()
     dev = _lib.device()
 
-    norb, ng, emax = WORKLOADS[args.workload]
+    kind, norb, ng, emax = WORKLOADS[args.workload]
     W = max(args.warmup, 3)
     K = max(args.steps, 1)
-    beta = 1.0/T_
-    sysm = UEGSystem(T_, L_, emax, mu=MU_, norb=norb, orbtype='u')
+    sysm, Tsys, mu, ng, sysname, solve_kw = build_system(args.workload)
+    beta = 1.0/Tsys
     ea, eb = sysm.u_energies_tot()
     ti, g, G = quadrature.ft_quad(ng, beta, 'lin')
-    Fa, Fb, Ia, Ib, Iabab = cc_utils.uft_integrals(sysm, ea, eb, beta, MU_)
+    Fa, Fb, Ia, Ib, Iabab = cc_utils.uft_integrals(sysm, ea, eb, beta, mu)
     Ds = (ft_utils.D1(ea, ea), ft_utils.D1(eb, eb), ft_utils.D2(ea, ea),
           ft_utils.D2u(ea, eb, ea, eb), ft_utils.D2(eb, eb))
-    solver = parallel.TauShardedUCCSD(Fa, Fb, Ia, Ib, Iabab, Ds, g, G, beta, ng, ti)
 
     def mp2_guess():
         def rep(x):
             return (-x).expand(*((ng,) + (-1,)*x.dim())).contiguous()
         return [quadrature.int_tbar(ng, rep(x), ti, d, G) for x, d in
                 zip((Fa.vo, Fb.vo, Ia.vvoo, Iabab.vvoo, Ib.vvoo), Ds)]
-    guess = mp2_guess()
-    solver.set_amplitudes(*guess)
+    solver = cc_utils.UccStep(mp2_guess(), Fa, Fb, Ia, Ib, Iabab, Ds, g, G, beta, ng, ti)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def timed(fn, n):
+        """n calls of fn between barriers; device time (CUDA events), max over ranks, per call."""
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev0.record()
+        out = None
+        for _ in range(n):
+            out = fn()
+        ev1.record()
+        barrier()
+        tt = torch.tensor([ev0.elapsed_time(ev1)*1e-3], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())/n, out
 
     # ---- device-resident timing -----------------------------------------
     for _ in range(W):
@@ -218,106 +316,55 @@ def main():
     if sampler:
         sampler.start()
     lib.kb200_launch_count_reset()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    ev0.record()
-    for _ in range(K):
-        E, res = solver.step(0.0)
-    ev1.record()
-    barrier()
+    t_step, (E, res) = timed(lambda: solver.step(0.0), K)
     launches = int(lib.kb200_launch_count())
-    t_dev = ev0.elapsed_time(ev1)*1e-3
     clocks = sampler.stop() if sampler else None
-    tt = torch.tensor([t_dev], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    t_step = float(tt.item())/K
 
     # ---- auxiliary: the same step without the closed-shell reduction (every beta block
     # evaluated, all 32 block GEMMs per grid point), for a like-for-like flop count
     t_general = None
-    closed = bool(solver.closed_shell)
-    fc = torch.tensor([1.0 if closed else 0.0], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(fc, op=dist.ReduceOp.MAX)      # ranks without grid points report False
-    if fc.item() > 0:
-        solver.closed_shell = False
+    flags = solver.flags()
+    closed = bool(flags["closed_shell"])
+    if closed:
+        solver.set_flags({"t0": flags["t0"], "closed_shell": False, "singlet": False,
+                          "antisym": flags["antisym"]})
         for _ in range(2):
             solver.step(0.0)
-        barrier()
-        ev0.record()
-        for _ in range(K):
-            solver.step(0.0)
-        ev1.record()
-        barrier()
-        tg = torch.tensor([ev0.elapsed_time(ev1)*1e-3], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(tg, op=dist.ReduceOp.MAX)
-        t_general = float(tg.item())/K
-        solver.closed_shell = closed
+        t_general, _ = timed(lambda: solver.step(0.0), max(3, K//4))
+        solver.set_flags(flags)
         solver.step(0.0)
-
-    # ---- optional per-phase breakdown of the sharded step (diagnostics, outside the timed region)
-    phases = None
-    if os.environ.get("KB200_PHASES"):
-        solver.phase_ms = {}
-        for _ in range(3):
-            solver.step(0.0)
-        phases = {k: v/3.0 for k, v in solver.phase_ms.items()}
-        solver.phase_ms = None
-        print("rank %d phases (ms/step): %s" % (rank, json.dumps(phases)), flush=True)
-
-    # ---- end-to-end: host amplitudes in pinned memory -> device -> iterate -> E,res to host
-    host = [x.cpu().pin_memory() for x in solver.old]
-    h2d = sum(x.numel()*8 for x in host)
-
-    def e2e_step():
-        # the host copy is the solver's own state: whether T[0] vanishes is already known
-        solver.set_local_amplitudes([x.to(dev, non_blocking=True) for x in host],
-                                    t0_zero=solver.t0_zero, closed_shell=solver.closed_shell)
-        return solver.step(0.0)
-    for _ in range(2):
-        e2e_step()
-    barrier()
-    ev0.record()
-    for _ in range(K):
-        Ee, rese = e2e_step()
-    ev1.record()
-    barrier()
-    tt[0] = ev0.elapsed_time(ev1)*1e-3
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    t_e2e = float(tt.item())/K
 
     # ---- live roofline of the dominant kernel (DMMA contraction GEMM) --------
     roof = None
     if rank == 0:
-        # the plan the step runs (closed-shell reduction when the inputs allow it), on the grid
-        # points the step evaluates (without tau_0 when the shortcut applies)
-        skip = 1 if (solver.t0_zero and solver.nloc > 1) else 0
-        nloc = solver.nloc - skip
-        mrows = closed and nloc >= ft_cc_equations.MIRROR_ROWS_MIN_BATCH
-        p = ft_cc_equations.stanton_plan("u", ft_cc_equations._u_sizes(Fa, Fb), -1.0,
-                                         mirror=closed, mirror_rows=mrows)
+        # the plan the step runs on this rank's own grid points
+        y0 = 1 if (flags["t0"] and ng > 1) else 0
+        rows = ft_cc_equations.needed_rows(ng, y0)
+        a, b = rows[0]
+        nloc = b - a
+        p = ft_cc_equations.stanton_plan(
+            "u", ft_cc_equations._u_sizes(Fa, Fb), -1.0, mirror=closed,
+            mirror_rows=nloc >= ft_cc_equations.MIRROR_ROWS_MIN_BATCH,
+            singlet=flags["singlet"], antisym=flags["antisym"])
         t = ft_cc_equations._u_integral_slots(
             Fa, Fb, Ia, Ib, Iabab, dev, [s for s in p.inputs if _plan.is_integral_slot(s)])
         for nm, x in zip(("t1.a", "t1.b", "t2.aa", "t2.ab", "t2.bb"), solver.old):
             if nm in p.shapes:
-                t[nm] = x[skip:]
+                t[nm] = x[a:b]
         for nm, x in zip(("o1.a", "o1.b", "o2.aa", "o2.ab", "o2.bb"), solver.old):
             if nm in p.shapes:
-                t[nm] = torch.empty_like(x[skip:])
+                t[nm] = torch.empty_like(x[a:b])
         tim = []
         for _ in range(3):
             tim = []
             p.run(t, nloc, timings=tim)
-        gemm = [(fl, dt) for kind, fl, dt, meta in tim if kind == 0]
+        gemm = [(fl, dt) for kind_, fl, dt, meta in tim if kind_ == 0]
         # the dominant kernel: every launch of the big-tile contraction kernel
         # (gemm_tab_kernel<4,4,32,32,...>: the m^6 block GEMMs -- full, half-K, half-row and
         # triangular members -- and the diagonal passes grouped with them); a launch group's time
         # is split over its members in proportion to their flops, so sums over members = sums
         # over launches
-        big = [(fl, dt, meta) for kind, fl, dt, meta in tim if kind == 0 and meta[4] in (0, 2, 3)]
+        big = [(fl, dt, meta) for kind_, fl, dt, meta in tim if kind_ == 0 and meta[4] in (0, 2, 3)]
         fl_big = sum(x[0] for x in big)
         dt_big = sum(x[1] for x in big)
         n_launch = max(1, sum(1 for x in big if x[2][8] >= 1))      # group leaders
@@ -341,83 +388,124 @@ def main():
                 "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach/peak,
                 "peak_source": "cuBLAS DGEMM 8192^3 measured in this run (MEASURED_PEAKS.json has no FP64 figure)",
                 "launches_per_step": n_launch, "contractions_per_step": len(big),
-                "m6_block_gemms_per_step": n_m6,
+                "m6_block_gemms_per_step": n_m6, "grid_points_in_launch": nloc,
                 "flops_per_launch": fl_big/n_launch, "avg_launch_s": dt_big/n_launch,
                 "gemm_share_of_plan": sum(d for _, d in gemm)/max(1e-12, sum(x[2] for x in tim)),
                 "plan_s": sum(x[2] for x in tim),
                 "traffic": _traffic(args.workload, world)}
+        t = None
+    if world > 1:
+        dist.barrier()
 
-    # ---- auxiliary: one Lambda iteration (reverse sweep, intermediates cached), N = 1 only
-    lam = None
-    if world == 1:
-        Ts = solver.old
-        Ls = ft_cc_equations.uccsd_lambda_guess(Fa, Fb, Ia, Ib, Iabab, Ts[0], Ts[1], beta, ng)
-
-        def lam_step(Lc):
-            return ft_cc_equations.uccsd_lambda_opt(Fa, Fb, Ia, Ib, Iabab, *Ts, *Lc, *Ds, ti, ng, g,
-                                                    G, beta, closed_shell=closed)
-        for _ in range(2):
-            Ls = lam_step(Ls)
-        torch.cuda.synchronize()
-        ev0.record()
-        nl = 3
-        for _ in range(nl):
-            Ls = lam_step(Ls)
-        ev1.record()
-        torch.cuda.synchronize()
-        lam = ev0.elapsed_time(ev1)*1e-3/nl
-        del Ls
+    # ---- the full calculation through the public API: run() + compute_ESN() ----------
+    full = None
+    if not args.no_full_solve:
+        h2d = sum(int(numpy.asarray(x).nbytes) for x in sysm.u_aint_tot()) + \
+            sum(int(numpy.asarray(x).nbytes) for x in sysm.u_fock_tot())
+        lt = LogTimes()
+        root = logging.getLogger()
+        old_level = root.level
+        root.setLevel(logging.INFO)
+        root.addHandler(lt)
+        try:
+            def solve():
+                cc = ccsd(sysm, T=Tsys, mu=mu, iprint=0, ngrid=ng, **solve_kw)
+                out = cc.run()
+                return cc, out
+            solve()                              # plans compiled, caches warm
+            lt.lines, lt.t = [], {}
+            barrier()
+            t0 = time.time()
+            cc, (Etot, Ecc) = solve()
+            torch.cuda.synchronize()
+            t_run = time.time() - t0
+            nt, _ = lt.iterations()
+            full = {"omega_tot": Etot, "omega_cc": Ecc, "t_iterations": nt,
+                    "time_to_convergence_s": lt.t.get("ccsd_s"), "run_wall_s": t_run}
+            if kind == "ueg" and norb <= 57:
+                barrier()
+                t0 = time.time()
+                cc.compute_ESN()
+                torch.cuda.synchronize()
+                full["compute_ESN_wall_s"] = time.time() - t0
+                _, nl = lt.iterations()
+                full.update({"lambda_iterations": nl, "lambda_time_to_convergence_s": lt.t.get("lambda_s"),
+                             "lambda_s_per_iteration": (lt.t["lambda_s"]/nl if nl and "lambda_s" in lt.t else None),
+                             "rdm_s": lt.t.get("rdm_s"), "derivative_s": lt.t.get("derivative_s"),
+                             "E": cc.E, "S": cc.S, "N": cc.N})
+            tt = torch.tensor([full["run_wall_s"]], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            full["run_wall_s"] = float(tt.item())
+            full["h2d_bytes"] = h2d
+            cc = None
+        finally:
+            root.removeHandler(lt)
+            root.setLevel(old_level)
 
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        threads = os.cpu_count() or 1
-        torch.set_num_threads(threads)
-        s_iter, t_res, t_int = cpu_port_step(norb, ng, args.cpu_points, threads)
-        cpu = {"value": s_iter, "unit": "s", "cores": threads, "kind": "port",
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and kind == "ueg" and norb <= 33:
+        threads = host_threads()
+        ctx, pools = set_blas_threads(threads)
+        with ctx:
+            npt = max(1, min(ng, args.cpu_points))
+            ints, amps, w = cpu_port_setup(norb, npt)
+            t_res = sum(cpu_port_point(norb, ng, ints, amps, w, y) for y in range(npt))
+            t_int = cpu_port_integration(norb, ng)
+        s_iter = t_res*ng/npt + t_int
+        cpu = {"value": s_iter, "unit": "s", "cores": threads, "kind": "port", "blas_pools": pools,
                "sample": "oracle Sz-blocked NumPy/BLAS residual on %d of %d grid points (%.1f s) + "
                          "NumPy integration (%.1f s), scaled to one iteration" %
-                         (args.cpu_points, ng, t_res, t_int)}
+                         (npt, ng, t_res, t_int)}
 
-    # rank 0 owns tau_0 (contiguous blocks from y = 0)
-    t0 = bool(solver.t0_zero) if rank == 0 else None
     if rank == 0:
         fl = algorithmic_flops(norb, ng)
         # tau_0 shortcut: T[0] = 0 identically (row 0 of G vanishes), so T̄[0] = drivers and that
         # grid point is not evaluated (SURVEY 8d allows it; the reference's own pointwise solver
         # does the same, kelvin/cc_utils.py:205-208).  TFLOP/s is quoted on the EXECUTED flops.
-        npts = ng - 1 if t0 else ng
-        fl_exec = algorithmic_flops(norb, npts)
-        if closed:
-            # executed 2*M*N*K of the reduced program (all contraction classes)
-            pc = ft_cc_equations.stanton_plan(
-                "u", ft_cc_equations._u_sizes(Fa, Fb), -1.0, mirror=True,
-                mirror_rows=npts >= ft_cc_equations.MIRROR_ROWS_MIN_BATCH)
-            fl_exec = float(pc.flops_per_point)*npts
+        t0f = bool(flags["t0"])
+        npts = ng - 1 if t0f else ng
+        pc = ft_cc_equations.stanton_plan(
+            "u", ft_cc_equations._u_sizes(Fa, Fb), -1.0, mirror=closed,
+            mirror_rows=closed and npts >= ft_cc_equations.MIRROR_ROWS_MIN_BATCH,
+            singlet=flags["singlet"], antisym=flags["antisym"])
+        fl_exec = float(pc.flops_per_point)*npts
+        e2e = None
+        if full is not None and full.get("t_iterations"):
+            nt = full["t_iterations"]
+            e2e = {"value": full["run_wall_s"]/nt, "unit": "s",
+                   "h2d_bytes_per_step": full["h2d_bytes"]//nt, "d2h_bytes_per_step": 160,
+                   "what": "ccsd(system, T, mu, ngrid).run() wall time / iterations: host NumPy "
+                           "integrals -> device, dressing, MP2 guess, symmetry checks on the device, "
+                           "%d iterations to convergence, energies back on the host" % nt}
         line = {
             "metric": "ft_ccsd_seconds_per_amplitude_iteration", "value": t_step, "unit": "s",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": t_step*1e3,
             "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": args.workload, "system": "UEG T=0.5 mu=7 L=1.942",
+            "config": {"workload": args.workload, "system": sysname,
                        "norb": norb, "ngrid": ng, "formulation": "u", "damp": 0.0,
-                       "parallelism": "tau%d" % world,
+                       "parallelism": "tau%d%s" % (world, "+hybrid" if world > 1 and parallel.hybrid_enabled() else ""),
                        "cache": "working set (amplitudes+integrals+intermediates) >> 126 MB L2",
                        "algorithmic_tflop_per_step": fl/1e12,
-                       "tau0_shortcut": t0, "tau_points_evaluated": ng - 1 if t0 else ng,
-                       "closed_shell_reduction": closed,
+                       "tau0_shortcut": t0f, "tau_points_evaluated": npts,
+                       "closed_shell_reduction": closed, "singlet_reduction": bool(flags["singlet"]),
                        "general_path_s_per_iteration": t_general,
                        "executed_tflop_per_step": fl_exec/1e12,
                        "fp64_tflops_whole_step": fl_exec/t_step/1e12,
-                       "published_cpu_s_per_iter_unknown_hw": 321.4 if norb == 33 else None,
-                       "lambda_s_per_iteration": lam,
+                       "published_cpu_s_per_iter_unknown_hw": 321.4 if (kind == "ueg" and norb == 33) else None,
                        "lambda_algorithmic_tflop": ng*92.0*norb**6/1e12},
-            "e2e": {"value": t_e2e, "unit": "s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 160},
+            "e2e": e2e,
+            "full_calculation": full,
             "gpu_launches": launches,
             "clocks": clocks,
             "roofline": roof,
             "cpu_baseline": cpu,
             "last_energy": E, "last_residual": res,
         }
+        if full is not None:
+            for k in ("time_to_convergence_s", "lambda_s_per_iteration", "rdm_s", "derivative_s"):
+                line[k] = full.get(k)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -106,6 +106,30 @@ int kb200_int_tbar_rows(int ng, int64_t n, const double* tbar, const double* D,
                         const double* ti, const double* G, double* out, int y0, int y1,
                         int mode, void* stream);
 
+/* As kb200_int_tbar_rows with explicit row strides (elements): tbar row x starts at
+ * tbar + x*tstride, out row y - y0 at out + (y - y0)*ostride -- the blocks of several tensors may
+ * share one (ng, Ntot) exchange buffer (tau-sharded runs all-gather ONE buffer). */
+int kb200_int_tbar_strided(int ng, int64_t n, const double* tbar, int64_t tstride,
+                           const double* D, const double* ti, const double* G, double* out,
+                           int64_t ostride, int y0, int y1, int mode, void* stream);
+
+/* The fused amplitude update of one block.  Replaces, in ONE pass over tbar and the amplitudes,
+ * kelvin/quadrature.py:292-317 (integration), kelvin/cc_utils.py:278-295 (residual norms,
+ * damping) and the block's term of kelvin/ft_cc_energy.py:35-72:
+ *   new[y]  = sum_x G[y,x] w(y,x) tbar[x]                      (never stored)
+ *   out4[0] = ||new - amp||^2, out4[1] = ||amp||^2 (before), amp <- alpha*amp + (1-alpha)*new,
+ *   out4[2] = ||amp||^2 (after),
+ *   out4[3] = sum_y g[y] sum_p (c2*amp[y,p] + c11*T1x[y,a,i]*T1y[y,b,j]) * W[p]   (W == NULL: 0)
+ * over rows y0 <= y < y1; p = (a,b,i,j) over (n/(nvb*noa*nob), nvb, noa, nob) when T1x/T1y are
+ * given (row strides t1xs/t1ys; they must already hold the UPDATED singles).  `scratch` needs
+ * kb200_reduce_scratch_doubles() doubles. */
+int kb200_int_tbar_update(int ng, int64_t n, const double* tbar, int64_t tstride,
+                          const double* D, const double* ti, const double* G, double* amp,
+                          int64_t astride, int y0, int y1, double alpha, const double* W,
+                          const double* T1x, const double* T1y, int64_t t1xs, int64_t t1ys,
+                          int nvb, int noa, int nob, const double* g, double c2, double c11,
+                          double* out4, double* scratch, int mode, void* stream);
+
 /* Replaces kelvin/quadrature.py:320-345 (int_L1, int_L2):
  *   out[s,q] = (1/g[s]) sum_y g[y]*G[y,s]*w(s,y,q)*L[y,q],
  *   w = exp(D[perm(q)]*(ti[s]-ti[y])) for y>=s, 1 otherwise.
@@ -119,6 +143,11 @@ int kb200_int_L(int ng, const int32_t dims[4] /*host*/, const int64_t dstride[4]
 int kb200_int_L_rows(int ng, const int32_t dims[4] /*host*/, const int64_t dstride[4] /*host*/,
                      const double* L, const double* D, const double* ti, const double* g,
                      const double* G, double* out, int s0, int s1, int mode, void* stream);
+
+int kb200_int_L_strided(int ng, const int32_t dims[4] /*host*/, const int64_t dstride[4] /*host*/,
+                        const double* L, int64_t lstride, const double* D, const double* ti,
+                        const double* g, const double* G, double* out, int64_t ostride, int s0,
+                        int s1, int mode, void* stream);
 
 /* ------------------------------------------------------------------------
  * Energy functional pieces.  Replaces kelvin/ft_cc_energy.py:7-32,35-72.
@@ -141,6 +170,12 @@ int kb200_dot_g(int ng, int64_t n, const double* X, const double* F, const doubl
  * then old <- alpha*old+(1-alpha)*new, out[2]=||old||^2 (after update). */
 int kb200_damp_norms(int64_t n, double* old, const double* neu, double alpha,
                      double* out3, double* scratch, void* stream);
+
+/* The same over ng grid points of n elements with row strides (elements): the blocks of one
+ * quantity may be column ranges of a wider (ng, Ntot) exchange buffer. */
+int kb200_damp_norms_rows(int ng, int64_t n, double* old, int64_t ostride, const double* neu,
+                          int64_t nstride, double alpha, double* out3, double* scratch,
+                          void* stream);
 
 /* ------------------------------------------------------------------------
  * Integral dressing.  Replaces kelvin/cc_utils.py:584-601,713-775:

@@ -22,6 +22,8 @@ EXPORTS = (
     "kb200_reduce_scratch_doubles", "kb200_energy_pair", "kb200_dot_g", "kb200_damp_norms",
     "kb200_dress4", "kb200_dress2", "kb200_gather4", "kb200_scatter4_add", "kb200_gsum", "kb200_scale_by", "kb200_dot_keep",
     "kb200_max_absdiff", "kb200_set_plan_streams",
+    "kb200_int_tbar_strided", "kb200_int_tbar_update", "kb200_int_L_strided",
+    "kb200_damp_norms_rows",
 )
 
 
@@ -60,9 +62,19 @@ def load():
     lib.kb200_int_L_rows.argtypes = [ctypes.c_int, ctypes.POINTER(i32), ctypes.POINTER(i64),
                                      vp, vp, vp, vp, vp, vp, ctypes.c_int, ctypes.c_int,
                                      ctypes.c_int, vp]
+    lib.kb200_int_tbar_strided.argtypes = [ctypes.c_int, i64, vp, i64, vp, vp, vp, vp, i64,
+                                           ctypes.c_int, ctypes.c_int, ctypes.c_int, vp]
+    lib.kb200_int_tbar_update.argtypes = [ctypes.c_int, i64, vp, i64, vp, vp, vp, vp, i64,
+                                          ctypes.c_int, ctypes.c_int, dbl, vp, vp, vp, i64, i64,
+                                          ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, dbl, dbl,
+                                          vp, vp, ctypes.c_int, vp]
+    lib.kb200_int_L_strided.argtypes = [ctypes.c_int, ctypes.POINTER(i32), ctypes.POINTER(i64),
+                                        vp, i64, vp, vp, vp, vp, vp, i64, ctypes.c_int,
+                                        ctypes.c_int, ctypes.c_int, vp]
     lib.kb200_energy_pair.argtypes = [ctypes.c_int] * 5 + [vp, vp, vp, vp, vp, dbl, dbl, vp, vp, vp]
     lib.kb200_dot_g.argtypes = [ctypes.c_int, i64, vp, vp, vp, vp, vp, vp]
     lib.kb200_damp_norms.argtypes = [i64, vp, vp, dbl, vp, vp, vp]
+    lib.kb200_damp_norms_rows.argtypes = [ctypes.c_int, i64, vp, i64, vp, i64, dbl, vp, vp, vp]
     lib.kb200_dress4.argtypes = [ctypes.POINTER(i32), vp, vp, vp, vp, vp, vp, vp]
     lib.kb200_dress2.argtypes = [ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, vp, vp]
     lib.kb200_gather4.argtypes = [ctypes.POINTER(i32), ctypes.POINTER(i64), vp,
@@ -107,6 +119,21 @@ def as_dev(x, dev=None):
     if isinstance(x, torch.Tensor):
         return x.to(device=dev, dtype=torch.float64).contiguous()
     return torch.as_tensor(x, dtype=torch.float64).to(dev).contiguous()
+
+
+def as_dev_rows(x, dev=None):
+    """As as_dev, but a device tensor whose grid points (leading axis) are rows of a wider
+    buffer is taken as it is: every kernel that walks the grid takes a row stride."""
+    dev = dev or device()
+    if isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == torch.float64 and x.dim() >= 1 \
+            and x.shape[0] > 0 and x[0].is_contiguous() \
+            and (x.shape[0] == 1 or x.stride(0) >= x[0].numel()):
+        return x
+    return as_dev(x, dev)
+
+
+def row_stride(x):
+    return int(x.stride(0)) if x.shape[0] > 1 else int(x[0].numel())
 
 
 _const_cache = {}

@@ -212,10 +212,22 @@ class _Stats(object):
         self.dev = dev
 
     def damp(self, k, old, new, alpha):
+        """old <- alpha*old + (1-alpha)*new with the three norms; the grid points (leading axis)
+        of either tensor may be rows of a wider buffer."""
         lib = _lib.load()
-        rc = lib.kb200_damp_norms(old.numel(), _lib.ptr(old), _lib.ptr(new), alpha,
-                                  self.buf.data_ptr() + 24*k, _lib.ptr(_lib.reduce_scratch(self.dev)),
-                                  _lib.stream_ptr())
+        out = self.buf.data_ptr() + 24*k
+        scr = _lib.ptr(_lib.reduce_scratch(self.dev))
+        if old.is_contiguous() and new.is_contiguous():
+            rc = lib.kb200_damp_norms(old.numel(), _lib.ptr(old), _lib.ptr(new), alpha, out, scr,
+                                      _lib.stream_ptr())
+        else:
+            if old.dim() < 2 or tuple(old.shape) != tuple(new.shape) \
+                    or not old[0].is_contiguous() or not new[0].is_contiguous():
+                raise Exception("damp: blocks must be contiguous within a grid point")
+            rc = lib.kb200_damp_norms_rows(old.shape[0], old[0].numel(), _lib.ptr(old),
+                                           _lib.row_stride(old), _lib.ptr(new),
+                                           _lib.row_stride(new), alpha, out, scr,
+                                           _lib.stream_ptr())
         _lib.check(rc, "kb200_damp_norms")
 
     def read(self):
@@ -229,7 +241,50 @@ def _norm(x):
     return math.sqrt(st.read()[0, 1])
 
 
-def ft_cc_iter(method, T1old, T2old, F, I, D1, D2, g, G, beta, ng, ti, iprint, conv_options):
+class GccStep(object):
+    """State and ONE damped iteration of the FT-CCSD fixed-point loop in general spin orbitals:
+    the loop body of kelvin/cc_utils.py:131-160.  Residual plan (sharded over the ranks when
+    torch.distributed is up), then per block ONE fused pass: integration, residual norm,
+    damping, new norm, energy term (kb200_int_tbar_update)."""
+
+    def __init__(self, T1old, T2old, F, I, D1, D2, g, G, beta, ng, ti):
+        dev = self.dev = _lib.device()
+        self.F, self.I, self.g, self.G, self.beta, self.ng, self.ti = F, I, g, G, beta, ng, ti
+        self.D1, self.D2 = _lib.as_dev(D1, dev), _lib.as_dev(D2, dev)
+        self.T1 = _lib.as_dev(T1old, dev).clone()
+        self.T2 = _lib.as_dev(T2old, dev).clone()
+        self.nl1 = _norm(self.T1) + 0.1
+        self.nl2 = _norm(self.T2) + 0.1
+        self.Iabij = ft_cc_energy.oovv_to_abij(I.oovv)
+        self.fai = _lib.as_dev(F.ov, dev).t().contiguous()
+        self.stats = torch.zeros(8, dtype=torch.float64, device=dev)
+        # T[0] == 0 is preserved by the update (row 0 of G vanishes): skip that grid point
+        self.t0 = ft_cc_equations.t0_is_zero(G, (self.T1, self.T2))
+        # a caller-supplied guess need not be antisymmetric: then the full sums are evaluated
+        self.antisym = ft_cc_equations.is_antisymmetric(self.T2)
+
+    def step(self, alpha):
+        """-> (E, res1 + res2) as logged by the reference."""
+        ng = self.ng
+        b1, b2 = ft_cc_equations.ccsd_stanton_bar(self.F, self.I, self.T1, self.T2,
+                                                  t0_zero=self.t0, antisym=self.antisym)
+        sp = self.stats.data_ptr()
+        quadrature.int_tbar_update(ng, b1, self.ti, self.D1, self.G, self.T1, alpha, sp,
+                                   g=self.g, W=self.fai, c2=1.0)
+        quadrature.int_tbar_update(ng, b2, self.ti, self.D2, self.G, self.T2, alpha, sp + 32,
+                                   g=self.g, W=self.Iabij, T1x=self.T1, T1y=self.T1,
+                                   c2=0.25, c11=0.5)
+        s = self.stats.cpu().numpy().reshape(2, 4)
+        res1 = math.sqrt(s[0, 0])/self.nl1
+        res2 = math.sqrt(s[1, 0])/self.nl2
+        self.nl1 = math.sqrt(s[0, 2]) + 0.1
+        self.nl2 = math.sqrt(s[1, 2]) + 0.1
+        E = float(s[0, 3] + s[1, 3])/self.beta
+        return E, res1 + res2
+
+
+def ft_cc_iter(method, T1old, T2old, F, I, D1, D2, g, G, beta, ng, ti, iprint, conv_options,
+               flags_out=None):
     """Fixed-point FT-CCSD loop, general spin orbitals (kelvin/cc_utils.py:111-173)."""
     tbeg = time.time()
     dev = _lib.device()
@@ -240,30 +295,41 @@ def ft_cc_iter(method, T1old, T2old, F, I, D1, D2, g, G, beta, ng, ti, iprint, c
     alpha = conv_options["damp"]
     i = 0
     Eold = 888888888.888888888
-    T1old = _lib.as_dev(T1old, dev).clone()
-    T2old = _lib.as_dev(T2old, dev).clone()
-    nl1 = _norm(T1old) + 0.1
-    nl2 = _norm(T2old) + 0.1
-    Iabij = ft_cc_energy.oovv_to_abij(I.oovv)
-    st = _Stats(2, dev)
-    # T[0] == 0 is preserved by the update (row 0 of G vanishes): skip that grid point
-    t0 = ft_cc_equations.t0_is_zero(G, (T1old, T2old))
-    while i < max_iter and not converged:
-        T1, T2 = form_new_ampl(method, F, I, T1old, T2old, D1, D2, ti, ng, G, t0_zero=t0)
-        # residuals, damping and new norms in one pass per tensor
-        st.damp(0, T1old, T1, alpha)
-        st.damp(1, T2old, T2, alpha)
-        E = ft_cc_energy.ft_cc_energy(T1old, T2old, F.ov, I.oovv, g, beta, eri_abij=Iabij)
-        s = st.read()
-        res1 = math.sqrt(s[0, 0])/nl1
-        res2 = math.sqrt(s[1, 0])/nl2
-        nl1 = math.sqrt(s[0, 2]) + 0.1
-        nl2 = math.sqrt(s[1, 2]) + 0.1
-        logging.info(' %2d  %.10f   %.4E' % (i + 1, E, res1 + res2))
-        i = i + 1
-        if numpy.abs(E - Eold) < ethresh and res1 + res2 < tthresh:
-            converged = True
-        Eold = E
+    if method == "CCSD":
+        st = GccStep(T1old, T2old, F, I, D1, D2, g, G, beta, ng, ti)
+        if flags_out is not None:
+            flags_out.update({"t0": st.t0, "antisym": st.antisym})
+        while i < max_iter and not converged:
+            E, res = st.step(alpha)
+            logging.info(' %2d  %.10f   %.4E' % (i + 1, E, res))
+            i = i + 1
+            if numpy.abs(E - Eold) < ethresh and res < tthresh:
+                converged = True
+            Eold = E
+        T1old, T2old = st.T1, st.T2
+    else:
+        T1old = _lib.as_dev(T1old, dev).clone()
+        T2old = _lib.as_dev(T2old, dev).clone()
+        nl1 = _norm(T1old) + 0.1
+        nl2 = _norm(T2old) + 0.1
+        Iabij = ft_cc_energy.oovv_to_abij(I.oovv)
+        st = _Stats(2, dev)
+        while i < max_iter and not converged:
+            T1, T2 = form_new_ampl(method, F, I, T1old, T2old, D1, D2, ti, ng, G)
+            # residuals, damping and new norms in one pass per tensor
+            st.damp(0, T1old, T1, alpha)
+            st.damp(1, T2old, T2, alpha)
+            E = ft_cc_energy.ft_cc_energy(T1old, T2old, F.ov, I.oovv, g, beta, eri_abij=Iabij)
+            s = st.read()
+            res1 = math.sqrt(s[0, 0])/nl1
+            res2 = math.sqrt(s[1, 0])/nl2
+            nl1 = math.sqrt(s[0, 2]) + 0.1
+            nl2 = math.sqrt(s[1, 2]) + 0.1
+            logging.info(' %2d  %.10f   %.4E' % (i + 1, E, res1 + res2))
+            i = i + 1
+            if numpy.abs(E - Eold) < ethresh and res1 + res2 < tthresh:
+                converged = True
+            Eold = E
     if not converged:
         logging.warning("{} did not converge!".format(method))
     tend = time.time()
@@ -271,12 +337,90 @@ def ft_cc_iter(method, T1old, T2old, F, I, D1, D2, g, G, beta, ng, ti, iprint, c
     return Eold, T1old, T2old
 
 
+class UccStep(object):
+    """State and ONE damped iteration of the unrestricted FT-CCSD fixed-point loop: the loop body
+    of kelvin/cc_utils.py:274-305.  Decides once per solve (device checks of the inputs) which
+    reductions of the program apply: tau_0 shortcut, closed shell (alpha == beta), singlet
+    (T2aa = T2ab - T2ab(a<->b)), permutational antisymmetry of the same-spin doubles."""
+
+    def __init__(self, amps, Fa, Fb, Ia, Ib, Iabab, Ds, g, G, beta, ng, ti, known=None):
+        dev = self.dev = _lib.device()
+        self.ints = (Fa, Fb, Ia, Ib, Iabab)
+        self.Ds = [_lib.as_dev(d, dev) for d in Ds]
+        self.g, self.G, self.beta, self.ng, self.ti = g, G, beta, ng, ti
+        self.old = [_lib.as_dev(x, dev).clone() for x in amps]
+        self.abij = (ft_cc_energy.oovv_to_abij(Ia.oovv), ft_cc_energy.oovv_to_abij(Iabab.oovv),
+                     ft_cc_energy.oovv_to_abij(Ib.oovv))
+        self.fT = (_lib.as_dev(Fa.ov, dev).t().contiguous(), _lib.as_dev(Fb.ov, dev).t().contiguous())
+        self.stats = torch.zeros(20, dtype=torch.float64, device=dev)
+        self.set_flags(known)
+
+    def set_flags(self, known=None):
+        """known: dict with any of t0, closed_shell, singlet, antisym decided by the caller
+        (e.g. a copy of this solver's own state); everything else is checked on the device."""
+        known = known or {}
+        old = self.old
+        Fa, Fb, Ia, Ib, Iabab = self.ints
+        self.t0 = known["t0"] if "t0" in known else ft_cc_equations.t0_is_zero(self.G, old)
+        self.cs = known["closed_shell"] if "closed_shell" in known else \
+            _closed_shell(Fa, Fb, Ia, Ib, Iabab, self.Ds, old)
+        self.singlet = known["singlet"] if "singlet" in known else \
+            bool(self.cs and ft_cc_equations.is_singlet(old[2], old[3]))
+        if "antisym" in known:
+            self.antisym = known["antisym"]
+        else:
+            self.antisym = bool(self.singlet) or (
+                ft_cc_equations.is_antisymmetric(old[2])
+                and (self.cs or ft_cc_equations.is_antisymmetric(old[4])))
+
+    def flags(self):
+        return {"t0": self.t0, "closed_shell": self.cs, "singlet": self.singlet,
+                "antisym": self.antisym}
+
+    def step(self, alpha):
+        """-> (E, res1 + res2) as logged by the reference (kelvin/cc_utils.py:297-305)."""
+        ng = self.ng
+        old = self.old
+        bars = ft_cc_equations.uccsd_stanton_bar(
+            *self.ints, *old, t0_zero=self.t0, closed_shell=self.cs, beta_copies=False,
+            singlet=self.singlet, antisym=self.antisym)
+        live = (0, 2, 3) if self.cs else (0, 1, 2, 3, 4)
+        # energy terms: singles with F.ov; doubles with <ij||ab> and the (already updated) singles
+        T1a, T1b = old[0], (old[0] if self.cs else old[1])
+        eterm = {0: dict(W=self.fT[0], c2=1.0), 1: dict(W=self.fT[1], c2=1.0),
+                 2: dict(W=self.abij[0], T1x=T1a, T1y=T1a, c2=0.25, c11=0.5),
+                 3: dict(W=self.abij[1], T1x=T1a, T1y=T1b, c2=1.0, c11=1.0),
+                 4: dict(W=self.abij[2], T1x=T1b, T1y=T1b, c2=0.25, c11=0.5)}
+        sp = self.stats.data_ptr()
+        for k in live:
+            quadrature.int_tbar_update(ng, bars[k], self.ti, self.Ds[k], self.G, old[k], alpha,
+                                       sp + 32*k, g=self.g, **eterm[k])
+        if self.cs:
+            # alpha == beta: the beta blocks are copies
+            old[1].copy_(old[0])
+            old[4].copy_(old[2])
+        s = self.stats.cpu().numpy().reshape(5, 4).copy()
+        if self.cs:
+            s[1] = s[0]
+            s[4] = s[2]
+        n = numpy.sqrt(s[:, :3])
+        nl1 = n[0, 1] + 0.1 + n[1, 1]
+        nl2 = n[2, 1] + 0.1 + n[3, 1] + n[4, 1]
+        res1 = n[0, 0]/nl1 + n[1, 0]/nl1
+        res2 = n[2, 0]/nl2 + n[3, 0]/nl2 + n[4, 0]/nl2
+        E = float(s[0, 3] + s[1, 3] + s[2, 3] + s[3, 3] + s[4, 3])/self.beta
+        return E, float(res1 + res2)
+
+
 def ft_ucc_iter(method, T1aold, T1bold, T2aaold, T2abold, T2bbold, Fa, Fb, Ia, Ib, Iabab,
-                D1a, D1b, D2aa, D2ab, D2bb, g, G, beta, ng, ti, iprint, conv_options):
+                D1a, D1b, D2aa, D2ab, D2bb, g, G, beta, ng, ti, iprint, conv_options,
+                flags_out=None):
     """Fixed-point FT-UCCSD loop (kelvin/cc_utils.py:245-317).  The norms nl1/nl2
-    are those of the amplitudes *before* the update, as in the reference."""
+    are those of the amplitudes *before* the update, as in the reference.
+    flags_out: dict that receives the symmetry verdicts of the solve (UccStep.flags)."""
+    if method != "CCSD":
+        raise Exception("Unrecognized method keyword for unrestricted calc")
     tbeg = time.time()
-    dev = _lib.device()
     converged = False
     ethresh = conv_options["econv"]
     tthresh = conv_options["tconv"]
@@ -284,39 +428,22 @@ def ft_ucc_iter(method, T1aold, T1bold, T2aaold, T2abold, T2bbold, Fa, Fb, Ia, I
     alpha = conv_options["damp"]
     i = 0
     Eold = 888888888.888888888
-    old = [_lib.as_dev(x, dev).clone() for x in (T1aold, T1bold, T2aaold, T2abold, T2bbold)]
-    abij = (ft_cc_energy.oovv_to_abij(Ia.oovv), ft_cc_energy.oovv_to_abij(Iabab.oovv),
-            ft_cc_energy.oovv_to_abij(Ib.oovv))
-    st = _Stats(5, dev)
-    # T[0] == 0 is preserved by the update (row 0 of G vanishes): skip that grid point
-    t0 = ft_cc_equations.t0_is_zero(G, old)
-    # closed shell (alpha == beta throughout, e.g. the UEG): the update preserves it, so the
-    # beta blocks are copies of the alpha ones and only the reduced program runs
-    cs = _closed_shell(Fa, Fb, Ia, Ib, Iabab, (D1a, D1b, D2aa, D2ab, D2bb), old)
+    st = UccStep((T1aold, T1bold, T2aaold, T2abold, T2bbold), Fa, Fb, Ia, Ib, Iabab,
+                 (D1a, D1b, D2aa, D2ab, D2bb), g, G, beta, ng, ti)
+    if flags_out is not None:
+        flags_out.update(st.flags())
     while i < max_iter and not converged:
-        T1out, T2out = form_new_ampl_u(
-            method, Fa, Fb, Ia, Ib, Iabab, old[0], old[1], old[2], old[3], old[4],
-            D1a, D1b, D2aa, D2ab, D2bb, ti, ng, G, t0_zero=t0, closed_shell=cs)
-        new = (T1out[0], T1out[1], T2out[0], T2out[1], T2out[2])
-        for k in range(5):
-            st.damp(k, old[k], new[k], alpha)
-        E = ft_cc_energy.ft_ucc_energy(old[0], old[1], old[2], old[3], old[4],
-                                       Fa.ov, Fb.ov, Ia.oovv, Ib.oovv, Iabab.oovv, g, beta,
-                                       abij=abij)
-        s = numpy.sqrt(st.read())
-        nl1 = s[0, 1] + 0.1 + s[1, 1]
-        nl2 = s[2, 1] + 0.1 + s[3, 1] + s[4, 1]
-        res1 = s[0, 0]/nl1 + s[1, 0]/nl1
-        res2 = s[2, 0]/nl2 + s[3, 0]/nl2 + s[4, 0]/nl2
-        logging.info(' %2d  %.10f   %.4E' % (i + 1, E, res1 + res2))
+        E, res = st.step(alpha)
+        logging.info(' %2d  %.10f   %.4E' % (i + 1, E, res))
         i = i + 1
-        if numpy.abs(E - Eold) < ethresh and res1 + res2 < tthresh:
+        if numpy.abs(E - Eold) < ethresh and res < tthresh:
             converged = True
         Eold = E
     if not converged:
         logging.warning("{} did not converge!".format(method))
     tend = time.time()
     logging.info("Total {} time: {:.4f} s".format(method, (tend - tbeg)))
+    old = st.old
     return Eold, (old[0], old[1]), (old[2], old[3], old[4])
 
 
@@ -432,6 +559,8 @@ def ft_lambda_iter(method, L1old, L2old, T1, T2, F, I, D1, D2, g, G, beta, ng, t
     nl1 = _norm(L1old) + 0.1
     nl2 = _norm(L2old) + 0.1
     st = _Stats(2, dev)
+    T1, T2 = _lib.as_dev(T1, dev), _lib.as_dev(T2, dev)
+    asym = ft_cc_equations.is_antisymmetric(T2) and ft_cc_equations.is_antisymmetric(L2old)
     while i < max_iter and not converged:
         if method == "LCCSD":
             L1, L2 = ft_cc_equations.lccsd_lambda_simple(
@@ -441,7 +570,7 @@ def ft_lambda_iter(method, L1old, L2old, T1, T2, F, I, D1, D2, g, G, beta, ng, t
             L2 = ft_cc_equations.lccd_lambda_simple(F, I, T2, L2old, D2, ti, ng, g, G, beta)
         elif method == "CCSD":
             L1, L2 = ft_cc_equations.ccsd_lambda_opt(
-                F, I, T1, T2, L1old, L2old, D1, D2, ti, ng, g, G, beta)
+                F, I, T1, T2, L1old, L2old, D1, D2, ti, ng, g, G, beta, antisym=asym)
         else:
             L1 = L1old
             L2 = ft_cc_equations.ccd_lambda_simple(F, I, T2, L2old, D2, ti, ng, g, G, beta)
@@ -484,17 +613,27 @@ def ft_ulambda_iter(method, L1ain, L1bin, L2aain, L2abin, L2bbin, T1aold, T1bold
     nl1 = nrm[0] + nrm[1] + 0.1
     nl2 = nrm[2] + 0.1 + nrm[4] + 4*nrm[3]
     st = _Stats(5, dev)
-    cs = _closed_shell(Fa, Fb, Ia, Ib, Iabab, (D1a, D1b, D2aa, D2ab, D2bb),
-                       (T1aold, T1bold, T2aaold, T2abold, T2bbold), old)
+    Ts = [_lib.as_dev(x, dev) for x in (T1aold, T1bold, T2aaold, T2abold, T2bbold)]
+    cs = _closed_shell(Fa, Fb, Ia, Ib, Iabab, (D1a, D1b, D2aa, D2ab, D2bb), Ts, old)
+    # caller-supplied guesses need not be antisymmetric: then the full sums are evaluated
+    asym = all(ft_cc_equations.is_antisymmetric(x) for x in
+               ([Ts[2], old[2]] + ([] if cs else [Ts[4], old[4]])))
+    live = (0, 2, 3) if cs else (0, 1, 2, 3, 4)
     while i < max_iter and not converged:
         new = ft_cc_equations.uccsd_lambda_opt(
-            Fa, Fb, Ia, Ib, Iabab, T1aold, T1bold, T2aaold, T2abold, T2bbold,
+            Fa, Fb, Ia, Ib, Iabab, *Ts,
             old[0], old[1], old[2], old[3], old[4], D1a, D1b, D2aa, D2ab, D2bb,
-            ti, ng, g, G, beta, closed_shell=cs)
-        for k in range(5):
+            ti, ng, g, G, beta, closed_shell=cs, antisym=asym)
+        for k in live:
             st.damp(k, old[k], new[k], alpha)
+        if cs:
+            old[1].copy_(old[0])
+            old[4].copy_(old[2])
         new = None
         s = numpy.sqrt(st.read())
+        if cs:
+            s[1] = s[0]
+            s[4] = s[2]
         res1 = s[0, 0]/nl1 + s[1, 0]/nl1
         res2 = s[2, 0]/nl2 + s[3, 0]/nl2 + s[4, 0]/nl2
         nl1 = s[0, 2] + s[1, 2] + 0.1

@@ -80,6 +80,9 @@ class ccsd(object):
         self.rorbv = None
         self._ints = None
         self._act = None
+        # symmetry verdicts of the amplitude solve (tau_0 shortcut, closed shell, singlet,
+        # antisymmetry; cc_utils.UccStep.flags), reused by the later residual passes
+        self._flags = {}
 
     # ------------------------------------------------------------------
     def run(self, T1=None, T2=None):
@@ -88,6 +91,21 @@ class ccsd(object):
         if self.sys.has_u():
             return self._ft_uccsd(T1in=T1, T2in=T2)
         return self._ft_ccsd(T1in=T1, T2in=T2)
+
+    def _u_flags(self):
+        """Keywords for further residual evaluations at the converged amplitudes (the verdicts of
+        the solve; amplitudes set from outside are re-examined by the callee)."""
+        f = self._flags
+        if not f:
+            return {}
+        return dict(t0_zero=bool(f.get("t0", False)), closed_shell=bool(f.get("closed_shell", False)),
+                    singlet=bool(f.get("singlet", False)), antisym=f.get("antisym"))
+
+    def _g_flags(self):
+        f = self._flags
+        if not f:
+            return {}
+        return dict(t0_zero=bool(f.get("t0", False)), antisym=f.get("antisym"))
 
     def _conv_options(self):
         return {"econv": self.econv, "tconv": self.tconv,
@@ -202,9 +220,10 @@ class ccsd(object):
                                            Qterm=False)
             logging.info('MP2 Energy: {:.10f}'.format(E2))
 
+            self._flags = {}
             Eccn, T1, T2 = cc_utils.ft_cc_iter(
                 method, T1old, T2old, F, I, D1, D2, g, G, self.beta_max, ng, ti, self.iprint,
-                self._conv_options())
+                self._conv_options(), flags_out=self._flags)
         else:
             T1, T2 = cc_utils.ft_cc_iter_extrap(
                 method, F, I, D1, D2, g, G, self.beta_max, ng, ti, self.iprint,
@@ -264,10 +283,11 @@ class ccsd(object):
                 Ia.oovv, Ib.oovv, Iabab.oovv, g, self.beta_max, Qterm=False)
             logging.info('MP2 Energy: {:.10f}'.format(E2))
 
+            self._flags = {}
             Eccn, T1, T2 = cc_utils.ft_ucc_iter(
                 method, T1aold, T1bold, T2aaold, T2abold, T2bbold, Fa, Fb, Ia, Ib, Iabab,
                 D1a, D1b, D2aa, D2ab, D2bb, g, G, self.beta_max, ng, ti, self.iprint,
-                self._conv_options())
+                self._conv_options(), flags_out=self._flags)
         else:
             T1, T2 = cc_utils.ft_ucc_iter_extrap(
                 method, Fa, Fb, Ia, Ib, Iabab, D1a, D1b, D2aa, D2ab, D2bb,
@@ -300,9 +320,14 @@ class ccsd(object):
                                     device=L2old.device)
         elif L1 is not None and L2 is not None:
             L1old, L2old = L1, L2
+        elif L2 is not None:
+            # L2 only: the reference starts the singles from zero (kelvin/ccsd.py:932-936)
+            L2old = L2
+            L1old = torch.zeros((ng,) + tuple(F.ov.shape), dtype=torch.float64,
+                                device=_lib.device())
         else:
-            # the reference allocates a mis-shaped zero guess here (quirk Q8); refuse instead
-            raise Exception("provide both L1 and L2 (or neither) as Lambda guess")
+            # L1 only: the reference allocates a mis-shaped zero L2 here (quirk Q8); refuse
+            raise Exception("provide L2 (or L1 and L2, or neither) as Lambda guess")
         L1, L2 = cc_utils.ft_lambda_iter(
             "CCSD" if self.singles else "CCD", L1old, L2old, self.T1, self.T2, F, I, D1, D2, g, G,
             self.beta_max, ng, ti,
@@ -544,11 +569,12 @@ class ccsd(object):
         if self.sys.has_u():
             ea, eb, Ds, (Fa, Fb, Ia, Ib, Iabab) = self._u_setup()
             t1, t2 = ft_cc_equations.uccsd_stanton(
-                Fa, Fb, Ia, Ib, Iabab, *self.T1, *self.T2, *Ds, ti, ng, Gnew)
+                Fa, Fb, Ia, Ib, Iabab, *self.T1, *self.T2, *Ds, ti, ng, Gnew, **self._u_flags())
             Tt = list(t1) + list(t2)
         else:
             en, D1, D2, F, I = self._g_setup()
-            Tt = list(ft_cc_equations.ccsd_stanton(F, I, self.T1, self.T2, D1, D2, ti, ng, Gnew))
+            Tt = list(ft_cc_equations.ccsd_stanton(F, I, self.T1, self.T2, D1, D2, ti, ng, Gnew,
+                                                   **self._g_flags()))
         gdev = _lib.const_dev(self.g, Tt[0].device)
         for X in Tt:
             X.mul_(gdev.view((ng,) + (1,)*(X.dim() - 1)))
@@ -700,7 +726,8 @@ class ccsd(object):
             dg = ft_cc_energy.ft_ucc_energy(*Ts, Fa.ov, Fb.ov, Ia.oovv, Ib.oovv, Iabab.oovv, gd, beta)
 
             def stanton(Gx):
-                t1, t2 = ft_cc_equations.uccsd_stanton(Fa, Fb, Ia, Ib, Iabab, *Ts, *Ds, ti, ng, Gx)
+                t1, t2 = ft_cc_equations.uccsd_stanton(Fa, Fb, Ia, Ib, Iabab, *Ts, *Ds, ti, ng, Gx,
+                                                       **self._u_flags())
                 return list(t1) + list(t2)
         else:
             en, D1, D2, F, I = self._g_setup()
@@ -711,7 +738,8 @@ class ccsd(object):
             dg = ft_cc_energy.ft_cc_energy(self.T1, self.T2, F.ov, I.oovv, gd, beta)
 
             def stanton(Gx):
-                return list(ft_cc_equations.ccsd_stanton(F, I, self.T1, self.T2, D1, D2, ti, ng, Gx))
+                return list(ft_cc_equations.ccsd_stanton(F, I, self.T1, self.T2, D1, D2, ti, ng, Gx,
+                                                         **self._g_flags()))
         Ls = [lb.as_dev(x) for x in Ls]
         dG = self._pair_LT(Ls, stanton(Gd), w)
         Tn = stanton(Gnew)

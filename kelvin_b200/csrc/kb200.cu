@@ -80,115 +80,232 @@ __global__ void final_sum_kernel(const double* part, int nblocks, int nv, double
 
 // ---------------------------------------------------------------------------
 // imaginary-time integration (quadrature.py:292-345)
+//
+// One thread per amplitude element.  The grid rows of the output are handled YC at a time with
+// their accumulators and running weights in REGISTERS; the input rows stream past once per
+// chunk straight from global memory (coalesced, independent of the arithmetic, so the loads
+// run ahead of the exp/FMA chain).  Nothing scales with ng except the loop lengths: any grid
+// size runs (the reference's tests go to ngrid = 2400).  ti and G sit in shared memory when
+// they fit (ng <= 72), else they are read through the read-only cache (warp-uniform addresses).
+// MODE 1: E_k = exp(D (tau_{k-1} - tau_k)) once per input row and chunk, weights as running
+// products (relative deviation <= ng eps); MODE 0: one exp per (x, y) pair, the reference's
+// literal formula.  UPD: the fused amplitude update -- the integrated row never goes to memory:
+// residual norm, damping, new norm and the energy contraction are done on the spot
+// (cc_utils.py:278-299 in one pass over T-bar and T).
 // ---------------------------------------------------------------------------
-constexpr int INT_THREADS = 128;
+constexpr int INT_THREADS = 256;
+constexpr int INT_SMEM_NG = 72;      // ng up to which ti and G are staged in shared memory
 
-// dynamic smem: tb[ng][128] (+ E[ng][128] for mode 1) + ti[ng]
-template <int MODE>
-__global__ void __launch_bounds__(INT_THREADS)
-    int_tbar_kernel(int ng, long long n, const double* __restrict__ tbar,
-                    const double* __restrict__ D, const double* __restrict__ ti,
-                    const double* __restrict__ G, double* __restrict__ out, int y0, int y1,
-                    int lower) {
-    extern __shared__ double sm[];
-    double* tb = sm;
-    double* E = sm + (size_t)ng * INT_THREADS;
-    double* tis = (MODE == 1) ? E + (size_t)ng * INT_THREADS : E;
-    const int tx = threadIdx.x;
-    for (int i = tx; i < ng; i += INT_THREADS) tis[i] = ti[i];
-    __syncthreads();
-    for (long long p0 = (long long)blockIdx.x * INT_THREADS; p0 < n;
-         p0 += (long long)gridDim.x * INT_THREADS) {
-        long long p = p0 + tx;
-        bool act = p < n;
-        double d = act ? D[p] : 0.0;
-        for (int x = 0; x < ng; ++x) tb[x * INT_THREADS + tx] = act ? tbar[(size_t)x * n + p] : 0.0;
-        if (MODE == 1)
-            for (int k = 1; k < ng; ++k) E[k * INT_THREADS + tx] = exp(d * (tis[k - 1] - tis[k]));
-        for (int y = y0; y < y1; ++y) {
-            const double* Gy = G + (size_t)y * ng;
-            double acc = 0.0;
-            if (MODE == 0) {
-                for (int x = 0; x < y; ++x) {
-                    double gw = __ldg(Gy + x);
-                    if (gw != 0.0) acc += gw * exp(d * (tis[x] - tis[y])) * tb[x * INT_THREADS + tx];
-                }
-            } else {
-                double w = 1.0;
-                for (int x = y - 1; x >= 0; --x) {
-                    w *= E[(x + 1) * INT_THREADS + tx];
-                    double gw = __ldg(Gy + x);
-                    if (gw != 0.0) acc += gw * w * tb[x * INT_THREADS + tx];
-                }
-            }
-            const int xend = lower ? y + 1 : ng;     // lower-triangular G: only x == y is left
-            for (int x = y; x < xend; ++x) {
-                double gw = __ldg(Gy + x);
-                if (gw != 0.0) acc += gw * tb[x * INT_THREADS + tx];
-            }
-            if (act) out[(size_t)(y - y0) * n + p] = acc;
-        }
-    }
-}
-
-struct Dims4 {
-    int d[4];
-    long long s[4];
+struct IntArgs {
+    int ng;
+    long long n;
+    const double* src;      // tbar / L: ng rows
+    long long sstride;
+    const double* D;
+    const double* ti;
+    const double* g;        // int_L and the energy term
+    const double* G;
+    double* out;            // plain: rows r0..r1 of the result;  UPD: the amplitudes (all ng rows)
+    long long ostride;
+    int r0, r1;
+    int lower;
+    // D addressed through strides (int_L: D is stored (v.., o..), L (o.., v..))
+    int dd[4];
+    long long ds[4];
+    int dstrided;
+    // fused update
+    double alpha;
+    const double* W;        // energy weights per element (f_ai or <ij||ab> in abij order) or null
+    const double* T1x;      // c11 term: T1x[y, a, i] * T1y[y, b, j]; null = none
+    const double* T1y;
+    long long t1xs, t1ys;
+    int nvb, noa, nob;
+    double c2, c11;
+    double* part;           // [4][gridDim.x]
 };
 
-template <int MODE>
+__device__ __forceinline__ double int_D(const IntArgs& a, long long p) {
+    if (!a.dstrided) return a.D[p];
+    unsigned r = (unsigned)p;                   // n < 2^31 (checked on the host)
+    unsigned i3 = r % (unsigned)a.dd[3]; r /= (unsigned)a.dd[3];
+    unsigned i2 = r % (unsigned)a.dd[2]; r /= (unsigned)a.dd[2];
+    unsigned i1 = r % (unsigned)a.dd[1]; r /= (unsigned)a.dd[1];
+    unsigned i0 = r;
+    return a.D[i0 * a.ds[0] + i1 * a.ds[1] + i2 * a.ds[2] + i3 * a.ds[3]];
+}
+
+template <int YC, int MODE, bool UPD>
 __global__ void __launch_bounds__(INT_THREADS)
-    int_L_kernel(int ng, long long n, Dims4 dm, const double* __restrict__ L,
-                 const double* __restrict__ D, const double* __restrict__ ti,
-                 const double* __restrict__ g, const double* __restrict__ G,
-                 double* __restrict__ out, int s0, int s1, int lower) {
+    int_tbar_kernel(const __grid_constant__ IntArgs a) {
     extern __shared__ double sm[];
-    double* lb = sm;
-    double* E = sm + (size_t)ng * INT_THREADS;
-    double* tis = (MODE == 1) ? E + (size_t)ng * INT_THREADS : E;
-    double* gs = tis + ng;
-    const int tx = threadIdx.x;
-    for (int i = tx; i < ng; i += INT_THREADS) {
-        tis[i] = ti[i];
-        gs[i] = g[i];
+    const int ng = a.ng;
+    const bool staged = ng <= INT_SMEM_NG;
+    const double* tis = a.ti;
+    const double* Gs = a.G;
+    if (staged) {
+        double* t_ = sm;
+        double* G_ = sm + ng;
+        for (int i = threadIdx.x; i < ng; i += INT_THREADS) t_[i] = a.ti[i];
+        for (int i = threadIdx.x; i < ng * ng; i += INT_THREADS) G_[i] = a.G[i];
+        __syncthreads();
+        tis = t_;
+        Gs = G_;
     }
-    __syncthreads();
-    for (long long p0 = (long long)blockIdx.x * INT_THREADS; p0 < n;
-         p0 += (long long)gridDim.x * INT_THREADS) {
-        long long p = p0 + tx;
-        bool act = p < n;
-        double d = 0.0;
-        if (act) {
-            unsigned r = (unsigned)p;               // n < 2^31 (checked on the host)
-            unsigned i3 = r % (unsigned)dm.d[3]; r /= (unsigned)dm.d[3];
-            unsigned i2 = r % (unsigned)dm.d[2]; r /= (unsigned)dm.d[2];
-            unsigned i1 = r % (unsigned)dm.d[1]; r /= (unsigned)dm.d[1];
-            unsigned i0 = r;
-            d = D[i0 * dm.s[0] + i1 * dm.s[1] + i2 * dm.s[2] + i3 * dm.s[3]];
+    double nrm[4] = {0.0, 0.0, 0.0, 0.0};
+    const double oma = 1.0 - a.alpha;
+    for (long long p = (long long)blockIdx.x * INT_THREADS + threadIdx.x; p < a.n;
+         p += (long long)gridDim.x * INT_THREADS) {
+        const double d = int_D(a, p);
+        const double* src = a.src + p;
+        double esum = 0.0;
+        unsigned ia = 0, ib = 0, ii = 0, ij = 0;
+        if (UPD && a.T1x != nullptr) {
+            unsigned r = (unsigned)p;
+            ij = r % (unsigned)a.nob; r /= (unsigned)a.nob;
+            ii = r % (unsigned)a.noa; r /= (unsigned)a.noa;
+            ib = r % (unsigned)a.nvb; r /= (unsigned)a.nvb;
+            ia = r;
         }
-        for (int y = 0; y < ng; ++y) lb[y * INT_THREADS + tx] = act ? L[(size_t)y * n + p] : 0.0;
-        if (MODE == 1)
-            for (int k = 1; k < ng; ++k) E[k * INT_THREADS + tx] = exp(d * (tis[k - 1] - tis[k]));
-        for (int s = s0; s < s1; ++s) {
-            double acc = 0.0;
-            for (int y = lower ? s : 0; y < s; ++y) {   // G[y,s] with y < s is the upper triangle
-                double gw = gs[y] * __ldg(G + (size_t)y * ng + s);
-                if (gw != 0.0) acc += gw * lb[y * INT_THREADS + tx];
+        for (int c0 = a.r0; c0 < a.r1; c0 += YC) {
+            const int ny = min(YC, a.r1 - c0);
+            double acc[YC], w[YC];
+#pragma unroll
+            for (int j = 0; j < YC; ++j) {
+                acc[j] = 0.0;
+                w[j] = 1.0;
             }
-            if (MODE == 0) {
-                for (int y = s; y < ng; ++y) {
-                    double gw = gs[y] * __ldg(G + (size_t)y * ng + s);
-                    if (gw != 0.0) acc += gw * exp(d * (tis[s] - tis[y])) * lb[y * INT_THREADS + tx];
-                }
-            } else {
-                double w = 1.0;
-                for (int y = s; y < ng; ++y) {
-                    if (y > s) w *= E[y * INT_THREADS + tx];
-                    double gw = gs[y] * __ldg(G + (size_t)y * ng + s);
-                    if (gw != 0.0) acc += gw * w * lb[y * INT_THREADS + tx];
+            // x < y: descending x, the weight of row y picks up one factor per step
+            for (int x = c0 + ny - 2; x >= 0; --x) {
+                const double tb = src[(size_t)x * a.sstride];
+                double e = 1.0;
+                if (MODE == 1) e = exp(d * (tis[x] - tis[x + 1]));
+#pragma unroll
+                for (int j = 0; j < YC; ++j) {
+                    const int y = c0 + j;
+                    if (j < ny && y > x) {
+                        if (MODE == 1) w[j] *= e;
+                        const double gw = Gs[y * ng + x];
+                        if (gw != 0.0) {
+                            const double wt = (MODE == 1) ? w[j] : exp(d * (tis[x] - tis[y]));
+                            acc[j] += gw * wt * tb;
+                        }
+                    }
                 }
             }
-            if (act) out[(size_t)(s - s0) * n + p] = acc / gs[s];
+            // x >= y: weight 1 (quirk Q4); only x == y survives for a lower-triangular G
+#pragma unroll
+            for (int j = 0; j < YC; ++j) {
+                const int y = c0 + j;
+                if (j < ny) {
+                    const int xend = a.lower ? y + 1 : ng;
+                    for (int x = y; x < xend; ++x) {
+                        const double gw = Gs[y * ng + x];
+                        if (gw != 0.0) acc[j] += gw * src[(size_t)x * a.sstride];
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < YC; ++j) {
+                const int y = c0 + j;
+                if (j < ny) {
+                    if (!UPD) {
+                        a.out[(size_t)(y - a.r0) * a.ostride + p] = acc[j];
+                    } else {
+                        double* op = a.out + (size_t)y * a.ostride + p;
+                        const double o = *op;
+                        const double df = acc[j] - o;
+                        nrm[0] += df * df;
+                        nrm[1] += o * o;
+                        const double u = a.alpha * o + oma * acc[j];
+                        *op = u;
+                        nrm[2] += u * u;
+                        if (a.W != nullptr) {
+                            double v = a.c2 * u;
+                            if (a.T1x != nullptr)
+                                v += a.c11 * a.T1x[(size_t)y * a.t1xs + (size_t)ia * a.noa + ii] *
+                                     a.T1y[(size_t)y * a.t1ys + (size_t)ib * a.nob + ij];
+                            esum += a.g[y] * v;
+                        }
+                    }
+                }
+            }
+        }
+        if (UPD && a.W != nullptr) nrm[3] += esum * a.W[p];
+    }
+    if (UPD) block_sum_store<4>(nrm, a.part);
+}
+
+// Lambda-bar[s] = (1/g_s) sum_y g_y G[y,s] w(s,y) L[y],  w = exp(D (tau_s - tau_y)) for y >= s
+// (running product over ascending y), 1 for y < s (quadrature.py:320-345).
+template <int YC, int MODE>
+__global__ void __launch_bounds__(INT_THREADS)
+    int_L_kernel(const __grid_constant__ IntArgs a) {
+    extern __shared__ double sm[];
+    const int ng = a.ng;
+    const bool staged = ng <= INT_SMEM_NG;
+    const double* tis = a.ti;
+    const double* Gs = a.G;
+    const double* gs = a.g;
+    if (staged) {
+        double* t_ = sm;
+        double* g_ = sm + ng;
+        double* G_ = sm + 2 * ng;
+        for (int i = threadIdx.x; i < ng; i += INT_THREADS) {
+            t_[i] = a.ti[i];
+            g_[i] = a.g[i];
+        }
+        for (int i = threadIdx.x; i < ng * ng; i += INT_THREADS) G_[i] = a.G[i];
+        __syncthreads();
+        tis = t_;
+        gs = g_;
+        Gs = G_;
+    }
+    for (long long p = (long long)blockIdx.x * INT_THREADS + threadIdx.x; p < a.n;
+         p += (long long)gridDim.x * INT_THREADS) {
+        const double d = int_D(a, p);
+        const double* src = a.src + p;
+        for (int c0 = a.r0; c0 < a.r1; c0 += YC) {
+            const int ns = min(YC, a.r1 - c0);
+            double acc[YC], w[YC];
+#pragma unroll
+            for (int j = 0; j < YC; ++j) {
+                acc[j] = 0.0;
+                w[j] = 1.0;
+            }
+            if (!a.lower) {
+                // G[y,s] with y < s is the upper triangle: weight 1
+#pragma unroll
+                for (int j = 0; j < YC; ++j) {
+                    const int s = c0 + j;
+                    if (j < ns)
+                        for (int y = 0; y < s; ++y) {
+                            const double gw = gs[y] * Gs[y * ng + s];
+                            if (gw != 0.0) acc[j] += gw * src[(size_t)y * a.sstride];
+                        }
+                }
+            }
+            for (int y = c0; y < ng; ++y) {
+                const double lv = src[(size_t)y * a.sstride];
+                double e = 1.0;
+                if (MODE == 1 && y > 0) e = exp(d * (tis[y - 1] - tis[y]));
+#pragma unroll
+                for (int j = 0; j < YC; ++j) {
+                    const int s = c0 + j;
+                    if (j < ns && y >= s) {
+                        if (MODE == 1 && y > s) w[j] *= e;
+                        const double gw = gs[y] * Gs[y * ng + s];
+                        if (gw != 0.0) {
+                            const double wt = (MODE == 1) ? w[j] : exp(d * (tis[s] - tis[y]));
+                            acc[j] += gw * wt * lv;
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < YC; ++j) {
+                const int s = c0 + j;
+                if (j < ns) a.out[(size_t)(s - a.r0) * a.ostride + p] = acc[j] / gs[s];
+            }
         }
     }
 }
@@ -253,6 +370,28 @@ __global__ void __launch_bounds__(RED_THREADS)
         double u = alpha * o + oma * w;
         old[p] = u;
         acc[2] += u * u;
+    }
+    block_sum_store<3>(acc, part);
+}
+
+// the same over ng rows with row strides (blocks that are column ranges of a wider buffer)
+__global__ void __launch_bounds__(RED_THREADS)
+    damp_norms_rows_kernel(int ng, long long n, double* old, long long os, const double* neu,
+                           long long ns, double alpha, double* part) {
+    double acc[3] = {0.0, 0.0, 0.0};
+    const double oma = 1.0 - alpha;
+    for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < n;
+         p += (long long)gridDim.x * blockDim.x) {
+        for (int y = 0; y < ng; ++y) {
+            double* op = old + (size_t)y * os + p;
+            const double o = *op, w = neu[(size_t)y * ns + p];
+            const double d = w - o;
+            acc[0] += d * d;
+            acc[1] += o * o;
+            const double u = alpha * o + oma * w;
+            *op = u;
+            acc[2] += u * u;
+        }
     }
     block_sum_store<3>(acc, part);
 }
@@ -554,6 +693,46 @@ int tile_bn(int tile) { return tile == 1 ? 32 : ((tile == 4 || tile == 5) ? 64 :
 int64_t op_workspace(const kb200_op& o) {
     if (o.kind != 0 || o.splitk <= 1) return 0;   // kinds 1, 2 need no workspace
     return (int64_t)o.batch * o.splitk * (int64_t)o.M * o.N * 8;
+}
+
+}  // namespace
+
+namespace {
+
+int int_grid(long long n) { return grid_for(n, INT_THREADS, 148 * 4); }
+
+size_t int_smem(int ng, int nvec) {
+    return ng <= INT_SMEM_NG ? ((size_t)ng * ng + (size_t)nvec * ng) * 8 : 0;
+}
+
+template <int YC, bool UPD>
+void launch_int_tbar(const IntArgs& a, int mode, cudaStream_t st) {
+    const int grid = int_grid(a.n);
+    const size_t smem = int_smem(a.ng, 1);
+    if (mode == 1)
+        int_tbar_kernel<YC, 1, UPD><<<grid, INT_THREADS, smem, st>>>(a);
+    else
+        int_tbar_kernel<YC, 0, UPD><<<grid, INT_THREADS, smem, st>>>(a);
+}
+
+template <int YC>
+void launch_int_L(const IntArgs& a, int mode, cudaStream_t st) {
+    const int grid = int_grid(a.n);
+    const size_t smem = int_smem(a.ng, 2);
+    if (mode == 1)
+        int_L_kernel<YC, 1><<<grid, INT_THREADS, smem, st>>>(a);
+    else
+        int_L_kernel<YC, 0><<<grid, INT_THREADS, smem, st>>>(a);
+}
+
+IntArgs int_args(int ng, int64_t n, const double* src, int64_t sstride, const double* D,
+                 const double* ti, const double* g, const double* G, double* out,
+                 int64_t ostride, int r0, int r1, int lower) {
+    IntArgs a;
+    memset(&a, 0, sizeof(a));
+    a.ng = ng; a.n = n; a.src = src; a.sstride = sstride; a.D = D; a.ti = ti; a.g = g; a.G = G;
+    a.out = out; a.ostride = ostride; a.r0 = r0; a.r1 = r1; a.lower = lower;
+    return a;
 }
 
 }  // namespace
@@ -1013,30 +1192,70 @@ int kb200_plan_run_timed(const kb200_op* ops, int nops, const uint32_t* tables,
 
 int kb200_int_tbar(int ng, int64_t n, const double* tbar, const double* D, const double* ti,
                    const double* G, double* out, int mode, void* stream) {
-    return kb200_int_tbar_rows(ng, n, tbar, D, ti, G, out, 0, ng, mode, stream);
+    return kb200_int_tbar_strided(ng, n, tbar, n, D, ti, G, out, n, 0, ng, mode, stream);
 }
 
 int kb200_int_tbar_rows(int ng, int64_t n, const double* tbar, const double* D, const double* ti,
                         const double* G, double* out, int y0, int y1, int mode, void* stream) {
+    return kb200_int_tbar_strided(ng, n, tbar, n, D, ti, G, out, n, y0, y1, mode, stream);
+}
+
+int kb200_int_tbar_strided(int ng, int64_t n, const double* tbar, int64_t tstride,
+                           const double* D, const double* ti, const double* G, double* out,
+                           int64_t ostride, int y0, int y1, int mode, void* stream) {
     // mode bit 1 (value 2): the caller guarantees G[y,x] == 0 for x > y (every quadrature of
     // kelvin/quadrature.py), which lets the kernel skip scanning the upper triangle
     const int lower = (mode & 2) ? 1 : 0;
     mode &= 1;
-    if (ng <= 0 || n < 0 || y0 < 0 || y1 > ng || y0 > y1) return fail(-1, "int_tbar: bad size");
-    if (y0 == y1) return 0;
-    if (n == 0) return 0;
+    if (ng <= 0 || n < 0 || y0 < 0 || y1 > ng || y0 > y1 || tstride < n || ostride < n)
+        return fail(-1, "int_tbar: bad size");
+    if (y0 == y1 || n == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
-    size_t smem = ((size_t)ng * INT_THREADS * (mode == 1 ? 2 : 1) + ng) * 8;
-    if (smem > 227 * 1024) return fail(-1, "int_tbar: ng too large for shared memory");
-    int grid = grid_for(n, INT_THREADS, 148 * 8);
-    if (mode == 1) {
-        cudaFuncSetAttribute(int_tbar_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        int_tbar_kernel<1><<<grid, INT_THREADS, smem, st>>>(ng, n, tbar, D, ti, G, out, y0, y1, lower);
-    } else {
-        cudaFuncSetAttribute(int_tbar_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        int_tbar_kernel<0><<<grid, INT_THREADS, smem, st>>>(ng, n, tbar, D, ti, G, out, y0, y1, lower);
-    }
+    IntArgs a = int_args(ng, n, tbar, tstride, D, ti, nullptr, G, out, ostride, y0, y1, lower);
+    if (y1 - y0 <= 4)
+        launch_int_tbar<4, false>(a, mode, st);
+    else if (y1 - y0 <= 8)
+        launch_int_tbar<8, false>(a, mode, st);
+    else if (y1 - y0 <= 12)
+        launch_int_tbar<12, false>(a, mode, st);
+    else
+        launch_int_tbar<16, false>(a, mode, st);
     KB_CHECK_LAUNCH("int_tbar_kernel");
+    return 0;
+}
+
+int kb200_int_tbar_update(int ng, int64_t n, const double* tbar, int64_t tstride,
+                          const double* D, const double* ti, const double* G, double* amp,
+                          int64_t astride, int y0, int y1, double alpha, const double* W,
+                          const double* T1x, const double* T1y, int64_t t1xs, int64_t t1ys,
+                          int nvb, int noa, int nob, const double* g, double c2, double c11,
+                          double* out4, double* scratch, int mode, void* stream) {
+    const int lower = (mode & 2) ? 1 : 0;
+    mode &= 1;
+    if (ng <= 0 || n <= 0 || y0 < 0 || y1 > ng || y0 >= y1 || tstride < n || astride < n)
+        return fail(-1, "int_tbar_update: bad size");
+    if ((T1x == nullptr) != (T1y == nullptr)) return fail(-1, "int_tbar_update: T1x/T1y");
+    if (W != nullptr && g == nullptr) return fail(-1, "int_tbar_update: energy term needs g");
+    if (T1x != nullptr && (n >= (1LL << 31) || nvb <= 0 || noa <= 0 || nob <= 0 ||
+                           n % ((long long)nvb * noa * nob) != 0))
+        return fail(-1, "int_tbar_update: bad block dims");
+    cudaStream_t st = (cudaStream_t)stream;
+    IntArgs a = int_args(ng, n, tbar, tstride, D, ti, g, G, amp, astride, y0, y1, lower);
+    a.alpha = alpha; a.W = W; a.T1x = T1x; a.T1y = T1y; a.t1xs = t1xs; a.t1ys = t1ys;
+    a.nvb = nvb; a.noa = noa; a.nob = nob; a.c2 = c2; a.c11 = c11; a.part = scratch;
+    const int grid = int_grid(n);
+    if (4LL * grid > 65536) return fail(-1, "int_tbar_update: scratch too small");
+    if (y1 - y0 <= 4)
+        launch_int_tbar<4, true>(a, mode, st);
+    else if (y1 - y0 <= 8)
+        launch_int_tbar<8, true>(a, mode, st);
+    else if (y1 - y0 <= 12)
+        launch_int_tbar<12, true>(a, mode, st);
+    else
+        launch_int_tbar<16, true>(a, mode, st);
+    KB_CHECK_LAUNCH("int_tbar_kernel(update)");
+    final_sum_kernel<<<4, 32, 0, st>>>(scratch, grid, 4, out4);
+    KB_CHECK_LAUNCH("final_sum_kernel");
     return 0;
 }
 
@@ -1049,30 +1268,41 @@ int kb200_int_L(int ng, const int32_t dims[4], const int64_t dstride[4], const d
 int kb200_int_L_rows(int ng, const int32_t dims[4], const int64_t dstride[4], const double* L,
                      const double* D, const double* ti, const double* g, const double* G,
                      double* out, int s0, int s1, int mode, void* stream) {
+    long long n = 1;
+    for (int i = 0; i < 4; ++i) n *= dims[i] > 0 ? dims[i] : 0;
+    return kb200_int_L_strided(ng, dims, dstride, L, n, D, ti, g, G, out, n, s0, s1, mode, stream);
+}
+
+int kb200_int_L_strided(int ng, const int32_t dims[4], const int64_t dstride[4], const double* L,
+                        int64_t lstride, const double* D, const double* ti, const double* g,
+                        const double* G, double* out, int64_t ostride, int s0, int s1, int mode,
+                        void* stream) {
     const int lower = (mode & 2) ? 1 : 0;
     mode &= 1;
     if (ng <= 0 || s0 < 0 || s1 > ng || s0 > s1) return fail(-1, "int_L: bad size");
     if (s0 == s1) return 0;
-    Dims4 dm;
     long long n = 1;
     for (int i = 0; i < 4; ++i) {
         if (dims[i] <= 0) return fail(-1, "int_L: bad dims");
-        dm.d[i] = dims[i];
-        dm.s[i] = dstride[i];
         n *= dims[i];
     }
     if (n >= (1LL << 31)) return fail(-1, "int_L: block too large");
+    if (lstride < n || ostride < n) return fail(-1, "int_L: bad stride");
     cudaStream_t st = (cudaStream_t)stream;
-    size_t smem = ((size_t)ng * INT_THREADS * (mode == 1 ? 2 : 1) + 2 * ng) * 8;
-    if (smem > 227 * 1024) return fail(-1, "int_L: ng too large for shared memory");
-    int grid = grid_for(n, INT_THREADS, 148 * 8);
-    if (mode == 1) {
-        cudaFuncSetAttribute(int_L_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        int_L_kernel<1><<<grid, INT_THREADS, smem, st>>>(ng, n, dm, L, D, ti, g, G, out, s0, s1, lower);
-    } else {
-        cudaFuncSetAttribute(int_L_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        int_L_kernel<0><<<grid, INT_THREADS, smem, st>>>(ng, n, dm, L, D, ti, g, G, out, s0, s1, lower);
+    IntArgs a = int_args(ng, n, L, lstride, D, ti, g, G, out, ostride, s0, s1, lower);
+    a.dstrided = 1;
+    for (int i = 0; i < 4; ++i) {
+        a.dd[i] = dims[i];
+        a.ds[i] = dstride[i];
     }
+    if (s1 - s0 <= 4)
+        launch_int_L<4>(a, mode, st);
+    else if (s1 - s0 <= 8)
+        launch_int_L<8>(a, mode, st);
+    else if (s1 - s0 <= 12)
+        launch_int_L<12>(a, mode, st);
+    else
+        launch_int_L<16>(a, mode, st);
     KB_CHECK_LAUNCH("int_L_kernel");
     return 0;
 }
@@ -1110,6 +1340,20 @@ int kb200_damp_norms(int64_t n, double* old, const double* neu, double alpha, do
     int grid = grid_for(n, RED_THREADS, RED_BLOCKS);
     damp_norms_kernel<<<grid, RED_THREADS, 0, st>>>(n, old, neu, alpha, scratch);
     KB_CHECK_LAUNCH("damp_norms_kernel");
+    final_sum_kernel<<<3, 32, 0, st>>>(scratch, grid, 3, out3);
+    KB_CHECK_LAUNCH("final_sum_kernel");
+    return 0;
+}
+
+int kb200_damp_norms_rows(int ng, int64_t n, double* old, int64_t ostride, const double* neu,
+                          int64_t nstride, double alpha, double* out3, double* scratch,
+                          void* stream) {
+    if (ng <= 0 || n <= 0 || ostride < n || nstride < n) return fail(-1, "damp_norms_rows: bad size");
+    cudaStream_t st = (cudaStream_t)stream;
+    int grid = grid_for(n, RED_THREADS, RED_BLOCKS);
+    damp_norms_rows_kernel<<<grid, RED_THREADS, 0, st>>>(ng, n, old, ostride, neu, nstride, alpha,
+                                                         scratch);
+    KB_CHECK_LAUNCH("damp_norms_rows_kernel");
     final_sum_kernel<<<3, 32, 0, st>>>(scratch, grid, 3, out3);
     KB_CHECK_LAUNCH("final_sum_kernel");
     return 0;

@@ -7,6 +7,7 @@ points.  One ``run`` = one C call (kb200_plan_run) that enqueues every kernel
 of the residual for that chunk on the current CUDA stream.
 """
 import ctypes
+from collections import OrderedDict
 
 import torch
 
@@ -15,7 +16,7 @@ from . import _lib, plan as _plan
 
 class Plan(object):
     def __init__(self, rops, mode, sizes, inputs, outputs, preset_outputs=(), name="plan",
-                 shapes=None, batched=None):
+                 shapes=None, batched=None, antisym=True):
         """rops: resolved ops; inputs/outputs: slot names supplied by the caller
         (outputs are overwritten by their first write unless listed in
         preset_outputs); all other slots are plan-owned scratch."""
@@ -27,7 +28,7 @@ class Plan(object):
         self.inputs = [s for s in self.shapes if s in set(inputs) or _plan.is_integral_slot(s)]
         self.outputs = [s for s in outputs if s in self.shapes]
         preset = list(self.inputs) + list(preset_outputs)
-        self.low = _plan.Lowered(rops, self.shapes, self.batched, preset)
+        self.low = _plan.Lowered(rops, self.shapes, self.batched, preset, antisym=antisym)
         self.derived = self.low.derived
         self.tmp_slots = [s for s in self.shapes if s not in self.inputs and s not in self.outputs
                           and s not in self.derived]
@@ -72,29 +73,37 @@ class Plan(object):
         self._tmp_nb = 0
         self._ws = None
 
-    def _ops_for(self, nb):
-        if nb not in self._ops:
-            arr = self.low.finalize(nb)
+    def _ops_for(self, nb, bstr=(), part=None):
+        key = (nb, bstr, part)
+        if key not in self._ops:
+            arr = self.low.finalize(nb, dict(bstr) if bstr else None, part)
             ws = _lib.load().kb200_plan_workspace_bytes(arr, len(arr))
-            self._ops[nb] = (arr, int(ws))
-        return self._ops[nb]
+            self._ops[key] = (arr, int(ws))
+        return self._ops[key]
 
     # -- run -----------------------------------------------------------------
-    def run(self, tensors, ng, chunk=None, timings=None):
-        """tensors: slot -> CUDA float64 tensor (batched slots: leading axis ng).
-        Scratch is allocated for `chunk` grid points at a time (default: all)."""
+    def run(self, tensors, ng, chunk=None, timings=None, part=None):
+        """tensors: slot -> CUDA float64 tensor (batched slots: leading axis ng; the grid points
+        of a batched slot may be rows of a wider buffer, i.e. any leading stride).
+        Scratch is allocated for `chunk` grid points at a time (default: all).
+        part = (rank, world): row-slabbed contractions (plan.hybrid_phases) do this rank's rows."""
         lib = _lib.load()
         dev = _lib.device()
         nb_max = ng if chunk is None else max(1, min(int(chunk), ng))
         self._ensure_tmp(nb_max, dev)
         names = self.low.slot_names
+        bstr = []
         for s in self.inputs + self.outputs:
             t = tensors[s]
             want = ((ng,) if self.batched[s] else ()) + tuple(self.shapes[s])
+            inner = t[0] if (self.batched[s] and t.dim() > 0 and t.shape[0] > 0) else t
             if tuple(t.shape) != want or t.dtype != torch.float64 or not t.is_cuda \
-                    or not t.is_contiguous():
+                    or not inner.is_contiguous():
                 raise Exception("plan %s: slot %s expects contiguous cuda float64 %s, got %s %s"
                                 % (self.name, s, want, tuple(t.shape), t.dtype))
+            if self.batched[s] and ng > 1 and t.stride(0) != inner.numel():
+                bstr.append((self.low.slot_index[s], int(t.stride(0))))
+        bstr = tuple(sorted(bstr))
         for name, (src, perm) in self.derived.items():
             st = tensors[src]
             key = (st.data_ptr(), st._version)
@@ -106,7 +115,7 @@ class Plan(object):
         y0 = 0
         while y0 < ng:
             nb = min(nb_max, ng - y0)
-            ops, wsb = self._ops_for(nb)
+            ops, wsb = self._ops_for(nb, bstr, part)
             tables = self._tables(dev)        # after finalize: it may add (batch-folded) tables
             if wsb > 0 and (self._ws is None or self._ws.numel()*8 < wsb or self._ws.device != dev):
                 self._ws = torch.empty((wsb + 7)//8, dtype=torch.float64, device=dev)
@@ -189,3 +198,131 @@ def clear_cache():
         if hasattr(p, "release"):
             p.release()
     _cache.clear()
+
+
+class PhasedPlan(object):
+    """A program evaluated by all ranks TOGETHER at the same grid points (plan.hybrid_phases):
+    one Plan per phase, the buffers that cross phases owned here, the distributed buffers laid
+    out back to back in one pool so that each exchange is ONE all-reduce over NVLink."""
+
+    def __init__(self, rops, mode, sizes, inputs, outputs, world, name="hybrid", antisym=True,
+                 min_work=None):
+        self.name, self.world = name, int(world)
+        shapes = _plan.slot_shapes(rops, mode, sizes)
+        self.outputs = [s for s in outputs if s in shapes]
+        self.hp = _plan.hybrid_phases(rops, shapes, self.outputs, self.world, min_work)
+        self.shapes = self.hp.shapes
+        self.batched = {s: not _plan.is_integral_slot(s) for s in self.shapes}
+        ext = set(s for s in self.shapes if s in set(inputs) or _plan.is_integral_slot(s))
+        self.inputs = [s for s in self.shapes if s in ext]
+        dset = set(self.hp.dslots)
+        phase_slots = []
+        for ops in self.hp.phases:
+            sl = []
+            for op in ops:
+                for s, _ in [op.out] + list(op.ins):
+                    if s not in sl:
+                        sl.append(s)
+            phase_slots.append(sl)
+        count = {}
+        for sl in phase_slots:
+            for s in sl:
+                count[s] = count.get(s, 0) + 1
+        # buffers owned here: everything distributed, and every scratch slot seen by two phases
+        self.shared = [s for s in self.shapes
+                       if s not in ext and s not in self.outputs and (s in dset or count.get(s, 0) > 1)]
+        self.plans = []
+        have = set(ext) | dset
+        for p, (ops, sl) in enumerate(zip(self.hp.phases, phase_slots)):
+            if not ops:
+                self.plans.append(None)
+                continue
+            ins = [s for s in sl if s in have]
+            outs = [s for s in sl if s not in have and (s in self.outputs or s in self.shared)]
+            sh = OrderedDict((s, self.shapes[s]) for s in sl)
+            self.plans.append(Plan(ops, mode, None, ins, outs, name="%s-phase%d" % (name, p),
+                                   shapes=sh, batched={s: self.batched[s] for s in sl},
+                                   antisym=antisym))
+            have.update(sl)
+        # pool layout: distributed buffers in exchange order
+        self._pool_off = {}
+        off = 0
+        for s in self.hp.dslots:
+            n = 1
+            for d in self.shapes[s]:
+                n *= d
+            self._pool_off[s] = (off, n)
+            off += n
+        self._pool_per_point = off
+        self._exch = []
+        for ex in self.hp.exchange:
+            if ex:
+                lo = self._pool_off[ex[0]][0]
+                hi = self._pool_off[ex[-1]][0] + self._pool_off[ex[-1]][1]
+                self._exch.append((lo, hi))
+            else:
+                self._exch.append(None)
+        self._bufs = None
+        self._nb = 0
+        self.flops_per_point = sum(p.flops_per_point for p in self.plans if p is not None)
+
+    def _ensure(self, nb, dev):
+        if self._bufs is not None and self._nb == nb and self._pool.device == dev:
+            return
+        # [buffer][grid point]: each exchange range is contiguous over all nb points
+        self._pool = torch.zeros(nb*self._pool_per_point, dtype=torch.float64, device=dev)
+        self._bufs = {}
+        for s, (off, n) in self._pool_off.items():
+            self._bufs[s] = self._pool[nb*off:nb*(off + n)].view((nb,) + tuple(self.shapes[s]))
+        for s in self.shared:
+            if s not in self._bufs:
+                alloc = torch.zeros if s.startswith(_plan.TRI_PREFIX) else torch.empty
+                self._bufs[s] = alloc((nb,) + tuple(self.shapes[s]), dtype=torch.float64, device=dev)
+        self._nb = nb
+
+    def n_ops(self):
+        return sum(p.n_ops() for p in self.plans if p is not None)
+
+    def release(self):
+        self._bufs = None
+        self._pool = None
+        self._nb = 0
+        for p in self.plans:
+            if p is not None:
+                p.release()
+
+    def begin(self, tensors, nb, rank):
+        """Start an evaluation: tensors = caller-supplied slots (inputs, integrals, outputs) for
+        nb grid points; clears the distributed buffers."""
+        dev = _lib.device()
+        self._ensure(nb, dev)
+        self._pool.zero_()
+        self._cur = (tensors, nb, (int(rank), self.world))
+
+    def run_phase(self, p):
+        tensors, nb, part = self._cur
+        pl = self.plans[p]
+        if pl is not None:
+            t = {}
+            for s in pl.inputs + pl.outputs:
+                t[s] = self._bufs[s] if s in self._bufs else tensors[s]
+            pl.run(t, nb, part=part)
+
+    def exchange_buffer(self, p):
+        """The flat buffer that has to be summed over the ranks after phase p, or None."""
+        rng = self._exch[p]
+        if rng is None:
+            return None
+        nb = self._cur[1]
+        return self._pool[nb*rng[0]:nb*rng[1]]
+
+    def run(self, tensors, nb, rank, group=None):
+        """All phases, with the exchanges as NCCL all-reduces on `group`."""
+        self.begin(tensors, nb, rank)
+        for p in range(len(self.plans)):
+            self.run_phase(p)
+            buf = self.exchange_buffer(p)
+            if buf is not None and self.world > 1:
+                import torch.distributed as dist
+                dist.all_reduce(buf, group=group)
+        self._cur = None

@@ -58,51 +58,66 @@ def _u_sizes(Fa, Fb):
 # add per term) only pay once the contractions are several waves of CTAs long
 MIRROR_ROWS_MIN_BATCH = int(os.environ.get("KB200_MIRROR_ROWS_MIN_BATCH", "4"))
 
+# closed shell: sum/difference (singlet/triplet channel) form of the paired ring contractions
+# (plan.sumdiff_pairs) and, when the amplitudes also satisfy T2aa = T2ab - T2ab(a<->b), the
+# same-spin doubles residual from the opposite-spin one (plan.singlet_reduce)
+SUMDIFF = int(os.environ.get("KB200_SUMDIFF", "1"))
+SINGLET = int(os.environ.get("KB200_SINGLET", "1"))
 
-# sum/difference form of the paired closed-shell ring contractions (plan.sumdiff_pairs): built and
-# CPU-tested, off until it has had its GPU parity run
-SUMDIFF = int(os.environ.get("KB200_SUMDIFF", "0"))
+_U_TIN = ("t1.a", "t1.b", "t2.aa", "t2.ab", "t2.bb")
+_U_TOUT = ("o1.a", "o1.b", "o2.aa", "o2.ab", "o2.bb")
+
+
+def _stanton_rops(mode, fac, mirror, mirror_rows, singlet, sumdiff, antisym):
+    T = programs.tensor_defs()
+    rops = _plan.expand(programs.stanton(fac), T, mode)
+    if mode == "g":
+        ins, outs = ("t1", "t2"), ("o1", "o2")
+    else:
+        ins, outs = _U_TIN, _U_TOUT
+    if mirror:
+        assert mode == "u"
+        rops = _plan.mirror_reduce(rops)
+        ins = tuple(s for s in ins if _plan.mirror_rep(s) == s)
+        outs = tuple(s for s in outs if _plan.mirror_rep(s) == s)
+        if singlet:
+            rops = _plan.singlet_reduce(rops)
+        if sumdiff:
+            rops = _plan.sumdiff_pairs(rops)
+        if mirror_rows:
+            rops = _plan.mirror_outputs(rops)
+    if antisym:
+        rops = _plan.antisym_outputs(rops)
+    return rops, ins, outs
 
 
 def stanton_plan(mode, sizes, fac=-1.0, mirror=False, mirror_rows=False, singlet=False,
-                 sumdiff=None):
+                 sumdiff=None, antisym=True, hybrid_world=None):
     """mirror (u only): the closed-shell reduction of the program (plan.mirror_reduce): only the
     alpha-leading block of every alpha <-> beta pair is evaluated; mirror_rows: additionally
     plan.mirror_outputs; singlet / sumdiff: additionally plan.singlet_reduce /
-    plan.sumdiff_pairs (neither is used by the loops yet)."""
-    mirror_rows = bool(mirror and mirror_rows)
-    singlet = bool(mirror and singlet)
+    plan.sumdiff_pairs.  antisym=False: nothing is assumed about the permutational symmetry of
+    the amplitudes (full sums over contracted pairs, full outputs, as the reference computes).
+    hybrid_world=P: the same program as an engine.PhasedPlan evaluated by P ranks together."""
+    mirror_rows = bool(mirror and mirror_rows and antisym)
+    singlet = bool(mirror and singlet and SINGLET and antisym)
     sumdiff = bool(mirror and (SUMDIFF if sumdiff is None else sumdiff))
     key = ("stanton", mode, tuple(sorted(sizes.items(), key=str)), fac, bool(mirror), mirror_rows,
-           singlet, sumdiff)
+           singlet, sumdiff, bool(antisym), hybrid_world)
 
     def build():
-        T = programs.tensor_defs()
-        rops = _plan.expand(programs.stanton(fac), T, mode)
-        if mode == "g":
-            ins, outs = ("t1", "t2"), ("o1", "o2")
-        else:
-            ins = ("t1.a", "t1.b", "t2.aa", "t2.ab", "t2.bb")
-            outs = ("o1.a", "o1.b", "o2.aa", "o2.ab", "o2.bb")
-        if mirror:
-            assert mode == "u"
-            rops = _plan.mirror_reduce(rops)
-            ins = tuple(s for s in ins if _plan.mirror_rep(s) == s)
-            outs = tuple(s for s in outs if _plan.mirror_rep(s) == s)
-            if singlet:
-                rops = _plan.singlet_reduce(rops)
-            if sumdiff:
-                rops = _plan.sumdiff_pairs(rops)
-            if mirror_rows:
-                rops = _plan.mirror_outputs(rops)
-        rops = _plan.antisym_outputs(rops)
-        return engine.Plan(rops, mode, sizes, ins, outs,
-                           name="stanton-" + mode + ("-closed" if mirror else ""))
+        rops, ins, outs = _stanton_rops(mode, fac, mirror, mirror_rows, singlet, sumdiff, antisym)
+        name = "stanton-" + mode + ("-closed" if mirror else "")
+        if hybrid_world:
+            return engine.PhasedPlan(rops, mode, sizes, ins, outs, hybrid_world,
+                                     name=name + "-hybrid", antisym=antisym)
+        return engine.Plan(rops, mode, sizes, ins, outs, name=name, antisym=antisym)
     return engine.cached(key, build)
 
 
 # ---------------------------------------------------------------------------
-# closed-shell detection (unrestricted inputs whose alpha and beta halves coincide)
+# symmetry detection (unrestricted inputs whose alpha and beta halves coincide;
+# permutational antisymmetry of caller-supplied doubles)
 # ---------------------------------------------------------------------------
 CLOSED_SHELL = int(os.environ.get("KB200_CLOSED_SHELL", "1"))
 CLOSED_SHELL_TOL = 1e-12
@@ -115,6 +130,42 @@ def _same(x, y, tol=CLOSED_SHELL_TOL):
         return True
     d, m = _lib.max_absdiff(x, y)
     return d <= tol*m
+
+
+def is_antisymmetric(X, tol=CLOSED_SHELL_TOL):
+    """X[y,p,q,r,s] == -X[y,q,p,r,s] == -X[y,p,q,s,r] to `tol` relative?  The contraction plans
+    sum antisymmetric contracted pairs over x < y and compute antisymmetric outputs on one
+    triangle (plan.ANTISYM, plan.antisym_outputs); the amplitude equations preserve the
+    antisymmetry of T2 / L2, but a caller-supplied guess need not have it -- the reference's
+    full double sums (cqcpy einsums, kelvin/ft_cc_equations.py:96-113) then give something else.
+    Device check, one grid point at a time; call it once per solve."""
+    X = _lib.as_dev_rows(X)
+    if X.dim() != 5 or X.shape[1] != X.shape[2] or X.shape[3] != X.shape[4]:
+        return False
+    for y in range(X.shape[0]):
+        x = X[y]
+        m = float(x.abs().max())
+        if m == 0.0:
+            continue
+        if float((x + x.transpose(0, 1)).abs().max()) > tol*m \
+                or float((x + x.transpose(2, 3)).abs().max()) > tol*m:
+            return False
+    return True
+
+
+def is_singlet(X2aa, X2ab, tol=CLOSED_SHELL_TOL):
+    """X2aa[y,p,q,r,s] == X2ab[y,p,q,r,s] - X2ab[y,q,p,r,s] (the same-spin block of a closed-shell
+    singlet state is the antisymmetrised opposite-spin one)?  True of the MP2 guess of a
+    spin-symmetric system and preserved by the update."""
+    X2aa, X2ab = _lib.as_dev_rows(X2aa), _lib.as_dev_rows(X2ab)
+    if tuple(X2aa.shape) != tuple(X2ab.shape):
+        return False
+    for y in range(X2aa.shape[0]):
+        ab = X2ab[y]
+        m = float(ab.abs().max())
+        if float((ab - ab.transpose(0, 1) - X2aa[y]).abs().max()) > tol*max(m, 1e-300):
+            return False
+    return True
 
 
 def closed_shell_integrals(Fa, Fb, Ia, Ib, Iabab):
@@ -173,6 +224,100 @@ def _u_integral_slots(Fa, Fb, Ia, Ib, Iabab, dev, needed):
 
 
 # ---------------------------------------------------------------------------
+# evaluation of a per-grid-point program over the rows of the grid, sharded over the ranks
+# ---------------------------------------------------------------------------
+def flat_rows(ng, shapes, dev):
+    """One (ng, Ntot) buffer and its blocks as (ng, *shape) views (rows of the wide buffer): the
+    blocks of one quantity travel in ONE collective (parallel.exchange_rows)."""
+    ns = []
+    for shp in shapes:
+        n = 1
+        for d in shp:
+            n *= int(d)
+        ns.append(n)
+    flat = torch.empty((ng, sum(ns)), dtype=torch.float64, device=dev)
+    views, off = [], 0
+    for shp, n in zip(shapes, ns):
+        views.append(flat[:, off:off + n].unflatten(1, tuple(int(d) for d in shp)))
+        off += n
+    return flat, views
+
+
+class RowCache(object):
+    """Per-grid-point tensors kept only for the rows this rank evaluates: `ranges` =
+    [(first global row, stop)] laid out back to back in the leading axis of every tensor."""
+    def __init__(self, ranges, tensors):
+        self.ranges, self.tensors = list(ranges), tensors
+
+    def local(self, a, b):
+        off = 0
+        for r0, r1 in self.ranges:
+            if r0 <= a and b <= r1:
+                return off + a - r0, off + b - r0
+            off += r1 - r0
+        raise Exception("RowCache: rows [%d, %d) are not held by this rank" % (a, b))
+
+    def nrows(self):
+        return sum(r1 - r0 for r0, r1 in self.ranges)
+
+
+def evaluate_rows(p, hybrid, t, flat, ng, y0, dev, cache=None):
+    """Fill the rows [y0, ng) of the outputs of plan `p` (column views of `flat`) on EVERY rank.
+    t: slot -> tensor, batched slots with all ng rows; cache: RowCache of further batched input
+    slots held for this rank's rows only; hybrid: callable returning the engine.PhasedPlan of
+    the same program (or None).  Single rank: one plan run.  Sharded (parallel.active()): own
+    rows locally, leftover rows together (hybrid) or by single owners, then one exchange."""
+    from . import parallel
+
+    def sliced(pl, a, b):
+        tt = {}
+        for s in pl.inputs + pl.outputs:
+            if cache is not None and s in cache.tensors:
+                la, lb = cache.local(a, b)
+                tt[s] = cache.tensors[s][la:lb]
+            else:
+                tt[s] = t[s][a:b] if pl.batched[s] else t[s]
+        return tt
+
+    def run(a, b):
+        if b > a:
+            p.run(sliced(p, a, b), b - a, _chunk_for(p, b - a, dev))
+
+    if not parallel.active():
+        run(y0, ng)
+        return
+    sh = parallel.Shards(ng, y0)
+    run(*sh.own)
+    owner_left = False
+    if sh.r > 0:
+        hp = None
+        if sh.use_hybrid() and hybrid is not None:
+            try:
+                hp = hybrid()
+            except ValueError:
+                hp = None             # program shape the partition does not cover: single owners
+        if hp is not None:
+            l0, l1 = sh.left
+            hp.run(sliced(hp, l0, l1), l1 - l0, sh.rank, parallel.group())
+        else:
+            owner_left = True
+            parallel.zero_foreign_left_rows(flat, sh)
+            mine = sh.owner_row()
+            if mine is not None:
+                run(mine, mine + 1)
+    parallel.exchange_rows(flat, sh, owner_left)
+
+
+def needed_rows(ng, y0=0):
+    """Row ranges of [y0, ng) this rank evaluates (alone or together with the others)."""
+    from . import parallel
+    if not parallel.active():
+        return [(y0, ng)]
+    sh = parallel.Shards(ng, y0)
+    return sh.my_rows(sh.use_hybrid())
+
+
+# ---------------------------------------------------------------------------
 # amplitude equations
 # ---------------------------------------------------------------------------
 def t0_is_zero(G, amps):
@@ -192,93 +337,102 @@ def t0_is_zero(G, amps):
     return True
 
 
-def _run_rows(p, t, ins, outs, drivers, ng, dev, t0_zero):
-    """Run the residual plan over the grid points; with t0_zero the first point is not
-    evaluated (its amplitudes are exactly zero): T̄[0] = drivers."""
-    if not t0_zero:
-        p.run(t, ng, _chunk_for(p, ng, dev))
-        return
-    full = {nm: t[nm] for nm in tuple(ins) + tuple(outs)}
-    if ng > 1:
-        for nm in full:
-            t[nm] = full[nm][1:]
-        p.run(t, ng - 1, _chunk_for(p, ng - 1, dev))
-    for nm, d in zip(outs, drivers):
-        full[nm][0].copy_(d)
-        full[nm][0].neg_()
-        t[nm] = full[nm]
-
-
-def ccsd_stanton_bar(F, I, T1old, T2old, fac=-1.0, t0_zero=False):
+def ccsd_stanton_bar(F, I, T1old, T2old, fac=-1.0, t0_zero=False, antisym=None):
     """T1bar, T2bar: drivers + fac*StantonTerms at every grid point, i.e. the
     state of T1new/T2new just before the integration at
     kelvin/ft_cc_equations.py:109.  t0_zero: the caller guarantees T1old[0] = T2old[0] = 0
-    (see t0_is_zero); the first grid point then costs nothing."""
+    (see t0_is_zero); the first grid point then costs nothing.  antisym: T2old is antisymmetric
+    (None: checked here, see is_antisymmetric).  The two blocks are column ranges of one
+    (ng, Ntot) buffer."""
     dev = _lib.device()
     T1old = _lib.as_dev(T1old, dev)
     T2old = _lib.as_dev(T2old, dev)
     ng = T1old.shape[0]
-    p = stanton_plan("g", _g_sizes(F), fac)
+    if antisym is None:
+        antisym = is_antisymmetric(T2old)
+    sizes = _g_sizes(F)
+    p = stanton_plan("g", sizes, fac, antisym=antisym)
     t = _g_integral_slots(F, I, dev)
     t["t1"], t["t2"] = T1old, T2old
-    o1 = t["o1"] = torch.empty_like(T1old)
-    o2 = t["o2"] = torch.empty_like(T2old)
-    _run_rows(p, t, ("t1", "t2"), ("o1", "o2"), (t["F.vo"], t["I.vvoo"]), ng, dev, t0_zero)
+    flat, (o1, o2) = flat_rows(ng, (T1old.shape[1:], T2old.shape[1:]), dev)
+    t["o1"], t["o2"] = o1, o2
+    y0 = 1 if (t0_zero and ng > 1) else 0
+    from . import parallel
+    hyb = (lambda: stanton_plan("g", sizes, fac, antisym=antisym,
+                                hybrid_world=parallel.world_info()[1]))
+    evaluate_rows(p, hyb, t, flat, ng, y0, dev)
+    if y0:
+        o1[0].copy_(t["F.vo"]).neg_()
+        o2[0].copy_(t["I.vvoo"]).neg_()
     return o1, o2
 
 
-def ccsd_stanton(F, I, T1old, T2old, D1, D2, ti, ng, G, t0_zero=False):
+def ccsd_stanton(F, I, T1old, T2old, D1, D2, ti, ng, G, t0_zero=False, antisym=None):
     """Time-dependent CCSD iteration using Stanton-Gauss intermediates
     (kelvin/ft_cc_equations.py:96-113)."""
-    T1bar, T2bar = ccsd_stanton_bar(F, I, T1old, T2old, t0_zero=t0_zero)
+    T1bar, T2bar = ccsd_stanton_bar(F, I, T1old, T2old, t0_zero=t0_zero, antisym=antisym)
     T1new = quadrature.int_tbar1(ng, T1bar, ti, D1, G)
     T2new = quadrature.int_tbar2(ng, T2bar, ti, D2, G)
     return T1new, T2new
 
 
 def uccsd_stanton_bar(Fa, Fb, Ia, Ib, Iabab, T1aold, T1bold, T2aaold, T2abold, T2bbold, fac=-1.0,
-                      t0_zero=False, closed_shell=False, beta_copies=True):
+                      t0_zero=False, closed_shell=False, beta_copies=True, singlet=False,
+                      antisym=None):
     """closed_shell: the caller guarantees mirror-symmetric integrals and amplitudes
     (closed_shell_integrals / closed_shell_amplitudes); the beta-leading blocks are then copies
-    of their alpha images and only the reduced program runs (plan.mirror_reduce).
-    beta_copies=False returns None in their place (the caller copies later)."""
+    of their alpha images and only the reduced program runs (plan.mirror_reduce);
+    singlet: additionally T2aa = T2ab - T2ab(a<->b) (is_singlet).
+    beta_copies=False returns None in the place of the beta blocks (the caller copies later).
+    antisym: T2aa/T2bb are antisymmetric (None: checked here)."""
     dev = _lib.device()
     ins = [_lib.as_dev(x, dev) for x in (T1aold, T1bold, T2aaold, T2abold, T2bbold)]
     ng = ins[0].shape[0]
-    neval = ng - 1 if (t0_zero and ng > 1) else ng
-    p = stanton_plan("u", _u_sizes(Fa, Fb), fac, mirror=closed_shell,
-                     mirror_rows=neval >= MIRROR_ROWS_MIN_BATCH)
+    if antisym is None:
+        antisym = bool(closed_shell and singlet) or \
+            (is_antisymmetric(ins[2]) and (closed_shell or is_antisymmetric(ins[4])))
+    y0 = 1 if (t0_zero and ng > 1) else 0
+    sizes = _u_sizes(Fa, Fb)
+    from . import parallel
+    nloc = max(b - a for a, b in needed_rows(ng, y0)) if ng > y0 else 0
+    kw = dict(mirror=closed_shell, singlet=singlet, antisym=antisym)
+    p = stanton_plan("u", sizes, fac, mirror_rows=nloc >= MIRROR_ROWS_MIN_BATCH, **kw)
     t = _u_integral_slots(Fa, Fb, Ia, Ib, Iabab, dev,
                           [s for s in p.inputs if _plan.is_integral_slot(s)])
-    in_names = ("t1.a", "t1.b", "t2.aa", "t2.ab", "t2.bb")
-    out_names = ("o1.a", "o1.b", "o2.aa", "o2.ab", "o2.bb")
     drivers = [Fa.vo, Fb.vo, Ia.vvoo, Iabab.vvoo, Ib.vvoo]
     live = [k for k in range(5) if not closed_shell or k in (0, 2, 3)]
+    flat, views = flat_rows(ng, [ins[k].shape[1:] for k in live], dev)
     outs = [None]*5
-    for k in live:
-        t[in_names[k]] = ins[k]
-        outs[k] = t[out_names[k]] = torch.empty_like(ins[k])
-    drv = [_lib.as_dev(drivers[k], dev) for k in live] if t0_zero else None
-    _run_rows(p, t, [in_names[k] for k in live], [out_names[k] for k in live], drv, ng, dev,
-              t0_zero)
+    for k, v in zip(live, views):
+        t[_U_TIN[k]] = ins[k]
+        outs[k] = t[_U_TOUT[k]] = v
+    hyb = (lambda: stanton_plan("u", sizes, fac, hybrid_world=parallel.world_info()[1], **kw))
+    evaluate_rows(p, hyb, t, flat, ng, y0, dev)
+    if y0:
+        for k in live:
+            outs[k][0].copy_(_lib.as_dev(drivers[k], dev)).neg_()
     if closed_shell and beta_copies:
-        outs[1] = outs[0].clone()
-        outs[4] = outs[2].clone()
+        outs[1] = outs[0]
+        outs[4] = outs[2]
     return tuple(outs)
 
 
 def uccsd_stanton(Fa, Fb, Ia, Ib, Iabab, T1aold, T1bold, T2aaold, T2abold,
                   T2bbold, D1a, D1b, D2aa, D2ab, D2bb, ti, ng, G, t0_zero=False,
-                  closed_shell=False):
+                  closed_shell=False, singlet=False, antisym=None):
     """Unrestricted CCSD iteration (kelvin/ft_cc_equations.py:130-164)."""
     b1a, b1b, b2aa, b2ab, b2bb = uccsd_stanton_bar(
         Fa, Fb, Ia, Ib, Iabab, T1aold, T1bold, T2aaold, T2abold, T2bbold, t0_zero=t0_zero,
-        closed_shell=closed_shell)
+        closed_shell=closed_shell, singlet=singlet, antisym=antisym)
     T1a = quadrature.int_tbar1(ng, b1a, ti, D1a, G)
-    T1b = quadrature.int_tbar1(ng, b1b, ti, D1b, G)
     T2aa = quadrature.int_tbar2(ng, b2aa, ti, D2aa, G)
     T2ab = quadrature.int_tbar2(ng, b2ab, ti, D2ab, G)
-    T2bb = quadrature.int_tbar2(ng, b2bb, ti, D2bb, G)
+    if closed_shell:
+        # equal denominators (checked with the integrals): the beta blocks are copies
+        T1b, T2bb = T1a.clone(), T2aa.clone()
+    else:
+        T1b = quadrature.int_tbar1(ng, b1b, ti, D1b, G)
+        T2bb = quadrature.int_tbar2(ng, b2bb, ti, D2bb, G)
     return (T1a, T1b), (T2aa, T2ab, T2bb)
 
 
@@ -296,7 +450,9 @@ def ccsd_stanton_single(ig, F, I, T1old, T2old, T1bar, T2bar, D1, D2, ti, ng, G)
     kelvin/ft_cc_equations.py:116-127): T1old/T2old are the amplitudes AT that point,
     T1bar/T2bar the (ng, ...) residual buffers, whose row ig is overwritten."""
     dev = _lib.device()
-    b1, b2 = ccsd_stanton_bar(F, I, _lib.as_dev(T1old, dev)[None], _lib.as_dev(T2old, dev)[None])
+    # the pointwise solver builds its iterates from zero by antisymmetry-preserving updates
+    b1, b2 = ccsd_stanton_bar(F, I, _lib.as_dev(T1old, dev)[None], _lib.as_dev(T2old, dev)[None],
+                              antisym=True)
     _store_row(T1bar, ig, b1[0])
     _store_row(T2bar, ig, b2[0])
     T1new = quadrature.int_tbar1_single(ng, ig, T1bar, ti, D1, G)
@@ -310,7 +466,8 @@ def uccsd_stanton_single(ig, Fa, Fb, Ia, Ib, Iabab, T1a, T1b, T2aa, T2ab,
     """Unrestricted single-point update (kelvin/ft_cc_equations.py:167-192)."""
     dev = _lib.device()
     bars = uccsd_stanton_bar(Fa, Fb, Ia, Ib, Iabab,
-                             *[_lib.as_dev(x, dev)[None] for x in (T1a, T1b, T2aa, T2ab, T2bb)])
+                             *[_lib.as_dev(x, dev)[None] for x in (T1a, T1b, T2aa, T2ab, T2bb)],
+                             antisym=True)
     bufs = (T1bara, T1barb, T2baraa, T2barab, T2barbb)
     for buf, b in zip(bufs, bars):
         _store_row(buf, ig, b[0])
@@ -334,53 +491,79 @@ def _reps(names):
     return tuple(s for s in names if _plan.mirror_rep(s) == s)
 
 
-def lambda_plan(mode, sizes, fac=-1.0, mirror=False):
+def _lambda_rops(mode, fac, mirror, antisym):
+    """(forward intermediates, reverse sweep) with the closed-shell rewrites of the sweep:
+    mirror-duplicate contractions done once (plan.merge_duplicates), the three quartets of ring
+    contractions as sum/difference pairs (plan.sumdiff_pairs), and the same-spin ladder adjoints
+    on their triangle (plan.antisym_outputs)."""
+    inter, rest = programs.lambda_rops(mode, fac)
+    if mirror:
+        inter, rest = _plan.mirror_reduce(inter), _plan.mirror_reduce(rest)
+        if SUMDIFF:
+            rest = _plan.sumdiff_pairs(_plan.merge_duplicates(rest))
+    if antisym:
+        rest = _plan.antisym_outputs(rest)
+    return inter, rest
+
+
+def lambda_plan(mode, sizes, fac=-1.0, mirror=False, antisym=True, hybrid_world=None):
     """Plan of -J(T)^T.Lbar - (F.ov + <ji||ba>t, I.oovv): intermediates of the
     forward residual followed by its mechanically derived reverse sweep."""
-    key = ("lambda", mode, tuple(sorted(sizes.items(), key=str)), fac, bool(mirror))
+    key = ("lambda", mode, tuple(sorted(sizes.items(), key=str)), fac, bool(mirror), bool(antisym),
+           hybrid_world)
 
     def build():
-        inter, rest = programs.lambda_rops(mode, fac)
+        inter, rest = _lambda_rops(mode, fac, mirror, antisym)
         if mode == "g":
             ins, outs = ("t1", "t2", "l1", "l2"), ("lo1", "lo2")
         else:
             ins, outs = _U_T + _U_L, _U_LO
         if mirror:
-            inter, rest = _plan.mirror_reduce(inter), _plan.mirror_reduce(rest)
             ins, outs = _reps(ins), _reps(outs)
-        return engine.Plan(inter + rest, mode, sizes, ins, outs,
-                           name="lambda-" + mode + ("-closed" if mirror else ""))
+        name = "lambda-" + mode + ("-closed" if mirror else "")
+        if hybrid_world:
+            return engine.PhasedPlan(inter + rest, mode, sizes, ins, outs, hybrid_world,
+                                     name=name + "-hybrid", antisym=antisym)
+        return engine.Plan(inter + rest, mode, sizes, ins, outs, name=name, antisym=antisym)
     return engine.cached(key, build)
 
 
-def lambda_split_plans(mode, sizes, fac=-1.0, mirror=False):
+def lambda_split_plans(mode, sizes, fac=-1.0, mirror=False, antisym=True, hybrid_world=None):
     """(prep, sweep): the amplitude-only forward intermediates (W_oooo, W_vvvv, W_ovvo,
     F_oo/vv/ov, tau ...) depend on T alone, which is fixed during the whole Lambda
     solve, so they are built once (prep) and every Lambda iteration runs only the
     reverse sweep (sweep) with the intermediates as inputs -- the 'cached W' cost
-    model of SURVEY.md 8(d) (92 m^6 instead of 128 m^6 per grid point)."""
-    key = ("lambda-split", mode, tuple(sorted(sizes.items(), key=str)), fac, bool(mirror))
+    model of SURVEY.md 8(d) (92 m^6 instead of 128 m^6 per grid point).
+    hybrid_world=P: the sweep as an engine.PhasedPlan evaluated by P ranks together."""
+    key = ("lambda-split", mode, tuple(sorted(sizes.items(), key=str)), fac, bool(mirror),
+           bool(antisym), hybrid_world)
 
     def build():
-        inter, rest = programs.lambda_rops(mode, fac)
+        inter, rest = _lambda_rops(mode, fac, mirror, antisym)
         tins = ("t1", "t2") if mode == "g" else _U_T
         lins = ("l1", "l2") if mode == "g" else _U_L
         louts = ("lo1", "lo2") if mode == "g" else _U_LO
         if mirror:
-            inter, rest = _plan.mirror_reduce(inter), _plan.mirror_reduce(rest)
             tins, lins, louts = _reps(tins), _reps(lins), _reps(louts)
         inter_slots = []
         for op in inter:
             if op.out[0] not in inter_slots:
                 inter_slots.append(op.out[0])
-        prep = engine.Plan(inter, mode, sizes, tins, inter_slots, name="lambda-prep-" + mode)
         used = set()
         for op in rest:
             for slot, _ in op.ins:
                 used.add(slot)
         keep = [s for s in inter_slots if s in used]
-        sweep = engine.Plan(rest, mode, sizes, tuple(tins) + tuple(lins) + tuple(keep), louts,
-                            name="lambda-sweep-" + mode)
+        sweep_ins = tuple(tins) + tuple(lins) + tuple(keep)
+        if hybrid_world:
+            sweep = engine.PhasedPlan(rest, mode, sizes, sweep_ins, louts, hybrid_world,
+                                      name="lambda-sweep-" + mode + "-hybrid", antisym=antisym)
+            sweep.cached_slots = keep
+            return None, sweep
+        prep = engine.Plan(inter, mode, sizes, tins, inter_slots, name="lambda-prep-" + mode,
+                           antisym=antisym)
+        sweep = engine.Plan(rest, mode, sizes, sweep_ins, louts, name="lambda-sweep-" + mode,
+                            antisym=antisym)
         sweep.cached_slots = keep
         prep.all_slots = inter_slots
         return prep, sweep
@@ -390,28 +573,46 @@ def lambda_split_plans(mode, sizes, fac=-1.0, mirror=False):
 _lam_cache = {"key": None, "val": None, "refs": None}
 
 
-def _lambda_intermediates(mode, sizes, ints_slots, tslots, ng, dev, mirror=False):
-    """Forward intermediates for the current amplitudes, cached across Lambda iterations."""
-    prep, sweep = lambda_split_plans(mode, sizes, mirror=mirror)
+def clear_solve_caches():
+    """Drop the per-solve caches (forward intermediates of the Lambda sweep, response-density
+    leaves).  They are keyed by the identity, address and version of the amplitude tensors; a
+    caller that overwrites those tensors through raw pointers must call this."""
+    _lam_cache.update(key=None, val=None, refs=None)
+    _rdm_cache.update(key=None, val=None, refs=None)
+
+
+def _lambda_intermediates(mode, sizes, ints_slots, tslots, ng, dev, mirror=False, antisym=True):
+    """Forward intermediates for the current amplitudes on the rows this rank evaluates, cached
+    across Lambda iterations (RowCache), or None when they do not fit."""
+    prep, sweep = lambda_split_plans(mode, sizes, mirror=mirror, antisym=antisym)
+    ranges = needed_rows(ng)
     # the cache entry keeps the key tensors alive: a live tensor's address cannot be handed to
     # another tensor, so equal (address, version) means the very same, unmodified tensors
     refs = list(tslots.values()) + list(ints_slots.values())
-    key = (mode, bool(mirror), ng, tuple((v.data_ptr(), v._version) for v in refs))
+    key = (mode, bool(mirror), bool(antisym), ng, tuple(ranges),
+           tuple((v.data_ptr(), v._version) for v in refs))
     if _lam_cache["key"] == key and all(a is b for a, b in zip(_lam_cache["refs"], refs)):
         return _lam_cache["val"]
     _lam_cache["key"] = None
     _lam_cache["val"] = None
     _lam_cache["refs"] = None
-    need = sum(8*ng*int(torch.tensor(prep.shapes[s]).prod()) for s in prep.all_slots)
+    nrows = sum(b - a for a, b in ranges)
+    need = sum(8*nrows*int(torch.tensor(prep.shapes[s]).prod()) for s in prep.all_slots)
     free, _ = torch.cuda.mem_get_info(dev)
     if need > 0.5*free:
         return None                      # too large to keep: use the fused (recompute) plan
-    t = dict(ints_slots)
-    t.update(tslots)
-    for s in prep.all_slots:
-        t[s] = torch.empty((ng,) + tuple(prep.shapes[s]), dtype=torch.float64, device=dev)
-    prep.run({k: v for k, v in t.items() if k in prep.shapes}, ng)
-    val = {s: t[s] for s in sweep.cached_slots}
+    bufs = {s: torch.empty((nrows,) + tuple(prep.shapes[s]), dtype=torch.float64, device=dev)
+            for s in prep.all_slots}
+    off = 0
+    for a, b in ranges:
+        t = dict(ints_slots)
+        for k, v in tslots.items():
+            t[k] = v[a:b]
+        for s in prep.all_slots:
+            t[s] = bufs[s][off:off + b - a]
+        prep.run({k: v for k, v in t.items() if k in prep.shapes}, b - a)
+        off += b - a
+    val = RowCache(ranges, {s: bufs[s] for s in sweep.cached_slots})
     _lam_cache["key"] = key
     _lam_cache["val"] = val
     _lam_cache["refs"] = refs
@@ -431,68 +632,84 @@ def lambda_guess_plan(mode, sizes, beta, ls_ts_fac):
     return engine.cached(key, build)
 
 
-def _l_like(T1, T2):
-    """Empty Lambda-shaped (o..v..) tensors matching amplitudes (v..o..)."""
-    L1 = torch.empty((T1.shape[0], T1.shape[2], T1.shape[1]), dtype=torch.float64, device=T1.device)
-    L2 = torch.empty((T2.shape[0], T2.shape[3], T2.shape[4], T2.shape[1], T2.shape[2]),
-                     dtype=torch.float64, device=T2.device)
-    return L1, L2
+def _l_shapes(T1, T2):
+    """Lambda-shaped (o..v..) block shapes matching amplitudes (v..o..)."""
+    return ((T1.shape[2], T1.shape[1]), (T2.shape[3], T2.shape[4], T2.shape[1], T2.shape[2]))
 
 
-def ccsd_lambda_opt(F, I, T1old, T2old, L1old, L2old, D1, D2, ti, ng, g, G, beta):
+def _lambda_rows(mode, sizes, t, tslots, flat, ng, dev, mirror, antisym):
+    """Evaluate the Lambda map on all rows: reverse sweep over cached forward intermediates when
+    they fit, else the fused program."""
+    from . import parallel
+    ints = {k: v for k, v in t.items() if _plan.is_integral_slot(k)}
+    cached = _lambda_intermediates(mode, sizes, ints, tslots, ng, dev, mirror=mirror,
+                                   antisym=antisym)
+    world = parallel.world_info()[1]
+    if cached is not None:
+        p = lambda_split_plans(mode, sizes, mirror=mirror, antisym=antisym)[1]
+        hyb = (lambda: lambda_split_plans(mode, sizes, mirror=mirror, antisym=antisym,
+                                          hybrid_world=world)[1])
+        evaluate_rows(p, hyb, t, flat, ng, 0, dev, cache=cached)
+    else:
+        p = lambda_plan(mode, sizes, mirror=mirror, antisym=antisym)
+        hyb = (lambda: lambda_plan(mode, sizes, mirror=mirror, antisym=antisym,
+                                   hybrid_world=world))
+        evaluate_rows(p, hyb, t, flat, ng, 0, dev)
+
+
+def ccsd_lambda_opt(F, I, T1old, T2old, L1old, L2old, D1, D2, ti, ng, g, G, beta, antisym=None):
     """Time-dependent CCSD Lambda iteration with intermediates
-    (kelvin/ft_cc_equations.py:385-409)."""
+    (kelvin/ft_cc_equations.py:385-409).  antisym: T2old and L2old are antisymmetric (None:
+    checked here)."""
     dev = _lib.device()
     T1old, T2old = _lib.as_dev(T1old, dev), _lib.as_dev(T2old, dev)
+    if antisym is None:
+        antisym = is_antisymmetric(T2old) and is_antisymmetric(L2old)
     L1int = quadrature.int_L1(ng, L1old, ti, D1, g, G)
     L2int = quadrature.int_L2(ng, L2old, ti, D2, g, G)
     sizes = _g_sizes(F)
     t = _g_integral_slots(F, I, dev)
-    cached = _lambda_intermediates("g", sizes, t, {"t1": T1old, "t2": T2old}, ng, dev)
     t.update({"t1": T1old, "t2": T2old, "l1": L1int, "l2": L2int})
-    t["lo1"], t["lo2"] = _l_like(T1old, T2old)
-    if cached is not None:
-        p = lambda_split_plans("g", sizes)[1]
-        t.update(cached)
-        p.run({k: v for k, v in t.items() if k in p.shapes}, ng, _chunk_for(p, ng, dev))
-    else:
-        p = lambda_plan("g", sizes)
-        p.run(t, ng, _chunk_for(p, ng, dev))
-    return t["lo1"], t["lo2"]
+    flat, (lo1, lo2) = flat_rows(ng, _l_shapes(T1old, T2old), dev)
+    t["lo1"], t["lo2"] = lo1, lo2
+    _lambda_rows("g", sizes, t, {"t1": T1old, "t2": T2old}, flat, ng, dev, False, antisym)
+    return lo1, lo2
 
 
 def uccsd_lambda_opt(Fa, Fb, Ia, Ib, Iabab, T1aold, T1bold, T2aaold, T2abold,
                      T2bbold, L1aold, L1bold, L2aaold, L2abold, L2bbold, D1a,
-                     D1b, D2aa, D2ab, D2bb, ti, ng, g, G, beta, closed_shell=False):
+                     D1b, D2aa, D2ab, D2bb, ti, ng, g, G, beta, closed_shell=False, antisym=None):
     """Unrestricted Lambda iteration (kelvin/ft_cc_equations.py:412-458).  closed_shell: as in
-    uccsd_stanton_bar (integrals, amplitudes and Lambda all mirror symmetric)."""
+    uccsd_stanton_bar (integrals, amplitudes and Lambda all mirror symmetric); the beta blocks of
+    the result are then the alpha tensors themselves."""
     dev = _lib.device()
     Ts = [_lib.as_dev(x, dev) for x in (T1aold, T1bold, T2aaold, T2abold, T2bbold)]
     assert(Ts[0].shape[0] == ng)
     live = (0, 2, 3) if closed_shell else (0, 1, 2, 3, 4)
     Lin = (L1aold, L1bold, L2aaold, L2abold, L2bbold)
+    if antisym is None:
+        antisym = all(is_antisymmetric(x) for x in
+                      ([Ts[2], Lin[2]] + ([] if closed_shell else [Ts[4], Lin[4]])))
     Ds = (D1a, D1b, D2aa, D2ab, D2bb)
     Ls = {k: quadrature.int_L(ng, Lin[k], ti, Ds[k], g, G) for k in live}
     sizes = _u_sizes(Fa, Fb)
-    pf = lambda_plan("u", sizes, mirror=closed_shell)
+    pf = lambda_plan("u", sizes, mirror=closed_shell, antisym=antisym)
     t = _u_integral_slots(Fa, Fb, Ia, Ib, Iabab, dev,
                           [s for s in pf.inputs if _plan.is_integral_slot(s)])
-    cached = _lambda_intermediates("u", sizes, t, {_U_T[k]: Ts[k] for k in live}, ng, dev,
-                                   mirror=closed_shell)
+    shp = _l_shapes(Ts[0], Ts[2]) + _l_shapes(Ts[1], Ts[4])
+    lshape = {0: shp[0], 1: shp[2], 2: shp[1], 4: shp[3],
+              3: (Ts[3].shape[3], Ts[3].shape[4], Ts[3].shape[1], Ts[3].shape[2])}
+    flat, views = flat_rows(ng, [lshape[k] for k in live], dev)
     outs = [None]*5
-    for k in live:
+    for k, v in zip(live, views):
         t[_U_T[k]] = Ts[k]
         t[_U_L[k]] = Ls[k]
-        outs[k] = t[_U_LO[k]] = torch.empty_like(Ls[k])
-    if cached is not None:
-        p = lambda_split_plans("u", sizes, mirror=closed_shell)[1]
-        t.update(cached)
-        p.run({k: v for k, v in t.items() if k in p.shapes}, ng, _chunk_for(p, ng, dev))
-    else:
-        pf.run(t, ng, _chunk_for(pf, ng, dev))
+        outs[k] = t[_U_LO[k]] = v
+    _lambda_rows("u", sizes, t, {_U_T[k]: Ts[k] for k in live}, flat, ng, dev, closed_shell,
+                 antisym)
     if closed_shell:
-        outs[1] = outs[0].clone()
-        outs[4] = outs[2].clone()
+        outs[1] = outs[0]
+        outs[4] = outs[2]
     return tuple(outs)
 
 
@@ -689,17 +906,23 @@ _rdm_cache = {"key": None, "val": None, "refs": None}
 
 def _rdm_leaves(mode, Ts, Ls, Ds, ti, ng, g, G):
     """Run the reverse sweep once per (T, L) and return
-    (dict of g-summed integral adjoints, list of g-summed integrated Lambdas)."""
+    (dict of g-summed integral adjoints, list of g-summed integrated Lambdas).
+    Sharded runs: every rank sweeps its own grid points (leftover points go to single owners)
+    and the weighted sums over the grid, sum_y g_y P(y) (kelvin/ft_cc_equations.py:717-720,
+    743-751), are completed by ONE all-reduce of the leaf buffer."""
+    from . import parallel
+    import numpy
     dev = _lib.device()
     Ts = [_lib.as_dev(x, dev) for x in Ts]
     Ls = [_lib.as_dev(x, dev) for x in Ls]
     key = (mode, ng, tuple((x.data_ptr(), x._version) for x in Ts + Ls),
-           tuple(float(v) for v in g), float(ti[-1]))
+           tuple(float(v) for v in g), tuple(float(v) for v in ti),
+           tuple(float(v) for v in numpy.asarray(G).reshape(-1)),
+           tuple(int(_lib.as_dev(d, dev).data_ptr()) for d in Ds))
     refs = Ts + Ls          # kept alive by the cache entry (see _lambda_intermediates)
     if _rdm_cache["key"] == key and all(a is b for a, b in zip(_rdm_cache["refs"], refs)):
         return _rdm_cache["val"]
     Lbar = [quadrature.int_L(ng, L, ti, D, g, G) for L, D in zip(Ls, Ds)]
-    t = {}
     if mode == "g":
         nv, no = Ts[0].shape[1:]
         sizes = {"o": int(no), "v": int(nv)}
@@ -712,14 +935,27 @@ def _rdm_leaves(mode, Ts, Ls, Ds, ti, ng, g, G):
                  ("v", "b"): int(nvb)}
         p = rdm_plan("u", sizes)
         names_t, names_l = _U_T, _U_L
-    for nm, x in zip(names_t, Ts):
-        t[nm] = x
-    for nm, x in zip(names_l, Lbar):
-        t[nm] = x
-    for leaf in p.leaves:
-        t[leaf] = torch.empty((ng,) + tuple(p.shapes[leaf]), dtype=torch.float64, device=dev)
-    p.run(t, ng, _chunk_for(p, ng, dev))
-    summed = {leaf: _gsum(t[leaf], g, dev) for leaf in p.leaves}
+    if parallel.active():
+        ranges = parallel.Shards(ng, 0).my_rows(False)
+    else:
+        ranges = [(0, ng)]
+    acc_flat, acc = flat_rows(1, [p.shapes[leaf] for leaf in p.leaves], dev)
+    acc_flat.zero_()
+    summed = {leaf: v[0] for leaf, v in zip(p.leaves, acc)}
+    gh = numpy.asarray(g, dtype=numpy.float64)
+    for a, b in ranges:
+        t = {}
+        for nm, x in zip(names_t, Ts):
+            t[nm] = x[a:b]
+        for nm, x in zip(names_l, Lbar):
+            t[nm] = x[a:b]
+        for leaf in p.leaves:
+            t[leaf] = torch.empty((b - a,) + tuple(p.shapes[leaf]), dtype=torch.float64, device=dev)
+        p.run(t, b - a, _chunk_for(p, b - a, dev))
+        for leaf in p.leaves:
+            summed[leaf].add_(_gsum(t[leaf], gh[a:b], dev))
+        t = None
+    parallel.sum_over_ranks(acc_flat)
     lsum = [_gsum(x, g, dev) for x in Lbar]
     p.release()
     _rdm_cache["key"] = key

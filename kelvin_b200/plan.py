@@ -179,13 +179,16 @@ def sz_ok(spins):
 
 class ROp(object):
     """Resolved op on concrete slots: out[letters] += coef * prod(ins)."""
-    __slots__ = ("out", "coef", "ins", "spin", "tri")
+    __slots__ = ("out", "coef", "ins", "spin", "tri", "slab")
 
-    def __init__(self, out, coef, ins, spin=None, tri=None):
+    def __init__(self, out, coef, ins, spin=None, tri=None, slab=False):
         self.out, self.coef, self.ins, self.spin = out, coef, ins, spin
         # tri: pairs of output letters (x, y); only the elements with x < y are computed and
         # written (see antisym_outputs)
         self.tri = tri
+        # slab: the rows of this contraction are dealt to the ranks that share the grid point
+        # (hybrid partition, see hybrid_phases); each rank writes only its own rows
+        self.slab = slab
 
     def __repr__(self):
         return "%s[%s] += %g %s" % (self.out[0], self.out[1], self.coef,
@@ -327,37 +330,157 @@ def mirror_reduce(rops):
 # closed shell: sum/difference form of paired contractions
 # ---------------------------------------------------------------------------
 SUMDIFF_PREFIX = "Qsd"
+DUP_PREFIX = "Qdup"
+
+
+def _swap_pos(ls, p, q):
+    ls = list(ls)
+    ls[p], ls[q] = ls[q], ls[p]
+    return "".join(ls)
+
+
+def _orientations(slot, ls):
+    """(sign, letters) of every way of reading an operand that its permutational antisymmetry
+    (antisym_pairs: known from the tensor class) makes equal up to the sign."""
+    res = [(1.0, ls)]
+    for p, q in antisym_pairs(slot):
+        res += [(-sg, _swap_pos(l, p, q)) for sg, l in list(res)]
+    return res
+
+
+def _relabel(op, la, lb, k, flip=True):
+    """Effective (coef, out letters) of binary op `op` once its operands are re-oriented (through
+    their antisymmetry; flip=False: as written only) and its letters renamed so that they read
+    [la], [lb] like the reference op; None when no orientation fits.  k: which operand of `op`
+    plays the first role."""
+    (sa_, lsa), (sb_, lsb) = op.ins[k], op.ins[1 - k]
+    if len(lsa) != len(la) or len(lsb) != len(lb):
+        return None
+    for sga, va in (_orientations(sa_, lsa) if flip else [(1.0, lsa)]):
+        for sgb, vb in (_orientations(sb_, lsb) if flip else [(1.0, lsb)]):
+            phi, ok = {}, True
+            for x, y in list(zip(va, la)) + list(zip(vb, lb)):
+                if phi.setdefault(x, y) != y:
+                    ok = False
+                    break
+            if not ok or len(set(phi.values())) != len(phi):
+                continue
+            if any(l not in phi for l in op.out[1]):
+                continue
+            return op.coef*sga*sgb, "".join(phi[l] for l in op.out[1])
+    return None
+
+
+def merge_duplicates(rops):
+    """Closed-shell (mirror_reduce'd) reverse sweeps contain pairs of contractions with the very
+    same operands whose results are added to one block under two index orders,
+
+        X[pqrs] += c A B        X[qpsr] += c A B
+
+    (the adjoint of a self-mirror block receives the contribution of its beta-leading image as
+    a transposed copy).  The contraction is done once into a scratch block T,
+
+        T[pqrs] (+)= c A B      ...      X[pqrs] += T[pqrs];  X[qpsr] += T[pqrs]
+
+    and every such pair with the same (X, two index orders) shares one T, so that the sum /
+    difference rewrite below still sees the members of its quartets in one output."""
+    ops = list(rops)
+    temps = {}            # (X, lo1, lo2) -> temp slot
+    used = set()
+    out = []
+    pend = {}             # temp -> (X, lo1, lo2, spin, position of the last contributing op)
+    n = len(ops)
+    partner = {}
+    for i in range(n):
+        a = ops[i]
+        if i in partner or len(a.ins) != 2 or a.tri is not None or len(a.out[1]) != 4 \
+                or len(set(a.ins[0][1]) & set(a.ins[1][1])) < 2:
+            continue                      # m^6 contractions only: a copy pass costs as much as an m^5 one
+        for j in range(i + 1, n):
+            b = ops[j]
+            if j in partner or len(b.ins) != 2 or b.out[0] != a.out[0] or b.tri is not None:
+                continue
+            if b.out[1] == a.out[1] or sorted(b.out[1]) != sorted(a.out[1]):
+                continue
+            r = _relabel(b, a.ins[0][1], a.ins[1][1], 0, flip=False)
+            if r is None or b.ins[0][0] != a.ins[0][0] or b.ins[1][0] != a.ins[1][0]:
+                continue
+            if abs(r[0] - a.coef) > 1e-14*abs(a.coef):
+                continue
+            # nothing in between may read X or write an operand
+            srcs = {a.ins[0][0], a.ins[1][0]}
+            if any(o.out[0] in srcs or any(sl == a.out[0] for sl, _ in o.ins)
+                   for o in ops[i + 1:j]):
+                continue
+            partner[i] = (j, r[1])
+            partner[j] = None
+            break
+    k = 0
+    last = {}
+    plan_ = []
+    for i, op in enumerate(ops):
+        if i in partner and partner[i] is None:
+            continue                                     # the duplicate: dropped
+        if i in partner:
+            j, lo2 = partner[i]
+            key = (op.out[0], op.out[1], lo2)
+            if key not in temps:
+                suf = op.out[0].partition(".")[2]
+                temps[key] = "%s%d%s" % (DUP_PREFIX, k, "." + suf.rstrip("~") if suf else "")
+                k += 1
+            t = temps[key]
+            plan_.append(ROp((t, op.out[1]), op.coef, list(op.ins), op.spin))
+            last[key] = (len(plan_) - 1, max(last.get(key, (0, 0))[1], j), op.spin)
+        else:
+            plan_.append(op)
+    # the two adds go in front of the first later reader of X (or at the end): later rewrites
+    # (sumdiff_pairs) then find nothing between the members of a group that reads T
+    inserts = []
+    for key, (pos, _, _) in last.items():
+        at = len(plan_)
+        for j in range(pos + 1, len(plan_)):
+            if any(sl == key[0] for sl, _ in plan_[j].ins):
+                at = j
+                break
+        inserts.append((at, key))
+    for at, key in sorted(inserts, key=lambda x: -x[0]):
+        X, lo1, lo2 = key
+        t = temps[key]
+        spin = last[key][2]
+        plan_[at:at] = [ROp((X, lo1), 1.0, [(t, lo1)], spin),
+                        ROp((X, lo2), 1.0, [(t, lo1)], spin)]
+    return plan_
 
 
 def sumdiff_pairs(rops):
     """Closed-shell (mirror_reduce'd) programs contain quartets of contractions
 
-        Xa += c A1 B1     Xa += c A2 B2     Xb += c A1 B2     Xb += c A2 B1
+        Xa += c A1 B1     Xa += c A2 B2     Xb += c' A1 B2     Xb += c' A2 B1
 
-    with identical index patterns (the W_ovvo.aaaa / W_ovvo.abab builds from Ia.oovv, Iabab.oovv
-    and t2x.aaaa, t2x.abba; the ring contractions rg.aaaa / rg.abab from t2.aa, t2.ab and those
-    two W blocks).  Since Xa + Xb gets c (A1+A2)(B1+B2) and Xa - Xb gets c (A1-A2)(B1-B2), two
-    contractions do the work of four:
+    with one index pattern (the W_ovvo.aaaa / W_ovvo.abab builds from Ia.oovv, Iabab.oovv and
+    t2x.aaaa, t2x.abba; the ring contractions rg.aaaa / rg.abab from t2.aa, t2.ab and those two
+    W blocks; their images in the Lambda sweep).  Since Xa/c + Xb/c' gets (A1+A2)(B1+B2) and
+    Xa/c - Xb/c' gets (A1-A2)(B1-B2), two contractions do the work of four:
 
         Ap = A1+A2, Am = A1-A2, Bp = B1+B2, Bm = B1-B2        (elementwise)
         S = c Ap Bp,  D = c Am Bm                              (2 contractions)
-        Xa += S/2 + D/2,  Xb += S/2 - D/2                      (elementwise)
+        Xa += S/2 + D/2,  Xb += (c'/c) (S/2 - D/2)             (elementwise)
 
-    This is the singlet/triplet channel decomposition of the closed-shell ring terms.  The
-    rewrite is placed where the last member of the quartet stood and is only done when nothing in
-    between reads Xa/Xb or writes an operand.  NOT enabled by default (KB200_SUMDIFF=1): built and
-    CPU-tested in round 1, waiting for its GPU parity run."""
+    This is the singlet/triplet channel decomposition of the closed-shell ring terms.  Members
+    are matched up to a renaming of their letters and up to the permutational antisymmetry of
+    same-spin operands (t2.aa[aeim] = t2.aa[eami]); Xb may carry its own index order.  The
+    rewrite is placed where the last member of the quartet stood and is only done when nothing
+    in between reads Xa/Xb or writes an operand."""
     ops = list(rops)
     k = 0
     while True:
         quartet = _find_quartet(ops)
         if quartet is None:
             return ops
-        i11, i22, i12, i21 = quartet
-        o11, o22, o12 = ops[i11], ops[i22], ops[i12]
+        (i11, i22, i12, i21), (A2, B2), lob, ratio = quartet
+        o11 = ops[i11]
         (A1, la), (B1, lb) = o11.ins
-        A2, B2 = o22.ins[0][0], o22.ins[1][0]
-        Xa, Xb = o11.out, o12.out
+        Xa, Xb = o11.out, (ops[i12].out[0], lob)
         c, spin = o11.coef, o11.spin
         tag = "%s%d" % (SUMDIFF_PREFIX, k)
         k += 1
@@ -370,54 +493,62 @@ def sumdiff_pairs(rops):
                ROp((S, lc), c, [(Ap, la), (Bp, lb)], spin),
                ROp((D, lc), c, [(Am, la), (Bm, lb)], spin),
                ROp(Xa, 0.5, [(S, lc)], spin), ROp(Xa, 0.5, [(D, lc)], spin),
-               ROp(Xb, 0.5, [(S, lc)], spin), ROp(Xb, -0.5, [(D, lc)], spin)]
-        last = max(quartet)
-        drop = set(quartet)
+               ROp(Xb, 0.5*ratio, [(S, lc)], spin), ROp(Xb, -0.5*ratio, [(D, lc)], spin)]
+        q = (i11, i22, i12, i21)
+        last = max(q)
+        drop = set(q)
         ops = [op for j, op in enumerate(ops[:last]) if j not in drop] + new + ops[last + 1:]
 
 
 def _find_quartet(ops):
-    def sig(op):
-        return (op.coef, op.out[1], op.ins[0][1], op.ins[1][1])
     cand = [j for j, op in enumerate(ops) if len(op.ins) == 2 and op.tri is None
             and len(op.out[1]) == 4 and not op.out[0].startswith(SUMDIFF_PREFIX)
             and len(set(op.ins[0][1]) & set(op.ins[1][1])) == 2]
-    for x, i11 in enumerate(cand):
+    for i11 in cand:
         o11 = ops[i11]
-        for i22 in cand[x + 1:]:
-            o22 = ops[i22]
-            if o22.out[0] != o11.out[0] or sig(o22) != sig(o11):
+        (A1, la), (B1, lb) = o11.ins
+        if A1 == B1:
+            continue
+        c = o11.coef
+        # every other candidate, read in the orientation of o11: (A slot, B slot) -> entries
+        table = {}
+        for j in cand:
+            if j == i11:
                 continue
-            A1, B1 = o11.ins[0][0], o11.ins[1][0]
-            A2, B2 = o22.ins[0][0], o22.ins[1][0]
-            if A1 == A2 or B1 == B2:
-                continue
-            i12 = i21 = None
-            for j in cand:
-                o = ops[j]
-                if o.out[0] == o11.out[0] or sig(o) != sig(o11):
-                    continue
-                pair = (o.ins[0][0], o.ins[1][0])
-                if pair == (A1, B2):
-                    i12 = j
-                elif pair == (A2, B1):
-                    i21 = j
-            if i12 is None or i21 is None or ops[i12].out[0] != ops[i21].out[0]:
-                continue
-            q = (i11, i22, i12, i21)
-            lo, hi = min(q), max(q)
-            Xs = {o11.out[0], ops[i12].out[0]}
-            srcs = {A1, A2, B1, B2}
-            ok = True
-            for j in range(lo, hi + 1):
-                if j in q:
-                    continue
-                o = ops[j]
-                if o.out[0] in srcs or any(sl in Xs for sl, _ in o.ins):
-                    ok = False
+            o = ops[j]
+            for kk in (0, 1):
+                r = _relabel(o, la, lb, kk)
+                if r is not None:
+                    table.setdefault((o.ins[kk][0], o.ins[1 - kk][0]), []).append((j, r[0], r[1]))
                     break
-            if ok:
-                return q
+        for (A2, B2), ents in table.items():
+            if A2 == A1 or B2 == B1 or A2 == B2:
+                continue
+            for i22, c22, lo22 in ents:
+                if ops[i22].out[0] != o11.out[0] or lo22 != o11.out[1] \
+                        or abs(c22 - c) > 1e-14*abs(c):
+                    continue
+                for i12, c12, lo12 in table.get((A1, B2), ()):
+                    for i21, c21, lo21 in table.get((A2, B1), ()):
+                        if ops[i12].out[0] != ops[i21].out[0] or ops[i12].out[0] == o11.out[0] \
+                                or lo12 != lo21 or abs(c12 - c21) > 1e-14*abs(c12) \
+                                or len({i11, i22, i12, i21}) != 4:
+                            continue
+                        q = (i11, i22, i12, i21)
+                        lo, hi = min(q), max(q)
+                        Xs = {o11.out[0], ops[i12].out[0]}
+                        srcs = {A1, A2, B1, B2}
+                        ok = True
+                        for j in range(lo, hi + 1):
+                            if j in q:
+                                continue
+                            o = ops[j]
+                            if o.out[0] in srcs or o.out[0] in Xs \
+                                    or any(sl in Xs for sl, _ in o.ins):
+                                ok = False
+                                break
+                        if ok:
+                            return q, (A2, B2), lo12, c12/c
     return None
 
 
@@ -589,6 +720,195 @@ def mirror_outputs(rops):
 
 
 # ---------------------------------------------------------------------------
+# hybrid partition: one grid point evaluated by several ranks
+# ---------------------------------------------------------------------------
+HYBRID_MIN_WORK = 1 << 24      # M*N*K from which a contraction is dealt out over the ranks
+DIST_SUFFIX = "^"
+
+
+class HybridProgram(object):
+    """Result of hybrid_phases: phases[p] = resolved ops of phase p; after phase p the
+    distributed buffers exchange[p] are summed over the ranks (one all-reduce: the engine lays
+    them out back to back); dslots = every distributed buffer (zero-filled before each run);
+    shapes = slot shapes including the distributed companions."""
+    def __init__(self, phases, exchange, dslots, shapes):
+        self.phases, self.exchange, self.dslots, self.shapes = phases, exchange, dslots, shapes
+
+
+def _contraction_sizes(op, shapes):
+    dims = {}
+    for slot, ls in [op.out] + list(op.ins):
+        for l, d in zip(ls, shapes[slot]):
+            dims[l] = d
+    (_, la), (_, lb) = op.ins
+    lc = op.out[1]
+    prod = lambda ls: int(numpy.prod([dims[l] for l in ls])) if ls else 1     # noqa: E731
+    M = prod([l for l in la if l in lc])
+    N = prod([l for l in lb if l in lc])
+    K = prod([l for l in la if l in lb])
+    if op.tri:
+        for ent in op.tri:
+            n = dims[ent[0]]
+            rel = ent[2] if len(ent) > 2 else "lt"
+            keep = (n*(n - 1)//2) if rel == "lt" else n
+            if ent[0] in la and ent[0] in lc:
+                M = M//(n*n)*keep
+            else:
+                N = N//(n*n)*keep
+    return M, N, K
+
+
+def hybrid_phases(rops, shapes, outputs, world, min_work=None, min_cols=64):
+    """Rewrite a resolved program so that `world` ranks evaluate it TOGETHER at the same grid
+    points (the partition inside a grid point, for grids with fewer points than
+    twice the number of GPUs).
+
+    * Every large contraction (M*N*K >= min_work) is marked `slab`: each rank computes a slab of
+      its rows.  Its result is a DISTRIBUTED contribution: the true value is the sum over ranks.
+    * A slot that receives distributed contributions gets a companion buffer S^ for them (or is
+      itself the distributed buffer when nothing else is written to it); everything else --
+      the m^5 and elementwise terms, small next to the m^6 ones -- is evaluated by every rank
+      (replicated), so replicated and distributed parts never mix in one buffer.
+    * Ops that are linear in a slot with a pending distributed part and do not contract it
+      (index-permuted adds, the four antisymmetric images, the triangle expansions) are applied
+      to both parts: the distributed part propagates without communication.
+    * A contraction needs its operands complete: the pending distributed buffers it reads are
+      summed over the ranks first (all-reduce) and merged (S += S^).  The program is cut into
+      phases at these points; the outputs are completed by a final exchange.
+
+    For the FT-CCSD residual this gives two exchanges per evaluation: the W intermediates, then
+    the doubles residual.  Accumulation orders change (sums over ranks), results agree with the
+    single-rank program to rounding."""
+    if min_work is None:
+        min_work = HYBRID_MIN_WORK
+    shapes = OrderedDict(shapes)
+    outputs = list(outputs)
+
+    def is_big(op):
+        if len(op.ins) != 2 or not (set(op.ins[0][1]) & set(op.ins[1][1])):
+            return False
+        M, N, K = _contraction_sizes(op, shapes)
+        return M*N*K >= min_work and min(M, N) > min_cols and max(M, N) >= 8*world
+
+    big = [is_big(op) for op in rops]
+
+    def sweep(rw):
+        """One pass over the program.  rw: slots known to receive replicated writes (these get
+        a companion buffer for their distributed part); None = dry run that finds them."""
+        dry = rw is None
+        hasR, dbuf, pending, read = set(), {}, set(), set()
+        wphase = {}                 # buffer -> phase of its last writer
+        phase_ops, merges, exch = [], [], {}
+        rwrites = set(outputs)      # outputs are completed into the caller's buffers
+
+        def emit(phase, op, target):
+            phase_ops.append((phase, len(phase_ops), op))
+            wphase[target] = max(wphase.get(target, 0), phase)
+
+        def avail(buf):
+            return wphase.get(buf, 0)
+
+        def dname(slot):
+            if slot not in dbuf:
+                if dry or slot in rw:
+                    dbuf[slot] = slot + DIST_SUFFIX
+                    shapes[dbuf[slot]] = shapes[slot]
+                else:
+                    dbuf[slot] = slot
+            return dbuf[slot]
+
+        def complete(slot):
+            """Phase from which the complete value of `slot` can be read; schedules the
+            exchange of its pending distributed part."""
+            if slot not in pending:
+                return avail(slot)
+            d = dbuf[slot]
+            p = avail(d)
+            exch.setdefault(p, []).append(d)
+            pending.discard(slot)
+            if d != slot:
+                ph = max(p + 1, avail(slot))
+                merges.append((ph, slot, d))
+                wphase[slot] = ph
+            else:
+                wphase[slot] = p + 1
+            hasR.add(slot)
+            return wphase[slot]
+
+        for op, b in zip(rops, big):
+            target = op.out[0]
+            if target in read:
+                raise ValueError("hybrid partition: %s is written after it was read: %r"
+                                 % (target, op))
+            contracted = len(op.ins) == 2 and bool(set(op.ins[0][1]) & set(op.ins[1][1]))
+            if contracted:
+                ph = 0
+                for sl, _ in op.ins:
+                    ph = max(ph, complete(sl))
+                    read.add(sl)
+                if b:
+                    d = dname(target)
+                    pending.add(target)
+                    emit(max(ph, avail(d)), ROp((d, op.out[1]), op.coef, list(op.ins), op.spin,
+                                                op.tri, slab=True), d)
+                else:
+                    hasR.add(target)
+                    rwrites.add(target)
+                    emit(max(ph, avail(target)), op, target)
+                continue
+            # no contracted index: linear in each operand
+            pend_in = [k for k, (sl, _) in enumerate(op.ins) if sl in pending]
+            if len(pend_in) > 1:
+                for k in pend_in[1:]:                   # a product of two incomplete tensors
+                    complete(op.ins[k][0])
+                pend_in = pend_in[:1]
+            for sl, _ in op.ins:
+                read.add(sl)
+            if not pend_in:
+                ph = max([avail(sl) for sl, _ in op.ins] + [avail(target)])
+                hasR.add(target)
+                rwrites.add(target)
+                emit(ph, op, target)
+                continue
+            k = pend_in[0]
+            src = op.ins[k][0]
+            d_src = dbuf[src]
+            others = [x for j, x in enumerate(op.ins) if j != k]
+            if d_src != src and src in hasR:
+                # replicated part of the source -> replicated part of the target
+                ph = max([avail(src), avail(target)] + [avail(sl) for sl, _ in others])
+                hasR.add(target)
+                rwrites.add(target)
+                emit(ph, ROp(op.out, op.coef, list(op.ins), op.spin, op.tri), target)
+            d = dname(target)
+            pending.add(target)
+            ins = list(op.ins)
+            ins[k] = (d_src, op.ins[k][1])
+            ph = max([avail(d_src), avail(d)] + [avail(sl) for sl, _ in others])
+            emit(ph, ROp((d, op.out[1]), op.coef, ins, op.spin, op.tri), d)
+        for sl in outputs:
+            if sl in pending:
+                complete(sl)
+        return rwrites, phase_ops, merges, exch, dbuf
+
+    rw, _, _, _, _ = sweep(None)
+    for k in [k for k in shapes if k.endswith(DIST_SUFFIX)]:
+        del shapes[k]
+    _, phase_ops, merges, exch, dbuf = sweep(rw)
+    nph = 1 + max([p for p, _, _ in phase_ops] + [p for p, _, _ in merges] + [0])
+    phases = [[] for _ in range(nph)]
+    for ph, slot, d in merges:
+        ls = "abcdefgh"[:len(shapes[slot])]
+        phases[ph].append(ROp((slot, ls), 1.0, [(d, ls)], None))
+    for ph, _, op in sorted(phase_ops, key=lambda x: (x[0], x[1])):
+        phases[ph].append(op)
+    exchange = [exch.get(p, []) for p in range(nph)]
+    order = [d for p in range(nph) for d in exchange[p]]
+    dslots = order + [d for d in dict.fromkeys(dbuf.values()) if d not in order]
+    return HybridProgram(phases, exchange, dslots, shapes)
+
+
+# ---------------------------------------------------------------------------
 # reverse mode (Lambda / RDM)
 # ---------------------------------------------------------------------------
 def adjoint(rops, wrt, seeds, bar=lambda s: s + "~"):
@@ -683,6 +1003,15 @@ class TableBank(object):
         return numpy.concatenate(self.chunks)
 
 
+def slab_rows(M, rank, world):
+    """Rows [lo, hi) of an M-row contraction dealt to `rank` of `world`: boundaries on multiples
+    of 8 rows (one DMMA row group)."""
+    g = (M + 7)//8
+    lo = min(M, (g*rank//world)*8)
+    hi = min(M, (g*(rank + 1)//world)*8)
+    return lo, hi
+
+
 N_SM = 148
 # CTA tile used for large contractions (see kb200.cu: tile ids); overridable for experiments
 import os as _os
@@ -730,12 +1059,15 @@ _TILE_BM = {0: 128, 1: 128, 2: 128, 3: 128, 4: 128, 5: 64, 6: 40, 7: 8}
 class Lowered(object):
     """A resolved program lowered to kb200_op descriptors + offset tables."""
 
-    def __init__(self, rops, slot_shapes, batched, preset=()):
+    def __init__(self, rops, slot_shapes, batched, preset=(), antisym=True):
         """slot_shapes: slot -> per-tau-point shape; batched: slot -> bool;
         preset: slots that already hold data when the plan starts (inputs and
         accumulate-into outputs); every other slot is overwritten (beta=0) by
-        its first write."""
+        its first write.  antisym=False: the amplitudes are NOT known to be antisymmetric (a
+        caller-supplied guess that failed the check): contracted pairs are summed in full, as
+        the reference does."""
         self.rops = rops
+        self.antisym = bool(antisym)
         self.slot_names = list(slot_shapes.keys())
         self.slot_index = {nm: k for k, nm in enumerate(self.slot_names)}
         self.slot_shapes = slot_shapes
@@ -745,6 +1077,7 @@ class Lowered(object):
         self.descs = []
         self._nfold = {}          # id(desc) -> N-index (dim, stride) lists on B and C (batch folding)
         self._src = {}            # id(desc) -> (resolved op, beta)
+        self._slab = set()        # id(desc) of the row-slabbed contractions
         self.flops = 0.0          # per tau point, executed (2*M*N*K)
         written = set(preset)
         for op in rops:
@@ -755,6 +1088,10 @@ class Lowered(object):
                     raise ValueError("slot %s read before it is written: %r" % (slot, op))
             d = self._lower(op, beta)
             self._src[id(d)] = (op, beta)
+            if getattr(op, "slab", False):
+                if d.kind != 0:
+                    raise ValueError("only contractions can be row-slabbed: %r" % op)
+                self._slab.add(id(d))
             self.descs.append(d)
         self.tables = self.bank.buffer()
         self.groups = [[k] for k in range(len(self.descs))]
@@ -1099,7 +1436,7 @@ class Lowered(object):
             d.tBn = self.bank.get_lt([(dims[l], sb[l]) for l in N], *tri_n)
             d.N = kept(N, tri_n)
         half = None
-        if ANTISYM and len(K) >= 2:
+        if ANTISYM and self.antisym and len(K) >= 2:
             for pa, qa in antisym_pairs(na):
                 x, y = la[pa], la[qa]
                 if x in K and y in K and any({lb[pb], lb[qb]} == {x, y} for pb, qb in antisym_pairs(nb)):
@@ -1139,8 +1476,11 @@ class Lowered(object):
         self.flops += 2.0 * d.M * d.N * d.K
         return d
 
-    def finalize(self, nbatch):
-        """Set the tau batch and the split-K factors; return the ctypes array."""
+    def finalize(self, nbatch, bstrides=None, part=None):
+        """Set the tau batch and the split-K factors; return the ctypes array.
+        bstrides: slot index -> distance (in doubles) between consecutive grid points of a
+        batched slot, when it differs from the slot's size (rows of a wider buffer);
+        part = (rank, world): row-slabbed contractions keep the rows of this rank only."""
         arr = (kb200_op * len(self.descs))()
         lead_size = {g[0]: len(g) for g in self.groups}
         gsize_of = {k: len(g) for g in self.groups for k in g}
@@ -1148,6 +1488,21 @@ class Lowered(object):
             ctypes.memmove(ctypes.byref(arr[k]), ctypes.byref(d), ctypes.sizeof(kb200_op))
             o = arr[k]
             o.group = lead_size.get(k, 0)
+            if bstrides:
+                if o.bsA != 0 and o.a in bstrides:
+                    o.bsA = bstrides[o.a]
+                if o.bsB != 0 and o.kind != 1 and o.b >= 0 and o.b in bstrides:
+                    o.bsB = bstrides[o.b]
+                if o.bsC != 0 and o.c in bstrides:
+                    o.bsC = bstrides[o.c]
+            if part is not None and id(d) in self._slab:
+                r, w = part
+                lo, hi = slab_rows(o.M, r, w)
+                if hi <= lo:
+                    raise ValueError("row slab of %d rows over %d ranks is empty" % (o.M, w))
+                o.tAm += lo
+                o.tCm += lo
+                o.M = hi - lo
             o.batch = nbatch if (o.bsC != 0 or o.bsA != 0 or (o.kind in (0, 3) and o.bsB != 0)) else 1
             if o.batch > 1 and o.bsC == 0:
                 raise ValueError("batched operands reduce into an unbatched output")

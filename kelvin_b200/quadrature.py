@@ -173,10 +173,11 @@ def _mode_bits(G, mode):
 def int_tbar(ng, tbar, ti, D, G, out=None, mode=None, rows=None):
     """out[y] = sum_x G[y,x] * exp(D*(ti[x]-ti[y]))_{x<y} * tbar[x]
     for any amplitude rank (kelvin/quadrature.py:292-317).  rows=(y0, y1)
-    restricts the output to those grid points (tau-sharded runs)."""
+    restricts the output to those grid points.  The grid points of tbar / out may be rows of a
+    wider buffer (any leading stride)."""
     lib = _lib.load()
     dev = _lib.device()
-    tbar = _lib.as_dev(tbar, dev)
+    tbar = _lib.as_dev_rows(tbar, dev)
     D = _lib.as_dev(D, dev)
     if tbar.shape[0] != ng or tuple(tbar.shape[1:]) != tuple(D.shape):
         raise Exception("int_tbar: shape mismatch {} vs ng={} D{}".format(
@@ -185,11 +186,49 @@ def int_tbar(ng, tbar, ti, D, G, out=None, mode=None, rows=None):
     if out is None:
         out = torch.empty((y1 - y0,) + tuple(D.shape), dtype=torch.float64, device=dev)
     n = D.numel()
+    if n == 0 or y1 == y0:
+        return out
     tid, Gd = _small(ti, dev), _small(G, dev)
-    rc = lib.kb200_int_tbar_rows(ng, n, _lib.ptr(tbar), _lib.ptr(D), _lib.ptr(tid), _lib.ptr(Gd),
-                                 _lib.ptr(out), y0, y1, _mode_bits(G, mode), _lib.stream_ptr())
+    rc = lib.kb200_int_tbar_strided(ng, n, _lib.ptr(tbar), _lib.row_stride(tbar), _lib.ptr(D),
+                                    _lib.ptr(tid), _lib.ptr(Gd), _lib.ptr(out),
+                                    _lib.row_stride(out), y0, y1, _mode_bits(G, mode),
+                                    _lib.stream_ptr())
     _lib.check(rc, "kb200_int_tbar")
     return out
+
+
+def int_tbar_update(ng, tbar, ti, D, G, amp, alpha, out4, g=None, W=None, T1x=None, T1y=None,
+                    c2=1.0, c11=0.0, mode=None, rows=None):
+    """The fused update of one amplitude block (kb200_int_tbar_update): integrates tbar
+    (kelvin/quadrature.py:292-317), measures ||new - amp||^2 and ||amp||^2, damps amp in place
+    and measures its new norm (kelvin/cc_utils.py:278-295), and accumulates the block's term of
+    the energy functional sum_y g_y (c2 amp + c11 T1x T1y).W (kelvin/ft_cc_energy.py:35-72) --
+    all in one pass; the integrated amplitudes are never stored.  out4: 4 device doubles."""
+    lib = _lib.load()
+    dev = _lib.device()
+    tbar = _lib.as_dev_rows(tbar, dev)
+    D = _lib.as_dev(D, dev)
+    if tbar.shape[0] != ng or tuple(tbar.shape[1:]) != tuple(D.shape) \
+            or tuple(amp.shape) != tuple(tbar.shape) or not amp[0].is_contiguous():
+        raise Exception("int_tbar_update: shape mismatch")
+    y0, y1 = (0, ng) if rows is None else rows
+    n = D.numel()
+    tid, Gd = _small(ti, dev), _small(G, dev)
+    gd = _small(g, dev) if g is not None else None
+    nvb = noa = nob = 1
+    if T1x is not None:
+        nvb, noa, nob = int(D.shape[1]), int(D.shape[2]), int(D.shape[3])
+    rc = lib.kb200_int_tbar_update(
+        ng, n, _lib.ptr(tbar), _lib.row_stride(tbar), _lib.ptr(D), _lib.ptr(tid), _lib.ptr(Gd),
+        _lib.ptr(amp), _lib.row_stride(amp), y0, y1, alpha,
+        _lib.ptr(W) if W is not None else None,
+        _lib.ptr(T1x) if T1x is not None else None, _lib.ptr(T1y) if T1y is not None else None,
+        _lib.row_stride(T1x) if T1x is not None else 0,
+        _lib.row_stride(T1y) if T1y is not None else 0, nvb, noa, nob,
+        _lib.ptr(gd) if gd is not None else None, c2, c11,
+        out4 if isinstance(out4, int) else _lib.ptr(out4), _lib.ptr(_lib.reduce_scratch(dev)),
+        _mode_bits(G, mode), _lib.stream_ptr())
+    _lib.check(rc, "kb200_int_tbar_update")
 
 
 def int_tbar1(ng, t1bar, ti, D1, G):
@@ -219,7 +258,7 @@ def int_L(ng, Lold, ti, D, g, G, out=None, mode=None, rows=None):
     with D indexed (v..,o..) and L indexed (o..,v..) (kelvin/quadrature.py:320-345)."""
     lib = _lib.load()
     dev = _lib.device()
-    Lold = _lib.as_dev(Lold, dev)
+    Lold = _lib.as_dev_rows(Lold, dev)
     D = _lib.as_dev(D, dev)
     r = D.dim()
     h = r // 2
@@ -236,10 +275,13 @@ def int_L(ng, Lold, ti, D, g, G, out=None, mode=None, rows=None):
     s0, s1 = (0, ng) if rows is None else rows
     if out is None:
         out = torch.empty((s1 - s0,) + tuple(Lold.shape[1:]), dtype=torch.float64, device=dev)
+    if out.numel() == 0:
+        return out
     tid, gd, Gd = _small(ti, dev), _small(g, dev), _small(G, dev)
-    rc = lib.kb200_int_L_rows(ng, cd, cs, _lib.ptr(Lold), _lib.ptr(D), _lib.ptr(tid),
-                              _lib.ptr(gd), _lib.ptr(Gd), _lib.ptr(out), s0, s1,
-                              _mode_bits(G, mode), _lib.stream_ptr())
+    rc = lib.kb200_int_L_strided(ng, cd, cs, _lib.ptr(Lold), _lib.row_stride(Lold), _lib.ptr(D),
+                                 _lib.ptr(tid), _lib.ptr(gd), _lib.ptr(Gd), _lib.ptr(out),
+                                 _lib.row_stride(out), s0, s1, _mode_bits(G, mode),
+                                 _lib.stream_ptr())
     _lib.check(rc, "kb200_int_L")
     return out
 

@@ -8,9 +8,10 @@ product never imports this module.
 import numpy
 
 
-def run_lowered(low, arrays, nbatch):
-    """arrays: slot name -> ndarray; batched slots have a leading tau axis."""
-    ops = low.finalize(nbatch)
+def run_lowered(low, arrays, nbatch, part=None):
+    """arrays: slot name -> ndarray; batched slots have a leading tau axis.
+    part = (rank, world): row-slabbed contractions do this rank's rows only."""
+    ops = low.finalize(nbatch, None, part)
     tabs = low.tables.astype(numpy.int64)
     arrays = dict(arrays)
     for nm, (src, perm) in low.derived.items():
@@ -53,3 +54,34 @@ def run_lowered(low, arrays, nbatch):
                 C[cidx] = o.alpha * val
             else:
                 C[cidx] = o.beta * C[cidx] + o.alpha * val
+
+
+def run_hybrid(hp, arrays_per_rank, nbatch, batched):
+    """Execute a plan.HybridProgram for every simulated rank (arrays_per_rank[r]: slot ->
+    ndarray holding the integrals, the inputs and the zero-filled distributed buffers) with the
+    exchanges done as sums over the simulated ranks."""
+    from kelvin_b200 import plan
+    world = len(arrays_per_rank)
+    have = set(arrays_per_rank[0])
+    for p, rops in enumerate(hp.phases):
+        if rops:
+            slots = []
+            for op in rops:
+                for sl, _ in [op.out] + list(op.ins):
+                    if sl not in slots:
+                        slots.append(sl)
+            sh = {s_: hp.shapes[s_] for s_ in slots}
+            preset = [s_ for s_ in slots if s_ in have]
+            for r in range(world):
+                arr = arrays_per_rank[r]
+                for s_ in slots:
+                    if s_ not in arr:
+                        fill = 0.0 if s_.startswith(plan.TRI_PREFIX) else numpy.nan
+                        arr[s_] = numpy.full(((nbatch,) if batched(s_) else ()) + tuple(sh[s_]), fill)
+                low = plan.Lowered(rops, sh, {s_: batched(s_) for s_ in slots}, preset)
+                run_lowered(low, arr, nbatch, part=(r, world))
+            have.update(slots)
+        for d in hp.exchange[p]:
+            tot = sum(arrays_per_rank[r][d] for r in range(world))
+            for r in range(world):
+                arrays_per_rank[r][d] = tot.copy()

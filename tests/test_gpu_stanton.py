@@ -62,10 +62,11 @@ def test_u_equals_g_on_spin_packed_inputs(built):
     assert numpy.abs(u[4].cpu().numpy() - g2[:, na:, na:, na:, na:]).max() < 1e-11*sc
 
 
-def test_tau_sharded_step_equals_reference_loop(built):
-    """The bench / multi-GPU step object (world size 1) reproduces one iteration of the
-    reference loop (kelvin/cc_utils.py:274-305): energy and residual as logged."""
-    from kelvin_b200 import cc_utils, ft_utils, parallel, quadrature
+def test_step_object_equals_reference_loop(built):
+    """The step object the loops and the bench share (fused integrate / damp / norm / energy
+    pass per block, closed-shell + singlet program) reproduces the iterations of the reference
+    loop (kelvin/cc_utils.py:274-305): energy and residual as logged."""
+    from kelvin_b200 import cc_utils, ft_utils, quadrature
     from kelvin_b200.ueg_system import UEGSystem
     T, mu, ng = 0.5, 7.0, 6
     s = UEGSystem(T, 1.942, 30.0, mu=mu, norb=7, orbtype='u')
@@ -78,8 +79,8 @@ def test_tau_sharded_step_equals_reference_loop(built):
     oints = odrv.uft_integrals(s, ea, eb, beta, mu)
     oD = [d.cpu().numpy() for d in Ds]
     amps = odrv.mp2_guess_u(*oints, *oD, ti, ng, G)
-    solver = parallel.TauShardedUCCSD(*ints, Ds, g, G, beta, ng, ti)
-    solver.set_amplitudes(*amps)
+    solver = cc_utils.UccStep(amps, *ints, Ds, g, G, beta, ng, ti)
+    assert solver.cs and solver.singlet and solver.antisym and solver.t0
     E1, r1 = solver.step(0.3)
     E2, r2 = solver.step(0.3)
     conv = {"econv": 0.0, "tconv": 0.0, "max_iter": 2, "damp": 0.3}
@@ -210,3 +211,145 @@ def test_closed_shell_mirror_rows(built):
     assert any(s.startswith(_plan.TRI_PREFIX + "m") for s in p.shapes)
     for got, ref in zip(red, full):
         assert _relerr(got, ref.cpu().numpy()) < 1e-12
+
+
+def test_closed_shell_singlet_and_sumdiff(built):
+    """Closed-shell inputs with T2aa = T2ab - T2ab(a<->b): the singlet-reduced program with the
+    sum/difference ring contractions (what the loops run for the UEG benchmark) equals the
+    general program; the detection accepts these amplitudes and rejects perturbed ones."""
+    from kelvin_b200 import ft_cc_equations as fe
+    n, ng = 9, 5
+    ints, amps, _ = util.random_u_closed(n, ng, seed=23)
+    assert fe.is_singlet(amps[2], amps[3]) and fe.is_antisymmetric(amps[2])
+    bad = amps[2].copy()
+    bad[1, 2, 3, 1, 0] += 1e-6
+    assert not fe.is_singlet(bad, amps[3]) and not fe.is_antisymmetric(bad)
+    full = fe.uccsd_stanton_bar(*ints, *amps)
+    for sd in (0, 1):
+        keep = fe.SUMDIFF
+        fe.SUMDIFF = sd
+        try:
+            red = fe.uccsd_stanton_bar(*ints, *amps, closed_shell=True, singlet=True)
+        finally:
+            fe.SUMDIFF = keep
+        for got, ref in zip(red, full):
+            assert _relerr(got, ref.cpu().numpy()) < 1e-12
+    p = fe.stanton_plan("u", fe._u_sizes(ints[0], ints[1]), -1.0, mirror=True, mirror_rows=True,
+                        singlet=True)
+    assert not any(s.startswith(("rg.aaaa", "Woooo.aa", "Wvvvv.aa")) for s in p.shapes)
+
+
+def test_non_antisymmetric_guess_takes_the_full_sums(built):
+    """A doubles guess that is NOT antisymmetric (the reference accepts any array): the half
+    sums over contracted pairs and the triangular outputs would silently compute something
+    else; the guard detects it and the plans without those rewrites reproduce the reference's
+    full double sums (oracle: the Stanton equations on the array as given)."""
+    from kelvin_b200 import ft_cc_equations as fe
+    from kelvin_oracle import cc_equations as ocq
+    n, ng = 6, 2
+    F, I, t1, t2 = util.random_g(n, ng, seed=31)
+    rng = numpy.random.default_rng(5)
+    t2 = t2 + 0.05*rng.standard_normal(t2.shape)
+    assert not fe.is_antisymmetric(t2)
+    b1, b2 = fe.ccsd_stanton_bar(F, I, t1, t2)
+    for y in range(ng):
+        R1, R2 = ocq.stanton_terms(F, I, t1[y], t2[y])
+        assert numpy.abs(b1[y].cpu().numpy() - (-F.vo - R1)).max() < 1e-11*numpy.abs(R1).max()
+        assert numpy.abs(b2[y].cpu().numpy() - (-I.vvoo - R2)).max() < 1e-11*numpy.abs(R2).max()
+    # with the antisymmetry assumed, the result differs visibly: the guard matters
+    w1, w2 = fe.ccsd_stanton_bar(F, I, t1, t2, antisym=True)
+    assert _relerr(w2, b2.cpu().numpy()) > 1e-6
+
+
+def test_general_program_large_tiles(built):
+    """The GENERAL unrestricted program (alpha != beta, na != nb) at a size where the hot kernel
+    configuration engages -- 128x128 full tiles, launch groups of 8, half sums over antisymmetric
+    contracted pairs, triangular outputs -- against the oracle's Sz-blocked port
+    (kelvin/ft_cc_equations.py:130-164)."""
+    from kelvin_b200 import ft_cc_equations as fe, plan as _plan
+    from kelvin_oracle import spin_blocked as sb
+    na, nb, ng = 20, 19, 2
+    ints, amps = util.random_u(na, nb, ng, seed=41, scale=0.05)
+    got = fe.uccsd_stanton_bar(*ints, *amps)
+    p = fe.stanton_plan("u", fe._u_sizes(ints[0], ints[1]), -1.0)
+    ops = p.low.finalize(ng)
+    big = [o for o in ops if o.kind == 0 and o.tile == _plan.BIG_TILE and o.K >= 300]
+    assert len(big) >= 24 and any(o.group == 8 for o in big)
+    assert sum(1 for op in p.low.rops if op.tri is not None) == 8
+    w = sb.wrap_integrals(*ints)
+    Fa, Fb, Ia, Ib, Iabab = ints
+    drv = (Fa.vo, Fb.vo, Ia.vvoo, Iabab.vvoo, Ib.vvoo)
+    for y in range(ng):
+        r1, r2 = sb.u_stanton_terms(*ints, (amps[0][y], amps[1][y]),
+                                    (amps[2][y], amps[3][y], amps[4][y]), wrapped=w)
+        for k, r in enumerate(list(r1) + list(r2)):
+            ref = -drv[k] - r
+            assert numpy.abs(got[k][y].cpu().numpy() - ref).max() < 1e-11*numpy.abs(ref).max(), k
+
+
+@pytest.mark.parametrize("prog", ["stanton-closed", "stanton", "lambda-closed"])
+def test_hybrid_partition_two_ranks_on_one_gpu(built, prog):
+    """plan.hybrid_phases / engine.PhasedPlan on the GPU: two 'ranks' (two PhasedPlan instances
+    driven in lockstep on one device, the exchanges done as sums of their buffers) evaluate the
+    same grid points together, each contracting its slab of the rows of every large contraction;
+    both end up with the single-rank result."""
+    import torch
+    from kelvin_b200 import _lib, engine, ft_cc_equations as fe, plan as _plan
+    dev = _lib.device()
+    n, ng = 12, 2
+    world = 2
+    if prog == "stanton":
+        ints, amps = util.random_u(n, n - 1, ng, seed=61, scale=0.1)
+        ref = fe.uccsd_stanton_bar(*ints, *amps)
+        rops, ins, outs = fe._stanton_rops("u", -1.0, False, False, False, False, True)
+        inputs = dict(zip(fe._U_TIN, amps))
+        live = range(5)
+    elif prog == "stanton-closed":
+        ints, amps, _ = util.random_u_closed(n, ng, seed=62, scale=0.1)
+        ref = fe.uccsd_stanton_bar(*ints, *amps, closed_shell=True, singlet=True)
+        rops, ins, outs = fe._stanton_rops("u", -1.0, True, False, True, True, True)
+        inputs = {k: v for k, v in zip(fe._U_TIN, amps) if k in ins}
+        live = (0, 2, 3)
+    else:
+        ints, amps, lam = util.random_u_closed(n, ng, seed=63, scale=0.1)
+        lam = [numpy.ascontiguousarray(x) for x in
+               (lam[0].transpose(0, 2, 1), lam[1].transpose(0, 2, 1), lam[2].transpose(0, 3, 4, 1, 2),
+                lam[3].transpose(0, 3, 4, 1, 2), lam[4].transpose(0, 3, 4, 1, 2))]
+        inter, rest = fe._lambda_rops("u", -1.0, True, True)
+        rops = inter + rest
+        ins, outs = fe._reps(fe._U_T + fe._U_L), fe._reps(fe._U_LO)
+        inputs = {k: v for k, v in zip(fe._U_T + fe._U_L, list(amps) + lam) if k in ins}
+        p1 = engine.Plan(rops, "u", fe._u_sizes(ints[0], ints[1]), ins, outs, name="ref")
+        t = fe._u_integral_slots(*ints, dev, [s for s in p1.inputs if _plan.is_integral_slot(s)])
+        t.update({k: _lib.as_dev(v, dev) for k, v in inputs.items()})
+        ref = [None]*5
+        for k, nm in enumerate(fe._U_LO):
+            if nm in outs:
+                ref[k] = t[nm] = torch.empty((ng,) + tuple(p1.shapes[nm]), dtype=torch.float64, device=dev)
+        p1.run(t, ng)
+        live = (0, 2, 3)
+    sizes = fe._u_sizes(ints[0], ints[1])
+    ranks = [engine.PhasedPlan(rops, "u", sizes, ins, outs, world, name="hyb%d" % r,
+                               min_work=n**5) for r in range(world)]
+    assert sum(1 for ph in ranks[0].hp.phases for op in ph if op.slab) >= 8
+    assert sum(1 for e in ranks[0].hp.exchange if e) >= 2
+    tens = []
+    for r, hp in enumerate(ranks):
+        t = fe._u_integral_slots(*ints, dev, [s for s in hp.inputs if _plan.is_integral_slot(s)])
+        t.update({k: _lib.as_dev(v, dev) for k, v in inputs.items()})
+        for nm in hp.outputs:
+            t[nm] = torch.empty((ng,) + tuple(hp.shapes[nm]), dtype=torch.float64, device=dev)
+        tens.append(t)
+        hp.begin(t, ng, r)
+    for p in range(len(ranks[0].plans)):
+        for hp in ranks:
+            hp.run_phase(p)
+        bufs = [hp.exchange_buffer(p) for hp in ranks]
+        if bufs[0] is not None:
+            tot = bufs[0] + bufs[1]
+            for b in bufs:
+                b.copy_(tot)
+    names = fe._U_LO if prog.startswith("lambda") else fe._U_TOUT
+    for r in range(world):
+        for k in live:
+            assert _relerr(tens[r][names[k]], ref[k].cpu().numpy()) < 1e-12, (r, k)

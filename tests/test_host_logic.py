@@ -108,52 +108,84 @@ def test_product_fails_loudly_without_cuda(built):
         quadrature.int_tbar(4, numpy.zeros((4, 2, 2)), ti, numpy.zeros((2, 2)), G)
 
 
-def test_shard_bounds():
-    from kelvin_b200.parallel import shard_bounds
-    for ng in (1, 7, 10, 16, 24, 40):
-        for world in (1, 2, 3, 4, 8):
-            b, chunk = shard_bounds(ng, world)
-            assert b[0][0] == 0 and b[-1][1] == ng
-            for (a0, a1), (b0, b1) in zip(b[:-1], b[1:]):
-                assert a1 == b0 and a1 - a0 <= chunk
-            assert sum(y1 - y0 for y0, y1 in b) == ng
+def test_shards_partition():
+    """parallel.Shards: q whole rows per rank, r leftover rows; every row of [y0, ng) is either
+    in exactly one rank's own block or a leftover row; owner mode gives each of the first r
+    ranks one leftover row."""
+    from kelvin_b200.parallel import Shards
+    for ng in (1, 2, 7, 10, 16, 24, 40):
+        for y0 in (0, 1):
+            for world in (1, 2, 3, 4, 8):
+                seen = []
+                owners = []
+                for rank in range(world):
+                    sh = Shards(ng, y0, rank, world)
+                    assert sh.q*world + sh.r == max(0, ng - y0)
+                    seen += list(range(*sh.own))
+                    if sh.owner_row() is not None:
+                        owners.append(sh.owner_row())
+                    rows = sh.my_rows(False)
+                    assert sum(b - a for a, b in rows) == sh.q + (1 if rank < sh.r else 0)
+                    if sh.r:
+                        assert sh.my_rows(True)[-1] == sh.left
+                sh = Shards(ng, y0, 0, world)
+                assert sorted(seen) == list(range(*sh.whole))
+                assert owners == list(range(*sh.left))
+                assert sh.whole[0] == min(y0, ng) or ng <= y0
+                assert sh.left[1] == ng
+    # ESN33 on 8 GPUs: 9 evaluated points -> one whole row each + one row shared by all
+    sh = Shards(10, 1, 3, 8)
+    assert (sh.q, sh.r, sh.own, sh.left) == (1, 1, (4, 5), (9, 10)) and sh.use_hybrid()
+    # UEG-57 (ng 16, tau_0 skipped) on 8 GPUs: 7 leftover rows go to single owners
+    assert not Shards(16, 1, 0, 8).use_hybrid()
 
 
-def _gloo_worker(rank, world, port, ng, q):
+def _gloo_worker(rank, world, port, ng, y0, q):
     import torch
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from kelvin_b200 import parallel
-    bounds, chunk = parallel.shard_bounds(ng, world)
-    y0, y1 = bounds[rank]
-    full = torch.arange(ng*6, dtype=torch.float64).reshape(ng, 2, 3)
-    obj = parallel.TauShardedUCCSD.__new__(parallel.TauShardedUCCSD)
-    obj.world, obj.rank, obj.chunk, obj.nloc, obj.group, obj.ng = world, rank, chunk, y1 - y0, None, ng
-    got = obj._allgather_rows(full[y0:y1].clone())[:ng]
-    stats = torch.tensor([float(y1 - y0)], dtype=torch.float64)
-    dist.all_reduce(stats)
-    q.put((rank, bool(torch.equal(got, full)), float(stats.item())))
+    assert parallel.active() and parallel.world_info() == (rank, world)
+    sh = parallel.Shards(ng, y0)
+    full = torch.arange(ng*6, dtype=torch.float64).reshape(ng, 6) + 1.0
+    ok = True
+    for owner_left in (True, False):
+        flat = torch.full((ng, 6), -7.0, dtype=torch.float64)
+        flat[:y0] = full[:y0]                      # rows nobody evaluates (tau_0: the drivers)
+        flat[sh.own[0]:sh.own[1]] = full[sh.own[0]:sh.own[1]]
+        if owner_left:
+            parallel.zero_foreign_left_rows(flat, sh)
+            if sh.owner_row() is not None:
+                flat[sh.owner_row()] = full[sh.owner_row()]
+        else:
+            # hybrid mode: the leftover rows were completed inside the evaluation on every rank
+            flat[sh.left[0]:sh.left[1]] = full[sh.left[0]:sh.left[1]]
+        parallel.exchange_rows(flat, sh, owner_left)
+        ok = ok and bool(torch.equal(flat, full))
+    acc = torch.full((3,), float(rank + 1), dtype=torch.float64)
+    parallel.sum_over_ranks(acc)
+    q.put((rank, ok, float(acc[0].item())))
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("ng", [5, 8])
-def test_tau_allgather_gloo_world2(ng):
-    """The N>1 exchange step (padded all-gather of the per-rank residual rows) on 2 CPU
-    ranks over gloo."""
+@pytest.mark.parametrize("ng,y0", [(5, 0), (8, 1), (10, 1), (2, 0)])
+def test_row_exchange_gloo_world2(ng, y0):
+    """The N>1 exchange step (in-place all-gather of the whole rows + sum of the owner-mode
+    leftover rows) and the response-density sum on 2 CPU ranks over gloo."""
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29500 + (os.getpid() + ng) % 2000
-    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, ng, q)) for r in range(2)]
+    port = 29500 + (os.getpid() + 7*ng + y0) % 2000
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, ng, y0, q)) for r in range(2)]
     for p in procs:
         p.start()
     res = [q.get(timeout=120) for _ in procs]
     for p in procs:
         p.join(timeout=60)
     for rank, ok, tot in res:
-        assert ok and tot == ng
+        assert ok and tot == 3.0
 
 
 def test_t0_is_zero_predicate():

@@ -411,3 +411,101 @@ def test_sumdiff_pairs(singlet):
     u0 = units(plan.antisym_outputs(plan.mirror_outputs(red)))
     u1 = units(plan.antisym_outputs(plan.mirror_outputs(sd)))
     assert u1 < u0 - (1.9 if singlet else 3.9)
+
+
+def test_lambda_sweep_closed_shell_rewrites():
+    """plan.merge_duplicates + plan.sumdiff_pairs + plan.antisym_outputs on the closed-shell
+    Lambda program: mirror-duplicate contractions done once, three quartets as sum/difference
+    pairs, same-spin ladder adjoints on their triangle; same Lambda map, fewer m^6 units."""
+    n, ng = 4, 2
+    ints, amps, lam = _closed_inputs(n, ng, 83)
+    Fa, Fb, Ia, Ib, Iabab = ints
+    src = {"Fa": Fa, "Fb": Fb, "Ia": Ia, "Ib": Ib, "Iabab": Iabab}
+    sizes = {("v", "a"): n, ("o", "a"): n, ("v", "b"): n, ("o", "b"): n}
+    tn = ("t1.a", "t1.b", "t2.aa", "t2.ab", "t2.bb")
+    ln = ("l1.a", "l1.b", "l2.aa", "l2.ab", "l2.bb")
+    inputs = dict(zip(tn, amps))
+    inputs.update(zip(ln, lam))
+    keep = {k: v for k, v in inputs.items() if plan.mirror_rep(k) == k}
+    inter, rest = programs.lambda_rops("u", -1.0)
+    inter, rest = plan.mirror_reduce(inter), plan.mirror_reduce(rest)
+    ref, _ = _run(inter + rest, "u", sizes, keep, src, ng)
+    md = plan.merge_duplicates(rest)
+    assert sum(1 for op in md if op.out[0].startswith(plan.DUP_PREFIX)) == 3
+    sd = plan.sumdiff_pairs(md)
+    assert sum(1 for op in sd if op.out[0].startswith(plan.SUMDIFF_PREFIX) and len(op.ins) == 2) == 6
+    new = plan.antisym_outputs(sd)
+    got, _ = _run(inter + new, "u", sizes, keep, src, ng)
+    for nm in ("lo1.a", "lo2.aa", "lo2.ab"):
+        assert numpy.abs(got[nm] - ref[nm]).max() < 1e-12*numpy.abs(ref[nm]).max(), nm
+    m = 33
+    big = {("v", "a"): m, ("o", "a"): m, ("v", "b"): m, ("o", "b"): m}
+
+    def units(ops):
+        shapes = plan.slot_shapes(ops, "u", big)
+        written, pres = set(), []
+        for op in ops:
+            for s, _ in op.ins:
+                if s not in written and s not in pres:
+                    pres.append(s)
+            written.add(op.out[0])
+        lw = plan.Lowered(ops, shapes, {s: not plan.is_integral_slot(s) for s in shapes}, pres)
+        return sum(2.0*d.M*d.N*d.K for d in lw.descs if d.kind == 0 and d.K >= 500)/(2.0*m**6)
+    assert units(new) < units(rest) - 10.0
+
+
+@pytest.mark.parametrize("prog", ["stanton", "stanton-closed", "lambda"])
+@pytest.mark.parametrize("world", [2, 3])
+def test_hybrid_phases(prog, world):
+    """plan.hybrid_phases: the ranks that share a grid point each contract a slab of the rows of
+    every large contraction; distributed parts are exchanged before they are contracted again
+    and at the end.  Simulated ranks (NumPy executor) reproduce the single-rank program."""
+    from plan_exec import run_hybrid
+    n, ng = 5, 2
+    sizes = {("v", "a"): n, ("o", "a"): n, ("v", "b"): n, ("o", "b"): n}
+    tn = ("t1.a", "t1.b", "t2.aa", "t2.ab", "t2.bb")
+    ln = ("l1.a", "l1.b", "l2.aa", "l2.ab", "l2.bb")
+    if prog == "stanton":
+        ints, amps = util.random_u(n, n, ng, seed=91)
+        inputs = dict(zip(tn, amps))
+        rops = plan.antisym_outputs(plan.expand(programs.stanton(-1.0), programs.tensor_defs(), "u"))
+        outs = ("o1.a", "o1.b", "o2.aa", "o2.ab", "o2.bb")
+    elif prog == "stanton-closed":
+        ints, amps, _ = util.random_u_closed(n, ng, seed=92)
+        inputs = {"t1.a": amps[0], "t2.aa": amps[2], "t2.ab": amps[3]}
+        red = plan.mirror_reduce(plan.expand(programs.stanton(-1.0), programs.tensor_defs(), "u"))
+        rops = plan.antisym_outputs(plan.sumdiff_pairs(plan.singlet_reduce(red)))
+        outs = ("o1.a", "o2.aa", "o2.ab")
+    else:
+        ints, amps, lam = _closed_inputs(n, ng, 93)
+        inputs = dict(zip(tn, amps))
+        inputs.update(zip(ln, lam))
+        inputs = {k: v for k, v in inputs.items() if plan.mirror_rep(k) == k}
+        inter, rest = programs.lambda_rops("u", -1.0)
+        rops = plan.mirror_reduce(inter) + plan.antisym_outputs(plan.sumdiff_pairs(
+            plan.merge_duplicates(plan.mirror_reduce(rest))))
+        outs = ("lo1.a", "lo2.aa", "lo2.ab")
+    Fa, Fb, Ia, Ib, Iabab = ints
+    src = {"Fa": Fa, "Fb": Fb, "Ia": Ia, "Ib": Ib, "Iabab": Iabab}
+    ref, _ = _run(rops, "u", sizes, inputs, src, ng)
+    shapes = plan.slot_shapes(rops, "u", sizes)
+    hp = plan.hybrid_phases(rops, shapes, outs, world, min_work=n**5, min_cols=8)
+    nslab = sum(1 for ph in hp.phases for op in ph if op.slab)
+    assert nslab >= 8 and len(hp.phases) >= 3 and any(hp.exchange)
+    batched = lambda s_: not plan.is_integral_slot(s_)      # noqa: E731
+    ranks = []
+    for r in range(world):
+        arr = {}
+        for s_, shp in hp.shapes.items():
+            if plan.is_integral_slot(s_):
+                pre, pat = s_.split(".")
+                arr[s_] = numpy.ascontiguousarray(getattr(src[pre], pat))
+            elif s_ in inputs:
+                arr[s_] = numpy.ascontiguousarray(inputs[s_])
+            elif s_ in hp.dslots:
+                arr[s_] = numpy.zeros((ng,) + tuple(shp))
+        ranks.append(arr)
+    run_hybrid(hp, ranks, ng, batched)
+    for r in range(world):
+        for nm in outs:
+            assert numpy.abs(ranks[r][nm] - ref[nm]).max() < 1e-12*numpy.abs(ref[nm]).max(), (r, nm)

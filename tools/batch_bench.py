@@ -31,7 +31,8 @@ def main():
         mr = bool(closed) and (ng >= ft_cc_equations.MIRROR_ROWS_MIN_BATCH if rows == "auto"
                                else rows == "1")
         if mr not in plans:
-            plans[mr] = ft_cc_equations.stanton_plan("u", sizes, -1.0, mirror=closed, mirror_rows=mr)
+            plans[mr] = ft_cc_equations.stanton_plan("u", sizes, -1.0, mirror=closed,
+                                                     mirror_rows=mr, singlet=closed)
         return plans[mr]
     p = plan_for(max(ngs))
     ints = ft_cc_equations._u_integral_slots(Fa, Fb, Ia, Ib, Iabab, dev,
@@ -40,6 +41,7 @@ def main():
                                               os.environ.get("KB200_GROUP", "8"), closed))
     for ng in ngs:
         p = plan_for(ng)
+        torch.manual_seed(0)
         t = dict(ints)
         for s in p.inputs + p.outputs:
             if s not in t:

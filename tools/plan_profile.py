@@ -22,8 +22,15 @@ def main():
     ea, eb = sysm.u_energies_tot()
     Fa, Fb, Ia, Ib, Iabab = cc_utils.uft_integrals(sysm, ea, eb, beta, MU_)
     sizes = ft_cc_equations._u_sizes(Fa, Fb)
-    p = ft_cc_equations.stanton_plan("u", sizes, -1.0, mirror=closed, mirror_rows=closed and ng >= ft_cc_equations.MIRROR_ROWS_MIN_BATCH) if which == "stanton" else \
-        ft_cc_equations.lambda_plan("u", sizes, -1.0, mirror=closed)
+    if which == "stanton":
+        p = ft_cc_equations.stanton_plan(
+            "u", sizes, -1.0, mirror=closed, singlet=closed,
+            mirror_rows=closed and ng >= ft_cc_equations.MIRROR_ROWS_MIN_BATCH)
+    elif which == "lambda-sweep":
+        p = ft_cc_equations.lambda_split_plans("u", sizes, -1.0, mirror=closed)[1]
+    else:
+        p = ft_cc_equations.lambda_plan("u", sizes, -1.0, mirror=closed)
+    torch.manual_seed(0)
     t = ft_cc_equations._u_integral_slots(Fa, Fb, Ia, Ib, Iabab, dev,
                                           [s for s in p.inputs if _plan.is_integral_slot(s)])
     m = norb
