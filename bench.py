@@ -408,11 +408,16 @@ def main():
         root.setLevel(logging.INFO)
         root.addHandler(lt)
         try:
+            do_esn = kind == "ueg" and norb <= 57
+
             def solve():
                 cc = ccsd(sysm, T=Tsys, mu=mu, iprint=0, ngrid=ng, **solve_kw)
                 out = cc.run()
                 return cc, out
-            solve()                              # plans compiled, caches warm
+            cc, _ = solve()                      # plans compiled, caches warm
+            if do_esn:
+                cc.compute_ESN()
+            cc = None
             lt.lines, lt.t = [], {}
             barrier()
             t0 = time.time()
@@ -422,7 +427,7 @@ def main():
             nt, _ = lt.iterations()
             full = {"omega_tot": Etot, "omega_cc": Ecc, "t_iterations": nt,
                     "time_to_convergence_s": lt.t.get("ccsd_s"), "run_wall_s": t_run}
-            if kind == "ueg" and norb <= 57:
+            if do_esn:
                 barrier()
                 t0 = time.time()
                 cc.compute_ESN()

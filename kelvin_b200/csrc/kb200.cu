@@ -923,7 +923,24 @@ struct MultiStream {
     }
 };
 
-static MultiStream g_ms[16];
+// one set of side streams per (device, caller stream): two plans that run concurrently on
+// different caller streams (a rank's own grid points and the grid point it shares with the other
+// ranks, parallel.py) must not queue behind each other on shared side streams
+constexpr int MS_PER_DEV = 4;
+static MultiStream g_ms[16][MS_PER_DEV];
+static cudaStream_t g_ms_owner[16][MS_PER_DEV];
+static int g_ms_used[16] = {0};
+
+static MultiStream* ms_for(int dev, cudaStream_t caller) {
+    for (int k = 0; k < g_ms_used[dev]; ++k)
+        if (g_ms_owner[dev][k] == caller) return &g_ms[dev][k];
+    if (g_ms_used[dev] < MS_PER_DEV) {
+        const int k = g_ms_used[dev]++;
+        g_ms_owner[dev][k] = caller;
+        return &g_ms[dev][k];
+    }
+    return nullptr;          // more caller streams than sets: that plan runs on one stream
+}
 
 static int g_plan_streams = -1;
 
@@ -1155,8 +1172,8 @@ static int run_plan_impl(const kb200_op* ops, int nops, const uint32_t* tables,
     MultiStream* ms = nullptr;
     int dev = 0;
     if (!ev && nops > 1 && plan_streams() > 1 && cudaGetDevice(&dev) == cudaSuccess && dev < 16) {
-        ms = &g_ms[dev];
-        if (ms->init(st, nslots)) return -2;
+        ms = ms_for(dev, st);
+        if (ms && ms->init(st, nslots)) return -2;
     }
     int rc = run_plan_body(ops, nops, tables, slots, nslots, workspace, workspace_bytes, st, ev, ms);
     // join even after an error: nothing may stay in flight on the side streams unordered

@@ -287,25 +287,42 @@ def evaluate_rows(p, hybrid, t, flat, ng, y0, dev, cache=None):
         run(y0, ng)
         return
     sh = parallel.Shards(ng, y0)
-    run(*sh.own)
     owner_left = False
-    if sh.r > 0:
-        hp = None
-        if sh.use_hybrid() and hybrid is not None:
-            try:
-                hp = hybrid()
-            except ValueError:
-                hp = None             # program shape the partition does not cover: single owners
-        if hp is not None:
-            l0, l1 = sh.left
+    hp = None
+    if sh.r > 0 and sh.use_hybrid() and hybrid is not None:
+        try:
+            hp = hybrid()
+        except ValueError:
+            hp = None                 # program shape the partition does not cover: single owners
+    if hp is not None:
+        # the shared grid points go first and on a side stream: their launches (small next to
+        # this rank's own) and the two exchanges they contain overlap the own grid points
+        l0, l1 = sh.left
+        cur = torch.cuda.current_stream()
+        side = _side_stream(dev)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
             hp.run(sliced(hp, l0, l1), l1 - l0, sh.rank, parallel.group())
-        else:
+        run(*sh.own)
+        cur.wait_stream(side)
+    else:
+        run(*sh.own)
+        if sh.r > 0:
             owner_left = True
             parallel.zero_foreign_left_rows(flat, sh)
             mine = sh.owner_row()
             if mine is not None:
                 run(mine, mine + 1)
     parallel.exchange_rows(flat, sh, owner_left)
+
+
+_side = {}
+
+
+def _side_stream(dev):
+    if dev.index not in _side:
+        _side[dev.index] = torch.cuda.Stream(device=dev)
+    return _side[dev.index]
 
 
 def needed_rows(ng, y0=0):

@@ -216,3 +216,94 @@ def test_contraction_skinny_streaming(built, k, n):
             p.run(t, nb)
             ref = -1.5*numpy.einsum("y%s,y%s->y%s" % (la, lb, lc), A, B) + (C0 if preset else 0.0)
             assert numpy.abs(t["C"].cpu().numpy() - ref).max() < 1e-11*numpy.abs(ref).max(), (la, lb, lc)
+
+
+@pytest.mark.parametrize("ng", [113, 320])
+def test_integration_large_grids(built, ng):
+    """No limit on the grid size (round 1 staged all rows in shared memory and refused
+    ngrid > ~113; the reference's own tests and examples use 200, 280, 320, 400 and 2400 points,
+    e.g. kelvin/tests/test_quadrature.py): output rows are processed 16 at a time in
+    registers, the grid arrays come from global memory beyond 72 points."""
+    from kelvin_b200 import quadrature
+    rng = numpy.random.default_rng(ng)
+    n = 3
+    e = util.random_D(n)
+    D2 = cqc.D2(e, e)
+    ti, g, G = odrv.simpsons(ng, 1.0)
+    tb = rng.standard_normal((ng,) + D2.shape)
+    for mode in (0, 1):
+        ref = odrv.int_tbar(ng, tb, ti, D2, G)
+        got = quadrature.int_tbar(ng, tb, ti, D2, G, mode=mode).cpu().numpy()
+        assert numpy.abs(got - ref).max() < 1e-11*numpy.abs(ref).max()
+        L2 = rng.standard_normal((ng, n, n, n, n))
+        ref = odrv.int_L(ng, L2, ti, D2, g, G)
+        got = quadrature.int_L(ng, L2, ti, D2, g, G, mode=mode).cpu().numpy()
+        assert numpy.abs(got - ref).max() < 1e-11*numpy.abs(ref).max()
+    # the driver runs on such a grid (MP2 guess + two iterations)
+    from kelvin_b200.ccsd import ccsd
+    from kelvin_b200.ueg_system import UEGSystem
+    s = UEGSystem(0.5, 2*numpy.pi, 1.2, mu=0.2, norb=7, orbtype='g')
+    cc = ccsd(s, T=0.5, mu=0.2, ngrid=ng, max_iter=2)
+    cc.run()
+
+
+def test_strided_rows_and_fused_update(built):
+    """Blocks that are column ranges of one wide (ng, Ntot) buffer: integration, int_L and the
+    damping kernel take row strides; the fused update (integration + residual norm + damping +
+    new norm + energy term in one pass, kb200_int_tbar_update) equals the separate kernels."""
+    import torch
+    from kelvin_b200 import cc_utils, ft_cc_energy, ft_cc_equations as fe, quadrature
+    rng = numpy.random.default_rng(3)
+    ng, n = 10, 6
+    F, I, t1, t2 = util.random_g(n, ng, seed=21)
+    e = util.random_D(n)
+    D1, D2 = cqc.D1(e, e), cqc.D2(e, e)
+    ti, g, G = odrv.simpsons(ng, 2.0)
+    flat, (b1, b2) = fe.flat_rows(ng, ((n, n), (n, n, n, n)), _dev(t1).device)
+    tb1, tb2 = rng.standard_normal(t1.shape), rng.standard_normal(t2.shape)
+    b1.copy_(_dev(tb1))
+    b2.copy_(_dev(tb2))
+    assert not b2.is_contiguous()
+    for rows in (None, (3, 7)):
+        ref = odrv.int_tbar(ng, tb2, ti, D2, G)
+        got = quadrature.int_tbar(ng, b2, ti, D2, G, rows=rows).cpu().numpy()
+        ref = ref if rows is None else ref[rows[0]:rows[1]]
+        assert numpy.abs(got - ref).max() < 1e-12*numpy.abs(ref).max()
+    L2 = numpy.ascontiguousarray(tb2.transpose(0, 3, 4, 1, 2))
+    lflat, (l2,) = fe.flat_rows(ng, ((n, n, n, n),), flat.device)
+    lflat[:, :] = 0.0
+    l2.copy_(_dev(L2))
+    wide = torch.zeros((ng, 3*n**4), dtype=torch.float64, device=flat.device)
+    l2w = wide[:, n**4:2*n**4].unflatten(1, (n, n, n, n))
+    l2w.copy_(l2)
+    ref = odrv.int_L(ng, L2, ti, D2, g, G)
+    got = quadrature.int_L(ng, l2w, ti, D2, g, G).cpu().numpy()
+    assert numpy.abs(got - ref).max() < 1e-12*numpy.abs(ref).max()
+    # fused update vs integrate -> damp_norms -> energy
+    alpha, beta = 0.3, 2.0
+    T1a, T2a = _dev(t1.copy()), _dev(t2.copy())
+    T1b, T2b = _dev(t1.copy()), _dev(t2.copy())
+    n1 = quadrature.int_tbar(ng, b1, ti, D1, G)
+    n2 = quadrature.int_tbar(ng, b2, ti, D2, G)
+    st = cc_utils._Stats(2, flat.device)
+    st.damp(0, T1a, n1, alpha)
+    st.damp(1, T2a, n2, alpha)
+    Eref = ft_cc_energy.ft_cc_energy(T1a, T2a, F.ov, I.oovv, g, beta)
+    sref = st.read()
+    stats = torch.zeros(8, dtype=torch.float64, device=flat.device)
+    fai = _dev(F.ov).t().contiguous()
+    Iabij = ft_cc_energy.oovv_to_abij(I.oovv)
+    quadrature.int_tbar_update(ng, b1, ti, D1, G, T1b, alpha, stats.data_ptr(), g=g, W=fai, c2=1.0)
+    quadrature.int_tbar_update(ng, b2, ti, D2, G, T2b, alpha, stats.data_ptr() + 32, g=g, W=Iabij,
+                               T1x=T1b, T1y=T1b, c2=0.25, c11=0.5)
+    s = stats.cpu().numpy().reshape(2, 4)
+    assert torch.equal(T1a, T1b) and torch.equal(T2a, T2b)
+    assert numpy.abs(s[:, :3] - sref).max() < 1e-12*numpy.abs(sref).max()
+    assert abs((s[0, 3] + s[1, 3])/beta - Eref) < 1e-12*abs(Eref)
+    # strided damping
+    T2c = _dev(t2.copy())
+    st2 = cc_utils._Stats(1, flat.device)
+    st2.damp(0, T2c, b2, alpha)
+    ref = alpha*t2 + (1 - alpha)*tb2
+    assert numpy.abs(T2c.cpu().numpy() - ref).max() < 1e-15
+    assert abs(st2.read()[0, 0] - numpy.sum((tb2 - t2)**2)) < 1e-12*numpy.sum((tb2 - t2)**2)
