@@ -600,12 +600,12 @@ int grid_for(long long n, int threads, int cap = 148 * 16) {
 // ---------------------------------------------------------------------------
 // GEMM dispatch
 // ---------------------------------------------------------------------------
-template <int WMs, int WNs, int WM, int WN, int AM, int BM_, int ST, bool ILV, int MINB>
-int launch_gemm_inst(const kb200::GemmGroup& grp, int splitk, cudaStream_t st) {
+template <int WMs, int WNs, int WM, int WN, int ST, bool ILV, int MINB = 1>
+int launch_gemm_modes(const kb200::GemmGroup& grp, int splitk, cudaStream_t st) {
     using namespace kb200;
     constexpr int BMt = WMs * WM, BNt = WNs * WN, NT = WMs * WNs * 32;
-    constexpr int smem = ST * (TileLoader<BMt, NT, AM>::STAGE + TileLoader<BNt, NT, BM_>::STAGE) * 8;
-    auto kern = gemm_tab_kernel<WMs, WNs, WM, WN, AM, BM_, ST, ILV, MINB>;
+    constexpr int smem = ST * (StageMax<BMt, NT>::value + StageMax<BNt, NT>::value) * 8;
+    auto kern = gemm_tab_kernel<WMs, WNs, WM, WN, ST, ILV, MINB>;
     static bool configured = false;
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -616,14 +616,6 @@ int launch_gemm_inst(const kb200::GemmGroup& grp, int splitk, cudaStream_t st) {
     kern<<<grid, NT, smem, st>>>(grp);
     KB_CHECK_LAUNCH("gemm_tab_kernel");
     return 0;
-}
-
-template <int WMs, int WNs, int WM, int WN, int ST, bool ILV, int MINB = 1>
-int launch_gemm_modes(const kb200::GemmGroup& p, int splitk, int am, int bm, cudaStream_t st) {
-    if (am == 0 && bm == 0) return launch_gemm_inst<WMs, WNs, WM, WN, 0, 0, ST, ILV, MINB>(p, splitk, st);
-    if (am == 0 && bm == 1) return launch_gemm_inst<WMs, WNs, WM, WN, 0, 1, ST, ILV, MINB>(p, splitk, st);
-    if (am == 1 && bm == 0) return launch_gemm_inst<WMs, WNs, WM, WN, 1, 0, ST, ILV, MINB>(p, splitk, st);
-    return launch_gemm_inst<WMs, WNs, WM, WN, 1, 1, ST, ILV, MINB>(p, splitk, st);
 }
 
 constexpr int LK_NW = KB200_LK_NW;       // warps per CTA of the long-K kernel
@@ -818,8 +810,12 @@ struct MultiStream {
 
     int init(cudaStream_t caller, int nslots) {
         if (!made) {
+            // the side streams inherit the priority of the caller's stream (a plan on a
+            // high-priority stream must not queue its launches behind another plan's)
+            int prio = 0;
+            if (cudaStreamGetPriority(caller, &prio) != cudaSuccess) prio = 0;
             for (int k = 1; k < NS; ++k)
-                if (cudaStreamCreateWithFlags(&s[k], cudaStreamNonBlocking) != cudaSuccess)
+                if (cudaStreamCreateWithPriority(&s[k], cudaStreamNonBlocking, prio) != cudaSuccess)
                     return fail(-2, "plan: cannot create side stream");
             if (cudaEventCreateWithFlags(&fork_ev, cudaEventDisableTiming) != cudaSuccess)
                 return fail(-2, "plan: cannot create event");
@@ -988,8 +984,7 @@ static int run_plan_body(const kb200_op* ops, int nops, const uint32_t* tables,
             int fsum = 0, rsum = 0;
             for (int m = 0; m < ng; ++m) {
                 const kb200_op& q = ops[i + m];
-                if (q.kind != 0 || q.tile != o.tile || q.a_mode != o.a_mode || q.b_mode != o.b_mode ||
-                    (ng > 1 && q.splitk > 1))
+                if (q.kind != 0 || q.tile != o.tile || (ng > 1 && q.splitk > 1))
                     return fail(-1, "plan: inconsistent group");
                 if (q.a < 0 || q.a >= nslots || q.c < 0 || q.c >= nslots || q.b < 0 || q.b >= nslots ||
                     q.K <= 0 || q.M <= 0 || q.N <= 0 || q.batch <= 0)
@@ -1013,6 +1008,8 @@ static int run_plan_body(const kb200_op* ops, int nops, const uint32_t* tables,
                 p.tilesM = (q.M + BMt - 1) / BMt;
                 p.tilesN = (q.N + BNt - 1) / BNt;
                 p.batch = q.batch;
+                p.amode = q.a_mode;
+                p.bmode = q.b_mode;
                 int fm = p.tilesM - ((q.M % BMt) ? 1 : 0), fn = p.tilesN - ((q.N % BNt) ? 1 : 0);
                 fsum += fm * fn * q.batch;
                 rsum += (p.tilesM * p.tilesN - fm * fn) * q.batch;
@@ -1031,17 +1028,17 @@ static int run_plan_body(const kb200_op* ops, int nops, const uint32_t* tables,
             }
             int rc;
             if (o.tile == 0)
-                rc = launch_gemm_modes<2, 4, 64, 32, 4, true>(grp, p.splitk, o.a_mode, o.b_mode, st);
+                rc = launch_gemm_modes<2, 4, 64, 32, 4, true>(grp, p.splitk, st);
             else if (o.tile == 1)
-                rc = launch_gemm_modes<8, 1, 16, 32, 4, true>(grp, p.splitk, o.a_mode, o.b_mode, st);
+                rc = launch_gemm_modes<8, 1, 16, 32, 4, true>(grp, p.splitk, st);
             else if (o.tile == 2)
-                rc = launch_gemm_modes<4, 4, 32, 32, 4, true>(grp, p.splitk, o.a_mode, o.b_mode, st);
+                rc = launch_gemm_modes<4, 4, 32, 32, 4, true>(grp, p.splitk, st);
             else if (o.tile == 3)
-                rc = launch_gemm_modes<2, 4, 64, 32, 4, false>(grp, p.splitk, o.a_mode, o.b_mode, st);
+                rc = launch_gemm_modes<2, 4, 64, 32, 4, false>(grp, p.splitk, st);
             else if (o.tile == 4)
-                rc = launch_gemm_modes<4, 2, 32, 32, 3, true, 2>(grp, p.splitk, o.a_mode, o.b_mode, st);
+                rc = launch_gemm_modes<4, 2, 32, 32, 3, true, 2>(grp, p.splitk, st);
             else if (o.tile == 5)
-                rc = launch_gemm_modes<2, 2, 32, 32, 3, true, 3>(grp, p.splitk, o.a_mode, o.b_mode, st);
+                rc = launch_gemm_modes<2, 2, 32, 32, 3, true, 3>(grp, p.splitk, st);
             else if (o.tile == 6) {
                 if (ng != 1 || o.M > 40 || o.N > 40) return fail(-1, "plan: bad long-K op");
                 if (o.M <= 24 && o.N <= 24)

@@ -41,6 +41,7 @@ struct GemmParams {
     double* partial;             // [batch][splitk][M][N] when splitk > 1
     int tilesM, tilesN;
     int batch;
+    int amode, bmode;            // operand contiguity (see TileLoader); per member of a launch
 };
 
 // Up to KB200_MAX_GROUP independent contractions of one kernel configuration share a launch:
@@ -218,13 +219,21 @@ struct TileLoader {
     }
 };
 
-// Row groups (8 rows) are dealt to the warps round-robin, so that in a ragged
-// edge tile every warp loses the same share of work and whole invalid groups
-// are skipped: edge tiles cost in proportion to their valid area.
-template <int WARPS_M, int WARPS_N, int WM, int WN, int AMODE, int BMODE, int STAGES, bool ILV,
-          int MINB>
-__global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, MINB)
-    gemm_tab_kernel(const __grid_constant__ GemmGroup grp) {
+// shared-memory doubles one stage of an R-row operand tile needs in either contiguity mode
+template <int R, int NT>
+struct StageMax {
+    static constexpr int value = TileLoader<R, NT, 0>::STAGE > TileLoader<R, NT, 1>::STAGE
+                                     ? TileLoader<R, NT, 0>::STAGE
+                                     : TileLoader<R, NT, 1>::STAGE;
+};
+
+// The tile loop for one member and one (AMODE, BMODE) pair; the kernel below picks the pair of
+// the member its CTA works on at run time (CTA-uniform), so contractions with different operand
+// contiguities share a launch: at small tau batches (tau-sharded runs) a launch of one or two
+// block GEMMs is a fraction of a wave of CTAs.
+template <int WARPS_M, int WARPS_N, int WM, int WN, int AMODE, int BMODE, int STAGES, bool ILV>
+__device__ __forceinline__ void gemm_tab_body(const GemmParams& p, int f_, bool in_full,
+                                              double* smem) {
     constexpr int BM = WARPS_M * WM;
     constexpr int BN = WARPS_N * WN;
     constexpr int NT = WARPS_M * WARPS_N * 32;
@@ -233,9 +242,8 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, MINB)
     using LA = TileLoader<BM, NT, AMODE>;
     using LB = TileLoader<BN, NT, BMODE>;
 
-    extern __shared__ double smem[];
     double* As = smem;
-    double* Bs = smem + STAGES * LA::STAGE;
+    double* Bs = smem + STAGES * StageMax<BM, NT>::value;
 
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -244,26 +252,6 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, MINB)
     const int wni = warp / WARPS_M;
     const int g = lane >> 2;
     const int t = lane & 3;
-
-    // CTA order: member by member, batch-major over the full tiles (CTAs that run together
-    // share one batch's operands in L2), then the ragged -- cheaper -- edge tiles of all
-    // members and batches, so the final partial wave is filled with the short CTAs.
-    int mi = 0;
-    int f_ = blockIdx.x;
-    bool in_full;
-    {
-        const int total_full = grp.fend[grp.n - 1];
-        in_full = f_ < total_full;
-        if (in_full) {
-            while (f_ >= grp.fend[mi]) ++mi;
-            if (mi) f_ -= grp.fend[mi - 1];
-        } else {
-            f_ -= total_full;
-            while (f_ >= grp.rend[mi]) ++mi;
-            if (mi) f_ -= grp.rend[mi - 1];
-        }
-    }
-    const GemmParams& p = grp.p[mi];
     int b, tm, tn;
     {
         const int rm = (p.M % BM) ? 1 : 0, rn = (p.N % BN) ? 1 : 0;
@@ -486,6 +474,45 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, MINB)
                 }
             }
         }
+    }
+}
+
+// Row groups (8 rows) are dealt to the warps round-robin, so that in a ragged
+// edge tile every warp loses the same share of work and whole invalid groups
+// are skipped: edge tiles cost in proportion to their valid area.
+template <int WARPS_M, int WARPS_N, int WM, int WN, int STAGES, bool ILV, int MINB>
+__global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, MINB)
+    gemm_tab_kernel(const __grid_constant__ GemmGroup grp) {
+    extern __shared__ double smem[];
+    // CTA order: member by member, batch-major over the full tiles (CTAs that run together
+    // share one batch's operands in L2), then the ragged -- cheaper -- edge tiles of all
+    // members and batches, so the final partial wave is filled with the short CTAs.
+    int mi = 0;
+    int f_ = blockIdx.x;
+    bool in_full;
+    {
+        const int total_full = grp.fend[grp.n - 1];
+        in_full = f_ < total_full;
+        if (in_full) {
+            while (f_ >= grp.fend[mi]) ++mi;
+            if (mi) f_ -= grp.fend[mi - 1];
+        } else {
+            f_ -= total_full;
+            while (f_ >= grp.rend[mi]) ++mi;
+            if (mi) f_ -= grp.rend[mi - 1];
+        }
+    }
+    const GemmParams& p = grp.p[mi];
+    if (p.amode == 0) {
+        if (p.bmode == 0)
+            gemm_tab_body<WARPS_M, WARPS_N, WM, WN, 0, 0, STAGES, ILV>(p, f_, in_full, smem);
+        else
+            gemm_tab_body<WARPS_M, WARPS_N, WM, WN, 0, 1, STAGES, ILV>(p, f_, in_full, smem);
+    } else {
+        if (p.bmode == 0)
+            gemm_tab_body<WARPS_M, WARPS_N, WM, WN, 1, 0, STAGES, ILV>(p, f_, in_full, smem);
+        else
+            gemm_tab_body<WARPS_M, WARPS_N, WM, WN, 1, 1, STAGES, ILV>(p, f_, in_full, smem);
     }
 }
 

@@ -295,15 +295,16 @@ def evaluate_rows(p, hybrid, t, flat, ng, y0, dev, cache=None):
         except ValueError:
             hp = None                 # program shape the partition does not cover: single owners
     if hp is not None:
-        # the shared grid points go first and on a side stream: their launches (small next to
-        # this rank's own) and the two exchanges they contain overlap the own grid points
+        # the shared grid points run on a high-priority side stream: their launches (small next
+        # to this rank's own) and the two exchanges they contain overlap the own grid points,
+        # which are enqueued first so that the device starts on the long part at once
         l0, l1 = sh.left
         cur = torch.cuda.current_stream()
         side = _side_stream(dev)
         side.wait_stream(cur)
-        with torch.cuda.stream(side):
-            hp.run(sliced(hp, l0, l1), l1 - l0, sh.rank, parallel.group())
         run(*sh.own)
+        with torch.cuda.stream(side):
+            hp.run(sliced(hp, l0, l1), l1 - l0, sh.rank, parallel.exchange_group())
         cur.wait_stream(side)
     else:
         run(*sh.own)
@@ -320,8 +321,10 @@ _side = {}
 
 
 def _side_stream(dev):
+    """High-priority stream for the grid points the ranks evaluate together: its many small
+    launches get the next free SM instead of waiting behind the own grid points' wide launches."""
     if dev.index not in _side:
-        _side[dev.index] = torch.cuda.Stream(device=dev)
+        _side[dev.index] = torch.cuda.Stream(device=dev, priority=-1)
     return _side[dev.index]
 
 

@@ -40,6 +40,7 @@ def configure(group=None, enabled=None, hybrid=None):
     """group: process group to shard over (default: the world); enabled=False: every rank
     evaluates every grid point (replicas); hybrid=False: leftover rows go to single owners."""
     _cfg["group"] = group
+    _cfg.pop("xgroup", None)
     if enabled is not None:
         _cfg["enabled"] = bool(enabled)
     if hybrid is not None:
@@ -48,6 +49,25 @@ def configure(group=None, enabled=None, hybrid=None):
 
 def group():
     return _cfg["group"]
+
+
+def exchange_group():
+    """Process group for the exchanges INSIDE an evaluation (hybrid partition): the same ranks,
+    but NCCL kernels on a high-priority stream, so that they are not queued behind the wide
+    contraction launches of the ranks' own grid points.  Created at first use (a collective call:
+    every rank gets here in the same evaluation)."""
+    if "xgroup" not in _cfg:
+        grp = _cfg["group"]
+        xg = grp
+        try:
+            if dist.get_backend(grp) == "nccl":
+                opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+                ranks = dist.get_process_group_ranks(grp if grp is not None else dist.group.WORLD)
+                xg = dist.new_group(ranks=ranks, backend="nccl", pg_options=opts)
+        except Exception:
+            xg = grp
+        _cfg["xgroup"] = xg
+    return _cfg["xgroup"]
 
 
 def world_info(grp=None):

@@ -1244,10 +1244,9 @@ class Lowered(object):
                 groups.append(list(range(len(order), len(order) + len(chain))))
                 order.extend(chain)
                 continue
+            # (the kernel takes the operand contiguity modes per member: only the tile must agree)
             lead = self.descs[ready[0]]
-            sig = (lead.tile, lead.a_mode, lead.b_mode)
-            grp = [i for i in ready
-                   if (self.descs[i].tile, self.descs[i].a_mode, self.descs[i].b_mode) == sig]
+            grp = [i for i in ready if self.descs[i].tile == lead.tile]
             # one slot may be accumulated into by only one member of a launch
             seen, pick = set(), []
             for i in grp:
