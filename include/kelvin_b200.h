@@ -61,6 +61,12 @@ typedef struct kb200_op {
     int32_t group;         /* kind 0: this op and the next group-1 ops (same tile/a_mode/b_mode,
                               splitk 1, mutually independent) share one launch; 0/1 = alone */
     int32_t reserved;      /* tile 7: bit 0 = rows (not columns) of C are the contiguous direction */
+    int64_t ldA, ldB;      /* > 0: the operand is a plain matrix -- its row and k tables are affine
+                              and the contiguous index (k for mode 0, row/column for mode 1) has
+                              stride 1; ld = pitch of the other index in elements.  With an even
+                              pitch and a 16-byte aligned base the kernel feeds the operand by TMA
+                              (cp.async.bulk.tensor through a tensor map built at launch) instead
+                              of the offset tables.  0: gathered through the tables. */
 } kb200_op;
 
 /* Bytes of workspace kb200_plan_run needs for these ops (split-K partials). */

@@ -258,6 +258,7 @@ class GccStep(object):
         self.Iabij = ft_cc_energy.oovv_to_abij(I.oovv)
         self.fai = _lib.as_dev(F.ov, dev).t().contiguous()
         self.stats = torch.zeros(8, dtype=torch.float64, device=dev)
+        self.work = {}            # residual buffers kept across iterations (stable addresses)
         # T[0] == 0 is preserved by the update (row 0 of G vanishes): skip that grid point
         self.t0 = ft_cc_equations.t0_is_zero(G, (self.T1, self.T2))
         # a caller-supplied guess need not be antisymmetric: then the full sums are evaluated
@@ -267,7 +268,8 @@ class GccStep(object):
         """-> (E, res1 + res2) as logged by the reference."""
         ng = self.ng
         b1, b2 = ft_cc_equations.ccsd_stanton_bar(self.F, self.I, self.T1, self.T2,
-                                                  t0_zero=self.t0, antisym=self.antisym)
+                                                  t0_zero=self.t0, antisym=self.antisym,
+                                                  work=self.work)
         sp = self.stats.data_ptr()
         quadrature.int_tbar_update(ng, b1, self.ti, self.D1, self.G, self.T1, alpha, sp,
                                    g=self.g, W=self.fai, c2=1.0)
@@ -353,6 +355,7 @@ class UccStep(object):
                      ft_cc_energy.oovv_to_abij(Ib.oovv))
         self.fT = (_lib.as_dev(Fa.ov, dev).t().contiguous(), _lib.as_dev(Fb.ov, dev).t().contiguous())
         self.stats = torch.zeros(20, dtype=torch.float64, device=dev)
+        self.work = {}            # residual buffers kept across iterations (stable addresses)
         self.set_flags(known)
 
     def set_flags(self, known=None):
@@ -383,7 +386,7 @@ class UccStep(object):
         old = self.old
         bars = ft_cc_equations.uccsd_stanton_bar(
             *self.ints, *old, t0_zero=self.t0, closed_shell=self.cs, beta_copies=False,
-            singlet=self.singlet, antisym=self.antisym)
+            singlet=self.singlet, antisym=self.antisym, work=self.work)
         live = (0, 2, 3) if self.cs else (0, 1, 2, 3, 4)
         # energy terms: singles with F.ov; doubles with <ij||ab> and the (already updated) singles
         T1a, T1b = old[0], (old[0] if self.cs else old[1])
@@ -561,6 +564,7 @@ def ft_lambda_iter(method, L1old, L2old, T1, T2, F, I, D1, D2, g, G, beta, ng, t
     st = _Stats(2, dev)
     T1, T2 = _lib.as_dev(T1, dev), _lib.as_dev(T2, dev)
     asym = ft_cc_equations.is_antisymmetric(T2) and ft_cc_equations.is_antisymmetric(L2old)
+    work = {}
     while i < max_iter and not converged:
         if method == "LCCSD":
             L1, L2 = ft_cc_equations.lccsd_lambda_simple(
@@ -570,7 +574,7 @@ def ft_lambda_iter(method, L1old, L2old, T1, T2, F, I, D1, D2, g, G, beta, ng, t
             L2 = ft_cc_equations.lccd_lambda_simple(F, I, T2, L2old, D2, ti, ng, g, G, beta)
         elif method == "CCSD":
             L1, L2 = ft_cc_equations.ccsd_lambda_opt(
-                F, I, T1, T2, L1old, L2old, D1, D2, ti, ng, g, G, beta, antisym=asym)
+                F, I, T1, T2, L1old, L2old, D1, D2, ti, ng, g, G, beta, antisym=asym, work=work)
         else:
             L1 = L1old
             L2 = ft_cc_equations.ccd_lambda_simple(F, I, T2, L2old, D2, ti, ng, g, G, beta)
@@ -619,11 +623,12 @@ def ft_ulambda_iter(method, L1ain, L1bin, L2aain, L2abin, L2bbin, T1aold, T1bold
     asym = all(ft_cc_equations.is_antisymmetric(x) for x in
                ([Ts[2], old[2]] + ([] if cs else [Ts[4], old[4]])))
     live = (0, 2, 3) if cs else (0, 1, 2, 3, 4)
+    work = {}
     while i < max_iter and not converged:
         new = ft_cc_equations.uccsd_lambda_opt(
             Fa, Fb, Ia, Ib, Iabab, *Ts,
             old[0], old[1], old[2], old[3], old[4], D1a, D1b, D2aa, D2ab, D2bb,
-            ti, ng, g, G, beta, closed_shell=cs, antisym=asym)
+            ti, ng, g, G, beta, closed_shell=cs, antisym=asym, work=work)
         for k in live:
             st.damp(k, old[k], new[k], alpha)
         if cs:

@@ -600,11 +600,77 @@ int grid_for(long long n, int threads, int cap = 148 * 16) {
 // ---------------------------------------------------------------------------
 // GEMM dispatch
 // ---------------------------------------------------------------------------
+// ---------------------------------------------------------------------------
+// TMA tensor maps for plain operands
+// ---------------------------------------------------------------------------
+typedef CUresult (*TmaEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+TmaEncodeFn tma_encoder() {
+    static TmaEncodeFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        const char* off = getenv("KB200_TMA");
+        if (off && atoi(off) == 0) return nullptr;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (TmaEncodeFn)p;
+    }
+    return fn;
+}
+
+// The operand as a 3-d tensor (contiguous index: nc elements; strided index: ns rows of pitch
+// ld; grid point: nb of stride bs) with a box of boxc x boxs x 1.  False when the layout does
+// not meet TMA's alignment rules (16-byte base and strides).
+bool make_tmap(CUtensorMap* tm, const double* base, long long nc, long long ns, long long ld, int nb,
+               long long bs, int boxc, int boxs) {
+    TmaEncodeFn enc = tma_encoder();
+    if (!enc || ld <= 0 || (ld & 1) || ((uintptr_t)base & 15) || nc <= 0 || ns <= 0) return false;
+    if (nb > 1 && (bs <= 0 || (bs & 1))) return false;
+    if (nc >= (1LL << 32) || ns >= (1LL << 32) || ld * 8 >= (1LL << 40) || bs * 8 >= (1LL << 40))
+        return false;
+    if (boxc > 256 || boxs > 256) return false;
+    cuuint64_t dims[3] = {(cuuint64_t)nc, (cuuint64_t)ns, (cuuint64_t)(nb > 1 ? nb : 1)};
+    cuuint64_t strides[2] = {(cuuint64_t)ld * 8, (cuuint64_t)(nb > 1 ? bs : ns * ld) * 8};
+    cuuint32_t box[3] = {(cuuint32_t)boxc, (cuuint32_t)boxs, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, (void*)base, dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
 template <int WMs, int WNs, int WM, int WN, int ST, bool ILV, int MINB = 1>
-int launch_gemm_modes(const kb200::GemmGroup& grp, int splitk, cudaStream_t st) {
+int launch_gemm_modes(kb200::GemmGroup& grp, const long long* ldA, const long long* ldB, int splitk,
+                      cudaStream_t st) {
     using namespace kb200;
     constexpr int BMt = WMs * WM, BNt = WNs * WN, NT = WMs * WNs * 32;
-    constexpr int smem = ST * (StageMax<BMt, NT>::value + StageMax<BNt, NT>::value) * 8;
+    constexpr int smem = ST * (StageMax<BMt, NT>::value + StageMax<BNt, NT>::value) * 8 + ST * 8;
+    for (int m = 0; m < grp.n; ++m) {
+        GemmParams& p = grp.p[m];
+        p.tmaA = p.tmaB = 0;
+        if (ldA[m] > 0) {
+            // mode 0: [rows][k contiguous], box (BK + 4) x BM; mode 1: [k][rows contiguous],
+            // box (BM + 4) x BK -- the padded pitches of TileLoader
+            p.tmaA = p.amode == 0
+                         ? make_tmap(&grp.tm[m][0], p.A, p.K, p.M, ldA[m], p.bsA ? p.batch : 1, p.bsA,
+                                     BK + 4, BMt)
+                         : make_tmap(&grp.tm[m][0], p.A, p.M, p.K, ldA[m], p.bsA ? p.batch : 1, p.bsA,
+                                     BMt + 4, BK);
+        }
+        if (ldB[m] > 0) {
+            p.tmaB = p.bmode == 0
+                         ? make_tmap(&grp.tm[m][1], p.B, p.K, p.N, ldB[m], p.bsB ? p.batch : 1, p.bsB,
+                                     BK + 4, BNt)
+                         : make_tmap(&grp.tm[m][1], p.B, p.N, p.K, ldB[m], p.bsB ? p.batch : 1, p.bsB,
+                                     BNt + 4, BK);
+        }
+    }
     auto kern = gemm_tab_kernel<WMs, WNs, WM, WN, ST, ILV, MINB>;
     static bool configured = false;
     if (!configured) {
@@ -979,6 +1045,7 @@ static int run_plan_body(const kb200_op* ops, int nops, const uint32_t* tables,
             int ng = o.group > 1 ? o.group : 1;
             if (ng > kb200::MAX_GROUP || i + ng > nops) return fail(-1, "plan: bad group");
             kb200::GemmGroup grp;
+            long long ldA[kb200::MAX_GROUP], ldB[kb200::MAX_GROUP];
             grp.n = ng;
             int BMt = tile_bm(o.tile), BNt = tile_bn(o.tile);
             int fsum = 0, rsum = 0;
@@ -1010,6 +1077,8 @@ static int run_plan_body(const kb200_op* ops, int nops, const uint32_t* tables,
                 p.batch = q.batch;
                 p.amode = q.a_mode;
                 p.bmode = q.b_mode;
+                ldA[m] = q.ldA;
+                ldB[m] = q.ldB;
                 int fm = p.tilesM - ((q.M % BMt) ? 1 : 0), fn = p.tilesN - ((q.N % BNt) ? 1 : 0);
                 fsum += fm * fn * q.batch;
                 rsum += (p.tilesM * p.tilesN - fm * fn) * q.batch;
@@ -1028,17 +1097,17 @@ static int run_plan_body(const kb200_op* ops, int nops, const uint32_t* tables,
             }
             int rc;
             if (o.tile == 0)
-                rc = launch_gemm_modes<2, 4, 64, 32, 4, true>(grp, p.splitk, st);
+                rc = launch_gemm_modes<2, 4, 64, 32, 4, true>(grp, ldA, ldB, p.splitk, st);
             else if (o.tile == 1)
-                rc = launch_gemm_modes<8, 1, 16, 32, 4, true>(grp, p.splitk, st);
+                rc = launch_gemm_modes<8, 1, 16, 32, 4, true>(grp, ldA, ldB, p.splitk, st);
             else if (o.tile == 2)
-                rc = launch_gemm_modes<4, 4, 32, 32, 4, true>(grp, p.splitk, st);
+                rc = launch_gemm_modes<4, 4, 32, 32, 4, true>(grp, ldA, ldB, p.splitk, st);
             else if (o.tile == 3)
-                rc = launch_gemm_modes<2, 4, 64, 32, 4, false>(grp, p.splitk, st);
+                rc = launch_gemm_modes<2, 4, 64, 32, 4, false>(grp, ldA, ldB, p.splitk, st);
             else if (o.tile == 4)
-                rc = launch_gemm_modes<4, 2, 32, 32, 3, true, 2>(grp, p.splitk, st);
+                rc = launch_gemm_modes<4, 2, 32, 32, 3, true, 2>(grp, ldA, ldB, p.splitk, st);
             else if (o.tile == 5)
-                rc = launch_gemm_modes<2, 2, 32, 32, 3, true, 3>(grp, p.splitk, st);
+                rc = launch_gemm_modes<2, 2, 32, 32, 3, true, 3>(grp, ldA, ldB, p.splitk, st);
             else if (o.tile == 6) {
                 if (ng != 1 || o.M > 40 || o.N > 40) return fail(-1, "plan: bad long-K op");
                 if (o.M <= 24 && o.N <= 24)

@@ -17,6 +17,7 @@
 //   direction in HBM, so global reads stay coalesced; both paddings make the
 //   DMMA fragment loads bank-conflict free (stride == 4 mod 16 doubles).
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -42,6 +43,8 @@ struct GemmParams {
     int tilesM, tilesN;
     int batch;
     int amode, bmode;            // operand contiguity (see TileLoader); per member of a launch
+    int tmaA, tmaB;              // 1: the operand is a plain matrix with 16-byte aligned rows and
+                                 // arrives through its TMA tensor map (GemmGroup::tm), else gathered
 };
 
 // Up to KB200_MAX_GROUP independent contractions of one kernel configuration share a launch:
@@ -49,11 +52,46 @@ struct GemmParams {
 // the last wave is paid once per group instead of once per contraction.
 constexpr int MAX_GROUP = 8;
 struct GemmGroup {
+    // TMA tensor maps of the plain operands, [member][A, B]: 3-d tensors (contiguous index, strided
+    // index, grid point).  The boxes over-fetch 4 elements of the contiguous index, which
+    // reproduces the padded shared-memory pitches of TileLoader (conflict-free fragment loads)
+    // with one cp.async.bulk.tensor per operand tile; out-of-range rows / k are zero-filled.
+    alignas(64) CUtensorMap tm[MAX_GROUP][2];
     GemmParams p[MAX_GROUP];
     int fend[MAX_GROUP];         // running end of the full-tile CTA ranges of the members
     int rend[MAX_GROUP];         // same for the ragged-tile CTAs (these come last in the grid)
     int n;
 };
+
+// ---- mbarrier / TMA primitives (sm_90+: cp.async.bulk.tensor -> SASS UTMALDG) ----
+__device__ __forceinline__ void mbar_init(uint32_t bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0,
+                                            int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5}], [%2];\n" ::"r"(dst),
+        "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
 
 __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc, bool valid) {
     unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -232,7 +270,8 @@ struct StageMax {
 // contiguities share a launch: at small tau batches (tau-sharded runs) a launch of one or two
 // block GEMMs is a fraction of a wave of CTAs.
 template <int WARPS_M, int WARPS_N, int WM, int WN, int AMODE, int BMODE, int STAGES, bool ILV>
-__device__ __forceinline__ void gemm_tab_body(const GemmParams& p, int f_, bool in_full,
+__device__ __forceinline__ void gemm_tab_body(const GemmParams& p, const CUtensorMap* tmA,
+                                              const CUtensorMap* tmB, int f_, bool in_full,
                                               double* smem) {
     constexpr int BM = WARPS_M * WM;
     constexpr int BN = WARPS_N * WN;
@@ -293,13 +332,47 @@ __device__ __forceinline__ void gemm_tab_body(const GemmParams& p, int f_, bool 
 
     const int mcnt = __popc(mval), ncnt = __popc(nval);   // valid groups form a prefix
 
+    // operand feed: TMA (one elected thread issues cp.async.bulk.tensor per operand tile, the
+    // stage's mbarrier counts the bytes) for plain operands, gathered 8-byte cp.async otherwise
+    const bool ta = p.tmaA != 0, tb = p.tmaB != 0;          // CTA-uniform
+    const bool tany = ta || tb;
     LA la;
     LB lb;
-    la.init(p.A + (long long)b * p.bsA, p.am, p.ak, m0, p.M, tid);
-    lb.init(p.B + (long long)b * p.bsB, p.bn, p.bk, n0, p.N, tid);
+    la.rows_full = true;
+    lb.rows_full = true;
+    if (!ta) la.init(p.A + (long long)b * p.bsA, p.am, p.ak, m0, p.M, tid);
+    if (!tb) lb.init(p.B + (long long)b * p.bsB, p.bn, p.bk, n0, p.N, tid);
     const uint32_t As_u = (uint32_t)__cvta_generic_to_shared(As);
     const uint32_t Bs_u = (uint32_t)__cvta_generic_to_shared(Bs);
     const bool rows_full = la.rows_full && lb.rows_full;
+    const uint32_t bar_u = (uint32_t)__cvta_generic_to_shared(
+        smem + STAGES * (StageMax<BM, NT>::value + StageMax<BN, NT>::value));
+    if (tany) {
+        if (tid == 0) {
+#pragma unroll
+            for (int s = 0; s < STAGES; ++s) mbar_init(bar_u + 8 * s, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        }
+        __syncthreads();
+    }
+    const uint32_t tx_bytes = (ta ? LA::STAGE * 8 : 0) + (tb ? LB::STAGE * 8 : 0);
+    const int bA = p.bsA ? b : 0, bB = p.bsB ? b : 0;       // grid-point coordinate (0: shared)
+    auto tma_issue = [&](int s, int k0) {
+        const uint32_t bar = bar_u + 8 * s;
+        mbar_expect_tx(bar, tx_bytes);
+        if (ta) {
+            if (AMODE == 0)
+                tma_load_3d(As_u + s * LA::STAGE * 8, tmA, bar, k0, m0, bA);
+            else
+                tma_load_3d(As_u + s * LA::STAGE * 8, tmA, bar, m0, k0, bA);
+        }
+        if (tb) {
+            if (BMODE == 0)
+                tma_load_3d(Bs_u + s * LB::STAGE * 8, tmB, bar, k0, n0, bB);
+            else
+                tma_load_3d(Bs_u + s * LB::STAGE * 8, tmB, bar, n0, k0, bB);
+        }
+    };
 
     double acc[MI][NI][2];
 #pragma unroll
@@ -307,17 +380,22 @@ __device__ __forceinline__ void gemm_tab_body(const GemmParams& p, int f_, bool 
 #pragma unroll
         for (int j = 0; j < NI; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-    la.prefetch_k(kbeg, kend, tid);
-    lb.prefetch_k(kbeg, kend, tid);
+    if (!ta) la.prefetch_k(kbeg, kend, tid);
+    if (!tb) lb.prefetch_k(kbeg, kend, tid);
 #pragma unroll
     for (int s = 0; s < STAGES - 1; ++s) {
-        la.advance_k();
-        lb.advance_k();
-        la.prefetch_k(kbeg + (s + 1) * BK, kend, tid);
-        lb.prefetch_k(kbeg + (s + 1) * BK, kend, tid);
+        if (!ta) {
+            la.advance_k();
+            la.prefetch_k(kbeg + (s + 1) * BK, kend, tid);
+        }
+        if (!tb) {
+            lb.advance_k();
+            lb.prefetch_k(kbeg + (s + 1) * BK, kend, tid);
+        }
         if (s < nk) {
-            la.load_all(As_u + s * LA::STAGE * 8);
-            lb.load_all(Bs_u + s * LB::STAGE * 8);
+            if (!ta) la.load_all(As_u + s * LA::STAGE * 8);
+            if (!tb) lb.load_all(Bs_u + s * LB::STAGE * 8);
+            if (tany && tid == 0) tma_issue(s, kbeg + s * BK);
         }
         cp_async_commit();
     }
@@ -325,6 +403,7 @@ __device__ __forceinline__ void gemm_tab_body(const GemmParams& p, int f_, bool 
     const bool full = (mval == (1u << MI) - 1u) && (nval == (1u << NI) - 1u);
     for (int kt = 0; kt < nk; ++kt) {
         cp_async_wait<STAGES - 2>();
+        if (tany) mbar_wait(bar_u + 8 * (kt % STAGES), (kt / STAGES) & 1);
 #ifndef KB200_EXP_NOSYNC
         __syncthreads();
 #endif
@@ -334,12 +413,15 @@ __device__ __forceinline__ void gemm_tab_body(const GemmParams& p, int f_, bool 
 #else
         const bool do_load = nxt < nk;
 #endif
-        la.advance_k();
-        lb.advance_k();
-        if (nxt + 1 < nk) {
-            la.prefetch_k(kbeg + (nxt + 1) * BK, kend, tid);
-            lb.prefetch_k(kbeg + (nxt + 1) * BK, kend, tid);
+        if (!ta) {
+            la.advance_k();
+            if (nxt + 1 < nk) la.prefetch_k(kbeg + (nxt + 1) * BK, kend, tid);
         }
+        if (!tb) {
+            lb.advance_k();
+            if (nxt + 1 < nk) lb.prefetch_k(kbeg + (nxt + 1) * BK, kend, tid);
+        }
+        if (tany && do_load && tid == 0) tma_issue(nxt % STAGES, kbeg + nxt * BK);
         const uint32_t an = As_u + (nxt % STAGES) * LA::STAGE * 8;
         const uint32_t bn = Bs_u + (nxt % STAGES) * LB::STAGE * 8;
         const double* as = As + (kt % STAGES) * LA::STAGE;
@@ -357,13 +439,13 @@ __device__ __forceinline__ void gemm_tab_body(const GemmParams& p, int f_, bool 
                 for (int j = 0; j < NI; ++j)
                     bf[j] = LB::frag(bs, (j * WARPS_N + wni) * 8 + g, k4 * 4 + t);
                 if (ILV) {
-                    la.template load_part<true>(an, k4);
-                    lb.template load_part<true>(bn, k4);
+                    if (!ta) la.template load_part<true>(an, k4);
+                    if (!tb) lb.template load_part<true>(bn, k4);
                 } else if (k4 == 0) {
 #pragma unroll
                     for (int q = 0; q < BK / 4; ++q) {
-                        la.template load_part<true>(an, q);
-                        lb.template load_part<true>(bn, q);
+                        if (!ta) la.template load_part<true>(an, q);
+                        if (!tb) lb.template load_part<true>(bn, q);
                     }
                 }
 #pragma unroll
@@ -373,8 +455,8 @@ __device__ __forceinline__ void gemm_tab_body(const GemmParams& p, int f_, bool 
             }
         } else {
             if (do_load) {
-                la.load_all(an);
-                lb.load_all(bn);
+                if (!ta) la.load_all(an);
+                if (!tb) lb.load_all(bn);
             }
             if (full) {
 #pragma unroll
@@ -483,7 +565,7 @@ __device__ __forceinline__ void gemm_tab_body(const GemmParams& p, int f_, bool 
 template <int WARPS_M, int WARPS_N, int WM, int WN, int STAGES, bool ILV, int MINB>
 __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, MINB)
     gemm_tab_kernel(const __grid_constant__ GemmGroup grp) {
-    extern __shared__ double smem[];
+    extern __shared__ __align__(128) double smem[];
     // CTA order: member by member, batch-major over the full tiles (CTAs that run together
     // share one batch's operands in L2), then the ragged -- cheaper -- edge tiles of all
     // members and batches, so the final partial wave is filled with the short CTAs.
@@ -505,14 +587,18 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, MINB)
     const GemmParams& p = grp.p[mi];
     if (p.amode == 0) {
         if (p.bmode == 0)
-            gemm_tab_body<WARPS_M, WARPS_N, WM, WN, 0, 0, STAGES, ILV>(p, f_, in_full, smem);
+            gemm_tab_body<WARPS_M, WARPS_N, WM, WN, 0, 0, STAGES, ILV>(p, &grp.tm[mi][0], &grp.tm[mi][1],
+                                                                         f_, in_full, smem);
         else
-            gemm_tab_body<WARPS_M, WARPS_N, WM, WN, 0, 1, STAGES, ILV>(p, f_, in_full, smem);
+            gemm_tab_body<WARPS_M, WARPS_N, WM, WN, 0, 1, STAGES, ILV>(p, &grp.tm[mi][0], &grp.tm[mi][1],
+                                                                         f_, in_full, smem);
     } else {
         if (p.bmode == 0)
-            gemm_tab_body<WARPS_M, WARPS_N, WM, WN, 1, 0, STAGES, ILV>(p, f_, in_full, smem);
+            gemm_tab_body<WARPS_M, WARPS_N, WM, WN, 1, 0, STAGES, ILV>(p, &grp.tm[mi][0], &grp.tm[mi][1],
+                                                                         f_, in_full, smem);
         else
-            gemm_tab_body<WARPS_M, WARPS_N, WM, WN, 1, 1, STAGES, ILV>(p, f_, in_full, smem);
+            gemm_tab_body<WARPS_M, WARPS_N, WM, WN, 1, 1, STAGES, ILV>(p, &grp.tm[mi][0], &grp.tm[mi][1],
+                                                                         f_, in_full, smem);
     }
 }
 

@@ -7,11 +7,16 @@ points.  One ``run`` = one C call (kb200_plan_run) that enqueues every kernel
 of the residual for that chunk on the current CUDA stream.
 """
 import ctypes
+import os
 from collections import OrderedDict
 
 import torch
 
 from . import _lib, plan as _plan
+
+
+GRAPHS = int(os.environ.get("KB200_GRAPH", "1"))
+PAD_SCRATCH = int(os.environ.get("KB200_PAD", "1"))
 
 
 class Plan(object):
@@ -28,7 +33,11 @@ class Plan(object):
         self.inputs = [s for s in self.shapes if s in set(inputs) or _plan.is_integral_slot(s)]
         self.outputs = [s for s in outputs if s in self.shapes]
         preset = list(self.inputs) + list(preset_outputs)
-        self.low = _plan.Lowered(rops, self.shapes, self.batched, preset, antisym=antisym)
+        # plan-owned 4-index scratch is stored with an even pitch of its trailing index pair
+        # (plan.padded_strides): rows of every matrix view start on 16-byte boundaries
+        pad = [s for s in self.shapes if s not in self.inputs and s not in self.outputs
+               and len(self.shapes[s]) == 4] if PAD_SCRATCH else []
+        self.low = _plan.Lowered(rops, self.shapes, self.batched, preset, antisym=antisym, pad=pad)
         self.derived = self.low.derived
         self.tmp_slots = [s for s in self.shapes if s not in self.inputs and s not in self.outputs
                           and s not in self.derived]
@@ -39,6 +48,7 @@ class Plan(object):
         self._tmp_dev = None
         self._ops = {}
         self._ws = None
+        self._graphs = {}         # launch signature -> [times seen, CUDA graph or None]
         self.flops_per_point = self.low.flops
 
     # -- device state ------------------------------------------------------
@@ -50,20 +60,15 @@ class Plan(object):
         return self._dev_tables
 
     def tmp_bytes_per_point(self):
-        n = 0
-        for s in self.tmp_slots:
-            m = 1
-            for d in self.shapes[s]:
-                m *= d
-            n += 8*m
-        return n
+        return sum(8*self.low.slot_size(s) for s in self.tmp_slots)
 
     def _ensure_tmp(self, nb, dev):
         if self._tmp is not None and self._tmp_nb >= nb and self._tmp_dev == dev:
             return
+        self._graphs = {}          # captured launches hold the old scratch addresses
         # triangle blocks (plan.antisym_outputs) must be zero outside the part the plan writes
         self._tmp = {s: (torch.zeros if s.startswith(_plan.TRI_PREFIX) else torch.empty)(
-            (nb,) + tuple(self.shapes[s]), dtype=torch.float64, device=dev)
+            (nb, self.low.slot_size(s)), dtype=torch.float64, device=dev)
             for s in self.tmp_slots}
         self._tmp_nb = nb
         self._tmp_dev = dev
@@ -72,6 +77,7 @@ class Plan(object):
         self._tmp = None
         self._tmp_nb = 0
         self._ws = None
+        self._graphs = {}
 
     def _ops_for(self, nb, bstr=(), part=None):
         key = (nb, bstr, part)
@@ -82,14 +88,41 @@ class Plan(object):
         return self._ops[key]
 
     # -- run -----------------------------------------------------------------
-    def run(self, tensors, ng, chunk=None, timings=None, part=None):
+    def run(self, tensors, ng, chunk=None, timings=None, part=None, graph=None):
         """tensors: slot -> CUDA float64 tensor (batched slots: leading axis ng; the grid points
         of a batched slot may be rows of a wider buffer, i.e. any leading stride).
         Scratch is allocated for `chunk` grid points at a time (default: all).
-        part = (rank, world): row-slabbed contractions (plan.hybrid_phases) do this rank's rows."""
+        part = (rank, world): row-slabbed contractions (plan.hybrid_phases) do this rank's rows.
+        graph: replay the plan's ~100 launches as ONE CUDA graph once the same call (same
+        tensors at the same addresses: the iteration loops keep their buffers) has been seen
+        twice; the first call runs eagerly, the second captures.  Default: KB200_GRAPH (on)."""
         lib = _lib.load()
         dev = _lib.device()
         nb_max = ng if chunk is None else max(1, min(int(chunk), ng))
+        if graph is None:
+            graph = GRAPHS
+        if graph and timings is None and nb_max >= ng and ng > 0:
+            sig = (ng, part, torch.cuda.current_stream().cuda_stream,
+                   tuple((s, tensors[s].data_ptr(), tensors[s].stride(0) if tensors[s].dim() else 0)
+                         for s in self.inputs + self.outputs))
+            ent = self._graphs.get(sig)
+            if ent is not None and ent[1] is not None:
+                ent[1].replay()
+                return
+            if ent is None:
+                if len(self._graphs) >= 6:
+                    self._graphs.pop(next(iter(self._graphs)))
+                self._graphs[sig] = [1, None]
+            elif not torch.cuda.is_current_stream_capturing():
+                ent[0] += 1
+                g = torch.cuda.CUDAGraph()
+                # thread-local capture mode: the NCCL watchdog thread of a sharded run keeps
+                # querying its events and must not invalidate the capture
+                with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                    self.run(tensors, ng, chunk, None, part, graph=False)
+                ent[1] = g
+                g.replay()
+                return
         self._ensure_tmp(nb_max, dev)
         names = self.low.slot_names
         bstr = []
@@ -111,7 +144,11 @@ class Plan(object):
             # the entry keeps its source tensor alive, so an equal (address, version) can only
             # be that same tensor (a freed tensor's address could be reused by another one)
             if have is None or have[0] != key or have[2] is not st:
-                self._derived_bufs[name] = (key, permute_copy(st, perm), st)
+                # (once per integral tensor: a torch copy into the padded layout)
+                buf = torch.zeros(self.low.slot_size(name), dtype=torch.float64, device=dev)
+                buf.as_strided(tuple(self.shapes[name]), tuple(self.low.strides_of(name))).copy_(
+                    st.permute(*perm))
+                self._derived_bufs[name] = (key, buf, st)
         y0 = 0
         while y0 < ng:
             nb = min(nb_max, ng - y0)

@@ -226,6 +226,20 @@ def _u_integral_slots(Fa, Fb, Ia, Ib, Iabab, dev, needed):
 # ---------------------------------------------------------------------------
 # evaluation of a per-grid-point program over the rows of the grid, sharded over the ranks
 # ---------------------------------------------------------------------------
+def _work_rows(work, name, ng, shapes, dev):
+    """flat_rows, kept in the caller's `work` dict across calls: the iteration loops hand the
+    same dict in every iteration, so the buffers -- and with them the addresses the captured
+    launch graphs of the plans refer to -- stay the same."""
+    shapes = [tuple(int(d) for d in shp) for shp in shapes]
+    if work is None:
+        return flat_rows(ng, shapes, dev)
+    key = (name, ng, tuple(shapes))
+    if work.get("_key_" + name) != key:
+        work[name] = flat_rows(ng, shapes, dev)
+        work["_key_" + name] = key
+    return work[name]
+
+
 def flat_rows(ng, shapes, dev):
     """One (ng, Ntot) buffer and its blocks as (ng, *shape) views (rows of the wide buffer): the
     blocks of one quantity travel in ONE collective (parallel.exchange_rows)."""
@@ -357,7 +371,7 @@ def t0_is_zero(G, amps):
     return True
 
 
-def ccsd_stanton_bar(F, I, T1old, T2old, fac=-1.0, t0_zero=False, antisym=None):
+def ccsd_stanton_bar(F, I, T1old, T2old, fac=-1.0, t0_zero=False, antisym=None, work=None):
     """T1bar, T2bar: drivers + fac*StantonTerms at every grid point, i.e. the
     state of T1new/T2new just before the integration at
     kelvin/ft_cc_equations.py:109.  t0_zero: the caller guarantees T1old[0] = T2old[0] = 0
@@ -374,7 +388,7 @@ def ccsd_stanton_bar(F, I, T1old, T2old, fac=-1.0, t0_zero=False, antisym=None):
     p = stanton_plan("g", sizes, fac, antisym=antisym)
     t = _g_integral_slots(F, I, dev)
     t["t1"], t["t2"] = T1old, T2old
-    flat, (o1, o2) = flat_rows(ng, (T1old.shape[1:], T2old.shape[1:]), dev)
+    flat, (o1, o2) = _work_rows(work, "bar", ng, (T1old.shape[1:], T2old.shape[1:]), dev)
     t["o1"], t["o2"] = o1, o2
     y0 = 1 if (t0_zero and ng > 1) else 0
     from . import parallel
@@ -398,7 +412,7 @@ def ccsd_stanton(F, I, T1old, T2old, D1, D2, ti, ng, G, t0_zero=False, antisym=N
 
 def uccsd_stanton_bar(Fa, Fb, Ia, Ib, Iabab, T1aold, T1bold, T2aaold, T2abold, T2bbold, fac=-1.0,
                       t0_zero=False, closed_shell=False, beta_copies=True, singlet=False,
-                      antisym=None):
+                      antisym=None, work=None):
     """closed_shell: the caller guarantees mirror-symmetric integrals and amplitudes
     (closed_shell_integrals / closed_shell_amplitudes); the beta-leading blocks are then copies
     of their alpha images and only the reduced program runs (plan.mirror_reduce);
@@ -421,7 +435,7 @@ def uccsd_stanton_bar(Fa, Fb, Ia, Ib, Iabab, T1aold, T1bold, T2aaold, T2abold, T
                           [s for s in p.inputs if _plan.is_integral_slot(s)])
     drivers = [Fa.vo, Fb.vo, Ia.vvoo, Iabab.vvoo, Ib.vvoo]
     live = [k for k in range(5) if not closed_shell or k in (0, 2, 3)]
-    flat, views = flat_rows(ng, [ins[k].shape[1:] for k in live], dev)
+    flat, views = _work_rows(work, "bar", ng, [ins[k].shape[1:] for k in live], dev)
     outs = [None]*5
     for k, v in zip(live, views):
         t[_U_TIN[k]] = ins[k]
@@ -652,6 +666,17 @@ def lambda_guess_plan(mode, sizes, beta, ls_ts_fac):
     return engine.cached(key, build)
 
 
+def _work_like(work, name, x, dev):
+    """Persistent buffer shaped like x in the caller's `work` dict (None: allocate afresh)."""
+    if work is None:
+        return None
+    shp = tuple(x.shape)
+    buf = work.get(name)
+    if buf is None or tuple(buf.shape) != shp:
+        buf = work[name] = torch.empty(shp, dtype=torch.float64, device=dev)
+    return buf
+
+
 def _l_shapes(T1, T2):
     """Lambda-shaped (o..v..) block shapes matching amplitudes (v..o..)."""
     return ((T1.shape[2], T1.shape[1]), (T2.shape[3], T2.shape[4], T2.shape[1], T2.shape[2]))
@@ -677,7 +702,8 @@ def _lambda_rows(mode, sizes, t, tslots, flat, ng, dev, mirror, antisym):
         evaluate_rows(p, hyb, t, flat, ng, 0, dev)
 
 
-def ccsd_lambda_opt(F, I, T1old, T2old, L1old, L2old, D1, D2, ti, ng, g, G, beta, antisym=None):
+def ccsd_lambda_opt(F, I, T1old, T2old, L1old, L2old, D1, D2, ti, ng, g, G, beta, antisym=None,
+                    work=None):
     """Time-dependent CCSD Lambda iteration with intermediates
     (kelvin/ft_cc_equations.py:385-409).  antisym: T2old and L2old are antisymmetric (None:
     checked here)."""
@@ -685,12 +711,12 @@ def ccsd_lambda_opt(F, I, T1old, T2old, L1old, L2old, D1, D2, ti, ng, g, G, beta
     T1old, T2old = _lib.as_dev(T1old, dev), _lib.as_dev(T2old, dev)
     if antisym is None:
         antisym = is_antisymmetric(T2old) and is_antisymmetric(L2old)
-    L1int = quadrature.int_L1(ng, L1old, ti, D1, g, G)
-    L2int = quadrature.int_L2(ng, L2old, ti, D2, g, G)
+    L1int = quadrature.int_L(ng, L1old, ti, D1, g, G, out=_work_like(work, "l1", L1old, dev))
+    L2int = quadrature.int_L(ng, L2old, ti, D2, g, G, out=_work_like(work, "l2", L2old, dev))
     sizes = _g_sizes(F)
     t = _g_integral_slots(F, I, dev)
     t.update({"t1": T1old, "t2": T2old, "l1": L1int, "l2": L2int})
-    flat, (lo1, lo2) = flat_rows(ng, _l_shapes(T1old, T2old), dev)
+    flat, (lo1, lo2) = _work_rows(work, "lo", ng, _l_shapes(T1old, T2old), dev)
     t["lo1"], t["lo2"] = lo1, lo2
     _lambda_rows("g", sizes, t, {"t1": T1old, "t2": T2old}, flat, ng, dev, False, antisym)
     return lo1, lo2
@@ -698,7 +724,8 @@ def ccsd_lambda_opt(F, I, T1old, T2old, L1old, L2old, D1, D2, ti, ng, g, G, beta
 
 def uccsd_lambda_opt(Fa, Fb, Ia, Ib, Iabab, T1aold, T1bold, T2aaold, T2abold,
                      T2bbold, L1aold, L1bold, L2aaold, L2abold, L2bbold, D1a,
-                     D1b, D2aa, D2ab, D2bb, ti, ng, g, G, beta, closed_shell=False, antisym=None):
+                     D1b, D2aa, D2ab, D2bb, ti, ng, g, G, beta, closed_shell=False, antisym=None,
+                     work=None):
     """Unrestricted Lambda iteration (kelvin/ft_cc_equations.py:412-458).  closed_shell: as in
     uccsd_stanton_bar (integrals, amplitudes and Lambda all mirror symmetric); the beta blocks of
     the result are then the alpha tensors themselves."""
@@ -711,7 +738,8 @@ def uccsd_lambda_opt(Fa, Fb, Ia, Ib, Iabab, T1aold, T1bold, T2aaold, T2abold,
         antisym = all(is_antisymmetric(x) for x in
                       ([Ts[2], Lin[2]] + ([] if closed_shell else [Ts[4], Lin[4]])))
     Ds = (D1a, D1b, D2aa, D2ab, D2bb)
-    Ls = {k: quadrature.int_L(ng, Lin[k], ti, Ds[k], g, G) for k in live}
+    Ls = {k: quadrature.int_L(ng, Lin[k], ti, Ds[k], g, G,
+                              out=_work_like(work, "l%d" % k, Lin[k], dev)) for k in live}
     sizes = _u_sizes(Fa, Fb)
     pf = lambda_plan("u", sizes, mirror=closed_shell, antisym=antisym)
     t = _u_integral_slots(Fa, Fb, Ia, Ib, Iabab, dev,
@@ -719,7 +747,7 @@ def uccsd_lambda_opt(Fa, Fb, Ia, Ib, Iabab, T1aold, T1bold, T2aaold, T2abold,
     shp = _l_shapes(Ts[0], Ts[2]) + _l_shapes(Ts[1], Ts[4])
     lshape = {0: shp[0], 1: shp[2], 2: shp[1], 4: shp[3],
               3: (Ts[3].shape[3], Ts[3].shape[4], Ts[3].shape[1], Ts[3].shape[2])}
-    flat, views = flat_rows(ng, [lshape[k] for k in live], dev)
+    flat, views = _work_rows(work, "lo", ng, [lshape[k] for k in live], dev)
     outs = [None]*5
     for k, v in zip(live, views):
         t[_U_T[k]] = Ts[k]

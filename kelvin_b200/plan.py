@@ -486,12 +486,17 @@ def sumdiff_pairs(rops):
         k += 1
         Ap, Am, Bp, Bm, S, D = [tag + x for x in ("Ap", "Am", "Bp", "Bm", "S", "D")]
         lc = Xa[1]
-        new = [ROp((Ap, la), 1.0, [(A1, la)], spin), ROp((Ap, la), 1.0, [(A2, la)], spin),
-               ROp((Am, la), 1.0, [(A1, la)], spin), ROp((Am, la), -1.0, [(A2, la)], spin),
-               ROp((Bp, lb), 1.0, [(B1, lb)], spin), ROp((Bp, lb), 1.0, [(B2, lb)], spin),
-               ROp((Bm, lb), 1.0, [(B1, lb)], spin), ROp((Bm, lb), -1.0, [(B2, lb)], spin),
-               ROp((S, lc), c, [(Ap, la), (Bp, lb)], spin),
-               ROp((D, lc), c, [(Am, la), (Bm, lb)], spin),
+        # the sums / differences are scratch: store them as the contraction wants to read them,
+        # [free indices][contracted indices, one order for both operands] -- plain matrices
+        kk = "".join(l for l in lb if l in la)
+        sa_ = "".join(l for l in la if l in lc) + kk
+        sb_ = "".join(l for l in lb if l in lc) + kk
+        new = [ROp((Ap, sa_), 1.0, [(A1, la)], spin), ROp((Ap, sa_), 1.0, [(A2, la)], spin),
+               ROp((Am, sa_), 1.0, [(A1, la)], spin), ROp((Am, sa_), -1.0, [(A2, la)], spin),
+               ROp((Bp, sb_), 1.0, [(B1, lb)], spin), ROp((Bp, sb_), 1.0, [(B2, lb)], spin),
+               ROp((Bm, sb_), 1.0, [(B1, lb)], spin), ROp((Bm, sb_), -1.0, [(B2, lb)], spin),
+               ROp((S, lc), c, [(Ap, sa_), (Bp, sb_)], spin),
+               ROp((D, lc), c, [(Am, sa_), (Bm, sb_)], spin),
                ROp(Xa, 0.5, [(S, lc)], spin), ROp(Xa, 0.5, [(D, lc)], spin),
                ROp(Xb, 0.5*ratio, [(S, lc)], spin), ROp(Xb, -0.5*ratio, [(D, lc)], spin)]
         q = (i11, i22, i12, i21)
@@ -947,7 +952,8 @@ class kb200_op(ctypes.Structure):
                 ("alpha", ctypes.c_double), ("beta", ctypes.c_double),
                 ("a_mode", ctypes.c_int32), ("b_mode", ctypes.c_int32),
                 ("tile", ctypes.c_int32), ("splitk", ctypes.c_int32),
-                ("group", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+                ("group", ctypes.c_int32), ("reserved", ctypes.c_int32),
+                ("ldA", ctypes.c_int64), ("ldB", ctypes.c_int64)]
 
 
 def _strides(shape):
@@ -955,6 +961,29 @@ def _strides(shape):
     for k in range(len(shape) - 2, -1, -1):
         st[k] = st[k + 1] * shape[k + 1]
     return st
+
+
+def padded_strides(shape):
+    """Strides of a plan-owned 4-index block: the trailing index pair is stored with an EVEN
+    pitch (1089 -> 1090 doubles at 33 orbitals), so that every row of the [p q][r s] matrix view
+    starts on a 16-byte boundary -- what TMA tensor maps and 16-byte copies need; with an odd
+    orbital count the natural strides are all 8 mod 16 bytes.  -> (strides, elements)."""
+    if len(shape) != 4:
+        return _strides(shape), int(numpy.prod(shape)) if len(shape) else 1
+    P = shape[2]*shape[3]
+    P += P & 1
+    return [shape[1]*P, P, shape[3], 1], shape[0]*shape[1]*P
+
+
+def _affine(group):
+    """[(dim, stride)] of a composite index -> stride of its last letter when the composite
+    value addresses memory affinely (each stride = next dim * next stride), else None."""
+    if not group:
+        return None
+    for (d0, s0), (d1, s1) in zip(group[:-1], group[1:]):
+        if s0 != d1*s1:
+            return None
+    return group[-1][1]
 
 
 class TableBank(object):
@@ -1020,6 +1049,9 @@ RANKK = int(_os.environ.get("KB200_RANKK", "1"))
 # re-laid-out integral copies for long-K contractions, so that both operands of the
 # whole-output-per-CTA kernel (tile 6) stream contiguously along k
 DERIVE = int(_os.environ.get("KB200_DERIVE", "1"))
+DERIVE_BIG = int(_os.environ.get("KB200_DERIVE_BIG", "1"))
+# plain integral operands of m^6 contractions with an odd row pitch: contract an aligned copy
+PAD_INTEGRALS = int(_os.environ.get("KB200_PAD_INTEGRALS", "1"))
 # fold the tau batch into the N index of matrix-vector-like contractions with a tau-independent
 # (integral) A operand: the integral block is then read once instead of once per grid point
 FOLD = int(_os.environ.get("KB200_FOLD", "1"))
@@ -1059,7 +1091,7 @@ _TILE_BM = {0: 128, 1: 128, 2: 128, 3: 128, 4: 128, 5: 64, 6: 40, 7: 8}
 class Lowered(object):
     """A resolved program lowered to kb200_op descriptors + offset tables."""
 
-    def __init__(self, rops, slot_shapes, batched, preset=(), antisym=True):
+    def __init__(self, rops, slot_shapes, batched, preset=(), antisym=True, pad=()):
         """slot_shapes: slot -> per-tau-point shape; batched: slot -> bool;
         preset: slots that already hold data when the plan starts (inputs and
         accumulate-into outputs); every other slot is overwritten (beta=0) by
@@ -1068,6 +1100,9 @@ class Lowered(object):
         the reference does."""
         self.rops = rops
         self.antisym = bool(antisym)
+        # pad: slots stored with padded_strides (plan-owned scratch; derived integral copies
+        # always are)
+        self.pad = set(pad)
         self.slot_names = list(slot_shapes.keys())
         self.slot_index = {nm: k for k, nm in enumerate(self.slot_names)}
         self.slot_shapes = slot_shapes
@@ -1113,9 +1148,9 @@ class Lowered(object):
         cslot = items[0][0].out[0]
         shp = self.slot_shapes[cslot]
         nd = len(shp)
-        stc = _strides(shp)
+        stc = self.strides_of(cslot)
         numel = lambda sl: int(numpy.prod(self.slot_shapes[sl]))  # noqa: E731
-        bs = lambda sl: numel(sl) if self.batched[sl] else 0      # noqa: E731
+        bs = lambda sl: self.slot_size(sl) if self.batched[sl] else 0      # noqa: E731
         terms = []
         votes = {}
         for op, beta in items:
@@ -1124,7 +1159,7 @@ class Lowered(object):
             strides = []
             for sl, ls in ins:
                 st = [0]*nd
-                for l, v in zip(ls, _strides(self.slot_shapes[sl])):
+                for l, v in zip(ls, self.strides_of(sl)):
                     st[pos[l]] = v
                 strides.append(st)
             xs, xl = ins[0]
@@ -1282,21 +1317,34 @@ class Lowered(object):
                     raise ValueError("dimension clash on %s in %r" % (l, op))
         return dims
 
-    def _stride_map(self, slot, ls):
-        return dict(zip(ls, _strides(self.slot_shapes[slot])))
+    def strides_of(self, slot):
+        if slot in self.pad:
+            return padded_strides(self.slot_shapes[slot])[0]
+        return _strides(self.slot_shapes[slot])
 
-    def _derive(self, slot, letters, new_letters):
+    def slot_size(self, slot):
+        """Elements one grid point of the slot occupies (padding included)."""
+        if slot in self.pad:
+            return padded_strides(self.slot_shapes[slot])[1]
+        return int(numpy.prod(self.slot_shapes[slot])) if len(self.slot_shapes[slot]) else 1
+
+    def _stride_map(self, slot, ls):
+        return dict(zip(ls, self.strides_of(slot)))
+
+    def _derive(self, slot, letters, new_letters, pad_only=False):
         """Register a re-laid-out copy of a tau-independent integral block:
         new[new_letters] = slot[letters].  Materialised once per integral tensor by the
-        engine (it is constant over iterations and grid points)."""
+        engine (it is constant over iterations and grid points).  pad_only: a copy in the same
+        index order, only for the padded (16-byte aligned) strides derived blocks are stored with."""
         perm = tuple(letters.index(l) for l in new_letters)
-        if perm == tuple(range(len(perm))):
+        if perm == tuple(range(len(perm))) and not pad_only:
             return slot
         name = "%s@%s" % (slot, "".join(str(p) for p in perm))
         if name not in self.derived:
             self.derived[name] = (slot, perm)
             shp = self.slot_shapes[slot]
             self.slot_shapes[name] = tuple(shp[p] for p in perm)
+            self.pad.add(name)
             self.batched[name] = False
             self.slot_index[name] = len(self.slot_names)
             self.slot_names.append(name)
@@ -1325,7 +1373,7 @@ class Lowered(object):
         sc = self._stride_map(*op.out)
         size = lambda grp: int(numpy.prod([dims[l] for l in grp])) if grp else 1  # noqa: E731
         tab = lambda grp, smap: self.bank.get([(dims[l], smap[l]) for l in grp])  # noqa: E731
-        bs = lambda slot: int(numpy.prod(self.slot_shapes[slot])) if self.batched[slot] else 0  # noqa: E731
+        bs = lambda slot: self.slot_size(slot) if self.batched[slot] else 0  # noqa: E731
         d.c = self.slot_index[op.out[0]]
         d.bsC = bs(op.out[0])
         d.alpha, d.beta = op.coef, beta
@@ -1382,6 +1430,30 @@ class Lowered(object):
                 new = "".join(N) + "".join(K)
                 nb, lb = self._derive(nb, lb, new), new
             sa, sb = self._stride_map(na, la), self._stride_map(nb, lb)
+        # m^6 contraction with an integral operand that is neither [rows][k] nor [k][rows] with k
+        # in the other operand's order (the W_ovvo builds read I.oovv[m,n,e,f] with rows (m,e)
+        # against k = (n,f)): contract a copy laid out [rows][k] instead (made once per solve),
+        # so that both operands are plain matrices
+        if DERIVE_BIG and min(size(M), size(N)) >= 128 and size(K) >= 256 \
+                and is_integral_slot(na) != is_integral_slot(nb):
+            odd = lambda sl: len(self.slot_shapes[sl]) == 4 and \
+                (self.slot_shapes[sl][2]*self.slot_shapes[sl][3]) % 2 == 1     # noqa: E731
+            if is_integral_slot(na):
+                ko = [l for l in lb if l in K]
+                if not _plain_order(la, M, ko):
+                    new = "".join(M) + "".join(ko)
+                    na, la = self._derive(na, la, new), new
+                elif PAD_INTEGRALS and odd(na):
+                    na = self._derive(na, la, la, pad_only=True)
+            else:
+                ko = [l for l in la if l in K]
+                if not _plain_order(lb, N, ko):
+                    new = "".join(N) + "".join(ko)
+                    nb, lb = self._derive(nb, lb, new), new
+                elif PAD_INTEGRALS and odd(nb):
+                    nb = self._derive(nb, lb, lb, pad_only=True)
+            sa, sb = self._stride_map(na, la), self._stride_map(nb, lb)
+            K = [l for l in la if l in lb]
         a_mode = 0 if la[-1] in K else 1
         b_mode = 0 if lb[-1] in K else 1
         # order of the contracted composite index: follow the operand that wants to be
@@ -1406,6 +1478,15 @@ class Lowered(object):
         else:
             M = self._order(M, sa, sc) if a_mode == 1 else self._order(M, sc, sa)
         N = self._order(N, sb, sc) if b_mode == 1 else self._order(N, sc, sb)
+        if not rankk and size(M) >= 128 and size(K) >= 256:
+            # large contractions: a row order that makes the operand a plain matrix (rows
+            # strided uniformly) beats following the output's order -- C is scattered anyway
+            Ma = sorted(M, key=lambda l: -sa[l])
+            if _affine([(dims[l], sa[l]) for l in Ma]) is not None:
+                M = Ma
+            Nb = sorted(N, key=lambda l: -sb[l])
+            if size(N) >= 64 and _affine([(dims[l], sb[l]) for l in Nb]) is not None:
+                N = Nb
         d.kind = 0
         d.a, d.b = self.slot_index[na], self.slot_index[nb]
         d.M, d.N, d.K = size(M), size(N), size(K)
@@ -1455,6 +1536,25 @@ class Lowered(object):
         if tri_n is not None:
             d.tCn = self.bank.get_lt([(dims[l], sc[l]) for l in N], *tri_n)
         d.a_mode, d.b_mode = a_mode, b_mode
+        # plain operands: the composite row and k indices address memory affinely and the
+        # contiguous one has unit stride -> ld = pitch of the other one (0: gathered).  The kernels
+        # may then use wide copies / TMA tensor maps instead of the offset tables.
+        d.ldA = d.ldB = 0
+        if half is None:
+            gm, gk = [(dims[l], sa[l]) for l in M], [(dims[l], sa[l]) for l in K]
+            fm, fk = _affine(gm), _affine(gk)
+            if tri_m is None and fm is not None and fk is not None:
+                if a_mode == 0 and fk == 1:
+                    d.ldA = fm
+                elif a_mode == 1 and fm == 1:
+                    d.ldA = fk
+            gn, gk = [(dims[l], sb[l]) for l in N], [(dims[l], sb[l]) for l in K]
+            fn, fk = _affine(gn), _affine(gk)
+            if tri_n is None and fn is not None and fk is not None:
+                if b_mode == 0 and fk == 1:
+                    d.ldB = fn
+                elif b_mode == 1 and fn == 1:
+                    d.ldB = fk
         # (batch folding rebuilds the N tables from these lists: not for triangular columns)
         self._nfold[id(d)] = None if tri_n is not None else \
             ([(dims[l], sb[l]) for l in N], [(dims[l], sc[l]) for l in N])
@@ -1502,6 +1602,7 @@ class Lowered(object):
                 o.tAm += lo
                 o.tCm += lo
                 o.M = hi - lo
+                o.ldA = 0                 # (the tensor map would have to start at row lo)
             o.batch = nbatch if (o.bsC != 0 or o.bsA != 0 or (o.kind in (0, 3) and o.bsB != 0)) else 1
             if o.batch > 1 and o.bsC == 0:
                 raise ValueError("batched operands reduce into an unbatched output")
@@ -1512,6 +1613,7 @@ class Lowered(object):
                 o.tBn = self.bank.get([(o.batch, o.bsB)] + nB)
                 o.tCn = self.bank.get([(o.batch, o.bsC)] + nC)
                 o.N = o.N * o.batch
+                o.ldB = 0
                 o.batch, o.bsB, o.bsC = 1, 0, 0
                 o.tile = 1 if o.M > 64 else 5
             if o.kind == 0:
@@ -1548,6 +1650,14 @@ class Lowered(object):
 # slot bookkeeping shared by the g and u back ends
 # ---------------------------------------------------------------------------
 _INT_SLOT = re.compile(r"^(I|Ia|Ib|Iabab|F|Fa|Fb)\.")
+
+
+def _plain_order(ls, rows, ko):
+    """Are the letters `ls` of an operand [rows...][ko] or [ko][rows...] (rows in any order, the
+    contracted letters exactly in the order `ko`)?"""
+    ls, ko, n = list(ls), list(ko), len(ko)
+    return (ls[-n:] == ko and set(ls[:-n]) == set(rows)) or \
+        (ls[:n] == ko and set(ls[n:]) == set(rows))
 
 
 def is_integral_slot(slot):

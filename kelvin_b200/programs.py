@@ -35,10 +35,18 @@ def tensor_defs():
     add("Xoo", "one", "tmp", True, "oo")
     add("Woooo", "amp2", "tmp", True, "oooo")
     add("Wvvvv", "amp2", "tmp", True, "vvvv")
-    add("Wovvo", "gen4", "tmp", True, "ovvo")
-    # stored [b,j,n,f]: the contracted pair (n,f) is contiguous with f innermost, the same
-    # inner index as I.oovv[mnef], so neither operand of the W_ovvo build gathers with a stride
+    # Storage orders of the ring-term intermediates are chosen so that every m^6 contraction
+    # reads both operands as plain matrices (rows x contiguous k, or k x contiguous columns):
+    # W_ovvo[m,b,e,j] is stored [e,m,b,j]: rows (m,e) of its build and the contracted pair (e,m)
+    # of the ring contraction lead, the columns (b,j) are contiguous;
+    add("Wovvo", "gen4", "tmp", True, "vovo", canon=(1, 2, 0, 3))
+    # t2x stored [b,j,n,f]: the contracted pair (n,f) is contiguous with f innermost, the same
+    # inner index as I.oovv[mnef];
     add("t2x", "gen4", "tmp", True, "voov", canon=(3, 0, 1, 2))
+    # t2r[a,i,e,m] = t2[a,e,i,m]: the amplitudes as the ring contraction reads them, rows (a,i)
+    # against the contiguous contracted pair (e,m) -- one permuted copy per iteration instead of
+    # a strided gather in every k-tile of three m^6 contractions.
+    add("t2r", "gen4", "tmp", True, "vovo", canon=(0, 2, 1, 3))
     add("Z", "gen4", "tmp", True, "vooo")
     add("rg", "gen4", "tmp", True, "vvoo")
     return T
@@ -71,16 +79,17 @@ Wvvvv[abef] += 1 I.vovv[bmef] t1[am]
 Wvvvv[abef] += 0.25 I.oovv[mnef] tau[abmn]
 t2x[bjnf] += 0.5 t2[fbjn]
 t2x[bjnf] += 1 t1[fj] t1[bn]
-Wovvo[mbej] += -1 I.vovo[bmej]
-Wovvo[mbej] += -1 I.vovv[bmef] t1[fj]
-Wovvo[mbej] += 1 I.ooov[mnje] t1[bn]
-Wovvo[mbej] += -1 I.oovv[mnef] t2x[bjnf]
+t2r[aiem] += 1 t2[aeim]
+Wovvo[embj] += -1 I.vovo[bmej]
+Wovvo[embj] += -1 I.vovv[bmef] t1[fj]
+Wovvo[embj] += 1 I.ooov[mnje] t1[bn]
+Wovvo[embj] += -1 I.oovv[mnef] t2x[bjnf]
 Xvv[be] += 1 Fvv[be]
 Xvv[be] += -0.5 t1[bm] Fov[me]
 Xoo[mj] += 1 Foo[mj]
 Xoo[mj] += 0.5 t1[ej] Fov[me]
 Z[bmij] += 1 I.vovo[bmej] t1[ei]
-rg[abij] += 1 t2[aeim] Wovvo[mbej]
+rg[abij] += 1 t2r[aiem] Wovvo[embj]
 rg[abij] += 1 t1[am] Z[bmij]
 """
 
@@ -126,12 +135,23 @@ def _parse_block(text, scale=1.0):
     return out
 
 
-def stanton(fac=-1.0, drivers=True):
+def _intermediates(relayout=True):
+    """relayout=False: the ring contraction reads t2 itself (no t2r copy): the form the reverse
+    sweeps are derived from (their closed-shell rewrites match on the amplitude slots)."""
+    text = _INTERMEDIATES
+    if not relayout:
+        text = text.replace("t2r[aiem] += 1 t2[aeim]\n", "")
+        text = text.replace("rg[abij] += 1 t2r[aiem] Wovvo[embj]", "rg[abij] += 1 t2[aeim] Wovvo[embj]")
+        assert "t2r" not in text
+    return _parse_block(text)
+
+
+def stanton(fac=-1.0, drivers=True, relayout=True):
     """Statements of one residual evaluation: o = drivers + fac*StantonTerms."""
     st = []
     if drivers:
         st += _parse_block(_DRIVERS)
-    st += _parse_block(_INTERMEDIATES)
+    st += _intermediates(relayout)
     st += _parse_block(_RESIDUAL, fac)
     return st
 
@@ -186,16 +206,16 @@ def _without_singles(stmts):
     return out
 
 
-def residual_program(method, fac=-1.0, drivers=True):
+def residual_program(method, fac=-1.0, drivers=True, relayout=True):
     """Statements of o = drivers + fac*R_method(t): CCSD = StantonTerms; CCD = the same with
     t1 = 0 (cqcpy _D_D + _D_DD, kelvin/ft_cc_equations.py:48-62); LCCSD / LCCD = the linear
     terms (kelvin/ft_cc_equations.py:11-45)."""
     if method not in METHODS:
         raise Exception("Unrecognized method keyword")
     if method == "CCSD":
-        return stanton(fac, drivers)
+        return stanton(fac, drivers, relayout)
     if method == "CCD":
-        body = _parse_block(_INTERMEDIATES) + _parse_block(_RESIDUAL, fac)
+        body = _intermediates(relayout) + _parse_block(_RESIDUAL, fac)
     else:
         body = []
         for st in _parse_block(_LINEAR):
@@ -241,7 +261,7 @@ def lambda_rops(mode, fac=-1.0, method="CCSD", beta=None):
     there is no lo1, and LCCD scales its energy term by 1/beta as the reference does (:308)."""
     from .plan import ROp, adjoint, expand, is_integral_slot
     T = tensor_defs()
-    fwd = expand(residual_program(method, 1.0, drivers=False), T, mode)
+    fwd = expand(residual_program(method, 1.0, drivers=False, relayout=False), T, mode)
     s1 = has_singles(method)
     if mode == "g":
         outs1, outs2 = (["o1"] if s1 else []), ["o2"]
@@ -348,7 +368,7 @@ def rdm_rops(mode):
     Inputs t1,t2,l1,l2 as in ``lambda_rops``."""
     from .plan import ROp, adjoint, expand, is_integral_slot
     T = tensor_defs()
-    fwd = expand(stanton(1.0, drivers=False), T, mode)
+    fwd = expand(stanton(1.0, drivers=False, relayout=False), T, mode)
     if mode == "g":
         outset = {"o1", "o2"}
         seed = {"o1~": ("l1", (1, 0), 1.0), "o2~": ("l2", (2, 3, 0, 1), 0.25)}

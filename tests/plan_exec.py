@@ -17,10 +17,25 @@ def run_lowered(low, arrays, nbatch, part=None):
     for nm, (src, perm) in low.derived.items():
         arrays[nm] = numpy.ascontiguousarray(arrays[src].transpose(perm))
     flat = {}
+    padded = {}
     for nm in low.slot_names:
         a = arrays[nm]
         assert a.flags.c_contiguous, nm
-        flat[nm] = a.reshape(-1)
+        if nm in low.pad:
+            # slots the plan stores with padded strides (plan.padded_strides): lay the data out
+            # that way in a flat buffer; the pads are poisoned -- nothing may ever read them
+            st, size = low.strides_of(nm), low.slot_size(nm)
+            lead = a.shape[:a.ndim - len(st)]
+            nb_ = int(numpy.prod(lead)) if lead else 1
+            buf = numpy.full(nb_*size, numpy.nan)
+            view = numpy.lib.stride_tricks.as_strided(
+                buf, shape=(nb_,) + tuple(a.shape[a.ndim - len(st):]),
+                strides=tuple(8*x for x in [size] + list(st)))
+            view[...] = a.reshape(view.shape)
+            flat[nm] = buf
+            padded[nm] = (view, a)
+        else:
+            flat[nm] = a.reshape(-1)
     for o in ops:
         A = flat[low.slot_names[o.a]]
         C = flat[low.slot_names[o.c]]
@@ -54,6 +69,9 @@ def run_lowered(low, arrays, nbatch, part=None):
                 C[cidx] = o.alpha * val
             else:
                 C[cidx] = o.beta * C[cidx] + o.alpha * val
+    for nm, (view, a) in padded.items():
+        if nm not in low.derived:
+            a[...] = view.reshape(a.shape)
 
 
 def run_hybrid(hp, arrays_per_rank, nbatch, batched):

@@ -94,7 +94,7 @@ def test_capi_exports_every_declared_symbol(built):
     assert _lib.load().kb200_version() >= 100
     # the descriptor struct has the layout the header promises
     from kelvin_b200.plan import kb200_op
-    assert ctypes.sizeof(kb200_op) == 4*4 + 3*8 + 4*4 + 3*8 + 6*8 + 2*8 + 6*4
+    assert ctypes.sizeof(kb200_op) == 4*4 + 3*8 + 4*4 + 3*8 + 6*8 + 2*8 + 6*4 + 2*8
 
 
 def test_product_fails_loudly_without_cuda(built):

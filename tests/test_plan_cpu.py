@@ -14,7 +14,11 @@ def _run(rops, mode, sizes, inputs, src, ng):
     shapes = plan.slot_shapes(rops, mode, sizes)
     batched = {s: not plan.is_integral_slot(s) for s in shapes}
     preset = [s for s in shapes if plan.is_integral_slot(s)] + list(inputs)
-    low = plan.Lowered(rops, shapes, batched, preset)
+    # scratch blocks are stored with padded strides, as the engine allocates them
+    outs = ("o1", "o2", "lo1", "lo2")
+    pad = [s for s in shapes if s not in preset and len(shapes[s]) == 4
+           and not s.startswith(outs) and "~" not in s]
+    low = plan.Lowered(rops, shapes, batched, preset, pad=pad)
     arrays = {}
     for s, shp in shapes.items():
         if plan.is_integral_slot(s):
