@@ -650,7 +650,7 @@ int launch_gemm_modes(kb200::GemmGroup& grp, const long long* ldA, const long lo
                       cudaStream_t st) {
     using namespace kb200;
     constexpr int BMt = WMs * WM, BNt = WNs * WN, NT = WMs * WNs * 32;
-    constexpr int smem = ST * (StageMax<BMt, NT>::value + StageMax<BNt, NT>::value) * 8 + ST * 8;
+    constexpr int smem = ST * (StageMax<BMt, NT>::value + StageMax<BNt, NT>::value) * 8 + 2 * ST * 8;
     for (int m = 0; m < grp.n; ++m) {
         GemmParams& p = grp.p[m];
         p.tmaA = p.tmaB = 0;
@@ -670,6 +670,8 @@ int launch_gemm_modes(kb200::GemmGroup& grp, const long long* ldA, const long lo
                          : make_tmap(&grp.tm[m][1], p.B, p.N, p.K, ldB[m], p.bsB ? p.batch : 1, p.bsB,
                                      BNt + 4, BK);
         }
+        // the kernel feeds a member either entirely by TMA or entirely by gathers
+        if (!(p.tmaA && p.tmaB)) p.tmaA = p.tmaB = 0;
     }
     auto kern = gemm_tab_kernel<WMs, WNs, WM, WN, ST, ILV, MINB>;
     static bool configured = false;

@@ -71,6 +71,9 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes)
                  : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     asm volatile(
         "{\n"
@@ -269,7 +272,8 @@ struct StageMax {
 // the member its CTA works on at run time (CTA-uniform), so contractions with different operand
 // contiguities share a launch: at small tau batches (tau-sharded runs) a launch of one or two
 // block GEMMs is a fraction of a wave of CTAs.
-template <int WARPS_M, int WARPS_N, int WM, int WN, int AMODE, int BMODE, int STAGES, bool ILV>
+template <int WARPS_M, int WARPS_N, int WM, int WN, int AMODE, int BMODE, int STAGES, bool ILV,
+          bool TMA>
 __device__ __forceinline__ void gemm_tab_body(const GemmParams& p, const CUtensorMap* tmA,
                                               const CUtensorMap* tmB, int f_, bool in_full,
                                               double* smem) {
@@ -334,8 +338,10 @@ __device__ __forceinline__ void gemm_tab_body(const GemmParams& p, const CUtenso
 
     // operand feed: TMA (one elected thread issues cp.async.bulk.tensor per operand tile, the
     // stage's mbarrier counts the bytes) for plain operands, gathered 8-byte cp.async otherwise
-    const bool ta = p.tmaA != 0, tb = p.tmaB != 0;          // CTA-uniform
-    const bool tany = ta || tb;
+    // (compile-time per body: both operands by TMA, or both gathered -- run-time tests inside
+    // the tile loop keep the compiler from interleaving the copies with the DMMA groups)
+    constexpr bool ta = TMA, tb = TMA;
+    constexpr bool tany = TMA;
     LA la;
     LB lb;
     la.rows_full = true;
@@ -347,10 +353,16 @@ __device__ __forceinline__ void gemm_tab_body(const GemmParams& p, const CUtenso
     const bool rows_full = la.rows_full && lb.rows_full;
     const uint32_t bar_u = (uint32_t)__cvta_generic_to_shared(
         smem + STAGES * (StageMax<BM, NT>::value + StageMax<BN, NT>::value));
+    // full[s]: the stage's bytes have landed (1 arrival + transaction count);
+    // empty[s]: every warp is done reading the stage (NT / 32 arrivals)
+    const uint32_t empty_u = bar_u + 8 * STAGES;
     if (tany) {
         if (tid == 0) {
 #pragma unroll
-            for (int s = 0; s < STAGES; ++s) mbar_init(bar_u + 8 * s, 1);
+            for (int s = 0; s < STAGES; ++s) {
+                mbar_init(bar_u + 8 * s, 1);
+                mbar_init(empty_u + 8 * s, NT / 32);
+            }
             asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
         }
         __syncthreads();
@@ -401,9 +413,61 @@ __device__ __forceinline__ void gemm_tab_body(const GemmParams& p, const CUtenso
     }
 
     const bool full = (mval == (1u << MI) - 1u) && (nval == (1u << NI) - 1u);
+    if (TMA) {
+        // TMA tile loop: NO block barrier.  Every warp waits for the stage's bytes (full
+        // barrier), multiplies, and releases the stage (empty barrier); one thread refills the
+        // stage released in the previous iteration once all warps have left it.  The warps may
+        // drift apart by up to STAGES - 1 k-tiles.
+        for (int kt = 0; kt < nk; ++kt) {
+            const int st_ = kt % STAGES;
+            mbar_wait(bar_u + 8 * st_, (kt / STAGES) & 1);
+            const int nxt = kt + STAGES - 1;
+            if (tid == 0 && nxt < nk) {
+                if (kt >= 1) mbar_wait(empty_u + 8 * ((kt - 1) % STAGES), ((kt - 1) / STAGES) & 1);
+                tma_issue(nxt % STAGES, kbeg + nxt * BK);
+            }
+            const double* as = As + st_ * LA::STAGE;
+            const double* bs = Bs + st_ * LB::STAGE;
+            if (full) {
+#pragma unroll
+                for (int k4 = 0; k4 < BK / 4; ++k4) {
+                    double af[MI], bf[NI];
+#pragma unroll
+                    for (int i = 0; i < MI; ++i)
+                        af[i] = LA::frag(as, (i * WARPS_M + wmi) * 8 + g, k4 * 4 + t);
+#pragma unroll
+                    for (int j = 0; j < NI; ++j)
+                        bf[j] = LB::frag(bs, (j * WARPS_N + wni) * 8 + g, k4 * 4 + t);
+#pragma unroll
+                    for (int i = 0; i < MI; ++i)
+#pragma unroll
+                        for (int j = 0; j < NI; ++j)
+                            dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+                }
+            } else {
+#pragma unroll
+                for (int k4 = 0; k4 < BK / 4; ++k4) {
+#pragma unroll
+                    for (int i = 0; i < MI; ++i) {
+                        if (i < mcnt) {
+                            double a = LA::frag(as, (i * WARPS_M + wmi) * 8 + g, k4 * 4 + t);
+#pragma unroll
+                            for (int j = 0; j < NI; ++j) {
+                                if (j < ncnt) {
+                                    double bb = LB::frag(bs, (j * WARPS_N + wni) * 8 + g, k4 * 4 + t);
+                                    dmma884(acc[i][j][0], acc[i][j][1], a, bb);
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty_u + 8 * st_);
+        }
+    } else
     for (int kt = 0; kt < nk; ++kt) {
         cp_async_wait<STAGES - 2>();
-        if (tany) mbar_wait(bar_u + 8 * (kt % STAGES), (kt / STAGES) & 1);
 #ifndef KB200_EXP_NOSYNC
         __syncthreads();
 #endif
@@ -585,21 +649,28 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32, MINB)
         }
     }
     const GemmParams& p = grp.p[mi];
+    const bool tma = p.tmaA && p.tmaB;
+#define GEMM_TAB_BODY(AM, BM_)                                                                      \
+    do {                                                                                            \
+        if (tma)                                                                                    \
+            gemm_tab_body<WARPS_M, WARPS_N, WM, WN, AM, BM_, STAGES, ILV, true>(                    \
+                p, &grp.tm[mi][0], &grp.tm[mi][1], f_, in_full, smem);                              \
+        else                                                                                        \
+            gemm_tab_body<WARPS_M, WARPS_N, WM, WN, AM, BM_, STAGES, ILV, false>(                   \
+                p, &grp.tm[mi][0], &grp.tm[mi][1], f_, in_full, smem);                              \
+    } while (0)
     if (p.amode == 0) {
         if (p.bmode == 0)
-            gemm_tab_body<WARPS_M, WARPS_N, WM, WN, 0, 0, STAGES, ILV>(p, &grp.tm[mi][0], &grp.tm[mi][1],
-                                                                         f_, in_full, smem);
+            GEMM_TAB_BODY(0, 0);
         else
-            gemm_tab_body<WARPS_M, WARPS_N, WM, WN, 0, 1, STAGES, ILV>(p, &grp.tm[mi][0], &grp.tm[mi][1],
-                                                                         f_, in_full, smem);
+            GEMM_TAB_BODY(0, 1);
     } else {
         if (p.bmode == 0)
-            gemm_tab_body<WARPS_M, WARPS_N, WM, WN, 1, 0, STAGES, ILV>(p, &grp.tm[mi][0], &grp.tm[mi][1],
-                                                                         f_, in_full, smem);
+            GEMM_TAB_BODY(1, 0);
         else
-            gemm_tab_body<WARPS_M, WARPS_N, WM, WN, 1, 1, STAGES, ILV>(p, &grp.tm[mi][0], &grp.tm[mi][1],
-                                                                         f_, in_full, smem);
+            GEMM_TAB_BODY(1, 1);
     }
+#undef GEMM_TAB_BODY
 }
 
 // ---------------------------------------------------------------------------
