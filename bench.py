@@ -187,6 +187,7 @@ def run_reference(args):
     for v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
         os.environ[v] = str(threads)          # before NumPy is imported in this process
     kind, norb, ng, _ = WORKLOADS[args.workload]
+    import numpy  # noqa: F401  (the BLAS pools exist once NumPy is loaded)
     ctx, pools = set_blas_threads(threads)
     with ctx:
         ints, amps, w = cpu_port_setup(norb, 2)

@@ -23,6 +23,9 @@ const char* kb200_last_error(void);
  * (bench.py's "gpu_launches"). */
 int64_t kb200_launch_count(void);
 void kb200_launch_count_reset(void);
+/* A captured plan (CUDA graph) replays its kernels without passing through this library: the
+ * caller adds the number of kernels the graph holds (counted while it was captured) per replay. */
+void kb200_launch_count_add(int64_t n);
 
 /* ------------------------------------------------------------------------
  * Contraction plans.

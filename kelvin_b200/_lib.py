@@ -23,7 +23,7 @@ EXPORTS = (
     "kb200_dress4", "kb200_dress2", "kb200_gather4", "kb200_scatter4_add", "kb200_gsum", "kb200_scale_by", "kb200_dot_keep",
     "kb200_max_absdiff", "kb200_set_plan_streams",
     "kb200_int_tbar_strided", "kb200_int_tbar_update", "kb200_int_L_strided",
-    "kb200_damp_norms_rows",
+    "kb200_damp_norms_rows", "kb200_launch_count_add",
 )
 
 
@@ -46,6 +46,8 @@ def load():
     lib.kb200_last_error.restype = ctypes.c_char_p
     lib.kb200_launch_count.restype = i64
     lib.kb200_launch_count_reset.restype = None
+    lib.kb200_launch_count_add.restype = None
+    lib.kb200_launch_count_add.argtypes = [i64]
     lib.kb200_reduce_scratch_doubles.restype = i64
     lib.kb200_plan_workspace_bytes.restype = i64
     lib.kb200_plan_workspace_bytes.argtypes = [ctypes.POINTER(kb200_op), ctypes.c_int]

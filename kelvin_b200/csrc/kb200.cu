@@ -803,6 +803,7 @@ int kb200_version(void) { return 100; }
 const char* kb200_last_error(void) { return g_err; }
 int64_t kb200_launch_count(void) { return g_launches.load(); }
 void kb200_launch_count_reset(void) { g_launches.store(0); }
+void kb200_launch_count_add(int64_t n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 int64_t kb200_reduce_scratch_doubles(void) { return 65536; }
 
 int kb200_dot_keep(int nkeep, const int32_t dims[4], const int64_t sA[5], const int64_t sB[5],

@@ -108,20 +108,25 @@ class Plan(object):
             ent = self._graphs.get(sig)
             if ent is not None and ent[1] is not None:
                 ent[1].replay()
+                lib.kb200_launch_count_add(ent[2])       # the kernels the graph holds
                 return
             if ent is None:
                 if len(self._graphs) >= 6:
                     self._graphs.pop(next(iter(self._graphs)))
-                self._graphs[sig] = [1, None]
+                self._graphs[sig] = [1, None, 0]
             elif not torch.cuda.is_current_stream_capturing():
                 ent[0] += 1
                 g = torch.cuda.CUDAGraph()
+                n0 = lib.kb200_launch_count()
                 # thread-local capture mode: the NCCL watchdog thread of a sharded run keeps
                 # querying its events and must not invalidate the capture
                 with torch.cuda.graph(g, capture_error_mode="thread_local"):
                     self.run(tensors, ng, chunk, None, part, graph=False)
+                ent[2] = int(lib.kb200_launch_count() - n0)
+                lib.kb200_launch_count_add(-ent[2])      # captured, not launched
                 ent[1] = g
                 g.replay()
+                lib.kb200_launch_count_add(ent[2])
                 return
         self._ensure_tmp(nb_max, dev)
         names = self.low.slot_names
