@@ -346,7 +346,7 @@ def main():
         p = ft_cc_equations.stanton_plan(
             "u", ft_cc_equations._u_sizes(Fa, Fb), -1.0, mirror=closed,
             mirror_rows=nloc >= ft_cc_equations.MIRROR_ROWS_MIN_BATCH,
-            singlet=flags["singlet"], antisym=flags["antisym"])
+            singlet=flags["singlet"], antisym=flags["antisym"], emit_aa=not flags["singlet"])
         t = ft_cc_equations._u_integral_slots(
             Fa, Fb, Ia, Ib, Iabab, dev, [s for s in p.inputs if _plan.is_integral_slot(s)])
         for nm, x in zip(("t1.a", "t1.b", "t2.aa", "t2.ab", "t2.bb"), solver.old):
@@ -474,7 +474,7 @@ def main():
         pc = ft_cc_equations.stanton_plan(
             "u", ft_cc_equations._u_sizes(Fa, Fb), -1.0, mirror=closed,
             mirror_rows=closed and npts >= ft_cc_equations.MIRROR_ROWS_MIN_BATCH,
-            singlet=flags["singlet"], antisym=flags["antisym"])
+            singlet=flags["singlet"], antisym=flags["antisym"], emit_aa=not flags["singlet"])
         fl_exec = float(pc.flops_per_point)*npts
         e2e = None
         if full is not None and full.get("t_iterations"):

@@ -362,6 +362,7 @@ class UccStep(object):
         """known: dict with any of t0, closed_shell, singlet, antisym decided by the caller
         (e.g. a copy of this solver's own state); everything else is checked on the device."""
         known = known or {}
+        self.finish()
         old = self.old
         Fa, Fb, Ia, Ib, Iabab = self.ints
         self.t0 = known["t0"] if "t0" in known else ft_cc_equations.t0_is_zero(self.G, old)
@@ -379,6 +380,13 @@ class UccStep(object):
     def flags(self):
         return {"t0": self.t0, "closed_shell": self.cs, "singlet": self.singlet,
                 "antisym": self.antisym}
+
+    def finish(self):
+        """Closed-shell runs: copy the alpha blocks into the beta ones (T1b, T2bb)."""
+        if getattr(self, "_beta_stale", False):
+            self.old[1].copy_(self.old[0])
+            self.old[4].copy_(self.old[2])
+            self._beta_stale = False
 
     def step(self, alpha):
         """-> (E, res1 + res2) as logged by the reference (kelvin/cc_utils.py:297-305)."""
@@ -398,10 +406,9 @@ class UccStep(object):
         for k in live:
             quadrature.int_tbar_update(ng, bars[k], self.ti, self.Ds[k], self.G, old[k], alpha,
                                        sp + 32*k, g=self.g, **eterm[k])
-        if self.cs:
-            # alpha == beta: the beta blocks are copies
-            old[1].copy_(old[0])
-            old[4].copy_(old[2])
+        # (alpha == beta: the beta blocks are copies of the alpha ones; nothing reads them during
+        # the iterations, so they are brought up to date once, in finish())
+        self._beta_stale = bool(self.cs)
         s = self.stats.cpu().numpy().reshape(5, 4).copy()
         if self.cs:
             s[1] = s[0]
@@ -444,6 +451,7 @@ def ft_ucc_iter(method, T1aold, T1bold, T2aaold, T2abold, T2bbold, Fa, Fb, Ia, I
         Eold = E
     if not converged:
         logging.warning("{} did not converge!".format(method))
+    st.finish()
     tend = time.time()
     logging.info("Total {} time: {:.4f} s".format(method, (tend - tbeg)))
     old = st.old

@@ -560,7 +560,7 @@ def _find_quartet(ops):
 # ---------------------------------------------------------------------------
 # closed-shell singlet: the same-spin doubles residual from the opposite-spin one
 # ---------------------------------------------------------------------------
-def singlet_reduce(rops, o1="o1.a", o2ab="o2.ab", o2aa="o2.aa"):
+def singlet_reduce(rops, o1="o1.a", o2ab="o2.ab", o2aa="o2.aa", emit_aa=True):
     """Closed-shell (mirror_reduce'd) residual programs whose amplitudes also satisfy the singlet
     relation T2aa[a,b,i,j] == T2ab[a,b,i,j] - T2ab[b,a,i,j] (true of the MP2 guess of a
     spin-symmetric system and preserved by the update): the residual obeys the same relation
@@ -570,8 +570,9 @@ def singlet_reduce(rops, o1="o1.a", o2ab="o2.ab", o2aa="o2.aa"):
 
         o2.aa[abij] = o2.ab[abij] - o2.ab[baij].
 
-    NOT wired into the solver loops yet (no GPU validation in round 1): ft_cc_equations.
-    stanton_plan(singlet=True) builds the plan, nothing calls it with True."""
+    emit_aa=False leaves the last step out: the caller derives the same-spin block from the
+    opposite-spin one itself (ft_cc_equations does so AFTER the multi-GPU exchange, which then
+    moves half the bytes)."""
     live = {o1, o2ab}
     kept = []
     for op in reversed(rops):
@@ -580,6 +581,8 @@ def singlet_reduce(rops, o1="o1.a", o2ab="o2.ab", o2aa="o2.aa"):
             for sl, _ in op.ins:
                 live.add(sl)
     kept.reverse()
+    if not emit_aa:
+        return kept
     spin = None
     for op in rops:
         if op.out[0] == o2aa:

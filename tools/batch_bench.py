@@ -32,7 +32,7 @@ def main():
                                else rows == "1")
         if mr not in plans:
             plans[mr] = ft_cc_equations.stanton_plan("u", sizes, -1.0, mirror=closed,
-                                                     mirror_rows=mr, singlet=closed)
+                                                     mirror_rows=mr, singlet=closed, emit_aa=not closed)
         return plans[mr]
     p = plan_for(max(ngs))
     ints = ft_cc_equations._u_integral_slots(Fa, Fb, Ia, Ib, Iabab, dev,

@@ -46,13 +46,14 @@ def main():
         st.step(0.0)
     sh = parallel.Shards(ng, 1)
     sizes = fe._u_sizes(Fa, Fb)
-    kw = dict(mirror=True, singlet=True, antisym=True)
+    kw = dict(mirror=True, singlet=True, antisym=True, emit_aa=False)
     nown = sh.own[1] - sh.own[0]
     pA = fe.stanton_plan("u", sizes, -1.0, mirror_rows=nown >= fe.MIRROR_ROWS_MIN_BATCH, **kw)
     pB = fe.stanton_plan("u", sizes, -1.0, hybrid_world=world, **kw) if (world > 1 and sh.r) else None
     t = fe._u_integral_slots(*ints, dev, [s for s in pA.inputs if _plan.is_integral_slot(s)])
-    live = (0, 2, 3)
+    live = (0, 3)
     flat, views = fe.flat_rows(ng, [st.old[k].shape[1:] for k in live], dev)
+    t[fe._U_TIN[2]] = st.old[2]
     for k, v in zip(live, views):
         t[fe._U_TIN[k]] = st.old[k]
         t[fe._U_TOUT[k]] = v

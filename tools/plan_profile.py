@@ -24,7 +24,7 @@ def main():
     sizes = ft_cc_equations._u_sizes(Fa, Fb)
     if which == "stanton":
         p = ft_cc_equations.stanton_plan(
-            "u", sizes, -1.0, mirror=closed, singlet=closed,
+            "u", sizes, -1.0, mirror=closed, singlet=closed, emit_aa=not closed,
             mirror_rows=closed and ng >= ft_cc_equations.MIRROR_ROWS_MIN_BATCH)
     elif which == "lambda-sweep":
         p = ft_cc_equations.lambda_split_plans("u", sizes, -1.0, mirror=closed)[1]
