@@ -139,6 +139,22 @@ int kb200_int_tbar_update(int ng, int64_t n, const double* tbar, int64_t tstride
                           int nvb, int noa, int nob, const double* g, double c2, double c11,
                           double* out4, double* scratch, int mode, void* stream);
 
+/* The *_h forms additionally take HOST copies of ti[ng], g[ng] and G[ng*ng] (NULL = not given):
+ * for the grid sizes of the reference's benchmarks (ng = 10, 16), all rows and a lower-triangular
+ * G they run a fully unrolled kernel that holds the quadrature in its parameter space -- same
+ * arithmetic, same summation order. */
+int kb200_int_tbar_strided_h(int ng, int64_t n, const double* tbar, int64_t tstride,
+                             const double* D, const double* ti, const double* G, double* out,
+                             int64_t ostride, int y0, int y1, int mode, const double* ti_h /*host*/,
+                             const double* G_h /*host*/, void* stream);
+int kb200_int_tbar_update_h(int ng, int64_t n, const double* tbar, int64_t tstride,
+                            const double* D, const double* ti, const double* G, double* amp,
+                            int64_t astride, int y0, int y1, double alpha, const double* W,
+                            const double* T1x, const double* T1y, int64_t t1xs, int64_t t1ys,
+                            int nvb, int noa, int nob, const double* g, double c2, double c11,
+                            double* out4, double* scratch, int mode, const double* ti_h /*host*/,
+                            const double* g_h /*host*/, const double* G_h /*host*/, void* stream);
+
 /* Replaces kelvin/quadrature.py:320-345 (int_L1, int_L2):
  *   out[s,q] = (1/g[s]) sum_y g[y]*G[y,s]*w(s,y,q)*L[y,q],
  *   w = exp(D[perm(q)]*(ti[s]-ti[y])) for y>=s, 1 otherwise.
@@ -157,6 +173,12 @@ int kb200_int_L_strided(int ng, const int32_t dims[4] /*host*/, const int64_t ds
                         const double* L, int64_t lstride, const double* D, const double* ti,
                         const double* g, const double* G, double* out, int64_t ostride, int s0,
                         int s1, int mode, void* stream);
+
+int kb200_int_L_strided_h(int ng, const int32_t dims[4] /*host*/, const int64_t dstride[4] /*host*/,
+                          const double* L, int64_t lstride, const double* D, const double* ti,
+                          const double* g, const double* G, double* out, int64_t ostride, int s0,
+                          int s1, int mode, const double* ti_h /*host*/, const double* g_h /*host*/,
+                          const double* G_h /*host*/, void* stream);
 
 /* ------------------------------------------------------------------------
  * Energy functional pieces.  Replaces kelvin/ft_cc_energy.py:7-32,35-72.

@@ -24,6 +24,7 @@ EXPORTS = (
     "kb200_max_absdiff", "kb200_set_plan_streams",
     "kb200_int_tbar_strided", "kb200_int_tbar_update", "kb200_int_L_strided",
     "kb200_damp_norms_rows", "kb200_launch_count_add",
+    "kb200_int_tbar_strided_h", "kb200_int_tbar_update_h", "kb200_int_L_strided_h",
 )
 
 
@@ -73,6 +74,15 @@ def load():
     lib.kb200_int_L_strided.argtypes = [ctypes.c_int, ctypes.POINTER(i32), ctypes.POINTER(i64),
                                         vp, i64, vp, vp, vp, vp, vp, i64, ctypes.c_int,
                                         ctypes.c_int, ctypes.c_int, vp]
+    lib.kb200_int_tbar_strided_h.argtypes = [ctypes.c_int, i64, vp, i64, vp, vp, vp, vp, i64,
+                                             ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, vp]
+    lib.kb200_int_tbar_update_h.argtypes = [ctypes.c_int, i64, vp, i64, vp, vp, vp, vp, i64,
+                                            ctypes.c_int, ctypes.c_int, dbl, vp, vp, vp, i64, i64,
+                                            ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, dbl, dbl,
+                                            vp, vp, ctypes.c_int, vp, vp, vp, vp]
+    lib.kb200_int_L_strided_h.argtypes = [ctypes.c_int, ctypes.POINTER(i32), ctypes.POINTER(i64),
+                                          vp, i64, vp, vp, vp, vp, vp, i64, ctypes.c_int,
+                                          ctypes.c_int, ctypes.c_int, vp, vp, vp, vp]
     lib.kb200_energy_pair.argtypes = [ctypes.c_int] * 5 + [vp, vp, vp, vp, vp, dbl, dbl, vp, vp, vp]
     lib.kb200_dot_g.argtypes = [ctypes.c_int, i64, vp, vp, vp, vp, vp, vp]
     lib.kb200_damp_norms.argtypes = [i64, vp, vp, dbl, vp, vp, vp]

@@ -93,7 +93,17 @@ __global__ void final_sum_kernel(const double* part, int nblocks, int nv, double
 // residual norm, damping, new norm and the energy contraction are done on the spot
 // (cc_utils.py:278-299 in one pass over T-bar and T).
 // ---------------------------------------------------------------------------
-constexpr int INT_THREADS = 256;
+#ifndef KB200_INT_THREADS
+#define KB200_INT_THREADS 128
+#endif
+#ifndef KB200_INT_MINB
+#define KB200_INT_MINB 4
+#endif
+#ifndef KB200_INT_XB
+#define KB200_INT_XB 4
+#endif
+constexpr int INT_THREADS = KB200_INT_THREADS;
+constexpr int INT_XB = KB200_INT_XB;  // input rows whose loads are in flight together
 constexpr int INT_SMEM_NG = 72;      // ng up to which ti and G are staged in shared memory
 
 struct IntArgs {
@@ -135,7 +145,7 @@ __device__ __forceinline__ double int_D(const IntArgs& a, long long p) {
 }
 
 template <int YC, int MODE, bool UPD>
-__global__ void __launch_bounds__(INT_THREADS)
+__global__ void __launch_bounds__(INT_THREADS, KB200_INT_MINB)
     int_tbar_kernel(const __grid_constant__ IntArgs a) {
     extern __shared__ double sm[];
     const int ng = a.ng;
@@ -168,26 +178,40 @@ __global__ void __launch_bounds__(INT_THREADS)
         }
         for (int c0 = a.r0; c0 < a.r1; c0 += YC) {
             const int ny = min(YC, a.r1 - c0);
-            double acc[YC], w[YC];
+            double acc[YC], w[YC], dg[YC], ov[YC];
+            // every load of the chunk that does not depend on arithmetic is issued up front
+            // (diagonal inputs, old amplitudes), the lower-triangle inputs in blocks of XB rows:
+            // dozens of independent 8-byte loads per thread are in flight instead of one
 #pragma unroll
             for (int j = 0; j < YC; ++j) {
                 acc[j] = 0.0;
                 w[j] = 1.0;
+                dg[j] = (j < ny) ? src[(size_t)(c0 + j) * a.sstride] : 0.0;
+                ov[j] = (UPD && j < ny) ? a.out[(size_t)(c0 + j) * a.ostride + p] : 0.0;
             }
             // x < y: descending x, the weight of row y picks up one factor per step
-            for (int x = c0 + ny - 2; x >= 0; --x) {
-                const double tb = src[(size_t)x * a.sstride];
-                double e = 1.0;
-                if (MODE == 1) e = exp(d * (tis[x] - tis[x + 1]));
+            for (int xb = c0 + ny - 2; xb >= 0; xb -= INT_XB) {
+                double tbv[INT_XB];
 #pragma unroll
-                for (int j = 0; j < YC; ++j) {
-                    const int y = c0 + j;
-                    if (j < ny && y > x) {
-                        if (MODE == 1) w[j] *= e;
-                        const double gw = Gs[y * ng + x];
-                        if (gw != 0.0) {
-                            const double wt = (MODE == 1) ? w[j] : exp(d * (tis[x] - tis[y]));
-                            acc[j] += gw * wt * tb;
+                for (int u = 0; u < INT_XB; ++u)
+                    tbv[u] = (xb - u >= 0) ? src[(size_t)(xb - u) * a.sstride] : 0.0;
+#pragma unroll
+                for (int u = 0; u < INT_XB; ++u) {
+                    const int x = xb - u;
+                    if (x < 0) break;
+                    const double tb = tbv[u];
+                    double e = 1.0;
+                    if (MODE == 1) e = exp(d * (tis[x] - tis[x + 1]));
+#pragma unroll
+                    for (int j = 0; j < YC; ++j) {
+                        const int y = c0 + j;
+                        if (j < ny && y > x) {
+                            if (MODE == 1) w[j] *= e;
+                            const double gw = Gs[y * ng + x];
+                            if (gw != 0.0) {
+                                const double wt = (MODE == 1) ? w[j] : exp(d * (tis[x] - tis[y]));
+                                acc[j] += gw * wt * tb;
+                            }
                         }
                     }
                 }
@@ -197,11 +221,13 @@ __global__ void __launch_bounds__(INT_THREADS)
             for (int j = 0; j < YC; ++j) {
                 const int y = c0 + j;
                 if (j < ny) {
-                    const int xend = a.lower ? y + 1 : ng;
-                    for (int x = y; x < xend; ++x) {
-                        const double gw = Gs[y * ng + x];
-                        if (gw != 0.0) acc[j] += gw * src[(size_t)x * a.sstride];
-                    }
+                    const double gd = Gs[y * ng + y];
+                    if (gd != 0.0) acc[j] += gd * dg[j];
+                    if (!a.lower)
+                        for (int x = y + 1; x < ng; ++x) {
+                            const double gw = Gs[y * ng + x];
+                            if (gw != 0.0) acc[j] += gw * src[(size_t)x * a.sstride];
+                        }
                 }
             }
 #pragma unroll
@@ -211,13 +237,12 @@ __global__ void __launch_bounds__(INT_THREADS)
                     if (!UPD) {
                         a.out[(size_t)(y - a.r0) * a.ostride + p] = acc[j];
                     } else {
-                        double* op = a.out + (size_t)y * a.ostride + p;
-                        const double o = *op;
+                        const double o = ov[j];
                         const double df = acc[j] - o;
                         nrm[0] += df * df;
                         nrm[1] += o * o;
                         const double u = a.alpha * o + oma * acc[j];
-                        *op = u;
+                        a.out[(size_t)y * a.ostride + p] = u;
                         nrm[2] += u * u;
                         if (a.W != nullptr) {
                             double v = a.c2 * u;
@@ -238,7 +263,7 @@ __global__ void __launch_bounds__(INT_THREADS)
 // Lambda-bar[s] = (1/g_s) sum_y g_y G[y,s] w(s,y) L[y],  w = exp(D (tau_s - tau_y)) for y >= s
 // (running product over ascending y), 1 for y < s (quadrature.py:320-345).
 template <int YC, int MODE>
-__global__ void __launch_bounds__(INT_THREADS)
+__global__ void __launch_bounds__(INT_THREADS, KB200_INT_MINB)
     int_L_kernel(const __grid_constant__ IntArgs a) {
     extern __shared__ double sm[];
     const int ng = a.ng;
@@ -284,19 +309,28 @@ __global__ void __launch_bounds__(INT_THREADS)
                         }
                 }
             }
-            for (int y = c0; y < ng; ++y) {
-                const double lv = src[(size_t)y * a.sstride];
-                double e = 1.0;
-                if (MODE == 1 && y > 0) e = exp(d * (tis[y - 1] - tis[y]));
+            for (int yb = c0; yb < ng; yb += INT_XB) {
+                double lvv[INT_XB];
 #pragma unroll
-                for (int j = 0; j < YC; ++j) {
-                    const int s = c0 + j;
-                    if (j < ns && y >= s) {
-                        if (MODE == 1 && y > s) w[j] *= e;
-                        const double gw = gs[y] * Gs[y * ng + s];
-                        if (gw != 0.0) {
-                            const double wt = (MODE == 1) ? w[j] : exp(d * (tis[s] - tis[y]));
-                            acc[j] += gw * wt * lv;
+                for (int u = 0; u < INT_XB; ++u)
+                    lvv[u] = (yb + u < ng) ? src[(size_t)(yb + u) * a.sstride] : 0.0;
+#pragma unroll
+                for (int u = 0; u < INT_XB; ++u) {
+                    const int y = yb + u;
+                    if (y >= ng) break;
+                    const double lv = lvv[u];
+                    double e = 1.0;
+                    if (MODE == 1 && y > 0) e = exp(d * (tis[y - 1] - tis[y]));
+#pragma unroll
+                    for (int j = 0; j < YC; ++j) {
+                        const int s = c0 + j;
+                        if (j < ns && y >= s) {
+                            if (MODE == 1 && y > s) w[j] *= e;
+                            const double gw = gs[y] * Gs[y * ng + s];
+                            if (gw != 0.0) {
+                                const double wt = (MODE == 1) ? w[j] : exp(d * (tis[s] - tis[y]));
+                                acc[j] += gw * wt * lv;
+                            }
                         }
                     }
                 }
@@ -306,6 +340,125 @@ __global__ void __launch_bounds__(INT_THREADS)
                 const int s = c0 + j;
                 if (j < ns) a.out[(size_t)(s - a.r0) * a.ostride + p] = acc[j] / gs[s];
             }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// The same integrations with the grid size as a template parameter (NG = 10: the reference's
+// benchmarks; 16: UEG-57), all rows, lower-triangular G.  Everything unrolls: the quadrature
+// matrix, the grid and the weights sit in the kernel's parameter space and enter the FP64
+// instructions as constant-bank operands, the NG inputs (and old amplitudes) of an element are
+// NG independent loads issued up front, and what remains per element is NG-1 exps and
+// NG(NG-1)/2 multiply + multiply-add pairs -- no index arithmetic, no branches, no shared memory.
+// Same arithmetic and summation order as the generic kernels.
+// ---------------------------------------------------------------------------
+template <int NG>
+struct IntFixed {
+    double G[NG * NG];      // int_tbar: G[y][x];  int_L: g[y] * G[y][s] at [y][s]
+    double ti[NG];
+    double g[NG];
+};
+
+template <int NG, int MODE, bool UPD>
+__global__ void __launch_bounds__(INT_THREADS)
+    int_tbar_fixed_kernel(const __grid_constant__ IntArgs a, const __grid_constant__ IntFixed<NG> c) {
+    double nrm[4] = {0.0, 0.0, 0.0, 0.0};
+    const double oma = 1.0 - a.alpha;
+    for (long long p = (long long)blockIdx.x * INT_THREADS + threadIdx.x; p < a.n;
+         p += (long long)gridDim.x * INT_THREADS) {
+        const double d = a.D[p];
+        const double* src = a.src + p;
+        double tb[NG], ov[NG], e[NG];
+#pragma unroll
+        for (int x = 0; x < NG; ++x) tb[x] = src[(size_t)x * a.sstride];
+        if (UPD) {
+#pragma unroll
+            for (int y = 0; y < NG; ++y) ov[y] = a.out[(size_t)y * a.ostride + p];
+        }
+        unsigned ia = 0, ib = 0, ii = 0, ij = 0;
+        if (UPD && a.T1x != nullptr) {
+            unsigned r = (unsigned)p;
+            ij = r % (unsigned)a.nob; r /= (unsigned)a.nob;
+            ii = r % (unsigned)a.noa; r /= (unsigned)a.noa;
+            ib = r % (unsigned)a.nvb; r /= (unsigned)a.nvb;
+            ia = r;
+        }
+        e[0] = 1.0;
+        if (MODE == 1) {
+#pragma unroll
+            for (int k = 1; k < NG; ++k) e[k] = exp(d * (c.ti[k - 1] - c.ti[k]));
+        }
+        double esum = 0.0;
+#pragma unroll
+        for (int y = 0; y < NG; ++y) {
+            double acc = 0.0, w = 1.0;
+#pragma unroll
+            for (int x = y - 1; x >= 0; --x) {
+                double wt;
+                if (MODE == 1) {
+                    w *= e[x + 1];
+                    wt = w;
+                } else {
+                    wt = exp(d * (c.ti[x] - c.ti[y]));
+                }
+                acc += c.G[y * NG + x] * wt * tb[x];
+            }
+            acc += c.G[y * NG + y] * tb[y];
+            if (!UPD) {
+                a.out[(size_t)y * a.ostride + p] = acc;
+            } else {
+                const double o = ov[y];
+                const double df = acc - o;
+                nrm[0] += df * df;
+                nrm[1] += o * o;
+                const double u = a.alpha * o + oma * acc;
+                a.out[(size_t)y * a.ostride + p] = u;
+                nrm[2] += u * u;
+                if (a.W != nullptr) {
+                    double v = a.c2 * u;
+                    if (a.T1x != nullptr)
+                        v += a.c11 * a.T1x[(size_t)y * a.t1xs + (size_t)ia * a.noa + ii] *
+                             a.T1y[(size_t)y * a.t1ys + (size_t)ib * a.nob + ij];
+                    esum += c.g[y] * v;
+                }
+            }
+        }
+        if (UPD && a.W != nullptr) nrm[3] += esum * a.W[p];
+    }
+    if (UPD) block_sum_store<4>(nrm, a.part);
+}
+
+template <int NG, int MODE>
+__global__ void __launch_bounds__(INT_THREADS)
+    int_L_fixed_kernel(const __grid_constant__ IntArgs a, const __grid_constant__ IntFixed<NG> c) {
+    for (long long p = (long long)blockIdx.x * INT_THREADS + threadIdx.x; p < a.n;
+         p += (long long)gridDim.x * INT_THREADS) {
+        const double d = int_D(a, p);
+        const double* src = a.src + p;
+        double lv[NG], e[NG];
+#pragma unroll
+        for (int y = 0; y < NG; ++y) lv[y] = src[(size_t)y * a.sstride];
+        e[0] = 1.0;
+        if (MODE == 1) {
+#pragma unroll
+            for (int k = 1; k < NG; ++k) e[k] = exp(d * (c.ti[k - 1] - c.ti[k]));
+        }
+#pragma unroll
+        for (int s = 0; s < NG; ++s) {
+            double acc = 0.0, w = 1.0;
+#pragma unroll
+            for (int y = s; y < NG; ++y) {
+                double wt;
+                if (MODE == 1) {
+                    if (y > s) w *= e[y];
+                    wt = w;
+                } else {
+                    wt = exp(d * (c.ti[s] - c.ti[y]));
+                }
+                acc += c.G[y * NG + s] * wt * lv[y];
+            }
+            a.out[(size_t)s * a.ostride + p] = acc / c.g[s];
         }
     }
 }
@@ -759,7 +912,7 @@ int64_t op_workspace(const kb200_op& o) {
 
 namespace {
 
-int int_grid(long long n) { return grid_for(n, INT_THREADS, 148 * 4); }
+int int_grid(long long n) { return grid_for(n, INT_THREADS, 148 * 16); }
 
 size_t int_smem(int ng, int nvec) {
     return ng <= INT_SMEM_NG ? ((size_t)ng * ng + (size_t)nvec * ng) * 8 : 0;
@@ -783,6 +936,46 @@ void launch_int_L(const IntArgs& a, int mode, cudaStream_t st) {
         int_L_kernel<YC, 1><<<grid, INT_THREADS, smem, st>>>(a);
     else
         int_L_kernel<YC, 0><<<grid, INT_THREADS, smem, st>>>(a);
+}
+
+// Fixed-grid fast path: host copies of ti / g / G given, all rows, G lower triangular.
+template <int NG>
+bool fill_fixed(IntFixed<NG>& c, const double* ti_h, const double* g_h, const double* G_h, bool forL) {
+    for (int y = 0; y < NG; ++y) {
+        c.ti[y] = ti_h[y];
+        c.g[y] = g_h ? g_h[y] : 0.0;
+        for (int x = 0; x < NG; ++x) {
+            if (x > y && G_h[y * NG + x] != 0.0) return false;      // not lower triangular
+            c.G[y * NG + x] = forL ? g_h[y] * G_h[y * NG + x] : G_h[y * NG + x];
+        }
+    }
+    return true;
+}
+
+template <int NG, bool UPD>
+bool launch_int_tbar_fixed(const IntArgs& a, int mode, const double* ti_h, const double* g_h,
+                           const double* G_h, cudaStream_t st) {
+    IntFixed<NG> c;
+    if (!fill_fixed<NG>(c, ti_h, g_h, G_h, false)) return false;
+    const int grid = int_grid(a.n);
+    if (mode == 1)
+        int_tbar_fixed_kernel<NG, 1, UPD><<<grid, INT_THREADS, 0, st>>>(a, c);
+    else
+        int_tbar_fixed_kernel<NG, 0, UPD><<<grid, INT_THREADS, 0, st>>>(a, c);
+    return true;
+}
+
+template <int NG>
+bool launch_int_L_fixed(const IntArgs& a, int mode, const double* ti_h, const double* g_h,
+                        const double* G_h, cudaStream_t st) {
+    IntFixed<NG> c;
+    if (!fill_fixed<NG>(c, ti_h, g_h, G_h, true)) return false;
+    const int grid = int_grid(a.n);
+    if (mode == 1)
+        int_L_fixed_kernel<NG, 1><<<grid, INT_THREADS, 0, st>>>(a, c);
+    else
+        int_L_fixed_kernel<NG, 0><<<grid, INT_THREADS, 0, st>>>(a, c);
+    return true;
 }
 
 IntArgs int_args(int ng, int64_t n, const double* src, int64_t sstride, const double* D,
@@ -1289,6 +1482,14 @@ int kb200_int_tbar_rows(int ng, int64_t n, const double* tbar, const double* D, 
 int kb200_int_tbar_strided(int ng, int64_t n, const double* tbar, int64_t tstride,
                            const double* D, const double* ti, const double* G, double* out,
                            int64_t ostride, int y0, int y1, int mode, void* stream) {
+    return kb200_int_tbar_strided_h(ng, n, tbar, tstride, D, ti, G, out, ostride, y0, y1, mode,
+                                    nullptr, nullptr, stream);
+}
+
+int kb200_int_tbar_strided_h(int ng, int64_t n, const double* tbar, int64_t tstride,
+                             const double* D, const double* ti, const double* G, double* out,
+                             int64_t ostride, int y0, int y1, int mode, const double* ti_h,
+                             const double* G_h, void* stream) {
     // mode bit 1 (value 2): the caller guarantees G[y,x] == 0 for x > y (every quadrature of
     // kelvin/quadrature.py), which lets the kernel skip scanning the upper triangle
     const int lower = (mode & 2) ? 1 : 0;
@@ -1298,6 +1499,15 @@ int kb200_int_tbar_strided(int ng, int64_t n, const double* tbar, int64_t tstrid
     if (y0 == y1 || n == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
     IntArgs a = int_args(ng, n, tbar, tstride, D, ti, nullptr, G, out, ostride, y0, y1, lower);
+    if (ti_h && G_h && y0 == 0 && y1 == ng) {
+        bool done = false;
+        if (ng == 10) done = launch_int_tbar_fixed<10, false>(a, mode, ti_h, nullptr, G_h, st);
+        else if (ng == 16) done = launch_int_tbar_fixed<16, false>(a, mode, ti_h, nullptr, G_h, st);
+        if (done) {
+            KB_CHECK_LAUNCH("int_tbar_fixed_kernel");
+            return 0;
+        }
+    }
     if (y1 - y0 <= 4)
         launch_int_tbar<4, false>(a, mode, st);
     else if (y1 - y0 <= 8)
@@ -1316,6 +1526,18 @@ int kb200_int_tbar_update(int ng, int64_t n, const double* tbar, int64_t tstride
                           const double* T1x, const double* T1y, int64_t t1xs, int64_t t1ys,
                           int nvb, int noa, int nob, const double* g, double c2, double c11,
                           double* out4, double* scratch, int mode, void* stream) {
+    return kb200_int_tbar_update_h(ng, n, tbar, tstride, D, ti, G, amp, astride, y0, y1, alpha, W, T1x,
+                                   T1y, t1xs, t1ys, nvb, noa, nob, g, c2, c11, out4, scratch, mode,
+                                   nullptr, nullptr, nullptr, stream);
+}
+
+int kb200_int_tbar_update_h(int ng, int64_t n, const double* tbar, int64_t tstride,
+                            const double* D, const double* ti, const double* G, double* amp,
+                            int64_t astride, int y0, int y1, double alpha, const double* W,
+                            const double* T1x, const double* T1y, int64_t t1xs, int64_t t1ys,
+                            int nvb, int noa, int nob, const double* g, double c2, double c11,
+                            double* out4, double* scratch, int mode, const double* ti_h,
+                            const double* g_h, const double* G_h, void* stream) {
     const int lower = (mode & 2) ? 1 : 0;
     mode &= 1;
     if (ng <= 0 || n <= 0 || y0 < 0 || y1 > ng || y0 >= y1 || tstride < n || astride < n)
@@ -1331,7 +1553,13 @@ int kb200_int_tbar_update(int ng, int64_t n, const double* tbar, int64_t tstride
     a.nvb = nvb; a.noa = noa; a.nob = nob; a.c2 = c2; a.c11 = c11; a.part = scratch;
     const int grid = int_grid(n);
     if (4LL * grid > 65536) return fail(-1, "int_tbar_update: scratch too small");
-    if (y1 - y0 <= 4)
+    bool done = false;
+    if (ti_h && G_h && (g_h || W == nullptr) && y0 == 0 && y1 == ng) {
+        if (ng == 10) done = launch_int_tbar_fixed<10, true>(a, mode, ti_h, g_h, G_h, st);
+        else if (ng == 16) done = launch_int_tbar_fixed<16, true>(a, mode, ti_h, g_h, G_h, st);
+    }
+    if (done) {
+    } else if (y1 - y0 <= 4)
         launch_int_tbar<4, true>(a, mode, st);
     else if (y1 - y0 <= 8)
         launch_int_tbar<8, true>(a, mode, st);
@@ -1363,6 +1591,14 @@ int kb200_int_L_strided(int ng, const int32_t dims[4], const int64_t dstride[4],
                         int64_t lstride, const double* D, const double* ti, const double* g,
                         const double* G, double* out, int64_t ostride, int s0, int s1, int mode,
                         void* stream) {
+    return kb200_int_L_strided_h(ng, dims, dstride, L, lstride, D, ti, g, G, out, ostride, s0, s1, mode,
+                                 nullptr, nullptr, nullptr, stream);
+}
+
+int kb200_int_L_strided_h(int ng, const int32_t dims[4], const int64_t dstride[4], const double* L,
+                          int64_t lstride, const double* D, const double* ti, const double* g,
+                          const double* G, double* out, int64_t ostride, int s0, int s1, int mode,
+                          const double* ti_h, const double* g_h, const double* G_h, void* stream) {
     const int lower = (mode & 2) ? 1 : 0;
     mode &= 1;
     if (ng <= 0 || s0 < 0 || s1 > ng || s0 > s1) return fail(-1, "int_L: bad size");
@@ -1380,6 +1616,15 @@ int kb200_int_L_strided(int ng, const int32_t dims[4], const int64_t dstride[4],
     for (int i = 0; i < 4; ++i) {
         a.dd[i] = dims[i];
         a.ds[i] = dstride[i];
+    }
+    if (ti_h && g_h && G_h && s0 == 0 && s1 == ng) {
+        bool done = false;
+        if (ng == 10) done = launch_int_L_fixed<10>(a, mode, ti_h, g_h, G_h, st);
+        else if (ng == 16) done = launch_int_L_fixed<16>(a, mode, ti_h, g_h, G_h, st);
+        if (done) {
+            KB_CHECK_LAUNCH("int_L_fixed_kernel");
+            return 0;
+        }
     }
     if (s1 - s0 <= 4)
         launch_int_L<4>(a, mode, st);

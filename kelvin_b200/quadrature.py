@@ -160,6 +160,15 @@ def _small(x, dev):
     return _lib.const_dev(x, dev)
 
 
+def _host(x):
+    """Host float64 copy of a small grid array (None for device tensors: the kernels then take
+    their generic path) as a ctypes pointer, kept alive by the returned array."""
+    if x is None or isinstance(x, torch.Tensor):
+        return None, None
+    a = numpy.ascontiguousarray(numpy.asarray(x, dtype=numpy.float64))
+    return a, a.ctypes.data_as(ctypes.c_void_p)
+
+
 def _mode_bits(G, mode):
     """Kernel mode word: bit 0 = product-form weights, bit 1 = G is lower triangular."""
     m = INT_MODE if mode is None else mode
@@ -189,10 +198,11 @@ def int_tbar(ng, tbar, ti, D, G, out=None, mode=None, rows=None):
     if n == 0 or y1 == y0:
         return out
     tid, Gd = _small(ti, dev), _small(G, dev)
-    rc = lib.kb200_int_tbar_strided(ng, n, _lib.ptr(tbar), _lib.row_stride(tbar), _lib.ptr(D),
-                                    _lib.ptr(tid), _lib.ptr(Gd), _lib.ptr(out),
-                                    _lib.row_stride(out), y0, y1, _mode_bits(G, mode),
-                                    _lib.stream_ptr())
+    (ka, th), (kb, Gh) = _host(ti), _host(G)
+    rc = lib.kb200_int_tbar_strided_h(ng, n, _lib.ptr(tbar), _lib.row_stride(tbar), _lib.ptr(D),
+                                      _lib.ptr(tid), _lib.ptr(Gd), _lib.ptr(out),
+                                      _lib.row_stride(out), y0, y1, _mode_bits(G, mode), th, Gh,
+                                      _lib.stream_ptr())
     _lib.check(rc, "kb200_int_tbar")
     return out
 
@@ -218,7 +228,8 @@ def int_tbar_update(ng, tbar, ti, D, G, amp, alpha, out4, g=None, W=None, T1x=No
     nvb = noa = nob = 1
     if T1x is not None:
         nvb, noa, nob = int(D.shape[1]), int(D.shape[2]), int(D.shape[3])
-    rc = lib.kb200_int_tbar_update(
+    (ka, th), (kb, gh), (kc, Gh) = _host(ti), _host(g), _host(G)
+    rc = lib.kb200_int_tbar_update_h(
         ng, n, _lib.ptr(tbar), _lib.row_stride(tbar), _lib.ptr(D), _lib.ptr(tid), _lib.ptr(Gd),
         _lib.ptr(amp), _lib.row_stride(amp), y0, y1, alpha,
         _lib.ptr(W) if W is not None else None,
@@ -227,7 +238,7 @@ def int_tbar_update(ng, tbar, ti, D, G, amp, alpha, out4, g=None, W=None, T1x=No
         _lib.row_stride(T1y) if T1y is not None else 0, nvb, noa, nob,
         _lib.ptr(gd) if gd is not None else None, c2, c11,
         out4 if isinstance(out4, int) else _lib.ptr(out4), _lib.ptr(_lib.reduce_scratch(dev)),
-        _mode_bits(G, mode), _lib.stream_ptr())
+        _mode_bits(G, mode), th, gh, Gh, _lib.stream_ptr())
     _lib.check(rc, "kb200_int_tbar_update")
 
 
@@ -278,10 +289,11 @@ def int_L(ng, Lold, ti, D, g, G, out=None, mode=None, rows=None):
     if out.numel() == 0:
         return out
     tid, gd, Gd = _small(ti, dev), _small(g, dev), _small(G, dev)
-    rc = lib.kb200_int_L_strided(ng, cd, cs, _lib.ptr(Lold), _lib.row_stride(Lold), _lib.ptr(D),
-                                 _lib.ptr(tid), _lib.ptr(gd), _lib.ptr(Gd), _lib.ptr(out),
-                                 _lib.row_stride(out), s0, s1, _mode_bits(G, mode),
-                                 _lib.stream_ptr())
+    (ka, th), (kb, gh), (kc, Gh) = _host(ti), _host(g), _host(G)
+    rc = lib.kb200_int_L_strided_h(ng, cd, cs, _lib.ptr(Lold), _lib.row_stride(Lold), _lib.ptr(D),
+                                   _lib.ptr(tid), _lib.ptr(gd), _lib.ptr(Gd), _lib.ptr(out),
+                                   _lib.row_stride(out), s0, s1, _mode_bits(G, mode), th, gh, Gh,
+                                   _lib.stream_ptr())
     _lib.check(rc, "kb200_int_L")
     return out
 

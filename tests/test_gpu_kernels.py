@@ -64,7 +64,8 @@ def test_contraction_large_tiles(built):
         assert numpy.abs(t["C"].cpu().numpy() - ref).max() < 1e-11*numpy.abs(ref).max()
 
 
-@pytest.mark.parametrize("ng,n,mode", [(10, 7, 0), (10, 7, 1), (5, 33, 1), (40, 5, 1), (2, 4, 0), (17, 6, 1)])
+@pytest.mark.parametrize("ng,n,mode", [(10, 7, 0), (10, 7, 1), (5, 33, 1), (40, 5, 1), (2, 4, 0), (17, 6, 1),
+                                        (16, 5, 1), (16, 5, 0)])
 def test_int_tbar(built, ng, n, mode):
     from kelvin_b200 import quadrature
     rng = numpy.random.default_rng(ng*100 + n)
@@ -84,7 +85,7 @@ def test_int_tbar(built, ng, n, mode):
     assert numpy.abs(got - ref).max() < 1e-12*numpy.abs(ref).max()
 
 
-@pytest.mark.parametrize("ng,n,mode", [(10, 6, 0), (10, 6, 1), (9, 7, 1), (40, 4, 1)])
+@pytest.mark.parametrize("ng,n,mode", [(10, 6, 0), (10, 6, 1), (9, 7, 1), (40, 4, 1), (16, 4, 1), (16, 4, 0)])
 def test_int_L(built, ng, n, mode):
     from kelvin_b200 import quadrature
     rng = numpy.random.default_rng(ng*10 + n)
@@ -297,7 +298,9 @@ def test_strided_rows_and_fused_update(built):
     quadrature.int_tbar_update(ng, b2, ti, D2, G, T2b, alpha, stats.data_ptr() + 32, g=g, W=Iabij,
                                T1x=T1b, T1y=T1b, c2=0.25, c11=0.5)
     s = stats.cpu().numpy().reshape(2, 4)
-    assert torch.equal(T1a, T1b) and torch.equal(T2a, T2b)
+    # (same arithmetic; the compiler contracts multiply-adds differently in the two kernels)
+    assert float((T1a - T1b).abs().max()) < 1e-14*float(T1a.abs().max())
+    assert float((T2a - T2b).abs().max()) < 1e-14*float(T2a.abs().max())
     assert numpy.abs(s[:, :3] - sref).max() < 1e-12*numpy.abs(sref).max()
     assert abs((s[0, 3] + s[1, 3])/beta - Eref) < 1e-12*abs(Eref)
     # strided damping

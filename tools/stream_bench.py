@@ -44,6 +44,12 @@ def main():
         rec("int_tbar mode %d (T2 block)" % mode, (16*ng + 8)*N,
             lambda: quadrature.int_tbar(ng, X, ti, D2, G, mode=mode), "ng-1 exps" if mode else "ng^2/2 exps")
     rec("int_L mode 1 (L2 block)", (16*ng + 8)*N, lambda: quadrature.int_L(ng, X, ti, D2, g, G, mode=1))
+    stats = torch.zeros(4, dtype=torch.float64, device=dev)
+    Iab0 = ft_cc_energy.oovv_to_abij(I4)
+    rec("int_tbar_update (fused, T2 block)", (24*ng + 16)*N,
+        lambda: quadrature.int_tbar_update(ng, X, ti, D2, G, Y, 0.3, stats, g=g, W=Iab0, T1x=T1, T1y=T1,
+                                           c2=0.25, c11=0.5),
+        "integrate + norms + damp + energy: read tbar, read+write T, D, <ij||ab>")
     st = cc_utils._Stats(1, dev)
     rec("damp_norms (T2 block)", 24*ng*N, lambda: st.damp(0, X, Y, 0.3), "read old,new; write old")
     Iab = ft_cc_energy.oovv_to_abij(I4)
@@ -56,7 +62,7 @@ def main():
     rec("dot_keep 'yijab,yabij->y'", 16*ng*N, lambda: _lib.dot_keep(X, "yijab", Y, "yabij", "y"))
     rec("dot_keep 'cdab,abcd->c'", 16*N, lambda: _lib.dot_keep(I4, "cdab", Iab, "abcd", "c"))
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    with open(os.path.join(ROOT, "gpurun_out", "stream_bench.txt"), "w") as f:
+    with open(os.path.join(ROOT, "gpurun_out", "r2_stream_bench.txt"), "w") as f:
         f.write("# streaming kernels, m=%d ng=%d, algorithmic bytes / CUDA-event time, peak = %.0f GB/s (MEASURED_PEAKS.json)\n" % (m, ng, peak))
         for r in rows:
             f.write("%-34s %8.1f MB %8.1f us %8.1f GB/s  frac %.2f  %s\n" % r)
