@@ -81,10 +81,11 @@ int kb200_plan_run(const kb200_op* ops /*host*/, int nops,
                    const uint32_t* tables, double* const* slots /*host*/, int nslots,
                    double* workspace, int64_t workspace_bytes, void* stream);
 
-/* Streams a plan run uses: 3 (default; KB200_STREAMS=1 in the environment selects 1) = the
- * independent launches of the plan overlap on two side streams that fork from and join the
- * caller's stream, with every read/write order on every slot kept by events (same results,
- * bit for bit); 1 = everything in plan order on the caller's stream.  Returns the old value. */
+/* Streams a plan run uses: 1 = everything in plan order on the caller's stream (KB200_STREAMS=1
+ * in the environment selects it); n >= 3 = two streams for the wide (m^6) launches plus n - 2
+ * (at most 6) for the small ones, default 2 + 6.  The side streams fork from and join the
+ * caller's stream, with every read/write order on every slot (and on each split-K workspace
+ * region) kept by events: same results, bit for bit.  Returns the old value. */
 int kb200_set_plan_streams(int n);
 
 /* Same as kb200_plan_run, but brackets every op with CUDA events on `stream`,

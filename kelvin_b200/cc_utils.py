@@ -15,7 +15,7 @@ import time
 import numpy
 import torch
 
-from . import _lib, ft_cc_energy, ft_cc_equations, ft_utils, quadrature
+from . import _lib, _trace, ft_cc_energy, ft_cc_equations, ft_utils, quadrature
 from .ov_blocks import one_e_blocks, two_e_blocks, two_e_blocks_full
 
 
@@ -392,9 +392,11 @@ class UccStep(object):
         """-> (E, res1 + res2) as logged by the reference (kelvin/cc_utils.py:297-305)."""
         ng = self.ng
         old = self.old
+        _trace.mark("step")
         bars = ft_cc_equations.uccsd_stanton_bar(
             *self.ints, *old, t0_zero=self.t0, closed_shell=self.cs, beta_copies=False,
             singlet=self.singlet, antisym=self.antisym, work=self.work)
+        _trace.mark("bars")
         live = (0, 2, 3) if self.cs else (0, 1, 2, 3, 4)
         # energy terms: singles with F.ov; doubles with <ij||ab> and the (already updated) singles
         T1a, T1b = old[0], (old[0] if self.cs else old[1])
@@ -409,7 +411,10 @@ class UccStep(object):
         # (alpha == beta: the beta blocks are copies of the alpha ones; nothing reads them during
         # the iterations, so they are brought up to date once, in finish())
         self._beta_stale = bool(self.cs)
+        _trace.mark("updated")
         s = self.stats.cpu().numpy().reshape(5, 4).copy()
+        _trace.mark("stats")
+        _trace.report()
         if self.cs:
             s[1] = s[0]
             s[4] = s[2]

@@ -1029,15 +1029,31 @@ int kb200_dot_keep(int nkeep, const int32_t dims[4], const int64_t sA[5], const 
     return 0;
 }
 
-int64_t kb200_plan_workspace_bytes(const kb200_op* ops, int nops) {
-    int64_t w = 0;
-    for (int i = 0; i < nops; ++i) {
-        int64_t x = op_workspace(ops[i]);
-        if (x > w) w = x;
-    }
-    return w;
+// Split-K partials: the wide launches share one region (they are ordered against each other
+// through it), the small launches have one region per small-launch stream so that independent
+// long-K reductions do not queue behind one another.
+constexpr int MS_NBIG = 2, MS_NSMALL_MAX = 6;
+
+static bool op_is_wide(const kb200_op& o) {
+    return o.kind == 0 && (o.tile == 0 || o.tile == 2 || o.tile == 3);
 }
 
+static void workspace_layout(const kb200_op* ops, int nops, int64_t* wide, int64_t* small) {
+    int64_t w = 0, v = 0;
+    for (int i = 0; i < nops; ++i) {
+        int64_t x = op_workspace(ops[i]);
+        if (op_is_wide(ops[i])) { if (x > w) w = x; }
+        else if (x > v) v = x;
+    }
+    *wide = (w + 255) & ~(int64_t)255;
+    *small = (v + 255) & ~(int64_t)255;
+}
+
+int64_t kb200_plan_workspace_bytes(const kb200_op* ops, int nops) {
+    int64_t w, v;
+    workspace_layout(ops, nops, &w, &v);
+    return w + MS_NSMALL_MAX * v;
+}
 
 // ---------------------------------------------------------------------------
 // Concurrent execution of a plan's independent launches.
@@ -1053,14 +1069,15 @@ int64_t kb200_plan_workspace_bytes(const kb200_op* ops, int nops) {
 // the start of the plan and join it at the end, so the call keeps stream semantics.
 // ---------------------------------------------------------------------------
 struct MultiStream {
-    static constexpr int NS = 3;
-    cudaStream_t s[NS] = {nullptr, nullptr, nullptr};
+    static constexpr int NS = MS_NBIG + MS_NSMALL_MAX;
+    int nsmall = MS_NSMALL_MAX;                     // small-launch streams in use (1 .. MS_NSMALL_MAX)
+    cudaStream_t s[NS] = {nullptr};
     bool made = false;
     std::vector<cudaEvent_t> pool;      // one event per launch of the current plan
     int used = 0;
     // per launch
     std::vector<int> l_stream, l_seq;
-    // per slot (last entry = workspace)
+    // per slot (then one pseudo-slot per workspace region: wide, small stream 0, 1, ...)
     std::vector<int> last_writer;               // launch id or -1
     std::vector<int> last_reader;               // [slot*NS + stream] launch id or -1
     int seq[NS];                                // launches issued per stream
@@ -1070,7 +1087,7 @@ struct MultiStream {
     cudaEvent_t fork_ev = nullptr;
     bool forked[NS];
 
-    int init(cudaStream_t caller, int nslots) {
+    int init(cudaStream_t caller, int nslots, int nstreams) {
         if (!made) {
             // the side streams inherit the priority of the caller's stream (a plan on a
             // high-priority stream must not queue its launches behind another plan's)
@@ -1083,13 +1100,16 @@ struct MultiStream {
                 return fail(-2, "plan: cannot create event");
             made = true;
         }
+        nsmall = nstreams - MS_NBIG;
+        if (nsmall < 1) nsmall = 1;
+        if (nsmall > MS_NSMALL_MAX) nsmall = MS_NSMALL_MAX;
         s[0] = caller;
         used = 0;
         nbig = 0;
         l_stream.clear();
         l_seq.clear();
-        last_writer.assign(nslots + 1, -1);
-        last_reader.assign((size_t)(nslots + 1) * NS, -1);
+        last_writer.assign(nslots + 1 + MS_NSMALL_MAX, -1);
+        last_reader.assign((size_t)(nslots + 1 + MS_NSMALL_MAX) * NS, -1);
         for (int a = 0; a < NS; ++a) {
             seq[a] = 0;
             last_on[a] = -1;
@@ -1108,11 +1128,36 @@ struct MultiStream {
         synced[S][T] = l_seq[launch];
         return 0;
     }
+    // Small launches: the stream whose tail is one of this launch's own dependencies (queueing
+    // behind it costs nothing), else the least recently used small stream.  Inside a captured
+    // graph the streams only define edges: this keeps the edges close to the true dependencies.
+    int pick_small(const kb200_op* ops, int i, int n) const {
+        int best = -1, best_id = -1;
+        for (int m = 0; m < n; ++m) {
+            const kb200_op& q = ops[i + m];
+            int dep[3] = {last_writer[q.c], last_writer[q.a],
+                          (q.kind != 1 && q.b >= 0) ? last_writer[q.b] : -1};
+            for (int k = 0; k < 3; ++k) {
+                const int id = dep[k];
+                if (id < 0) continue;
+                const int T = l_stream[id];
+                if (T >= MS_NBIG && T < MS_NBIG + nsmall && last_on[T] == id && id > best_id) {
+                    best = T;
+                    best_id = id;
+                }
+            }
+        }
+        if (best >= 0) return best;
+        best = MS_NBIG;
+        for (int T = MS_NBIG; T < MS_NBIG + nsmall; ++T)
+            if (last_on[T] < last_on[best]) best = T;
+        return best;
+    }
+    static int workspace_slot(int nslots, int S) { return S < MS_NBIG ? nslots : nslots + 1 + (S - MS_NBIG); }
     // stream for the launch made of ops[i .. i+n): inserts the waits it needs
     int begin(const kb200_op* ops, int i, int n, int nslots, cudaStream_t* out) {
         const kb200_op& o = ops[i];
-        const bool big = o.kind == 0 && (o.tile == 0 || o.tile == 2 || o.tile == 3);
-        const int S = big ? (nbig++ & 1) : 2;
+        const int S = op_is_wide(o) ? (nbig++ & 1) : pick_small(ops, i, n);
         if (!forked[S]) {
             if (cudaStreamWaitEvent(s[S], fork_ev, 0) != cudaSuccess)
                 return fail(-2, "plan: fork wait");
@@ -1131,7 +1176,7 @@ struct MultiStream {
             int wr[2], nw = 0;
             if (q.c < 0 || q.c >= nslots) return fail(-1, "plan: bad slot");
             wr[nw++] = q.c;
-            if (op_workspace(q) > 0) wr[nw++] = nslots;          // split-K partials
+            if (op_workspace(q) > 0) wr[nw++] = workspace_slot(nslots, S);   // split-K partials
             for (int k = 0; k < nw; ++k) {
                 if (wait_for(S, last_writer[wr[k]])) return -2;
                 for (int T = 0; T < NS; ++T)
@@ -1162,7 +1207,7 @@ struct MultiStream {
             const kb200_op& q = ops[i + m];
             int wr[2], nw = 0;
             wr[nw++] = q.c;
-            if (op_workspace(q) > 0) wr[nw++] = nslots;
+            if (op_workspace(q) > 0) wr[nw++] = workspace_slot(nslots, S);
             for (int k = 0; k < nw; ++k) {
                 last_writer[wr[k]] = id;
                 for (int T = 0; T < NS; ++T) last_reader[(size_t)wr[k] * NS + T] = -1;
@@ -1202,17 +1247,25 @@ static MultiStream* ms_for(int dev, cudaStream_t caller) {
 
 static int g_plan_streams = -1;
 
+// 1 = everything on the caller's stream; n >= 3 = two streams for the wide launches plus n - 2
+// for the small ones; anything else = the default (2 + 6)
+static int clamp_streams(int n) {
+    if (n == 1) return 1;
+    if (n < 3) return MS_NBIG + MS_NSMALL_MAX;
+    return n > MS_NBIG + MS_NSMALL_MAX ? MS_NBIG + MS_NSMALL_MAX : n;
+}
+
 static int plan_streams() {
     if (g_plan_streams < 0) {
         const char* e = getenv("KB200_STREAMS");
-        g_plan_streams = (e && atoi(e) == 1) ? 1 : 3;
+        g_plan_streams = clamp_streams(e ? atoi(e) : 0);
     }
     return g_plan_streams;
 }
 
 int kb200_set_plan_streams(int n) {
     const int old = plan_streams();
-    g_plan_streams = (n == 1) ? 1 : 3;
+    g_plan_streams = clamp_streams(n);
     return old;
 }
 
@@ -1221,9 +1274,15 @@ static int run_plan_body(const kb200_op* ops, int nops, const uint32_t* tables,
                          int64_t workspace_bytes, cudaStream_t st0, cudaEvent_t* ev,
                          MultiStream* ms) {
     int prev_i = -1, prev_n = 0, prev_S = 0;
+    int64_t ws_wide = 0, ws_small = 0;
+    workspace_layout(ops, nops, &ws_wide, &ws_small);
+    if (ws_wide + MS_NSMALL_MAX * ws_small > 0 &&
+        (workspace == nullptr || ws_wide + MS_NSMALL_MAX * ws_small > workspace_bytes))
+        return fail(-1, "plan: workspace too small");
     for (int i = 0; i < nops; ++i) {
         const kb200_op& o = ops[i];
         cudaStream_t st = st0;
+        int S_cur = 0;
         if (ms) {
             if (prev_i >= 0 && ms->end(ops, prev_i, prev_n, nslots, prev_S)) return -2;
             int n = ((o.kind == 0 || o.kind == 3) && o.group > 1) ? o.group : 1;
@@ -1231,7 +1290,12 @@ static int run_plan_body(const kb200_op* ops, int nops, const uint32_t* tables,
             int S = ms->begin(ops, i, n, nslots, &st);
             if (S < 0) return S;
             prev_i = i; prev_n = n; prev_S = S;
+            S_cur = S;
         }
+        // split-K partials of this launch: the wide region, or the region of its small stream
+        double* ws_op = workspace;
+        if (workspace != nullptr && !op_is_wide(o))
+            ws_op = workspace + (ws_wide + (int64_t)(S_cur >= MS_NBIG ? S_cur - MS_NBIG : 0) * ws_small) / 8;
         if (ev) cudaEventRecord(ev[2 * i], st);
         if (o.a < 0 || o.a >= nslots || o.c < 0 || o.c >= nslots) return fail(-1, "plan: bad slot");
         if (o.M <= 0 || o.N <= 0 || o.batch <= 0) return fail(-1, "plan: empty op");
@@ -1267,7 +1331,7 @@ static int run_plan_body(const kb200_op* ops, int nops, const uint32_t* tables,
                 p.splitk = (q.K + p.kchunk - 1) / p.kchunk;
                 p.bsA = q.bsA; p.bsB = q.bsB; p.bsC = q.bsC;
                 p.alpha = q.alpha; p.beta = q.beta;
-                p.partial = workspace;
+                p.partial = ws_op;
                 p.tilesM = (q.M + BMt - 1) / BMt;
                 p.tilesN = (q.N + BNt - 1) / BNt;
                 p.batch = q.batch;
@@ -1289,7 +1353,8 @@ static int run_plan_body(const kb200_op* ops, int nops, const uint32_t* tables,
             const kb200::GemmParams& p = grp.p[0];
             if (p.splitk > 1) {
                 int64_t need = (int64_t)o.batch * p.splitk * (int64_t)o.M * o.N * 8;
-                if (workspace == nullptr || need > workspace_bytes) return fail(-1, "plan: workspace too small");
+                if (ws_op == nullptr || need > (op_is_wide(o) ? ws_wide : ws_small))
+                    return fail(-1, "plan: workspace too small");
             }
             int rc;
             if (o.tile == 0)
@@ -1325,7 +1390,10 @@ static int run_plan_body(const kb200_op* ops, int nops, const uint32_t* tables,
             if (rc) return rc;
             if (p.splitk > 1) {
                 long long total = (long long)o.M * o.N * o.batch;
-                kb200::splitk_reduce_kernel<<<grid_for(total, 256), 256, 0, st>>>(p, o.batch);
+                if (p.splitk >= 32 && total <= 32LL * 148 * 8)
+                    kb200::splitk_reduce_wide_kernel<<<(unsigned)((total + 31) / 32), dim3(32, 16), 0, st>>>(p, o.batch);
+                else
+                    kb200::splitk_reduce_kernel<<<grid_for(total, 256), 256, 0, st>>>(p, o.batch);
                 KB_CHECK_LAUNCH("splitk_reduce_kernel");
             }
             if (ev) {
@@ -1435,7 +1503,7 @@ static int run_plan_impl(const kb200_op* ops, int nops, const uint32_t* tables,
     int dev = 0;
     if (!ev && nops > 1 && plan_streams() > 1 && cudaGetDevice(&dev) == cudaSuccess && dev < 16) {
         ms = ms_for(dev, st);
-        if (ms && ms->init(st, nslots)) return -2;
+        if (ms && ms->init(st, nslots, plan_streams())) return -2;
     }
     int rc = run_plan_body(ops, nops, tables, slots, nslots, workspace, workspace_bytes, st, ev, ms);
     // join even after an error: nothing may stay in flight on the side streams unordered

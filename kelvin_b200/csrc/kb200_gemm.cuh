@@ -1093,6 +1093,37 @@ __global__ void splitk_reduce_kernel(const GemmParams p, int batch) {
     }
 }
 
+// the same for long split-K chains over a tiny output (the K = m^3 contractions into m x m
+// blocks, split-K of a few hundred): 32 consecutive outputs x 16 slices of the chain per CTA,
+// fixed summation order (slice-strided partial sums, then the 16 slices in order)
+__global__ void __launch_bounds__(512) splitk_reduce_wide_kernel(const GemmParams p, int batch) {
+    __shared__ double sh[16][33];
+    const size_t mn = (size_t)p.M * p.N;
+    const size_t total = mn * batch;
+    const size_t idx = (size_t)blockIdx.x * 32 + threadIdx.x;
+    double s = 0.0;
+    int b = 0;
+    size_t r = 0;
+    if (idx < total) {
+        b = (int)(idx / mn);
+        r = idx - (size_t)b * mn;
+        const double* P = p.partial + (size_t)b * p.splitk * mn + r;
+        for (int ks = threadIdx.y; ks < p.splitk; ks += 16) s += P[(size_t)ks * mn];
+    }
+    sh[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y == 0 && idx < total) {
+#pragma unroll
+        for (int k = 1; k < 16; ++k) s += sh[k][threadIdx.x];
+        const int row = (int)(r / p.N);
+        const int col = (int)(r - (size_t)row * p.N);
+        double* dst = p.C + (long long)b * p.bsC + p.cm[row] + p.cn[col];
+        double v = p.alpha * s;
+        if (p.beta != 0.0) v += p.beta * (*dst);
+        *dst = v;
+    }
+}
+
 // kind 2: rank-K update with small K and N (<= 64): the n^5 "dressing" terms
 //   C[m, n] (+)= alpha * sum_k A[m, k] * B[k, n],   M ~ n^3 rows, K, N ~ n.
 // These move 24 bytes per C element for ~2K flops: HBM-bound.  One thread owns one

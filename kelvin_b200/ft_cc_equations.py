@@ -19,7 +19,7 @@ import os
 
 import torch
 
-from . import _lib, engine, plan as _plan, programs, quadrature
+from . import _lib, _trace, engine, plan as _plan, programs, quadrature
 
 _F_NAMES = ("oo", "ov", "vo", "vv")
 
@@ -337,12 +337,15 @@ def evaluate_rows(p, hybrid, t, flat, ng, y0, dev, cache=None):
         if sh.q > 1:
             # several own points: enqueue the long part first, the device starts on it at once
             run(*sh.own)
+            _trace.mark("own")
         with torch.cuda.stream(side):
             hp.run(sliced(hp, l0, l1), l1 - l0, sh.rank, parallel.exchange_group())
+            _trace.mark("shared")
         if sh.q <= 1:
             # one own point is as short as the shared one: the shared one, with its two
             # synchronisations with the other ranks, goes first (measured: 2.97 vs 3.29 ms)
             run(*sh.own)
+            _trace.mark("own")
         cur.wait_stream(side)
     else:
         run(*sh.own)
@@ -352,7 +355,9 @@ def evaluate_rows(p, hybrid, t, flat, ng, y0, dev, cache=None):
             mine = sh.owner_row()
             if mine is not None:
                 run(mine, mine + 1)
+    _trace.mark("rows")
     parallel.exchange_rows(flat, sh, owner_left)
+    _trace.mark("exchanged")
 
 
 _side = {}

@@ -59,6 +59,40 @@ def main():
         ms = e0.elapsed_time(e1)/n
         chk = float(sum(t[s].double().abs().sum() for s in p.outputs))
         print("ng=%2d  %8.3f ms/run  %6.3f ms/point  checksum %.15e" % (ng, ms, ms/ng, chk))
+        if os.environ.get("KB200_BATCH_TIMELINE"):
+            timeline(lambda: p.run(t, ng), ng)
+
+
+def timeline(fn, ng):
+    """Kernel timeline of one run (torch.profiler / CUPTI): start, duration, stream of every
+    kernel, plus how many SM-filling GEMM kernels overlap -- gpurun_out/timeline_ng<ng>.txt."""
+    from torch.profiler import profile, ProfilerActivity
+    fn()
+    torch.cuda.synchronize()
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        fn()
+        torch.cuda.synchronize()
+    ev = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
+    ev.sort(key=lambda e: e.time_range.start)
+    if not ev:
+        print("no device events")
+        return
+    t0 = ev[0].time_range.start
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    end = max(e.time_range.end for e in ev)
+    busy = 0.0
+    cur_end = t0
+    for e in ev:
+        a, b = e.time_range.start, e.time_range.end
+        if b > cur_end:
+            busy += b - max(a, cur_end)
+            cur_end = b
+    with open(os.path.join(ROOT, "gpurun_out", "timeline_ng%d.txt" % ng), "w") as f:
+        f.write("# %d kernels, span %.1f us, some kernel running %.1f us\n" % (len(ev), end - t0, busy))
+        for e in ev:
+            f.write("%9.1f %8.1f  s%-3s %s\n" % (e.time_range.start - t0, e.time_range.end - e.time_range.start,
+                                              getattr(e, "device_resource_id", "?"), e.name[:90]))
+    print("timeline: %d kernels, span %.1f us, union of kernel intervals %.1f us" % (len(ev), end - t0, busy))
 
 
 if __name__ == "__main__":
