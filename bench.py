@@ -235,6 +235,27 @@ def build_system(workload):
         dict(max_iter=80, econv=1e-11)
 
 
+def step_profile(fn, world):
+    """Kernel timeline of one step on rank 0 (torch.profiler / CUPTI) into
+    gpurun_out/step_timeline_n<world>.txt -- a tuning aid, not part of the measurement."""
+    import torch
+    from torch.profiler import profile, ProfilerActivity
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        fn()
+        torch.cuda.synchronize()
+    ev = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
+    ev.sort(key=lambda e: e.time_range.start)
+    if not ev:
+        return
+    t0 = ev[0].time_range.start
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open(os.path.join("gpurun_out", "step_timeline_n%d.txt" % world), "w") as f:
+        f.write("# start us, duration us, stream, kernel\n")
+        for e in ev:
+            f.write("%9.1f %8.1f  s%-3s %s\n" % (e.time_range.start - t0, e.time_range.end - e.time_range.start,
+                                              getattr(e, "device_resource_id", "?"), e.name[:100]))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -320,6 +341,8 @@ def main():
     t_step, (E, res) = timed(lambda: solver.step(0.0), K)
     launches = int(lib.kb200_launch_count())
     clocks = sampler.stop() if sampler else None
+    if os.environ.get("KB200_STEP_PROFILE") and rank == 0:
+        step_profile(lambda: solver.step(0.0), world)
 
     # ---- auxiliary: the same step without the closed-shell reduction (every beta block
     # evaluated, all 32 block GEMMs per grid point), for a like-for-like flop count

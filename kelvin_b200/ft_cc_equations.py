@@ -57,6 +57,11 @@ def _u_sizes(Fa, Fb):
 # opposite-spin ladder terms (plan.mirror_outputs): the extra launches (diagonal pass + mirrored
 # add per term) only pay once the contractions are several waves of CTAs long
 MIRROR_ROWS_MIN_BATCH = int(os.environ.get("KB200_MIRROR_ROWS_MIN_BATCH", "4"))
+# tau batch up to which the large contractions accumulate into scratch slots of their own so that
+# a whole dependency level of them shares one launch (plan.split_accumulators); beyond it the
+# launches are many waves long and the extra elementwise adds do not pay
+SPLIT_ACC = os.environ.get("KB200_SPLIT_ACC", "1") != "0"
+SPLIT_ACC_MAX_BATCH = int(os.environ.get("KB200_SPLIT_ACC_MAX_BATCH", "2"))
 
 # closed shell: sum/difference (singlet/triplet channel) form of the paired ring contractions
 # (plan.sumdiff_pairs) and, when the amplitudes also satisfy T2aa = T2ab - T2ab(a<->b), the
@@ -68,7 +73,8 @@ _U_TIN = ("t1.a", "t1.b", "t2.aa", "t2.ab", "t2.bb")
 _U_TOUT = ("o1.a", "o1.b", "o2.aa", "o2.ab", "o2.bb")
 
 
-def _stanton_rops(mode, fac, mirror, mirror_rows, singlet, sumdiff, antisym, emit_aa=True):
+def _stanton_rops(mode, fac, mirror, mirror_rows, singlet, sumdiff, antisym, emit_aa=True,
+                  split_acc=False):
     T = programs.tensor_defs()
     rops = _plan.expand(programs.stanton(fac), T, mode)
     if mode == "g":
@@ -90,27 +96,31 @@ def _stanton_rops(mode, fac, mirror, mirror_rows, singlet, sumdiff, antisym, emi
             rops = _plan.mirror_outputs(rops)
     if antisym:
         rops = _plan.antisym_outputs(rops)
+    if split_acc:
+        rops = _plan.split_accumulators(rops)
     return rops, ins, outs
 
 
 def stanton_plan(mode, sizes, fac=-1.0, mirror=False, mirror_rows=False, singlet=False,
-                 sumdiff=None, antisym=True, hybrid_world=None, emit_aa=True):
+                 sumdiff=None, antisym=True, hybrid_world=None, emit_aa=True, split_acc=False):
     """mirror (u only): the closed-shell reduction of the program (plan.mirror_reduce): only the
     alpha-leading block of every alpha <-> beta pair is evaluated; mirror_rows: additionally
     plan.mirror_outputs; singlet / sumdiff: additionally plan.singlet_reduce /
     plan.sumdiff_pairs.  antisym=False: nothing is assumed about the permutational symmetry of
     the amplitudes (full sums over contracted pairs, full outputs, as the reference computes).
-    hybrid_world=P: the same program as an engine.PhasedPlan evaluated by P ranks together."""
+    hybrid_world=P: the same program as an engine.PhasedPlan evaluated by P ranks together.
+    split_acc: plan.split_accumulators (for runs of 1-2 grid points per launch)."""
     mirror_rows = bool(mirror and mirror_rows and antisym)
+    split_acc = bool(split_acc and SPLIT_ACC and not hybrid_world)
     singlet = bool(mirror and singlet and SINGLET and antisym)
     sumdiff = bool(mirror and (SUMDIFF if sumdiff is None else sumdiff))
     emit_aa = bool(emit_aa or not singlet)
     key = ("stanton", mode, tuple(sorted(sizes.items(), key=str)), fac, bool(mirror), mirror_rows,
-           singlet, sumdiff, bool(antisym), hybrid_world, emit_aa)
+           singlet, sumdiff, bool(antisym), hybrid_world, emit_aa, split_acc)
 
     def build():
         rops, ins, outs = _stanton_rops(mode, fac, mirror, mirror_rows, singlet, sumdiff, antisym,
-                                        emit_aa)
+                                        emit_aa, split_acc)
         name = "stanton-" + mode + ("-closed" if mirror else "")
         if hybrid_world:
             return engine.PhasedPlan(rops, mode, sizes, ins, outs, hybrid_world,
@@ -462,7 +472,8 @@ def uccsd_stanton_bar(Fa, Fb, Ia, Ib, Iabab, T1aold, T1bold, T2aaold, T2abold, T
     # singlet runs: the programs produce T̄1a and T̄2ab only; T̄2aa = T̄2ab - T̄2ab(a<->b) is formed
     # for all grid points AFTER the exchange, which then moves half the bytes
     kw = dict(mirror=closed_shell, singlet=singlet, antisym=antisym, emit_aa=not sing)
-    p = stanton_plan("u", sizes, fac, mirror_rows=nloc >= MIRROR_ROWS_MIN_BATCH, **kw)
+    p = stanton_plan("u", sizes, fac, mirror_rows=nloc >= MIRROR_ROWS_MIN_BATCH,
+                     split_acc=0 < nloc <= SPLIT_ACC_MAX_BATCH, **kw)
     setup = None if work is None else work.get("_setup")
     if setup is not None and setup[0] is p and all(a is b for a, b in zip(setup[1], ins)):
         t = setup[2]

@@ -505,6 +505,38 @@ def sumdiff_pairs(rops):
         ops = [op for j, op in enumerate(ops[:last]) if j not in drop] + new + ops[last + 1:]
 
 
+SPLIT_PREFIX = "Acc"
+
+
+def _is_large(op):
+    """Two 4-index operands contracted over two letters into a 4-index output (an m^6 term)."""
+    return (len(op.ins) == 2 and len(op.out[1]) == 4 and all(len(ls) == 4 for _, ls in op.ins)
+            and len(set(op.ins[0][1]) & set(op.ins[1][1])) == 2)
+
+
+def split_accumulators(rops):
+    """Small tau batches (1-2 grid points per launch, the tau-sharded case): every large
+    contraction after the first that accumulates into one slot gets a scratch slot of its own and
+    an elementwise add.  The large contractions of one dependency level are then mutually
+    independent and share ONE launch: at batch 1 the ten m^6 launches of the closed-shell
+    residual go out as 5 + 5 tiles-of-81 (3 + 3 waves of 148 CTAs) instead of 5 + 3 + 2
+    (3 + 2 + 2 waves).  Costs one scratch block per split term; triangular and row-slabbed
+    contractions are left alone."""
+    seen, out, k = {}, [], 0
+    for op in rops:
+        if _is_large(op) and op.tri is None and not op.slab:
+            cnt = seen.get(op.out[0], 0)
+            seen[op.out[0]] = cnt + 1
+            if cnt >= 1:
+                tmp = "%s%d" % (SPLIT_PREFIX, k)
+                k += 1
+                out.append(ROp((tmp, op.out[1]), op.coef, op.ins, op.spin))
+                out.append(ROp(op.out, 1.0, [(tmp, op.out[1])], op.spin))
+                continue
+        out.append(op)
+    return out
+
+
 def _find_quartet(ops):
     cand = [j for j, op in enumerate(ops) if len(op.ins) == 2 and op.tri is None
             and len(op.out[1]) == 4 and not op.out[0].startswith(SUMDIFF_PREFIX)
@@ -1063,6 +1095,8 @@ RANKK_MIN_M = 4096    # rows from which the rank-K streaming kernel is used
 # independent contractions of one kernel configuration launched together (kb200_gemm.cuh
 # MAX_GROUP); 1 disables grouping and keeps the program order
 MAX_GROUP = int(_os.environ.get("KB200_GROUP", "8"))
+# accumulations into one slot commute in the schedule (0: they keep their program order)
+COMMUTE_ACC = _os.environ.get("KB200_COMMUTE_ACC", "1") != "0"
 # consecutive index-permuted sums / outer products into one output fused into one pass (kind 3)
 FUSE_EW = int(_os.environ.get("KB200_FUSE", "1"))
 # contracted index pairs in which both operands are antisymmetric are summed over x < y only
@@ -1218,37 +1252,49 @@ class Lowered(object):
         kept, so each output sees its accumulations in the program order (bit-identical
         results); scratch slots are never aliased, so no liveness changes."""
         n = len(self.descs)
-        reads, writes = [], []
+        reads, writes, commut = [], [], []
         for d in self.descs:
             r = {d.a}
             if d.kind != 1:
                 r.add(d.b)
-            if d.beta != 0.0:
+            # X += ... with X not among the operands: such accumulations into one slot commute
+            # (COMMUTE_ACC); they are still never in flight together (the runner orders every
+            # write after write), only their order is left to the scheduler
+            cm = bool(COMMUTE_ACC and d.beta == 1.0 and d.c not in r)
+            if d.beta != 0.0 and not cm:
                 r.add(d.c)
             reads.append(r)
             writes.append(d.c)
+            commut.append(cm)
         npred = [0]*n
         succ = [[] for _ in range(n)]
-        last_write = {}
-        readers = {}
+        base = {}        # slot -> last op that overwrote it (or updated it non-commutatively)
+        acc = {}         # slot -> commuting accumulations since then
+        readers = {}     # slot -> ops that read it since then
         for i in range(n):
             pre = set()
             for s_ in reads[i]:
-                if s_ in last_write:
-                    pre.add(last_write[s_])
+                if s_ in base:
+                    pre.add(base[s_])
+                pre.update(acc.get(s_, ()))
             w = writes[i]
-            if w in last_write:
-                pre.add(last_write[w])
-            for j in readers.get(w, ()):
-                pre.add(j)
+            if w in base:
+                pre.add(base[w])
+            pre.update(readers.get(w, ()))
+            if not commut[i]:
+                pre.update(acc.get(w, ()))
             pre.discard(i)
             for j in pre:
                 succ[j].append(i)
             npred[i] = len(pre)
             for s_ in reads[i]:
                 readers.setdefault(s_, []).append(i)
-            last_write[w] = i
-            readers[w] = []
+            if commut[i]:
+                acc.setdefault(w, []).append(i)
+            else:
+                base[w] = i
+                acc[w] = []
+                readers[w] = []
         ready = sorted(i for i in range(n) if npred[i] == 0)
         order, groups, chains = [], [], []
 

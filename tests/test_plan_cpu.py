@@ -417,6 +417,39 @@ def test_sumdiff_pairs(singlet):
     assert u1 < u0 - (1.9 if singlet else 3.9)
 
 
+def test_split_accumulators():
+    """plan.split_accumulators: later large contractions into one slot go through scratch slots
+    of their own; same residual, and at the benchmark size the m^6 contractions of the
+    closed-shell singlet program need fewer launch groups."""
+    n, ng = 4, 2
+    ints, amps, _ = util.random_u_closed(n, ng, seed=72)
+    Fa, Fb, Ia, Ib, Iabab = ints
+    src = {"Fa": Fa, "Fb": Fb, "Ia": Ia, "Ib": Ib, "Iabab": Iabab}
+    sizes = {("v", "a"): n, ("o", "a"): n, ("v", "b"): n, ("o", "b"): n}
+    ins = {"t1.a": amps[0], "t2.aa": amps[2], "t2.ab": amps[3]}
+    red = plan.mirror_reduce(plan.expand(programs.stanton(-1.0), programs.tensor_defs(), "u"))
+    base = plan.antisym_outputs(plan.sumdiff_pairs(plan.singlet_reduce(red)))
+    split = plan.split_accumulators(base)
+    assert sum(1 for op in split if op.out[0].startswith(plan.SPLIT_PREFIX)) >= 2
+    ref, _ = _run(red, "u", sizes, ins, src, ng)
+    got, _ = _run(split, "u", sizes, ins, src, ng)
+    for nm in ("o1.a", "o2.aa", "o2.ab"):
+        assert numpy.abs(got[nm] - ref[nm]).max() < 1e-12*numpy.abs(ref[nm]).max(), nm
+    m = 33
+    big = {("v", "a"): m, ("o", "a"): m, ("v", "b"): m, ("o", "b"): m}
+
+    def launches(ops):
+        shapes = plan.slot_shapes(ops, "u", big)
+        pres = [s for s in shapes if plan.is_integral_slot(s)] + [s for s in ins if s in shapes]
+        lw = plan.Lowered(ops, shapes, {s: not plan.is_integral_slot(s) for s in shapes}, pres)
+        return [len(g) for g in lw.groups if lw.descs[g[0]].kind == 0 and lw.descs[g[0]].K >= 500
+                and lw.descs[g[0]].tile in (0, 2)]
+    emit = plan.singlet_reduce(red, emit_aa=False)
+    g0 = launches(plan.antisym_outputs(plan.sumdiff_pairs(emit)))
+    g1 = launches(plan.split_accumulators(plan.antisym_outputs(plan.sumdiff_pairs(emit))))
+    assert sum(g0) == sum(g1) == 10 and len(g1) < len(g0), (g0, g1)
+
+
 def test_lambda_sweep_closed_shell_rewrites():
     """plan.merge_duplicates + plan.sumdiff_pairs + plan.antisym_outputs on the closed-shell
     Lambda program: mirror-duplicate contractions done once, three quartets as sum/difference

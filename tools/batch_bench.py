@@ -30,10 +30,12 @@ def main():
     def plan_for(ng):
         mr = bool(closed) and (ng >= ft_cc_equations.MIRROR_ROWS_MIN_BATCH if rows == "auto"
                                else rows == "1")
-        if mr not in plans:
-            plans[mr] = ft_cc_equations.stanton_plan("u", sizes, -1.0, mirror=closed,
-                                                     mirror_rows=mr, singlet=closed, emit_aa=not closed)
-        return plans[mr]
+        sa = ng <= ft_cc_equations.SPLIT_ACC_MAX_BATCH
+        if (mr, sa) not in plans:
+            plans[mr, sa] = ft_cc_equations.stanton_plan(
+                "u", sizes, -1.0, mirror=closed, mirror_rows=mr, singlet=closed, emit_aa=not closed,
+                split_acc=sa)
+        return plans[mr, sa]
     p = plan_for(max(ngs))
     ints = ft_cc_equations._u_integral_slots(Fa, Fb, Ia, Ib, Iabab, dev,
                                              [s for s in p.inputs if _plan.is_integral_slot(s)])
