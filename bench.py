@@ -235,7 +235,7 @@ def build_system(workload):
         dict(max_iter=80, econv=1e-11)
 
 
-def step_profile(fn, world):
+def step_profile(fn, world, write=True):
     """Kernel timeline of one step on rank 0 (torch.profiler / CUPTI) into
     gpurun_out/step_timeline_n<world>.txt -- a tuning aid, not part of the measurement."""
     import torch
@@ -245,7 +245,7 @@ def step_profile(fn, world):
         torch.cuda.synchronize()
     ev = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
     ev.sort(key=lambda e: e.time_range.start)
-    if not ev:
+    if not ev or not write:
         return
     t0 = ev[0].time_range.start
     os.makedirs("gpurun_out", exist_ok=True)
@@ -341,8 +341,9 @@ def main():
     t_step, (E, res) = timed(lambda: solver.step(0.0), K)
     launches = int(lib.kb200_launch_count())
     clocks = sampler.stop() if sampler else None
-    if os.environ.get("KB200_STEP_PROFILE") and rank == 0:
-        step_profile(lambda: solver.step(0.0), world)
+    if os.environ.get("KB200_STEP_PROFILE"):
+        # (every rank takes the extra step: it contains collectives)
+        step_profile(lambda: solver.step(0.0), world, rank == 0)
 
     # ---- auxiliary: the same step without the closed-shell reduction (every beta block
     # evaluated, all 32 block GEMMs per grid point), for a like-for-like flop count

@@ -358,11 +358,25 @@ def evaluate_rows(p, hybrid, t, flat, ng, y0, dev, cache=None):
             _trace.mark("own")
         cur.wait_stream(side)
     else:
-        run(*sh.own)
+        mine = sh.owner_row() if sh.r > 0 else None
         if sh.r > 0:
             owner_left = True
             parallel.zero_foreign_left_rows(flat, sh)
-            mine = sh.owner_row()
+        if mine is not None and sh.q == 1:
+            # one own row + one leftover row: two equally spaced grid points are ONE batch of 2
+            # (a strided view of the row buffer), not two launches of batch 1
+            a, step = sh.own[0], mine - sh.own[0]
+            tt = {}
+            for s_ in p.inputs + p.outputs:
+                if cache is not None and s_ in cache.tensors:
+                    la, _ = cache.local(a, a + 1)
+                    lb, _ = cache.local(mine, mine + 1)
+                    tt[s_] = cache.tensors[s_][la:lb + 1:lb - la]
+                else:
+                    tt[s_] = t[s_][a:mine + 1:step] if p.batched[s_] else t[s_]
+            p.run(tt, 2, _chunk_for(p, 2, dev))
+        else:
+            run(*sh.own)
             if mine is not None:
                 run(mine, mine + 1)
     _trace.mark("rows")

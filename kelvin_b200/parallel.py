@@ -33,7 +33,17 @@ except Exception:  # pragma: no cover
 
 _cfg = {"group": None,
         "enabled": os.environ.get("KB200_SHARD", "1") != "0",
-        "hybrid": os.environ.get("KB200_HYBRID", "1") != "0"}
+        "hybrid": os.environ.get("KB200_HYBRID", "1") != "0",
+        "spin_orbitals": None}
+
+# up to this many spin orbitals a grid point is a ~1 ms chain of launches (ESN33: 66), see
+# Shards.use_hybrid
+SMALL_SYSTEM = 80
+
+
+def set_work_hint(spin_orbitals):
+    """Size of the system the next sharded evaluations belong to (the solvers call this)."""
+    _cfg["spin_orbitals"] = None if spin_orbitals is None else int(spin_orbitals)
 
 
 def configure(group=None, enabled=None, hybrid=None):
@@ -108,8 +118,16 @@ class Shards(object):
     def use_hybrid(self):
         """Deal the leftover rows out by contraction rows (all ranks together) rather than one
         row per rank?  Owner mode costs the busiest rank q + 1 rows, the hybrid q + r/P plus the
-        replicated m^5 terms and two exchanges per leftover row (about a tenth of a row)."""
-        return hybrid_enabled() and self.r > 0 and self.r*(1.0/self.world + 0.1) < 1.0
+        replicated m^5 terms and two exchanges per leftover row (about a tenth of a row) -- and a
+        chain of ~100 small launches.  For small systems with ONE row per rank that chain is as
+        long as the row itself (ESN33 on 8 B200: own row 1.49 ms, own + shared 3.0 ms, two rows
+        as one batch of 2: 2.67 ms), so the leftover rows go to single owners there."""
+        if not hybrid_enabled() or self.r <= 0:
+            return False
+        n = _cfg["spin_orbitals"]
+        if self.q == 1 and n is not None and n <= SMALL_SYSTEM:
+            return False
+        return self.r*(1.0/self.world + 0.1) < 1.0
 
     def owner_row(self):
         """Owner mode: the leftover row this rank evaluates alone, or None."""

@@ -37,7 +37,7 @@ def main():
     logging.getLogger().addHandler(h)
     # 19 plane waves, ngrid 6: tau_0 skipped -> 5 evaluated points: 2 per rank + 1 leftover;
     # the m^6 contractions (361^3) are large enough to be dealt out by rows
-    T, mu, ng = 0.5, 7.0, 6
+    T, mu, ng = 0.5, 7.0, int(os.environ.get("KB200_TEST_NG", "6"))
     s = UEGSystem(T, 1.942, 30.0, mu=mu, norb=19, orbtype='u')
     cc = ccsd(s, T=T, mu=mu, ngrid=ng, max_iter=3, damp=0.0)
     om = cc.run()

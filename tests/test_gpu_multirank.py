@@ -51,3 +51,20 @@ def test_two_ranks_match_one_rank(built, tmp_path, hybrid):
     for k in ("omega", "E", "S", "N", "lam_norm", "t2_checksum", "n1rdm_trace"):
         assert abs(one[k] - two[k]) <= 1e-12*max(1.0, abs(one[k])), (k, one[k], two[k])
     assert two["ranks_agree"]
+
+
+def test_owner_rows_as_one_batch(built, tmp_path):
+    """ngrid 4 on 2 ranks without the shared evaluation: 3 evaluated points = 1 per rank + 1
+    leftover, which rank 0 runs together with its own point as one strided batch of 2."""
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    env = {"KB200_TEST_NG": "4", "KB200_HYBRID": "0"}
+    one = _run(1, "one4", tmp_path, env)
+    two = _run(2, "two4", tmp_path, env)
+    assert two["world"] == 2 and two["sharded"] and not two["hybrid_used"]
+    for k in ("traj_E", "traj_res"):
+        a, b = numpy.array(one[k]), numpy.array(two[k])
+        assert numpy.abs(a - b).max() <= 1e-12*max(1.0, numpy.abs(a).max()), k
+    for k in ("omega", "E", "S", "N", "lam_norm", "t2_checksum", "n1rdm_trace"):
+        assert abs(one[k] - two[k]) <= 1e-12*max(1.0, abs(one[k])), (k, one[k], two[k])
+    assert two["ranks_agree"]
