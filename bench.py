@@ -235,6 +235,16 @@ def build_system(workload):
         dict(max_iter=80, econv=1e-11)
 
 
+def partition_label(parallel, ng, t0, world):
+    """How the grid points that do not divide evenly over the ranks are evaluated."""
+    if world <= 1:
+        return ""
+    sh = parallel.Shards(ng, 1 if (t0 and ng > 1) else 0, 0, world)
+    if sh.r == 0:
+        return ""
+    return "+hybrid" if sh.use_hybrid() else "+owner"
+
+
 def step_profile(fn, world, write=True):
     """Kernel timeline of one step on rank 0 (torch.profiler / CUPTI) into
     gpurun_out/step_timeline_n<world>.txt -- a tuning aid, not part of the measurement."""
@@ -370,7 +380,8 @@ def main():
         p = ft_cc_equations.stanton_plan(
             "u", ft_cc_equations._u_sizes(Fa, Fb), -1.0, mirror=closed,
             mirror_rows=nloc >= ft_cc_equations.MIRROR_ROWS_MIN_BATCH,
-            singlet=flags["singlet"], antisym=flags["antisym"], emit_aa=not flags["singlet"])
+            singlet=flags["singlet"], antisym=flags["antisym"], emit_aa=not flags["singlet"],
+            split_acc=0 < max(y - x for x, y in rows) <= ft_cc_equations.SPLIT_ACC_MAX_BATCH)
         t = ft_cc_equations._u_integral_slots(
             Fa, Fb, Ia, Ib, Iabab, dev, [s for s in p.inputs if _plan.is_integral_slot(s)])
         for nm, x in zip(("t1.a", "t1.b", "t2.aa", "t2.ab", "t2.bb"), solver.old):
@@ -515,7 +526,7 @@ def main():
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": args.workload, "system": sysname,
                        "norb": norb, "ngrid": ng, "formulation": "u", "damp": 0.0,
-                       "parallelism": "tau%d%s" % (world, "+hybrid" if world > 1 and parallel.hybrid_enabled() else ""),
+                       "parallelism": "tau%d%s" % (world, partition_label(parallel, ng, t0f, world)),
                        "cache": "working set (amplitudes+integrals+intermediates) >> 126 MB L2",
                        "algorithmic_tflop_per_step": fl/1e12,
                        "tau0_shortcut": t0f, "tau_points_evaluated": npts,
