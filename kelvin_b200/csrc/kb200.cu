@@ -1157,6 +1157,12 @@ struct MultiStream {
     // stream for the launch made of ops[i .. i+n): inserts the waits it needs
     int begin(const kb200_op* ops, int i, int n, int nslots, cudaStream_t* out) {
         const kb200_op& o = ops[i];
+        for (int m = 0; m < n; ++m) {
+            const kb200_op& q = ops[i + m];
+            if (q.a < 0 || q.a >= nslots || q.c < 0 || q.c >= nslots ||
+                (q.kind != 1 && (q.b >= nslots || (q.kind != 3 && q.b < 0))))
+                return fail(-1, "plan: bad slot");
+        }
         const int S = op_is_wide(o) ? (nbig++ & 1) : pick_small(ops, i, n);
         if (!forked[S]) {
             if (cudaStreamWaitEvent(s[S], fork_ev, 0) != cudaSuccess)
