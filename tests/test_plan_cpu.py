@@ -450,6 +450,49 @@ def test_split_accumulators():
     assert sum(g0) == sum(g1) == 10 and len(g1) < len(g0), (g0, g1)
 
 
+def test_schedule_commuting_accumulations_keep_reader_order():
+    """Accumulations into one slot may be reordered by the scheduler, but every op that READS a
+    slot still comes after all the writes that preceded it in the program, and every overwrite
+    after all earlier readers: checked on the scheduled order of the closed-shell program by
+    replaying both orders symbolically (set of contributions seen by each reader)."""
+    n = 24      # large enough for the m^6 terms to count as wide launches (K = n^2 >= 512)
+    sizes = {("v", "a"): n, ("o", "a"): n, ("v", "b"): n, ("o", "b"): n}
+    red = plan.mirror_reduce(plan.expand(programs.stanton(-1.0), programs.tensor_defs(), "u"))
+    ops = plan.split_accumulators(plan.antisym_outputs(plan.sumdiff_pairs(plan.singlet_reduce(red))))
+    shapes = plan.slot_shapes(ops, "u", sizes)
+    pres = [s for s in shapes if plan.is_integral_slot(s)] + ["t1.a", "t2.aa", "t2.ab"]
+    batched = {s: not plan.is_integral_slot(s) for s in shapes}
+
+    def replay(low):
+        """slot -> frozenset of (op signature) contributions at the time of each read, per reader."""
+        state, seen = {}, {}
+        for d, op in zip(low.descs, low.rops):
+            sig = repr(op)
+            nm = low.slot_names
+            reads = [nm[d.a]] + ([nm[d.b]] if d.kind != 1 and d.b >= 0 else [])
+            for s_ in reads:
+                seen.setdefault(sig, []).append((s_, state.get(s_, frozenset())))
+            if d.beta == 0.0:
+                state[nm[d.c]] = frozenset([sig])
+            else:
+                state[nm[d.c]] = state.get(nm[d.c], frozenset()) | frozenset([sig])
+        return seen, state
+    old = plan.COMMUTE_ACC
+    try:
+        plan.COMMUTE_ACC = False
+        ref = plan.Lowered(ops, shapes, batched, pres)
+        plan.COMMUTE_ACC = True
+        got = plan.Lowered(ops, shapes, batched, pres)
+    finally:
+        plan.COMMUTE_ACC = old
+    assert [repr(o) for o in ref.rops] != [repr(o) for o in got.rops]      # the order did change
+    seen_ref, state_ref = replay(ref)
+    seen_got, state_got = replay(got)
+    assert state_ref == state_got
+    assert {k: sorted(v, key=repr) for k, v in seen_ref.items()} == \
+        {k: sorted(v, key=repr) for k, v in seen_got.items()}
+
+
 def test_lambda_sweep_closed_shell_rewrites():
     """plan.merge_duplicates + plan.sumdiff_pairs + plan.antisym_outputs on the closed-shell
     Lambda program: mirror-duplicate contractions done once, three quartets as sum/difference
