@@ -228,6 +228,44 @@ def pueg_fixture():
     print("pueg", Etot, Ecc, cc.E, cc.S, cc.N)
 
 
+def uegscf_fixture():
+    """UEG with HF orbital energies (kelvin/ueg_scf_system.py), parameters of
+    kelvin/tests/test_ft_deriv.py:277-292 (u path) and the same system through the g path."""
+    from kelvin.ueg_scf_system import UEGSCFSystem
+    T, mu = 0.1, 0.1
+    L = 2*numpy.pi/numpy.sqrt(1.0)
+    out = {}
+    for orb in ("u", "g"):
+        s = UEGSCFSystem(T, L, 1.2, mu=mu, norb=7, orbtype=orb)
+        out["N_" + orb] = s.N
+        out["mp1_" + orb] = s.get_mp1()
+        if orb == "u":
+            out["ea"] = s.u_energies_tot()[0]
+            out["fa"], out["fb"] = s.u_fock_tot()
+            out["mp1den_u"] = numpy.stack(s.u_mp1_den())
+            out["fdd_u"] = numpy.stack(s.u_fock_d_den())
+            out["fdt_u"] = numpy.stack(s.u_fock_d_tot(numpy.arange(7.0), numpy.arange(7.0) + 1.0))
+            out["dmp1_u"] = s.u_d_mp1(numpy.arange(7.0), numpy.arange(7.0) + 1.0)
+        else:
+            out["en"] = s.g_energies_tot()
+            out["f"] = s.g_fock_tot()
+            out["mp1den_g"] = s.g_mp1_den()
+            out["fdd_g"] = s.g_fock_d_den()
+            out["fdt_g"] = s.g_fock_d_tot(numpy.arange(14.0))
+            out["dmp1_g"] = s.g_d_mp1(numpy.arange(14.0))
+        cc = ccsd(s, T=T, mu=mu, iprint=0, max_iter=50, damp=0.2, ngrid=8)
+        Etot, Ecc = cc.run()
+        cc.compute_ESN()
+        out.update({"Etot_" + orb: Etot, "Ecc_" + orb: Ecc, "E_" + orb: cc.E, "S_" + orb: cc.S,
+                    "Ncc_" + orb: cc.N})
+        if orb == "u":
+            out["T2ab"] = cc.T2[1]
+        else:
+            out["T2"] = cc.T2
+        print("uegscf", orb, repr(Etot), repr(Ecc), repr(cc.E), repr(cc.S), repr(cc.N))
+    numpy.savez_compressed(os.path.join(HERE, "uegscf7.npz"), **out)
+
+
 def esn19_tight_fixture():
     """BASELINE config 0 (bench/ueg_ft_ccsd_ESN19.py:5-22) converged TIGHTLY (econv 1e-12,
     tconv 1e-10) by the unmodified reference drivers: the scalars north_star asks to reproduce
@@ -249,6 +287,8 @@ if __name__ == "__main__":
         esn19_tight_fixture()
     elif len(sys.argv) > 1 and sys.argv[1] == "pueg":
         pueg_fixture()
+    elif len(sys.argv) > 1 and sys.argv[1] == "uegscf":
+        uegscf_fixture()
     elif len(sys.argv) > 1 and sys.argv[1] == "active":
         active_fixtures()
     elif len(sys.argv) > 1 and sys.argv[1] == "variants":

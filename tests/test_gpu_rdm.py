@@ -197,3 +197,28 @@ def test_pueg_on_gpu(built):
     cc.compute_ESN()
     assert abs(cc.E - float(ref["E"])) < 1e-9 and abs(cc.S - float(ref["S"])) < 1e-9
     assert abs(cc.N - float(ref["N_"])) < 1e-9
+
+
+@pytest.mark.parametrize("orb", ["u", "g"])
+def test_uegscf_on_gpu(built, orb):
+    """UEG with Hartree-Fock orbital energies (kelvin/ueg_scf_system.py; parameters of
+    kelvin/tests/test_ft_deriv.py:277-292) through run() and compute_ESN() on the GPU against the
+    unmodified reference drivers (tests/golden/uegscf7.npz)."""
+    import os
+    from kelvin_b200.ccsd import ccsd
+    from kelvin_b200.ueg_scf_system import UEGSCFSystem
+    ref = numpy.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "uegscf7.npz"))
+    T, mu = 0.1, 0.1
+    s = UEGSCFSystem(T, 2*numpy.pi, 1.2, mu=mu, norb=7, orbtype=orb)
+    cc = ccsd(s, T=T, mu=mu, iprint=0, max_iter=50, damp=0.2, ngrid=8)
+    Etot, Ecc = cc.run()
+    assert abs(Etot - float(ref["Etot_" + orb])) < 1e-10
+    assert abs(Ecc - float(ref["Ecc_" + orb])) < 1e-11
+    if orb == "u":
+        assert numpy.abs(cc.T2[1].cpu().numpy() - ref["T2ab"]).max() < 1e-9
+    else:
+        assert numpy.abs(cc.T2.cpu().numpy() - ref["T2"]).max() < 1e-9
+    cc.compute_ESN()
+    assert abs(cc.E - float(ref["E_" + orb])) < 1e-9
+    assert abs(cc.S - float(ref["S_" + orb])) < 1e-9
+    assert abs(cc.N - float(ref["Ncc_" + orb])) < 1e-9

@@ -250,3 +250,55 @@ def test_pueg_system_matches_reference_fixture():
     assert abs(Ecc - float(ref["Ecc"])) < 1e-12
     assert abs(Ecc - (-0.001403909274)) < 1e-8
     assert numpy.abs(T2 - ref["T2"]).max() < 1e-10
+
+
+def test_uegscf_system_matches_reference_fixture():
+    """kelvin_b200.ueg_scf_system.UEGSCFSystem (HF orbital energies of the zero-temperature
+    reference determinant) against the arrays of the unmodified kelvin/ueg_scf_system.py
+    (tests/golden/make_golden.py uegscf; parameters of kelvin/tests/test_ft_deriv.py:277-292), and
+    -- through the CPU oracle loops -- against the reference drivers' grand potential for it on
+    the g and the u path."""
+    from kelvin_b200.ueg_scf_system import UEGSCFSystem
+    from kelvin_oracle import cqc, driver as odrv
+    ref = numpy.load(os.path.join(HERE, "golden", "uegscf7.npz"))
+    T, mu, ng = 0.1, 0.1, 8
+    beta = 1.0/T
+    su = UEGSCFSystem(T, 2*numpy.pi, 1.2, mu=mu, norb=7)
+    sg = UEGSCFSystem(T, 2*numpy.pi, 1.2, mu=mu, norb=7, orbtype='g')
+    assert su.has_u() and not sg.has_u() and su.verify(T, mu) and not su.verify(T, 0.2)
+    assert list(su.oidx) == [0] and list(su.goidx) == [0, 7]
+    assert abs(su.N - float(ref["N_u"])) < 1e-14 and abs(sg.N - float(ref["N_g"])) < 1e-14
+    assert abs(su.get_mp1() - float(ref["mp1_u"])) < 1e-14
+    assert abs(sg.get_mp1() - float(ref["mp1_g"])) < 1e-14
+    assert numpy.abs(su.u_energies_tot()[0] - ref["ea"]).max() < 1e-15
+    assert numpy.abs(sg.g_energies_tot() - ref["en"]).max() < 1e-15
+    fa, fb = su.u_fock_tot()
+    assert numpy.abs(fa - ref["fa"]).max() < 1e-14 and numpy.abs(fb - ref["fb"]).max() < 1e-14
+    assert numpy.abs(sg.g_fock_tot() - ref["f"]).max() < 1e-14
+    assert numpy.abs(numpy.stack(su.u_mp1_den()) - ref["mp1den_u"]).max() < 1e-14
+    assert numpy.abs(sg.g_mp1_den() - ref["mp1den_g"]).max() < 1e-14
+    assert numpy.abs(numpy.stack(su.u_fock_d_den()) - ref["fdd_u"]).max() < 1e-14
+    assert numpy.abs(sg.g_fock_d_den() - ref["fdd_g"]).max() < 1e-14
+    v = numpy.arange(7.0)
+    assert numpy.abs(numpy.stack(su.u_fock_d_tot(v, v + 1.0)) - ref["fdt_u"]).max() < 1e-14
+    assert numpy.abs(sg.g_fock_d_tot(numpy.arange(14.0)) - ref["fdt_g"]).max() < 1e-14
+    assert abs(su.u_d_mp1(v, v + 1.0) - float(ref["dmp1_u"])) < 1e-14
+    assert abs(sg.g_d_mp1(numpy.arange(14.0)) - float(ref["dmp1_g"])) < 1e-14
+    conv = {"econv": 1e-8, "tconv": 1e-5, "max_iter": 50, "damp": 0.2}
+    ti, g, G = odrv.simpsons(ng, beta)
+    # g path
+    en = sg.g_energies_tot()
+    F, I = odrv.ft_integrals(sg, en, beta, mu)
+    D1, D2 = cqc.D1(en, en), cqc.D2(en, en)
+    T1, T2 = odrv.mp2_guess_g(F, I, D1, D2, ti, ng, G)
+    Ecc, T1, T2, hist = odrv.ft_cc_iter(T1, T2, F, I, D1, D2, g, G, beta, ng, ti, conv)
+    assert abs(Ecc - float(ref["Ecc_g"])) < 1e-12
+    assert numpy.abs(T2 - ref["T2"]).max() < 1e-10
+    # u path
+    ea, eb = su.u_energies_tot()
+    Fa, Fb, Ia, Ib, Iabab = odrv.uft_integrals(su, ea, eb, beta, mu)
+    Ds = (cqc.D1(ea, ea), cqc.D1(eb, eb), cqc.D2(ea, ea), cqc.D2u(ea, eb, ea, eb), cqc.D2(eb, eb))
+    amps = odrv.mp2_guess_u(Fa, Fb, Ia, Ib, Iabab, *Ds, ti, ng, G)
+    Ecc, T1s, T2s, hist = odrv.ft_ucc_iter(*amps, Fa, Fb, Ia, Ib, Iabab, *Ds, g, G, beta, ng, ti, conv)
+    assert abs(Ecc - float(ref["Ecc_u"])) < 1e-12
+    assert numpy.abs(T2s[1] - ref["T2ab"]).max() < 1e-10
