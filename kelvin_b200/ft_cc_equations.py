@@ -331,7 +331,7 @@ def evaluate_rows(p, hybrid, t, flat, ng, y0, dev, cache=None):
     sh = parallel.Shards(ng, y0)
     owner_left = False
     hp = None
-    if sh.r > 0 and sh.use_hybrid() and hybrid is not None:
+    if sh.r > 0 and sh.use_hybrid(small_owner=cache is None) and hybrid is not None:
         try:
             hp = hybrid()
         except ValueError:
@@ -362,18 +362,12 @@ def evaluate_rows(p, hybrid, t, flat, ng, y0, dev, cache=None):
         if sh.r > 0:
             owner_left = True
             parallel.zero_foreign_left_rows(flat, sh)
-        if mine is not None and sh.q == 1:
+        if mine is not None and sh.q == 1 and cache is None:
             # one own row + one leftover row: two equally spaced grid points are ONE batch of 2
             # (a strided view of the row buffer), not two launches of batch 1
             a, step = sh.own[0], mine - sh.own[0]
-            tt = {}
-            for s_ in p.inputs + p.outputs:
-                if cache is not None and s_ in cache.tensors:
-                    la, _ = cache.local(a, a + 1)
-                    lb, _ = cache.local(mine, mine + 1)
-                    tt[s_] = cache.tensors[s_][la:lb + 1:lb - la]
-                else:
-                    tt[s_] = t[s_][a:mine + 1:step] if p.batched[s_] else t[s_]
+            tt = {s_: (t[s_][a:mine + 1:step] if p.batched[s_] else t[s_])
+                  for s_ in p.inputs + p.outputs}
             p.run(tt, 2, _chunk_for(p, 2, dev))
         else:
             run(*sh.own)
@@ -395,13 +389,14 @@ def _side_stream(dev):
     return _side[dev.index]
 
 
-def needed_rows(ng, y0=0):
-    """Row ranges of [y0, ng) this rank evaluates (alone or together with the others)."""
+def needed_rows(ng, y0=0, small_owner=True):
+    """Row ranges of [y0, ng) this rank evaluates (alone or together with the others);
+    small_owner as in parallel.Shards.use_hybrid (False for evaluations over a RowCache)."""
     from . import parallel
     if not parallel.active():
         return [(y0, ng)]
     sh = parallel.Shards(ng, y0)
-    return sh.my_rows(sh.use_hybrid())
+    return sh.my_rows(sh.use_hybrid(small_owner=small_owner))
 
 
 # ---------------------------------------------------------------------------
@@ -693,7 +688,7 @@ def _lambda_intermediates(mode, sizes, ints_slots, tslots, ng, dev, mirror=False
     """Forward intermediates for the current amplitudes on the rows this rank evaluates, cached
     across Lambda iterations (RowCache), or None when they do not fit."""
     prep, sweep = lambda_split_plans(mode, sizes, mirror=mirror, antisym=antisym)
-    ranges = needed_rows(ng)
+    ranges = needed_rows(ng, small_owner=False)
     # the cache entry keeps the key tensors alive: a live tensor's address cannot be handed to
     # another tensor, so equal (address, version) means the very same, unmodified tensors
     refs = list(tslots.values()) + list(ints_slots.values())

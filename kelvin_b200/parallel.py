@@ -115,17 +115,19 @@ class Shards(object):
         self.whole = (self.y0, self.y0 + self.world*self.q)
         self.left = (self.whole[1], self.ng)
 
-    def use_hybrid(self):
+    def use_hybrid(self, small_owner=True):
         """Deal the leftover rows out by contraction rows (all ranks together) rather than one
         row per rank?  Owner mode costs the busiest rank q + 1 rows, the hybrid q + r/P plus the
         replicated m^5 terms and two exchanges per leftover row (about a tenth of a row) -- and a
         chain of ~100 small launches.  For small systems with ONE row per rank that chain is as
         long as the row itself (ESN33 on 8 B200: own row 1.49 ms, own + shared 3.0 ms, two rows
-        as one batch of 2: 2.67 ms), so the leftover rows go to single owners there."""
+        as one batch of 2: 2.67 ms), so the leftover rows go to single owners there
+        (small_owner=False: not for this call -- the Lambda sweep over cached intermediates keeps
+        the shared evaluation)."""
         if not hybrid_enabled() or self.r <= 0:
             return False
         n = _cfg["spin_orbitals"]
-        if self.q == 1 and n is not None and n <= SMALL_SYSTEM:
+        if small_owner and self.q == 1 and n is not None and n <= SMALL_SYSTEM:
             return False
         return self.r*(1.0/self.world + 0.1) < 1.0
 
