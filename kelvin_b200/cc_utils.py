@@ -249,8 +249,6 @@ class GccStep(object):
 
     def __init__(self, T1old, T2old, F, I, D1, D2, g, G, beta, ng, ti):
         dev = self.dev = _lib.device()
-        from . import parallel
-        parallel.set_work_hint(sum(F.ov.shape))
         self.F, self.I, self.g, self.G, self.beta, self.ng, self.ti = F, I, g, G, beta, ng, ti
         self.D1, self.D2 = _lib.as_dev(D1, dev), _lib.as_dev(D2, dev)
         self.T1 = _lib.as_dev(T1old, dev).clone()
@@ -349,8 +347,6 @@ class UccStep(object):
 
     def __init__(self, amps, Fa, Fb, Ia, Ib, Iabab, Ds, g, G, beta, ng, ti, known=None):
         dev = self.dev = _lib.device()
-        from . import parallel
-        parallel.set_work_hint(sum(Fa.ov.shape) + sum(Fb.ov.shape))
         self.ints = (Fa, Fb, Ia, Ib, Iabab)
         self.Ds = [_lib.as_dev(d, dev) for d in Ds]
         self.g, self.G, self.beta, self.ng, self.ti = g, G, beta, ng, ti

@@ -17,7 +17,7 @@ import time
 import numpy
 import torch
 
-from . import _lib, cc_utils, ft_cc_energy, ft_cc_equations, ft_mp, ft_utils, parallel, quadrature
+from . import _lib, cc_utils, ft_cc_energy, ft_cc_equations, ft_mp, ft_utils, quadrature
 
 
 class ccsd(object):
@@ -159,7 +159,6 @@ class ccsd(object):
                 D2 = ft_utils.D2(en, en)
                 F, I = cc_utils.ft_integrals(self.sys, en, self.beta, self.mu)
             self._ints = ("g", en, D1, D2, F, I)
-        parallel.set_work_hint(sum(self._ints[4].ov.shape))
         return self._ints[1:]
 
     def _u_setup(self):
@@ -182,7 +181,6 @@ class ccsd(object):
             D2ab = ft_utils.D2u(eva, evb, eoa, eob)
             D2bb = ft_utils.D2(evb, eob)
             self._ints = ("u", ea, eb, (D1a, D1b, D2aa, D2ab, D2bb), (Fa, Fb, Ia, Ib, Iabab))
-        parallel.set_work_hint(sum(self._ints[4][0].ov.shape) + sum(self._ints[4][1].ov.shape))
         return self._ints[1:]
 
     def _ft_ccsd(self, T1in=None, T2in=None):

@@ -331,7 +331,7 @@ def evaluate_rows(p, hybrid, t, flat, ng, y0, dev, cache=None):
     sh = parallel.Shards(ng, y0)
     owner_left = False
     hp = None
-    if sh.r > 0 and sh.use_hybrid(small_owner=cache is None) and hybrid is not None:
+    if sh.r > 0 and sh.use_hybrid() and hybrid is not None:
         try:
             hp = hybrid()
         except ValueError:
@@ -389,14 +389,13 @@ def _side_stream(dev):
     return _side[dev.index]
 
 
-def needed_rows(ng, y0=0, small_owner=True):
-    """Row ranges of [y0, ng) this rank evaluates (alone or together with the others);
-    small_owner as in parallel.Shards.use_hybrid (False for evaluations over a RowCache)."""
+def needed_rows(ng, y0=0):
+    """Row ranges of [y0, ng) this rank evaluates (alone or together with the others)."""
     from . import parallel
     if not parallel.active():
         return [(y0, ng)]
     sh = parallel.Shards(ng, y0)
-    return sh.my_rows(sh.use_hybrid(small_owner=small_owner))
+    return sh.my_rows(sh.use_hybrid())
 
 
 # ---------------------------------------------------------------------------
@@ -688,7 +687,7 @@ def _lambda_intermediates(mode, sizes, ints_slots, tslots, ng, dev, mirror=False
     """Forward intermediates for the current amplitudes on the rows this rank evaluates, cached
     across Lambda iterations (RowCache), or None when they do not fit."""
     prep, sweep = lambda_split_plans(mode, sizes, mirror=mirror, antisym=antisym)
-    ranges = needed_rows(ng, small_owner=False)
+    ranges = needed_rows(ng)
     # the cache entry keeps the key tensors alive: a live tensor's address cannot be handed to
     # another tensor, so equal (address, version) means the very same, unmodified tensors
     refs = list(tslots.values()) + list(ints_slots.values())

@@ -33,17 +33,7 @@ except Exception:  # pragma: no cover
 
 _cfg = {"group": None,
         "enabled": os.environ.get("KB200_SHARD", "1") != "0",
-        "hybrid": os.environ.get("KB200_HYBRID", "1") != "0",
-        "spin_orbitals": None}
-
-# up to this many spin orbitals a grid point is a ~1 ms chain of launches (ESN33: 66), see
-# Shards.use_hybrid
-SMALL_SYSTEM = 80
-
-
-def set_work_hint(spin_orbitals):
-    """Size of the system the next sharded evaluations belong to (the solvers call this)."""
-    _cfg["spin_orbitals"] = None if spin_orbitals is None else int(spin_orbitals)
+        "hybrid": os.environ.get("KB200_HYBRID", "1") != "0"}
 
 
 def configure(group=None, enabled=None, hybrid=None):
@@ -115,21 +105,14 @@ class Shards(object):
         self.whole = (self.y0, self.y0 + self.world*self.q)
         self.left = (self.whole[1], self.ng)
 
-    def use_hybrid(self, small_owner=True):
+    def use_hybrid(self):
         """Deal the leftover rows out by contraction rows (all ranks together) rather than one
         row per rank?  Owner mode costs the busiest rank q + 1 rows, the hybrid q + r/P plus the
         replicated m^5 terms and two exchanges per leftover row (about a tenth of a row) -- and a
-        chain of ~100 small launches.  For small systems with ONE row per rank that chain is as
-        long as the row itself (ESN33 on 8 B200: own row 1.49 ms, own + shared 3.0 ms, two rows
-        as one batch of 2: 2.67 ms), so the leftover rows go to single owners there
-        (small_owner=False: not for this call -- the Lambda sweep over cached intermediates keeps
-        the shared evaluation)."""
-        if not hybrid_enabled() or self.r <= 0:
-            return False
-        n = _cfg["spin_orbitals"]
-        if small_owner and self.q == 1 and n is not None and n <= SMALL_SYSTEM:
-            return False
-        return self.r*(1.0/self.world + 0.1) < 1.0
+        chain of ~100 small launches, which for the smallest benchmark is as long as a row itself
+        (ESN33 on 8 B200: own row 1.49 ms, own + shared 3.0 ms, an owner's two rows as one batch
+        2.67 ms + the wait of the other ranks: a tie, measured 3.45 ms with the shared row)."""
+        return hybrid_enabled() and self.r > 0 and self.r*(1.0/self.world + 0.1) < 1.0
 
     def owner_row(self):
         """Owner mode: the leftover row this rank evaluates alone, or None."""

@@ -138,16 +138,6 @@ def test_shards_partition():
     assert (sh.q, sh.r, sh.own, sh.left) == (1, 1, (4, 5), (9, 10)) and sh.use_hybrid()
     # UEG-57 (ng 16, tau_0 skipped) on 8 GPUs: 7 leftover rows go to single owners
     assert not Shards(16, 1, 0, 8).use_hybrid()
-    # ... and for a small system with one row per rank the shared evaluation is a launch chain as
-    # long as the row itself: the leftover row goes to one owner (which runs a batch of 2)
-    from kelvin_b200 import parallel
-    parallel.set_work_hint(66)
-    try:
-        assert not Shards(10, 1, 3, 8).use_hybrid() and Shards(10, 1, 3, 4).use_hybrid()
-        parallel.set_work_hint(114)
-        assert Shards(10, 1, 3, 8).use_hybrid()
-    finally:
-        parallel.set_work_hint(None)
 
 
 def _gloo_worker(rank, world, port, ng, y0, q):
