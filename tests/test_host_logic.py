@@ -188,6 +188,25 @@ def test_row_exchange_gloo_world2(ng, y0):
         assert ok and tot == 3.0
 
 
+@pytest.mark.parametrize("ng,y0", [(10, 1), (7, 0)])
+def test_row_exchange_gloo_world4(ng, y0):
+    """The same on 4 CPU ranks: ESN33's grid on 4 ranks (2 whole rows each + 1 leftover) and a grid
+    with one whole row per rank and three leftover rows."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() + 7*ng + y0) % 2000
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 4, port, ng, y0, q)) for r in range(4)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(r[0] for r in res) == [0, 1, 2, 3]
+    for rank, ok, tot in res:
+        assert ok and tot == 10.0
+
+
 def test_t0_is_zero_predicate():
     """The tau_0 shortcut is only taken when row 0 of G vanishes and every amplitude block is
     exactly zero at the first grid point."""
